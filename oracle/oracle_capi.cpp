@@ -1,0 +1,259 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see c6_rng.hpp header note).
+// C interface over c6_oracle.hpp for ctypes (tests/, bench.py cpu_baseline / --impl reference,
+// __graft_entry__.smoke()).  Nothing here is linked into the shipped library.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "c6_oracle.hpp"
+
+using namespace c6o;
+
+namespace {
+Board board_from_i8(const int8_t* b) {
+    Board out;
+    for (int r = 0; r < BOARD_SIZE; ++r)
+        for (int c = 0; c < BOARD_SIZE; ++c) out[r][c] = player_from(b[r * BOARD_SIZE + c]);
+    return out;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- deterministic evaluators usable as the reference `Callback` (connect6.hpp:14) -------------
+// SURVEY B.4.  Bit-identical to the engine's device twin (csrc/c6_rng.cuh: det_eval_*).
+static inline uint64_t oriented_key(const float* board) {
+    const Zobrist& z = zobrist();
+    uint64_t k = 0;
+    for (int i = 0; i < BOARD_CAPACITY; ++i) {
+        if (board[i] < 0.f) k ^= z.z[0][i];
+        if (board[i] > 0.f) k ^= z.z[1][i];
+    }
+    return k;
+}
+void det_eval_callback(int player, float* values, float* policies, int len) {
+    for (int n = 0; n < len; ++n) {
+        float* b = policies + (size_t)n * BOARD_CAPACITY;
+        uint64_t h = splitmix64(oriented_key(b) ^ (player < 0 ? 0xB1ACull : 0x3417Eull));
+        values[n] = (float)(uint32_t)(h >> 40) * (1.0f / 8388608.0f) - 1.0f;
+        for (int i = 0; i < BOARD_CAPACITY; ++i)
+            b[i] = (float)(uint32_t)(splitmix64(h + (uint64_t)i + 1) >> 40) * (1.0f / 16777216.0f);
+    }
+}
+// priors in [-1,1) like RandomEvaluator (negative priors exercise the sqrt(S-n) quirk)
+void neg_eval_callback(int player, float* values, float* policies, int len) {
+    for (int n = 0; n < len; ++n) {
+        float* b = policies + (size_t)n * BOARD_CAPACITY;
+        uint64_t h = splitmix64(oriented_key(b) ^ (player < 0 ? 0xB1ACull : 0x3417Eull));
+        values[n] = (float)(uint32_t)(h >> 40) * (1.0f / 8388608.0f) - 1.0f;
+        for (int i = 0; i < BOARD_CAPACITY; ++i)
+            b[i] = (float)(uint32_t)(splitmix64(h + (uint64_t)i + 1) >> 40) * (1.0f / 8388608.0f) - 1.0f;
+    }
+}
+// SURVEY B.1 hand-derived trace evaluator
+void const_eval_callback(int, float* values, float* policies, int len) {
+    for (int n = 0; n < len; ++n) values[n] = 0.5f;
+    for (size_t i = 0; i < (size_t)len * BOARD_CAPACITY; ++i) policies[i] = 0.25f;
+}
+
+// ---- small pieces -------------------------------------------------------------------------------
+int oracle_search(const int8_t* board) { return (int)search(board_from_i8(board)); }
+
+void oracle_augment_way8(const int8_t* board, int8_t* out) {
+    auto v = augment_way8(board_from_i8(board));
+    for (int s = 0; s < 8; ++s)
+        for (int r = 0; r < BOARD_SIZE; ++r)
+            for (int c = 0; c < BOARD_SIZE; ++c) out[s * BOARD_CAPACITY + r * BOARD_SIZE + c] = (int8_t)v[s][r][c];
+}
+void oracle_recover_way8(const float* in, float* out) {
+    std::vector<FBoard> p(8);
+    for (int s = 0; s < 8; ++s) std::memcpy(&p[s][0][0], in + s * BOARD_CAPACITY, sizeof(FBoard));
+    FBoard r = recover_way8(p);
+    std::memcpy(out, &r[0][0], sizeof(FBoard));
+}
+uint64_t oracle_zobrist(int white, int cell) { return zobrist().z[white ? 1 : 0][cell]; }
+void oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    std::memcpy(out, r.v, 16);
+}
+double oracle_det_log(double x) { return det_log(x); }
+double oracle_det_exp(double x) { return det_exp(x); }
+double oracle_gamma(uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1, double shape) {
+    PhiloxStream st(a, b, c, k0, k1);
+    return gamma_sample(st, shape);
+}
+
+// Random playout (default_policy/mod.rs:186-203 rollout loop) from the empty board with the
+// engine's Philox stream: stone n of playout p picks index (u32 * remaining) >> 32 of the
+// row-major list of empty cells; counter (p_lo, p_hi, n/4, 0) lane n%4, key (seed^PLAY, 0).
+void oracle_playout(uint32_t seed, uint64_t playout, int* winner, int* stones, int8_t* final_board) {
+    Simulate sim;
+    sim.possible = Simulate::possible_from(sim.board);
+    int n = 0;
+    Philox4 blk{};
+    while (search(sim.board) == Player::None && !sim.possible.empty()) {
+        if ((n & 3) == 0)
+            blk = philox4x32_10((uint32_t)playout, (uint32_t)(playout >> 32), (uint32_t)(n >> 2), 0,
+                                seed ^ DOMAIN_PLAYOUT, 0);
+        uint32_t u = blk.v[n & 3];
+        size_t pick = (size_t)(((uint64_t)u * (uint64_t)sim.possible.size()) >> 32);
+        // `possible` stays in row-major order: simulate_in removes order-preservingly and the
+        // rollout never rolls back (default_policy/mod.rs:190-199), so this is the k-th empty cell.
+        Pos p = sim.possible[pick];
+        sim.simulate_in(p.first, p.second);
+        ++n;
+    }
+    *winner = (int)search(sim.board);
+    *stones = n;
+    if (final_board)
+        for (int r = 0; r < BOARD_SIZE; ++r)
+            for (int c = 0; c < BOARD_SIZE; ++c) final_board[r * BOARD_SIZE + c] = (int8_t)sim.board[r][c];
+}
+
+// ---- scripted game (agent_impl/tests.rs TestPolicy) ------------------------------------------
+struct ScriptPolicy : Policy {
+    const int* moves;
+    int n, i = 0;
+    ScriptPolicy(const int* m, int n_) : moves(m), n(n_) {}
+    std::optional<Pos> next(const Game&) override {
+        if (i >= n) return std::nullopt;
+        Pos p(moves[2 * i], moves[2 * i + 1]);
+        ++i;
+        return p;
+    }
+};
+// returns path length, or -1 on Err (err_out gets the description); paths: per entry turn + 225 cells + row + col (ints)
+int oracle_script_game(const int* moves, int n, int* winner, int* paths, char* err_out) {
+    ScriptPolicy pol(moves, n);
+    PlayResult r = agent_play(pol);
+    if (!r.error.empty()) {
+        std::strncpy(err_out, r.error.c_str(), 63);
+        return -1;
+    }
+    *winner = (int)r.winner;
+    for (size_t k = 0; k < r.path.size(); ++k) {
+        int* p = paths + k * (BOARD_CAPACITY + 3);
+        p[0] = (int)r.path[k].turn;
+        for (int i = 0; i < BOARD_CAPACITY; ++i) p[1 + i] = (int)r.path[k].board[i / BOARD_SIZE][i % BOARD_SIZE];
+        p[1 + BOARD_CAPACITY] = r.path[k].pos.first;
+        p[2 + BOARD_CAPACITY] = r.path[k].pos.second;
+    }
+    return (int)r.path.size();
+}
+
+// ---- self-play ----------------------------------------------------------------------------------
+struct OracleParams {
+    int32_t num_simulation;
+    float epsilon;
+    double dirichlet_alpha;
+    float c_puct;
+    uint32_t seed;
+    int32_t noise_mode;  // 0 none (epsilon must be 0), 1 philox
+    int32_t tie_mode;    // 0 lowest index, 1 random
+    int32_t faithful;    // 0 lean, 1 reference cost model
+    int32_t evaluator;   // 0 callback, 1 philox random evaluator
+    int32_t max_moves;   // stop after this many stones (<=0: play to the end)
+};
+
+struct OracleGameOut {
+    int32_t winner;
+    int32_t n_moves;
+    int32_t finished;     // 0 when cut by max_moves
+    int32_t moves[BOARD_CAPACITY];             // row*15+col
+    int32_t turns[BOARD_CAPACITY];             // -1/+1 side that placed the stone
+    uint64_t sims, sum_ck, sum_cleaf, sum_depth, evals, max_nodes;
+};
+
+static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, OracleGameOut* out,
+                     int32_t* child_visits, int32_t* root_visit, float* root_qsum) {
+    HyperParameter hp;
+    hp.num_simulation = p.num_simulation, hp.epsilon = p.epsilon, hp.dirichlet_alpha = p.dirichlet_alpha,
+    hp.c_puct = p.c_puct;
+    std::unique_ptr<Evaluator> ev;
+    if (p.evaluator == 1)
+        ev.reset(new PhiloxRandomEvaluator());
+    else
+        ev.reset(new CppEval(cb));
+    AlphaZeroPolicy pol(ev.get(), hp);
+    pol.az.tie = p.tie_mode ? TieBreak::Random : TieBreak::LowestIndex;
+    pol.az.noise = p.noise_mode ? NoiseMode::Philox : NoiseMode::None;
+    pol.az.faithful = p.faithful != 0;
+    pol.az.ctx.seed = p.seed;
+    pol.az.ctx.game_id = game_id;
+    pol.trace = child_visits != nullptr;
+
+    // Agent::play with an optional stone limit (bounded samples for timing)
+    Game game;
+    out->winner = 0, out->n_moves = 0, out->finished = 1;
+    for (;;) {
+        if (p.max_moves > 0 && out->n_moves >= p.max_moves) {
+            out->finished = 0;
+            break;
+        }
+        auto pos = pol.next(game);
+        if (!pos) break;
+        out->moves[out->n_moves] = pos->first * BOARD_SIZE + pos->second;
+        out->turns[out->n_moves] = (int)game.turn;
+        out->n_moves += 1;
+        std::string err = game.set(*pos);
+        if (!err.empty()) std::abort();
+        Player e = game.is_game_end();
+        if (e != Player::None) {
+            out->winner = (int)e;
+            break;
+        }
+    }
+    const SearchStats& s = pol.az.stats;
+    out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf, out->sum_depth = s.sum_depth,
+    out->evals = s.evals, out->max_nodes = s.max_nodes;
+    if (child_visits) {
+        for (size_t m = 0; m < pol.child_visits.size(); ++m) {
+            std::memcpy(child_visits + m * BOARD_CAPACITY, pol.child_visits[m].data(), BOARD_CAPACITY * 4);
+            root_visit[m] = pol.root_visit[m];
+            root_qsum[m] = pol.root_qsum[m];
+        }
+    }
+}
+
+// One game.  child_visits: [225][225] i32 (row m = the root's children before stone m), may be NULL.
+void oracle_self_play(Callback cb, const OracleParams* p, uint32_t game_id, OracleGameOut* out,
+                      int32_t* child_visits, int32_t* root_visit, float* root_qsum) {
+    play_one(cb, *p, game_id, out, child_visits, root_visit, root_qsum);
+}
+
+// n_games games on n_threads OS threads, one game per task like AsyncAgent::run
+// (agent/async_agent/mod.rs:100-137).  Returns wall seconds; outs[n_games].
+double oracle_self_play_many(Callback cb, const OracleParams* p, uint32_t first_game_id, int n_games,
+                             int n_threads, OracleGameOut* outs) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    std::atomic<int> nextg{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&]() {
+            for (;;) {
+                int g = nextg.fetch_add(1);
+                if (g >= n_games) break;
+                play_one(cb, *p, first_game_id + (uint32_t)g, &outs[g], nullptr, nullptr, nullptr);
+            }
+        });
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int oracle_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
+
+// 16M-board style batch win check (config 3a): boards as int8 [n][225]
+void oracle_search_batch(const int8_t* boards, int64_t n, int8_t* winners, int n_threads) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([=]() {
+            for (int64_t i = t; i < n; i += n_threads)
+                winners[i] = (int8_t)search(board_from_i8(boards + i * BOARD_CAPACITY));
+        });
+    for (auto& x : th) x.join();
+}
+}
