@@ -1,0 +1,373 @@
+// C-ABI of libcppconnect6 (see include/connect6_b200.h).
+//   Part 1 mirrors Connect6/cppbind/libcppconnect6/src/lib.rs and cppbind/{rawobj,cppeval,cpp_policy,ffi_test}.
+//   Part 2 exposes the engine to C / ctypes.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <stdexcept>
+
+#include "../../include/connect6_b200.h"
+#include "c6_board.cuh"
+#include "c6_engine.cuh"
+#include "connect6_host.hpp"
+
+using namespace c6;
+
+static_assert(sizeof(c6_path) == 912, "Path layout (connect6.hpp:26-31)");
+static_assert(sizeof(c6_play_result) == 24, "PlayResult layout (connect6.hpp:33-37)");
+static_assert(sizeof(c6_vec) == 16, "Vec layout (connect6.hpp:39-42)");
+static_assert(sizeof(c6_record) == sizeof(GameRecord), "record layout");
+
+static thread_local std::string g_err;
+
+[[noreturn]] static void die(const char* where, const char* what) {
+    // the reference unwraps and aborts across the FFI (lib.rs:40,107,168)
+    std::fprintf(stderr, "libcppconnect6 (B200 engine): %s: %s\n", where, what);
+    std::fflush(stderr);
+    std::abort();
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+static uint32_t env_seed() {
+    const char* v = std::getenv("C6_SEED");
+    if (v && *v) return (uint32_t)std::strtoul(v, nullptr, 0);
+    std::random_device rd;  // the reference seeds from the OS (thread_rng)
+    return rd();
+}
+
+// RawPlayResult::with_result (rawobj/mod.rs:91-108): Path = board BEFORE the stone (agent_impl/mod.rs:139-143)
+static c6_play_result expand_record(const GameRecord& r, c6_alloc_path alloc) {
+    c6_play_result out;
+    out.winner = r.winner;
+    out.len = r.n_moves;
+    out.paths = alloc(r.n_moves);
+    int board[C6_BOARD_SIZE][C6_BOARD_SIZE];
+    std::memset(board, 0, sizeof board);
+    for (int m = 0; m < r.n_moves; ++m) {
+        int turn = turn_of(m);
+        c6_path& p = out.paths[m];
+        p.turn = turn;
+        std::memcpy(p.board, board, sizeof board);
+        p.row = r.moves[m] / 15, p.col = r.moves[m] % 15;
+        board[p.row][p.col] = turn;
+    }
+    return out;
+}
+
+static void print_game_debug(const GameRecord& r) {
+    // Agent::debug transcript (agent_impl/mod.rs:127-129,147-161,173-175); per-move time is not
+    // observable for a batched search, printed as 0.0.
+    connect6::Game g;
+    for (int m = 0; m < r.n_moves; ++m) {
+        g.print(stdout);
+        connect6::SetResult sr;
+        g.set({(size_t)(r.moves[m] / 15), (size_t)(r.moves[m] % 15)}, &sr);
+        std::printf("%s (%c, %c), remain %d, 0.0 elapsed\n", sr.player == connect6::Player::Black ? "Black" : "White",
+                    (char)(sr.position.first + 0x61), (char)(sr.position.second + 0x41), sr.num_remain);
+    }
+    g.print(stdout);
+    std::fflush(stdout);
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+// Part 1
+// ------------------------------------------------------------------------------------------------
+c6_vec cpp_self_play(c6_callback callback, c6_alloc_path alloc_path, c6_alloc_result alloc_result, int num_simulation,
+                     float epsilon, double dirichlet_alpha, float c_puct, bool debug, int num_game_thread) {
+    if (!callback) die("cpp_self_play", "null evaluator callback");
+    const int n = num_game_thread;  // the reference runs exactly this many games, one task each (lib.rs:110-123)
+    c6_vec out;
+    out.len = n > 0 ? n : 0;
+    out.vec = alloc_result(out.len);
+    if (n <= 0) return out;
+    try {
+        Config cfg;
+        cfg.num_simulation = num_simulation, cfg.epsilon = epsilon, cfg.dirichlet_alpha = dirichlet_alpha, cfg.c_puct = c_puct;
+        cfg.seed = env_seed();
+        cfg.device = env_int("C6_DEVICE", 0);
+        cfg.slots = std::min(n, env_int("C6_MAX_CONCURRENT", 8192));
+        cfg.log2_records = env_int("C6_LOG2_RECORDS", 18);
+        cfg.evaluator = EVAL_CALLBACK;
+        Engine eng(cfg);
+        auto t0 = std::chrono::steady_clock::now();
+        eng.start(0, n);
+        eng.run_callback_to_end(callback, debug);
+        std::vector<GameRecord> rec = eng.records();
+        double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int i = 0; i < n; ++i) {
+            if (debug && n == 1) print_game_debug(rec[i]);
+            if (debug && n != 1) std::printf("run: %d, elapsed %.3fs\n", i, el);  // async_agent/mod.rs:117-124
+            out.vec[i] = expand_record(rec[i], alloc_path);
+        }
+    } catch (const std::exception& e) {
+        die("cpp_self_play", e.what());
+    }
+    return out;
+}
+
+// CppPolicy + Agent::play (cpp_policy/mod.rs:22-36, agent_impl/mod.rs:121-178): no search, host loop.
+c6_vec cpp_play(c6_policy_callback callback, c6_alloc_path alloc_path, c6_alloc_result alloc_result, bool debug,
+                int num_game_thread) {
+    if (!callback) die("cpp_play", "null policy callback");
+    const int n = num_game_thread;
+    c6_vec out;
+    out.len = n > 0 ? n : 0;
+    out.vec = alloc_result(out.len);
+    for (int i = 0; i < out.len; ++i) {
+        connect6::CppPolicy pol(callback);
+        connect6::Agent agent(pol, debug && n == 1);
+        connect6::PlayResult res;
+        std::string err = agent.play(res);
+        if (!err.empty()) die("cpp_play", err.c_str());
+        c6_play_result& r = out.vec[i];
+        r.winner = (int)res.winner;
+        r.len = (int)res.path.size();
+        r.paths = alloc_path(r.len);
+        for (int m = 0; m < r.len; ++m) {
+            c6_path& p = r.paths[m];
+            p.turn = (int)res.path[m].turn;
+            for (int a = 0; a < 15; ++a)
+                for (int b = 0; b < 15; ++b) p.board[a][b] = (int)res.path[m].board[a][b];
+            p.row = (int)res.path[m].pos.first, p.col = (int)res.path[m].pos.second;
+        }
+    }
+    return out;
+}
+
+c6_play_result cpp_play_with(c6_callback, c6_alloc_path, int, float, double, float) {
+    die("cpp_play_with", "interactive play is not built yet (SURVEY.md §8f rank 3)");
+}
+
+c6_path test_new_raw_path(void) {  // ffi_test/mod.rs:13-15
+    c6_path p;
+    std::memset(&p, 0, sizeof p);
+    return p;
+}
+c6_path test_with_raw_path(void) {  // ffi_test/mod.rs:19-34
+    c6_path p;
+    for (int i = 0; i < 15; ++i)
+        for (int j = 0; j < 15; ++j) p.board[i][j] = (i * 15 + j) % 3 - 1;
+    p.turn = 1, p.row = 0, p.col = 15 % 5 + 1;
+    return p;
+}
+c6_path test_echo_raw_path(int turn, int* board, int row, int col) {  // :38-57
+    c6_path p;
+    std::memcpy(p.board, board, sizeof p.board);
+    p.turn = turn, p.row = row, p.col = col;
+    return p;
+}
+c6_play_result test_with_raw_play_result(c6_alloc_path allocator) {  // :61-86
+    c6_play_result r;
+    r.winner = -1, r.len = 10, r.paths = allocator(10);
+    int player = -1;
+    for (int i = 0; i < 10; ++i) {
+        c6_path& p = r.paths[i];
+        std::memset(&p, 0, sizeof p);
+        for (int j = 0; j < i + 1; ++j) p.board[j][j] = (i + j) % 3 - 1;
+        p.turn = player, p.row = i, p.col = i + 1;
+        player = -player;
+    }
+    return r;
+}
+c6_play_result test_echo_raw_play_result(int winner, c6_path* path, int len, c6_alloc_path allocator) {  // :90-121
+    auto norm = [](int v) { return v == -1 ? -1 : (v == 1 ? 1 : 0); };  // Player::from
+    c6_play_result r;
+    r.winner = norm(winner), r.len = len, r.paths = allocator(len);
+    for (int i = 0; i < len; ++i) {
+        c6_path& p = r.paths[i];
+        for (int a = 0; a < 15; ++a)
+            for (int b = 0; b < 15; ++b) p.board[a][b] = norm(path[i].board[a][b]);
+        p.turn = norm(path[i].turn), p.row = path[i].row, p.col = path[i].col;
+    }
+    return r;
+}
+c6_vec_int test_with_raw_vec(c6_alloc_int allocator) {  // :125-129
+    c6_vec_int v;
+    v.len = 6, v.vec = allocator(6);
+    for (int i = 0; i < 6; ++i) v.vec[i] = i;
+    return v;
+}
+c6_vec_int test_echo_raw_vec(int* ptr, int len, c6_alloc_int allocator) {  // :133-145
+    c6_vec_int v;
+    v.len = len, v.vec = allocator(len);
+    for (int i = 0; i < len; ++i) v.vec[i] = ptr[i];
+    return v;
+}
+// CppEval::eval on host boards (cppeval/mod.rs:27-43): values pre-zeroed, policies = board_to_float
+c6_vec_float test_echo_cppeval(int turn, int* boards, int len, c6_callback callback, c6_alloc_float allocator) {  // :149-197
+    auto norm = [](int v) { return v == -1 ? -1 : (v == 1 ? 1 : 0); };
+    std::vector<float> values((size_t)len, 0.f), pol((size_t)len * 225);
+    for (size_t i = 0; i < pol.size(); ++i) pol[i] = (float)norm(boards[i]);
+    callback(norm(turn), values.data(), pol.data(), len);
+    c6_vec_float v;
+    v.len = len + len * 225, v.vec = allocator(v.len);
+    std::memcpy(v.vec, values.data(), (size_t)len * 4);
+    std::memcpy(v.vec + len, pol.data(), pol.size() * 4);
+    return v;
+}
+c6_vec_int test_cpp_policy(float* board, c6_policy_callback callback, c6_alloc_int allocator) {  // :201-224
+    connect6::Board b;
+    for (int i = 0; i < 15; ++i)
+        for (int j = 0; j < 15; ++j) b[i][j] = connect6::player_from((int)board[i * 15 + j]);
+    connect6::CppPolicy pol(callback);
+    auto res = pol.callback(b);
+    c6_vec_int v;
+    v.len = res ? 2 : 0, v.vec = allocator(v.len);
+    if (res) v.vec[0] = (int)res->first, v.vec[1] = (int)res->second;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Part 2
+// ------------------------------------------------------------------------------------------------
+struct c6_engine {
+    std::unique_ptr<Engine> eng;
+    int64_t total = 0;
+};
+
+#define C6_TRY(...)                      \
+    try {                                \
+        __VA_ARGS__;                     \
+        return 0;                        \
+    } catch (const std::exception& ex) { \
+        g_err = ex.what();               \
+        return 1;                        \
+    }
+
+void c6_default_config(c6_config* cfg) {
+    Config d;
+    cfg->num_simulation = d.num_simulation, cfg->epsilon = d.epsilon, cfg->dirichlet_alpha = d.dirichlet_alpha;
+    cfg->c_puct = d.c_puct, cfg->seed = d.seed, cfg->device = 0, cfg->slots = 1, cfg->log2_records = d.log2_records;
+    cfg->evaluator = C6_EVAL_CALLBACK, cfg->trace = 0, cfg->max_moves = 0;
+}
+const char* c6_last_error(void) { return g_err.c_str(); }
+int c6_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+static Config to_config(const c6_config* c) {
+    Config cfg;
+    cfg.num_simulation = c->num_simulation, cfg.epsilon = c->epsilon, cfg.dirichlet_alpha = c->dirichlet_alpha;
+    cfg.c_puct = c->c_puct, cfg.seed = c->seed, cfg.device = c->device, cfg.slots = c->slots;
+    cfg.log2_records = c->log2_records, cfg.evaluator = c->evaluator, cfg.trace = c->trace, cfg.max_moves = c->max_moves;
+    return cfg;
+}
+c6_engine* c6_engine_create(const c6_config* cfg) {
+    try {
+        auto* e = new c6_engine();
+        e->eng.reset(new Engine(to_config(cfg)));
+        return e;
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return nullptr;
+    }
+}
+void c6_engine_destroy(c6_engine* e) { delete e; }
+int c6_engine_start(c6_engine* e, uint32_t first, int64_t total) { C6_TRY(e->total = total; e->eng->start(first, total)) }
+int c6_engine_step_device(c6_engine* e) { C6_TRY(e->eng->step_device()) }
+int c6_engine_wave_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->wave_callback(cb)) }
+int c6_engine_run_device(c6_engine* e) { C6_TRY(e->eng->run_device_to_end()) }
+int c6_engine_run_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->run_callback_to_end(cb, false)) }
+int c6_engine_sync(c6_engine* e) { C6_TRY(e->eng->sync()) }
+int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { C6_TRY(*ms = e->eng->timed_steps_device(steps)) }
+int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, double* h2d, double* d2h) {
+    C6_TRY(*ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h))
+}
+int c6_engine_stats(c6_engine* e, c6_stats* out) {
+    C6_TRY(Stats s = e->eng->stats(); out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf,
+           out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,
+           out->peak_rec = s.peak_rec, out->peak_lnk = s.peak_lnk, out->kernel_launches = (uint64_t)e->eng->kernel_launches(),
+           out->bytes_per_game = e->eng->bytes_per_game())
+}
+int64_t c6_engine_games_done(c6_engine* e) {
+    try {
+        return e->eng->games_done();
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+int c6_engine_records(c6_engine* e, c6_record* out, int64_t n) {
+    C6_TRY(auto r = e->eng->records(); if ((int64_t)r.size() < n) n = (int64_t)r.size();
+           std::memcpy(out, r.data(), (size_t)n * sizeof(GameRecord)))
+}
+int c6_engine_trace(c6_engine* e, int32_t* cv, int32_t* rn, float* rw) {
+    C6_TRY(std::vector<int32_t> a, b; std::vector<float> c; e->eng->trace(a, b, c);
+           std::memcpy(cv, a.data(), a.size() * 4); std::memcpy(rn, b.data(), b.size() * 4);
+           std::memcpy(rw, c.data(), c.size() * 4))
+}
+int c6_self_play_device(const c6_config* cfg, uint32_t first, int64_t n_games, c6_record* out, c6_stats* stats) {
+    c6_engine* e = c6_engine_create(cfg);
+    if (!e) return 1;
+    int rc = c6_engine_start(e, first, n_games);
+    if (!rc) rc = c6_engine_run_device(e);
+    if (!rc && out) rc = c6_engine_records(e, out, n_games);
+    if (!rc && stats) rc = c6_engine_stats(e, stats);
+    c6_engine_destroy(e);
+    return rc;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(_e));  \
+    } while (0)
+
+int c6_win_check_host(const uint32_t* boards, int8_t* winners, int64_t n, int device) {
+    C6_TRY(CK(cudaSetDevice(device)); uint32_t* db = nullptr; int8_t* dw = nullptr; if (n > 0) {
+        CK(cudaMalloc(&db, (size_t)n * 64));
+        CK(cudaMalloc(&dw, (size_t)n));
+        CK(cudaMemcpy(db, boards, (size_t)n * 64, cudaMemcpyHostToDevice));
+        launch_win_check(db, dw, n, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(winners, dw, (size_t)n, cudaMemcpyDeviceToHost));
+        cudaFree(db), cudaFree(dw);
+    })
+}
+
+int c6_bench_win_check(int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter, uint32_t* boards_out,
+                       int8_t* winners_out, int64_t n_out) {
+    C6_TRY(CK(cudaSetDevice(device)); uint32_t* db = nullptr; int8_t* dw = nullptr; CK(cudaMalloc(&db, (size_t)n * 64));
+           CK(cudaMalloc(&dw, (size_t)n)); cudaStream_t s; CK(cudaStreamCreate(&s)); launch_random_boards(db, n, seed, s);
+           launch_win_check(db, dw, n, s);  // warm-up
+           CK(cudaStreamSynchronize(s)); cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+           CK(cudaEventRecord(a, s)); for (int i = 0; i < iters; ++i) launch_win_check(db, dw, n, s);
+           CK(cudaEventRecord(b, s)); CK(cudaEventSynchronize(b)); float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+           *ms_per_iter = iters > 0 ? ms / iters : 0.f; if (n_out > n) n_out = n; if (boards_out && n_out > 0)
+               CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+           if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
+           cudaEventDestroy(a), cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(db), cudaFree(dw))
+}
+
+int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter, int8_t* winners_out,
+                      uint8_t* stones_out, uint32_t* boards_out, int64_t n_out, uint64_t* total_stones) {
+    C6_TRY(CK(cudaSetDevice(device)); int8_t* dw = nullptr; uint8_t* ds = nullptr; uint32_t* db = nullptr;
+           CK(cudaMalloc(&dw, (size_t)n)); CK(cudaMalloc(&ds, (size_t)n)); CK(cudaMalloc(&db, (size_t)n * 64)); cudaStream_t s;
+           CK(cudaStreamCreate(&s)); launch_playouts(first, n, seed, dw, ds, db, s); CK(cudaStreamSynchronize(s));
+           cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s));
+           for (int i = 0; i < iters; ++i) launch_playouts(first, n, seed, dw, ds, db, s); CK(cudaEventRecord(b, s));
+           CK(cudaEventSynchronize(b)); float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+           *ms_per_iter = iters > 0 ? ms / iters : 0.f; if (n_out > n) n_out = n;
+           if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
+           if (stones_out && n_out > 0) CK(cudaMemcpy(stones_out, ds, (size_t)n_out, cudaMemcpyDeviceToHost));
+           if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+           if (total_stones) {
+               std::vector<uint8_t> hs((size_t)n);
+               CK(cudaMemcpy(hs.data(), ds, (size_t)n, cudaMemcpyDeviceToHost));
+               uint64_t t = 0;
+               for (uint8_t x : hs) t += x;
+               *total_stones = t;
+           } cudaEventDestroy(a),
+           cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db))
+}
+
+}  // extern "C"

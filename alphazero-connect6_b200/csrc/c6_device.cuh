@@ -1,0 +1,816 @@
+// Device-side building blocks of the self-play engine (one warp per game).
+// Included only by c6_engine.cu.  Reference citations: LC = /root/reference/Connect6/libconnect6/src.
+#pragma once
+#include "c6_board.cuh"
+#include "c6_engine.cuh"
+#include "c6_rng.cuh"
+
+namespace c6 {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct Dev {
+    Rec* rec;
+    uint32_t* lnk;
+    Slot* idx;
+    uint32_t* expB;  // [G][Ecap][16] bitboards of expanded nodes (8 words black, 8 white)
+    uint32_t* exp_rec;
+    uint64_t* exp_key;
+    uint32_t* path;  // [G][232]
+    GameState* gs;
+    GameRecord* records;
+    const uint64_t* Z;  // [2][256] Zobrist keys by bit position
+    int* cursor;
+    unsigned long long* gcount;  // [0] games finished, [1] next game offset to start, [2] error count
+    float* bboards;              // evaluator batch, API layout float[len][15][15] (in: boards, out: policies)
+    float* bvalues;              // float[len]
+    int* gcounts;                // [0] leaves with Black to move, [1] White
+    int32_t* tr_visits;
+    int32_t* tr_n;
+    float* tr_w;
+    uint32_t R, L, I, E;  // capacities per game (powers of two except E)
+    int G;
+    long long total_games;
+    uint32_t first_id;
+    int num_sim;
+    float eps;
+    double alpha;
+    float cpuct;
+    uint32_t seed;
+    int trace;
+    int max_moves;
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// memory helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Slot load_slot(const Slot* p) {  // L2-coherent (slots are CAS targets)
+    uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+    Slot s;
+    s.key = ((uint64_t)v.y << 32) | v.x;
+    s.idx = v.z;
+    s.epoch = v.w;
+    return s;
+}
+__device__ __forceinline__ Slot cas_slot(Slot* p, const Slot& expect, const Slot& desired) {
+    unsigned long long e0 = expect.key, e1 = ((unsigned long long)expect.epoch << 32) | expect.idx;
+    unsigned long long d0 = desired.key, d1 = ((unsigned long long)desired.epoch << 32) | desired.idx;
+    unsigned long long o0, o1;
+    asm volatile(
+        "{\n\t.reg .b128 e, d, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(p)
+        : "memory");
+    Slot o;
+    o.key = o0, o.idx = (uint32_t)o1, o.epoch = (uint32_t)(o1 >> 32);
+    return o;
+}
+__device__ __forceinline__ Rec load_rec(const Rec* p) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    Rec r;
+    r.n = (int32_t)v.x, r.w = __uint_as_float(v.y), r.p = __uint_as_float(v.z), r.link = v.w;
+    return r;
+}
+__device__ __forceinline__ void store_rec(Rec* p, const Rec& r) {
+    *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)r.n, __float_as_uint(r.w), __float_as_uint(r.p), r.link);
+}
+__device__ __forceinline__ uint32_t hash_slot(uint64_t key) { return (uint32_t)(key ^ (key >> 32)); }
+
+// insert (key -> idx) for the current epoch; keys inserted concurrently by the lanes of the warp are
+// distinct and not yet present.  `pos`/`seen` = first non-current slot found by a preceding lookup.
+__device__ __forceinline__ void index_insert(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val,
+                                             uint32_t pos, Slot seen) {
+    Slot want;
+    want.key = key, want.idx = val, want.epoch = epoch;
+    for (;;) {
+        Slot old = cas_slot(&idx[pos], seen, want);
+        if (old.key == seen.key && old.idx == seen.idx && old.epoch == seen.epoch) return;
+        seen = old;  // what is really there
+        while (seen.epoch == epoch) {  // taken by another key of this epoch: keep probing
+            pos = (pos + 1) & Imask;
+            seen = load_slot(&idx[pos]);
+        }
+    }
+}
+// lookup; returns true and idx if present, else false with (pos, seen) = the free slot reached
+__device__ __forceinline__ bool index_find(const Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t& pos,
+                                           Slot& seen, uint32_t& val) {
+    for (;;) {
+        if (seen.epoch != epoch) return false;
+        if (seen.key == key) {
+            val = seen.idx;
+            return true;
+        }
+        pos = (pos + 1) & Imask;
+        seen = load_slot(&idx[pos]);
+    }
+}
+
+struct Leaf {
+    uint32_t B[8], W[8];
+    uint64_t key;
+    int stones;
+    uint32_t rec;
+    int depth;
+};
+
+struct Warp {  // per-warp view of one game slot
+    Rec* rec;
+    uint32_t* lnk;
+    Slot* idx;
+    uint32_t* expB;
+    uint32_t* exp_rec;
+    uint64_t* exp_key;
+    uint32_t* path;
+    GameState* gs;
+    const uint64_t* Z;  // shared-memory copy
+    int lane;
+};
+
+__device__ __forceinline__ Warp make_warp(const Dev& D, int g, const uint64_t* Zs, int lane) {
+    Warp w;
+    w.rec = D.rec + (size_t)g * D.R;
+    w.lnk = D.lnk + (size_t)g * D.L;
+    w.idx = D.idx + (size_t)g * D.I;
+    w.expB = D.expB + (size_t)g * D.E * 16;
+    w.exp_rec = D.exp_rec + (size_t)g * D.E;
+    w.exp_key = D.exp_key + (size_t)g * D.E;
+    w.path = D.path + (size_t)g * 232;
+    w.gs = D.gs + g;
+    w.Z = Zs;
+    w.lane = lane;
+    return w;
+}
+
+__device__ __forceinline__ void set_error(Warp& w, const Dev& D, int code) {
+    if (w.lane == 0) {
+        w.gs->status = ST_ERROR;
+        w.gs->err = code;
+        atomicAdd(D.gcount + 2, 1ull);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: AlphaZero::select / maximum_from, LC/policy/alphazero_policy/mod.rs:243-323, looped as in
+// search() :417-420.  Returns with L describing the leaf (a node with N == 0).
+// ------------------------------------------------------------------------------------------------
+template <bool NOISE>
+__device__ void descend(const Dev& D, Warp& w, Leaf& L) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    const uint32_t Rm = D.R - 1, Lm = D.L - 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) L.B[j] = g.B[j], L.W[j] = g.W[j];
+    L.key = g.key;
+    L.stones = g.stones;
+    uint32_t cur = g.root;
+    int depth = 0;
+    unsigned long long ck_sum = 0;
+    const float eps = D.eps, one_m_eps = 1.f - D.eps, cpuct = D.cpuct;
+    for (;;) {
+        Rec r = load_rec(&w.rec[cur]);
+        if (r.n == 0) break;  // no children: leaf (:251-253)
+        if (lane == 0) w.path[depth] = cur;
+        const int C = CELLS - L.stones;
+        const int turn = turn_of(L.stones);
+        ck_sum += (unsigned)C;
+        uint32_t chosen_bit = 0, child = 0;
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
+        if (C == 1) {  // single child: taken without scoring (:254-257)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (e[j]) chosen_bit = 32 * j + (__ffs((int)e[j]) - 1);
+            child = w.lnk[r.link & Lm];
+        } else {
+            uint32_t ci[8];
+            int cn[8];
+            float cw[8], cp[8];
+            int pre = 0, s_local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ci[j] = NIL;
+                if ((e[j] >> lane) & 1u) {
+                    int k = pre + __popc(e[j] & ((1u << lane) - 1u));
+                    ci[j] = w.lnk[(r.link + (uint32_t)k) & Lm];
+                }
+                pre += __popc(e[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cn[j] = 0, cw[j] = 0.f, cp[j] = 0.f;
+                if (ci[j] != NIL) {
+                    Rec ch = load_rec(&w.rec[ci[j] & Rm]);
+                    cn[j] = ch.n, cw[j] = ch.w, cp[j] = ch.p;
+                    s_local += ch.n;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
+            const float visit_sum = (float)s_local;  // :265
+            float nz[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nz[j] = 0.f;
+            if (NOISE) {
+                // Dirichlet(alpha; C) drawn at every node with C >= 2 (:262,283): Gamma draws keyed
+                // (sim, depth, child k), summed lane-partial then butterfly (fixed order), scaled.
+                double gl[8];
+                double part = 0.0;
+                int pre2 = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    gl[j] = 0.0;
+                    if ((e[j] >> lane) & 1u) {
+                        int k = pre2 + __popc(e[j] & ((1u << lane) - 1u));
+                        PhiloxStream st(g.sim_index, (uint32_t)depth, (uint32_t)k, D.seed ^ DOMAIN_NOISE, g.game_id);
+                        gl[j] = gamma_sample(st, D.alpha);
+                        part = part + gl[j];
+                    }
+                    pre2 += __popc(e[j]);
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(FULL, part, off);
+                if (!(part > 0.0)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nz[j] = (float)(1.0 / (double)C);
+                } else {
+                    double inv = 1.0 / part;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nz[j] = (float)(gl[j] * inv);
+                }
+            }
+            float bs = 0.f;
+            uint32_t bb = NIL, bc = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (ci[j] != NIL) {
+                    float visit = (float)cn[j];
+                    float q = cn[j] > 0 ? cw[j] / visit : 0.f;              // q_value (:77-79)
+                    float prob = eps * nz[j] + one_m_eps * cp[j];           // :269
+                    float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
+                    float sc = (turn < 0 ? -q : q) + cpuct * u;             // :272-280
+                    if (bb == NIL || sc > bs) bs = sc, bb = 32u * j + lane, bc = ci[j];
+                }
+            }
+            // maximum; exact ties -> lowest row-major index (the reference picks uniformly, :291-295)
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                float os = __shfl_xor_sync(FULL, bs, off);
+                uint32_t ob = __shfl_xor_sync(FULL, bb, off), oc = __shfl_xor_sync(FULL, bc, off);
+                bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
+                if (take) bs = os, bb = ob, bc = oc;
+            }
+            chosen_bit = bb, child = bc;
+        }
+        // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
+        const uint32_t wj = chosen_bit >> 5, m = 1u << (chosen_bit & 31);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t mm = (j == (int)wj) ? m : 0u;
+            if (turn < 0) L.B[j] |= mm; else L.W[j] |= mm;
+        }
+        L.key ^= w.Z[(turn > 0 ? 256 : 0) + chosen_bit];
+        L.stones += 1;
+        cur = child & Rm;
+        depth += 1;
+    }
+    L.rec = cur;
+    L.depth = depth;
+    if (lane == 0) {
+        g.sum_ck += ck_sum;
+        g.sum_depth += (unsigned)depth;
+        g.sims += 1;
+    }
+    __syncwarp();
+}
+
+// update(): LC/policy/alphazero_policy/mod.rs:386-408 — only the leaf's parent takes the value,
+// every ancestor (leaf excluded) gets visit += 1.
+__device__ __forceinline__ void backup(const Dev& D, Warp& w, int depth, float v) {
+    __syncwarp();
+    for (int i = w.lane; i < depth; i += 32) {
+        uint32_t a = w.path[i];
+        Rec r = load_rec(&w.rec[a]);
+        r.n += 1;
+        if (i == depth - 1) r.w = r.w + v;
+        store_rec(&w.rec[a], r);
+    }
+    __syncwarp();
+}
+
+// expand(): LC/policy/alphazero_policy/mod.rs:350-377 for a non-full leaf, given value and masked
+// priors pr[j] (this lane's cells), followed by update().
+__device__ inline void expand_leaf(const Dev& D, Warp& w, const Leaf& L, const float (&pr)[8], float v) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
+    const int C = CELLS - L.stones;
+    const int turn = turn_of(L.stones);
+    const uint32_t epoch = g.epoch;
+    const uint32_t link_base = g.lnk_head;
+    const uint32_t rec_base = g.rec_head;
+    if (g.lnk_head - g.lnk_tail + (uint32_t)C > D.L) return set_error(w, D, ERR_LNK_FULL);
+    if (g.rec_head - g.rec_tail + (uint32_t)C > D.R) return set_error(w, D, ERR_REC_FULL);
+    if (g.exp_count + 1 > D.E) return set_error(w, D, ERR_EXP_FULL);
+    uint32_t e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
+    // phase A: first probe of every child key, all loads in flight together
+    uint64_t ck[8];
+    uint32_t pos[8];
+    Slot seen[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ck[j] = 0, pos[j] = 0;
+        seen[j].key = 0, seen[j].idx = 0, seen[j].epoch = 0;
+        if ((e[j] >> lane) & 1u) {
+            ck[j] = L.key ^ w.Z[(turn > 0 ? 256 : 0) + 32 * j + lane];
+            pos[j] = hash_slot(ck[j]) & Im;
+            seen[j] = load_slot(&w.idx[pos[j]]);
+        }
+    }
+    // phase B: resolve (entry(hash).or_insert, :367-370)
+    uint32_t child[8];
+    unsigned newmask = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        child[j] = NIL;
+        if ((e[j] >> lane) & 1u) {
+            uint32_t val;
+            if (index_find(w.idx, Im, epoch, ck[j], pos[j], seen[j], val))
+                child[j] = val;
+            else
+                newmask |= 1u << j;
+        }
+    }
+    __syncwarp();
+    // new records are laid out contiguously in row-major child order
+    uint32_t base = rec_base;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        unsigned bal = __ballot_sync(FULL, (newmask >> j) & 1u);
+        if ((newmask >> j) & 1u) child[j] = (base + __popc(bal & ((1u << lane) - 1u))) & Rm;
+        base += __popc(bal);
+    }
+    // phase C: write records / priors, publish keys, write the link run
+    int pre = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if ((e[j] >> lane) & 1u) {
+            if ((newmask >> j) & 1u) {
+                Rec nr;
+                nr.n = 0, nr.w = 0.f, nr.p = pr[j], nr.link = NIL;
+                store_rec(&w.rec[child[j]], nr);
+                index_insert(w.idx, Im, epoch, ck[j], child[j], pos[j], seen[j]);
+            } else {
+                w.rec[child[j]].p = pr[j];  // n_prob is overwritten by the last expanding parent (:371)
+            }
+            int k = pre + __popc(e[j] & ((1u << lane) - 1u));
+            w.lnk[(link_base + (uint32_t)k) & Lm] = child[j];
+        }
+        pre += __popc(e[j]);
+    }
+    // the leaf itself: visit += 1, children attached (:353-357,374-377); remember its board for the collector
+    const uint32_t ec = g.exp_count;
+    if (lane < 16) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (lane == j) word = L.B[j];
+            if (lane == j + 8) word = L.W[j];
+        }
+        w.expB[(size_t)ec * 16 + lane] = word;
+    }
+    if (lane == 0) {
+        Rec lr = load_rec(&w.rec[L.rec]);
+        lr.n += 1;
+        lr.link = link_base & Lm;
+        store_rec(&w.rec[L.rec], lr);
+        w.exp_rec[ec] = L.rec;
+        w.exp_key[ec] = L.key;
+        g.exp_count = ec + 1;
+        g.lnk_head = link_base + (uint32_t)C;
+        g.rec_head = base;
+        g.sum_cleaf += (unsigned)C;
+        g.evals += 1;
+        uint32_t ur = base - g.rec_tail, ul = g.lnk_head - g.lnk_tail;
+        if (ur > g.peak_rec) g.peak_rec = ur;
+        if (ul > g.peak_lnk) g.peak_lnk = ul;
+    }
+    backup(D, w, L.depth, v);
+}
+
+// full-board leaf: LC/policy/alphazero_policy/mod.rs:338-348 (no evaluator call, no visit increment)
+__device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, const Leaf& L) {
+    float v = (float)win_check(L.B, L.W);
+    backup(D, w, L.depth, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// game start / collection / move
+// ------------------------------------------------------------------------------------------------
+__device__ inline void init_game(const Dev& D, Warp& w, uint32_t game_id) {
+    GameState& g = *w.gs;
+    if (w.lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.B[j] = 0, g.W[j] = 0;
+        g.key = 0, g.root = 0, g.stones = 0, g.status = ST_ACTIVE, g.winner = 0, g.err = 0;
+        g.game_id = game_id;
+        g.epoch += 1;
+        g.rec_head = 1, g.rec_tail = 0, g.lnk_head = 0, g.lnk_tail = 0, g.exp_count = 0;
+        g.sim_index = 0, g.sims_this_move = 0, g.n_moves = 0, g.need_eval = 0;
+        Rec r;
+        r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
+        store_rec(&w.rec[0], r);
+        uint32_t pos = hash_slot(0ull) & (D.I - 1);
+        Slot seen = load_slot(&w.idx[pos]);
+        uint32_t val;
+        if (!index_find(w.idx, D.I - 1, g.epoch, 0ull, pos, seen, val))
+            index_insert(w.idx, D.I - 1, g.epoch, 0ull, 0u, pos, seen);
+    }
+    __syncwarp();
+}
+
+// After a real move: keep exactly the records that can ever be reached again — expanded nodes whose
+// board contains the new root board, and their children — compacted into the free part of the rings
+// (the reference keeps every deeper node forever, LC/policy/alphazero_policy/mod.rs:474-487; nodes
+// that do not contain the root can never be looked up again, so dropping them changes nothing).
+__device__ inline void collect(const Dev& D, Warp& w) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
+    const uint32_t old_rec_head = g.rec_head, old_lnk_head = g.lnk_head;
+    const uint32_t old_rec_tail = g.rec_tail, old_lnk_tail = g.lnk_tail;
+    uint32_t rec_head = old_rec_head, lnk_head = old_lnk_head;
+    const uint32_t epoch = g.epoch + 1;
+    uint32_t rootB[8], rootW[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rootB[j] = g.B[j], rootW[j] = g.W[j];
+    const uint32_t n_exp = g.exp_count;
+    uint32_t wcur = 0;
+    unsigned long long copied = 0;
+    bool overflow = false;
+    for (uint32_t ei = 0; ei < n_exp; ++ei) {
+        uint32_t eb[8], ew[8];
+        bool sup = true;
+        int est = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            eb[j] = w.expB[(size_t)ei * 16 + j];
+            ew[j] = w.expB[(size_t)ei * 16 + 8 + j];
+            sup = sup && ((eb[j] & rootB[j]) == rootB[j]) && ((ew[j] & rootW[j]) == rootW[j]);
+            est += __popc(eb[j]) + __popc(ew[j]);
+        }
+        if (!sup) continue;
+        const uint32_t erec = w.exp_rec[ei];
+        const uint64_t ekey = w.exp_key[ei];
+        const int C = CELLS - est;
+        const int turn = turn_of(est);
+        if (rec_head - old_rec_tail + (uint32_t)C + 1 > D.R || lnk_head - old_lnk_tail + (uint32_t)C > D.L) {
+            overflow = true;
+            break;
+        }
+        // the node's own record
+        Rec old = load_rec(&w.rec[erec]);
+        uint32_t new_e, old_link;
+        if (old.link == FWD) {
+            new_e = (uint32_t)old.n;
+            old_link = w.rec[new_e].link;
+        } else {
+            new_e = rec_head & Rm;
+            rec_head += 1;
+            old_link = old.link;
+            if (lane == 0) {
+                store_rec(&w.rec[new_e], old);
+                Rec f;
+                f.n = (int32_t)new_e, f.w = 0.f, f.p = 0.f, f.link = FWD;
+                store_rec(&w.rec[erec], f);
+                uint32_t pos = hash_slot(ekey) & Im;
+                Slot seen = load_slot(&w.idx[pos]);
+                while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
+                index_insert(w.idx, Im, epoch, ekey, new_e, pos, seen);
+            }
+            copied += 1;
+        }
+        __syncwarp();
+        const uint32_t new_link = lnk_head;
+        lnk_head += (uint32_t)C;
+        if (lane == 0) w.rec[new_e].link = new_link & Lm;
+        // children
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ~(eb[j] | ew[j]) & valid_mask(j);
+        uint32_t ci[8];
+        Rec ch[8];
+        int pre = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ci[j] = NIL;
+            if ((e[j] >> lane) & 1u) {
+                int k = pre + __popc(e[j] & ((1u << lane) - 1u));
+                ci[j] = w.lnk[(old_link + (uint32_t)k) & Lm] & Rm;
+            }
+            pre += __popc(e[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (ci[j] != NIL) ch[j] = load_rec(&w.rec[ci[j]]);
+        pre = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bool mine = (e[j] >> lane) & 1u;
+            bool need = mine && ch[j].link != FWD;
+            unsigned bal = __ballot_sync(FULL, need);
+            if (mine) {
+                uint32_t ni;
+                if (need) {
+                    ni = (rec_head + __popc(bal & ((1u << lane) - 1u))) & Rm;
+                    store_rec(&w.rec[ni], ch[j]);
+                    Rec f;
+                    f.n = (int32_t)ni, f.w = 0.f, f.p = 0.f, f.link = FWD;
+                    store_rec(&w.rec[ci[j]], f);
+                    uint64_t key = ekey ^ w.Z[(turn > 0 ? 256 : 0) + 32 * j + lane];
+                    uint32_t pos = hash_slot(key) & Im;
+                    Slot seen = load_slot(&w.idx[pos]);
+                    while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
+                    index_insert(w.idx, Im, epoch, key, ni, pos, seen);
+                } else {
+                    ni = (uint32_t)ch[j].n;
+                }
+                int k = pre + __popc(e[j] & ((1u << lane) - 1u));
+                w.lnk[(new_link + (uint32_t)k) & Lm] = ni;
+            }
+            rec_head += __popc(bal);
+            copied += __popc(bal);
+            pre += __popc(e[j]);
+        }
+        // keep the entry (in-place compaction of the expanded list: wcur <= ei)
+        if (lane < 16) w.expB[(size_t)wcur * 16 + lane] = w.expB[(size_t)ei * 16 + lane];
+        if (lane == 0) w.exp_rec[wcur] = new_e, w.exp_key[wcur] = ekey;
+        wcur += 1;
+        __syncwarp();
+    }
+    if (overflow) return set_error(w, D, ERR_REC_FULL);
+    // the root itself (unexpanded roots are not on the expanded list)
+    Rec rr = load_rec(&w.rec[g.root]);
+    uint32_t new_root;
+    if (rr.link == FWD) {
+        new_root = (uint32_t)rr.n;
+    } else {
+        new_root = rec_head & Rm;
+        rec_head += 1;
+        copied += 1;
+        if (lane == 0) {
+            store_rec(&w.rec[new_root], rr);
+            uint32_t pos = hash_slot(g.key) & Im;
+            Slot seen = load_slot(&w.idx[pos]);
+            while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
+            index_insert(w.idx, Im, epoch, g.key, new_root, pos, seen);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        g.root = new_root;
+        g.epoch = epoch;
+        g.rec_tail = old_rec_head, g.rec_head = rec_head;
+        g.lnk_tail = old_lnk_head, g.lnk_head = lnk_head;
+        g.exp_count = wcur;
+        g.gc_copied += copied;
+    }
+    __syncwarp();
+}
+
+__device__ inline void finish_game(const Dev& D, Warp& w, int winner, int finished) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    GameRecord* out = D.records + (g.game_id - D.first_id);
+    for (int i = lane; i < 232; i += 32) out->moves[i] = g.moves[i];
+    unsigned long long ng = 0;
+    if (lane == 0) {
+        out->winner = (int8_t)winner;
+        out->n_moves = (uint8_t)g.n_moves;
+        out->finished = (uint8_t)finished;
+        out->game_id = g.game_id;
+        g.winner = winner;
+        atomicAdd(D.gcount + 0, 1ull);
+        ng = atomicAdd(D.gcount + 1, 1ull);
+    }
+    ng = __shfl_sync(FULL, ng, 0);
+    __syncwarp();
+    if ((long long)ng < D.total_games)
+        init_game(D, w, D.first_id + (uint32_t)ng);
+    else if (lane == 0)
+        g.status = ST_DONE;
+    __syncwarp();
+}
+
+// policy() + the tail of next() + one iteration of Agent::play:
+// LC/policy/alphazero_policy/mod.rs:433-452,471-488 and LC/agent/agent_impl/mod.rs:131-171.
+__device__ inline void finish_move(const Dev& D, Warp& w) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    const uint32_t Rm = D.R - 1, Lm = D.L - 1;
+    Rec r = load_rec(&w.rec[g.root]);
+    if (lane == 0) g.sims_this_move = 0;
+    uint32_t B[8], W[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) B[j] = g.B[j], W[j] = g.W[j];
+    const int stones = g.stones;
+    const uint32_t gi = g.game_id - D.first_id;
+    int32_t* trv = D.trace ? D.tr_visits + ((size_t)gi * CELLS + g.n_moves) * CELLS : nullptr;
+    if (D.trace && lane == 0) {
+        D.tr_n[(size_t)gi * CELLS + g.n_moves] = r.n;
+        D.tr_w[(size_t)gi * CELLS + g.n_moves] = r.w;
+    }
+    if (r.n == 0) {  // no children: policy() -> None -> Agent::play ends with winner None (:135-137)
+        if (trv)
+            for (int i = lane; i < CELLS; i += 32) trv[i] = -1;
+        return finish_game(D, w, 0, 1);
+    }
+    uint32_t e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = ~(B[j] | W[j]) & valid_mask(j);
+    uint32_t ci[8];
+    int cn[8];
+    int pre = 0, s_local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ci[j] = NIL, cn[j] = 0;
+        if ((e[j] >> lane) & 1u) {
+            int k = pre + __popc(e[j] & ((1u << lane) - 1u));
+            ci[j] = w.lnk[(r.link + (uint32_t)k) & Lm] & Rm;
+        }
+        pre += __popc(e[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (ci[j] != NIL) cn[j] = w.rec[ci[j]].n, s_local += cn[j];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
+    const float visit_sum = (float)s_local;
+    if (trv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t bit = 32u * j + lane;
+            if ((valid_mask(j) >> lane) & 1u) trv[cell_of_bit(bit)] = (ci[j] != NIL) ? cn[j] : -1;
+        }
+    }
+    float bp = 0.f;
+    uint32_t bb = NIL, bc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (ci[j] != NIL) {
+            float visit = (float)cn[j];
+            float p = visit / (visit_sum - visit + 1.f);  // :444-447
+            if (bb == NIL || p >= bp) bp = p, bb = 32u * j + lane, bc = ci[j];  // max_by keeps the LAST maximum
+        }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        float op = __shfl_xor_sync(FULL, bp, off);
+        uint32_t ob = __shfl_xor_sync(FULL, bb, off), oc = __shfl_xor_sync(FULL, bc, off);
+        bool take = ob != NIL && (bb == NIL || op > bp || (op == bp && ob > bb));
+        if (take) bp = op, bb = ob, bc = oc;
+    }
+    // Game::set (LC/game/game_impl/mod.rs:148-169) + is_game_end
+    const int turn = turn_of(stones);
+    const uint32_t wj = bb >> 5, m = 1u << (bb & 31);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t mm = (j == (int)wj) ? m : 0u;
+        if (turn < 0) B[j] |= mm; else W[j] |= mm;
+    }
+    const int winner = win_check(B, W);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.B[j] = B[j], g.W[j] = W[j];
+        g.key ^= w.Z[(turn > 0 ? 256 : 0) + bb];
+        g.stones = stones + 1;
+        g.moves[g.n_moves] = (uint8_t)cell_of_bit(bb);
+        g.n_moves += 1;
+        g.root = bc;
+    }
+    __syncwarp();
+    if (winner != 0) return finish_game(D, w, winner, 1);
+    if (stones + 1 == CELLS) return finish_game(D, w, 0, 1);  // next() on a full board returns None
+    if (D.max_moves > 0 && g.n_moves >= D.max_moves) return finish_game(D, w, 0, 0);
+    collect(D, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device evaluators (twins of the oracle's; each yields value and this lane's masked priors)
+// ------------------------------------------------------------------------------------------------
+// RandomEvaluator (LC/policy/alphazero_policy/mod.rs:137-169) on Philox, fused with get_from (:218-234)
+// and recover_way8 (augment.rs:75-92): draw s of original cell (r,c) is what plane s shows at its
+// image of (r,c), so the recovered prior needs exactly the 8 draws of its own cell.
+__device__ __forceinline__ float eval_philox(const Dev& D, Warp& w, const Leaf& L, float (&pr)[8]) {
+    const GameState& g = *w.gs;
+    const uint32_t k0 = D.seed ^ DOMAIN_EVAL, k1 = g.game_id, sim = g.sim_index;
+    Philox4 va = philox4x32_10(sim, CELLS, 0, 0, k0, k1), vb = philox4x32_10(sim, CELLS, 1, 0, k0, k1);
+    float sum = 0.f;
+    sum = sum + u32_to_pm1(va.x), sum = sum + u32_to_pm1(va.y), sum = sum + u32_to_pm1(va.z), sum = sum + u32_to_pm1(va.w);
+    sum = sum + u32_to_pm1(vb.x), sum = sum + u32_to_pm1(vb.y), sum = sum + u32_to_pm1(vb.z), sum = sum + u32_to_pm1(vb.w);
+    const float value = sum / 8.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        pr[j] = 0.f;
+        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
+        if ((ej >> w.lane) & 1u) {
+            uint32_t cell = (uint32_t)cell_of_bit(32u * j + w.lane);
+            Philox4 a = philox4x32_10(sim, cell, 0, 0, k0, k1), b = philox4x32_10(sim, cell, 1, 0, k0, k1);
+            float t0 = u32_to_pm1(a.x) + u32_to_pm1(a.y), t1 = u32_to_pm1(a.z) + u32_to_pm1(a.w);
+            float t2 = u32_to_pm1(b.x) + u32_to_pm1(b.y), t3 = u32_to_pm1(b.z) + u32_to_pm1(b.w);
+            float total = 0.f;
+            total = total + t0, total = total + t1, total = total + t2, total = total + t3;
+            pr[j] = total / 8.f;
+        }
+    }
+    return value;
+}
+
+// DetEval / NegEval: hash of the oriented board, evaluated on each of the 8 planes.
+template <bool NEG>
+__device__ __forceinline__ float eval_hash(const Dev& D, Warp& w, const Leaf& L, float (&pr)[8]) {
+    const int lane = w.lane;
+    const int turn = turn_of(L.stones);
+    uint64_t h[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        uint64_t k = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t bit = 32u * j + lane;
+            int r = (int)(bit >> 4), c = (int)(bit & 15), rr, cc;
+            sym_fwd(s, r, c, rr, cc);
+            if ((L.B[j] >> lane) & 1u) k ^= w.Z[rr * 16 + cc];
+            if ((L.W[j] >> lane) & 1u) k ^= w.Z[256 + rr * 16 + cc];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) k ^= __shfl_xor_sync(FULL, k, off);
+        h[s] = splitmix64(k ^ (turn < 0 ? 0xB1ACull : 0x3417Eull));
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) sum = sum + ((float)(uint32_t)(h[s] >> 40) * (1.0f / 8388608.0f) - 1.0f);
+    const float value = sum / 8.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        pr[j] = 0.f;
+        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
+        if ((ej >> lane) & 1u) {
+            uint32_t bit = 32u * j + lane;
+            int r = (int)(bit >> 4), c = (int)(bit & 15);
+            float pv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                int rr, cc;
+                sym_fwd(s, r, c, rr, cc);
+                uint32_t x = (uint32_t)(splitmix64(h[s] + (uint64_t)(rr * 15 + cc) + 1) >> 40);
+                pv[s] = NEG ? ((float)x * (1.0f / 8388608.0f) - 1.0f) : ((float)x * (1.0f / 16777216.0f));
+            }
+            float total = 0.f;
+            total = total + (pv[0] + pv[1]), total = total + (pv[2] + pv[3]);
+            total = total + (pv[4] + pv[5]), total = total + (pv[6] + pv[7]);
+            pr[j] = total / 8.f;
+        }
+    }
+    return value;
+}
+
+// get_from() on an evaluator batch in the API layout (values[8], policies[8][225]) for this leaf.
+__device__ __forceinline__ float eval_from_batch(const float* __restrict__ values, const float* __restrict__ pol,
+                                                 Warp& w, const Leaf& L, float (&pr)[8]) {
+    const int lane = w.lane;
+    float myv = lane < 8 ? values[lane] : 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) sum = sum + __shfl_sync(FULL, myv, s);  // iter().sum::<f32>() order (:224)
+    const float value = sum / 8.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        pr[j] = 0.f;
+        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
+        if ((ej >> lane) & 1u) {
+            uint32_t bit = 32u * j + lane;
+            int r = (int)(bit >> 4), c = (int)(bit & 15);
+            float pv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                int rr, cc;
+                sym_fwd(s, r, c, rr, cc);
+                pv[s] = pol[s * CELLS + rr * 15 + cc];
+            }
+            float total = 0.f;  // recover_way8 order: ((((0+t0)+t1)+t2)+t3)/8, t_i = p[2i] + flip(p[2i+1])
+            total = total + (pv[0] + pv[1]), total = total + (pv[2] + pv[3]);
+            total = total + (pv[4] + pv[5]), total = total + (pv[6] + pv[7]);
+            pr[j] = (total / 8.f) * 1.0f;  // * (cell empty) mask (:227-232)
+        }
+    }
+    return value;
+}
+#endif  // __CUDACC__
+
+}  // namespace c6

@@ -1,0 +1,557 @@
+// Kernels + host driver of the batched self-play engine.  See c6_engine.cuh / DESIGN.md.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "c6_device.cuh"
+
+namespace c6 {
+
+static thread_local std::string g_last_error;
+const char* last_error() { return g_last_error.c_str(); }
+
+#define C6_CUDA(call)                                                                                 \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            char _buf[512];                                                                           \
+            std::snprintf(_buf, sizeof _buf, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                          __LINE__, cudaGetErrorString(_e));                                          \
+            g_last_error = _buf;                                                                      \
+            throw std::runtime_error(_buf);                                                           \
+        }                                                                                             \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_zobrist(const Dev& D, uint64_t* Zs) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) Zs[i] = D.Z[i];
+    __syncthreads();
+}
+
+__global__ void k_start(Dev D, int n_start) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    if (g < n_start)
+        init_game(D, w, D.first_id + (uint32_t)g);
+    else if (lane == 0)
+        w.gs->status = ST_DONE;
+}
+
+// Device-evaluator path: one whole move (num_sim searches, move choice, collection) per game.
+// Persistent warps pull game slots from a counter, so unequal game lengths balance themselves.
+template <int EVAL, bool NOISE>
+__global__ void __launch_bounds__(128) k_move_device(Dev D) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(D.cursor, 1);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= D.G) break;
+        Warp w = make_warp(D, g, Zs, lane);
+        if (w.gs->status != ST_ACTIVE) continue;
+        for (int s = 0; s < D.num_sim; ++s) {
+            Leaf L;
+            descend<NOISE>(D, w, L);
+            if (L.stones == CELLS) {
+                terminal_leaf(D, w, L);
+            } else {
+                float pr[8];
+                float v;
+                if (EVAL == EVAL_PHILOX)
+                    v = eval_philox(D, w, L, pr);
+                else if (EVAL == EVAL_DET)
+                    v = eval_hash<false>(D, w, L, pr);
+                else
+                    v = eval_hash<true>(D, w, L, pr);
+                expand_leaf(D, w, L, pr, v);
+            }
+            if (lane == 0) w.gs->sim_index += 1;
+            __syncwarp();
+            if (w.gs->status != ST_ACTIVE) break;
+        }
+        if (w.gs->status == ST_ACTIVE) finish_move(D, w);
+    }
+}
+
+// Callback path, kernel 1: descend to the leaf and park it in the game state.
+template <bool NOISE>
+__global__ void __launch_bounds__(128) k_select(Dev D) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    GameState& gs = *w.gs;
+    if (gs.status != ST_ACTIVE) {
+        if (lane == 0) gs.need_eval = 0;
+        return;
+    }
+    Leaf L;
+    descend<NOISE>(D, w, L);
+    int need = 1;
+    if (L.stones == CELLS) {
+        terminal_leaf(D, w, L);
+        need = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (lane == j) gs.leafB[j] = L.B[j], gs.leafW[j] = L.W[j];
+    if (lane == 0) {
+        gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key;
+        gs.need_eval = need;
+    }
+}
+
+// Callback path, kernel 2: order the leaves into a Black-to-move group followed by a White-to-move
+// group (the Callback ABI takes one `player` per call, CB/libcppconnect6/src/cppbind/cppeval/mod.rs:8-13).
+__global__ void k_rank(Dev D) {
+    __shared__ int sB[1024], sW[1024];
+    const int t = threadIdx.x, per = (D.G + 1023) / 1024;
+    int nb = 0, nw = 0;
+    for (int i = 0; i < per; ++i) {
+        int g = t * per + i;
+        if (g < D.G && D.gs[g].need_eval) (turn_of(D.gs[g].leaf_stones) < 0 ? nb : nw) += 1;
+    }
+    sB[t] = nb, sW[t] = nw;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int vb = t >= off ? sB[t - off] : 0, vw = t >= off ? sW[t - off] : 0;
+        __syncthreads();
+        sB[t] += vb, sW[t] += vw;
+        __syncthreads();
+    }
+    const int totalB = sB[1023], totalW = sW[1023];
+    int ob = sB[t] - nb, ow = sW[t] - nw;
+    for (int i = 0; i < per; ++i) {
+        int g = t * per + i;
+        if (g < D.G && D.gs[g].need_eval) {
+            if (turn_of(D.gs[g].leaf_stones) < 0)
+                D.gs[g].batch_pos = ob++;
+            else
+                D.gs[g].batch_pos = totalB + ow++;
+        }
+    }
+    if (t == 0) D.gcounts[0] = totalB, D.gcounts[1] = totalW;
+}
+
+// Callback path, kernel 3: augment_way8 + board_to_float for every leaf, written in the API layout
+// float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73, CB/.../cpp_support.rs:10-18).
+__global__ void __launch_bounds__(128) k_gather(Dev D) {
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    const GameState& gs = D.gs[g];
+    if (!gs.need_eval) return;
+    uint32_t B[8], W[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) B[j] = gs.leafB[j], W[j] = gs.leafW[j];
+    float* out = D.bboards + (size_t)gs.batch_pos * 8 * CELLS;
+    for (int i = lane; i < 8 * CELLS; i += 32) {
+        int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
+        sym_inv(s, rr, cc, r, c);
+        uint32_t bit = (uint32_t)(r * 16 + c);
+        uint32_t bw = 0, ww = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((int)(bit >> 5) == j) bw = B[j], ww = W[j];
+        float v = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
+        out[i] = v;
+    }
+    if (lane < 8) D.bvalues[(size_t)gs.batch_pos * 8 + lane] = 0.f;
+}
+
+// Callback path, kernel 4: recover_way8 + expansion + backup, then the move if the budget is spent.
+__global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    GameState& gs = *w.gs;
+    if (gs.status != ST_ACTIVE) return;
+    if (gs.need_eval) {
+        Leaf L;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
+        L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
+        float pr[8];
+        float v = eval_from_batch(D.bvalues + (size_t)gs.batch_pos * 8, D.bboards + (size_t)gs.batch_pos * 8 * CELLS,
+                                  w, L, pr);
+        expand_leaf(D, w, L, pr, v);
+    }
+    __syncwarp();
+    if (gs.status != ST_ACTIVE) return;
+    int done = 0;
+    if (lane == 0) {
+        gs.sim_index += 1;
+        gs.sims_this_move += 1;
+        gs.need_eval = 0;
+        done = gs.sims_this_move >= D.num_sim;
+    }
+    done = __shfl_sync(FULL, done, 0);
+    if (done) finish_move(D, w);
+}
+
+// num_simulation == 0: policy() sees an unexpanded root -> None -> the game ends at once.
+__global__ void __launch_bounds__(128) k_finish_only(Dev D) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    if (w.gs->status == ST_ACTIVE) finish_move(D, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DeviceArrays {
+    Dev dev{};
+    float* h_boards = nullptr;  // pinned
+    float* h_values = nullptr;
+    int* h_counts = nullptr;
+    unsigned long long* h_gcount = nullptr;
+    size_t rec_bytes = 0, lnk_bytes = 0, idx_bytes = 0;
+    int sm_count = 0;
+    int persistent_blocks = 0;
+};
+
+static void make_zobrist(uint64_t* Zb) {  // same sequence as the test oracle's table, by bit position
+    std::memset(Zb, 0, 512 * sizeof(uint64_t));
+    uint64_t s = 0xC0221EC76B200ull;
+    for (int p = 0; p < 2; ++p)
+        for (int i = 0; i < CELLS; ++i) {
+            s = splitmix64(s);
+            Zb[p * 256 + (i / 15) * 16 + (i % 15)] = s;
+        }
+}
+
+size_t Engine::bytes_per_game() const {
+    size_t R = (size_t)1 << cfg_.log2_records;
+    return R * sizeof(Rec) + 2 * R * sizeof(uint32_t) + 2 * R * sizeof(Slot) + d_->dev.E * (64 + 4 + 8) + 232 * 4 +
+           sizeof(GameState);
+}
+
+Engine::Engine(const Config& cfg) : cfg_(cfg) {
+    if (cfg_.slots < 1) throw std::runtime_error("c6: slots must be >= 1");
+    if (cfg_.log2_records < 10 || cfg_.log2_records > 24) throw std::runtime_error("c6: log2_records out of range [10,24]");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_last_error = "c6: no CUDA device available (this library has no CPU fallback)";
+        throw std::runtime_error(g_last_error);
+    }
+    C6_CUDA(cudaSetDevice(cfg_.device));
+    C6_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    d_ = new DeviceArrays();
+    Dev& D = d_->dev;
+    D.G = cfg_.slots;
+    D.R = 1u << cfg_.log2_records;
+    D.L = D.R * 2;
+    D.I = D.R * 2;
+    D.E = 4096;
+    D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.alpha = cfg_.dirichlet_alpha, D.cpuct = cfg_.c_puct;
+    D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves;
+    const size_t G = (size_t)D.G;
+    d_->rec_bytes = G * D.R * sizeof(Rec);
+    d_->lnk_bytes = G * D.L * sizeof(uint32_t);
+    d_->idx_bytes = G * D.I * sizeof(Slot);
+    size_t free_b = 0, total_b = 0;
+    C6_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t need = d_->rec_bytes + d_->lnk_bytes + d_->idx_bytes + G * D.E * 76 + G * (8 * CELLS + 8) * 4 + (64u << 20);
+    if (need > free_b) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf,
+                      "c6: node pool for %d games at 2^%d records needs %.1f GB, device has %.1f GB free; lower "
+                      "C6_LOG2_RECORDS or the number of concurrent games",
+                      D.G, cfg_.log2_records, need / 1e9, free_b / 1e9);
+        g_last_error = buf;
+        throw std::runtime_error(buf);
+    }
+    C6_CUDA(cudaMalloc(&D.rec, d_->rec_bytes));
+    C6_CUDA(cudaMalloc(&D.lnk, d_->lnk_bytes));
+    C6_CUDA(cudaMalloc(&D.idx, d_->idx_bytes));
+    C6_CUDA(cudaMemsetAsync(D.idx, 0, d_->idx_bytes, stream_));  // epoch 0 = never valid
+    C6_CUDA(cudaMalloc(&D.expB, G * D.E * 64));
+    C6_CUDA(cudaMalloc(&D.exp_rec, G * D.E * 4));
+    C6_CUDA(cudaMalloc(&D.exp_key, G * D.E * 8));
+    C6_CUDA(cudaMalloc(&D.path, G * 232 * 4));
+    C6_CUDA(cudaMalloc(&D.gs, G * sizeof(GameState)));
+    C6_CUDA(cudaMemsetAsync(D.gs, 0, G * sizeof(GameState), stream_));
+    uint64_t hz[512];
+    make_zobrist(hz);
+    uint64_t* dz = nullptr;
+    C6_CUDA(cudaMalloc(&dz, sizeof hz));
+    C6_CUDA(cudaMemcpyAsync(dz, hz, sizeof hz, cudaMemcpyHostToDevice, stream_));
+    D.Z = dz;
+    C6_CUDA(cudaMalloc(&D.cursor, sizeof(int)));
+    C6_CUDA(cudaMalloc(&D.gcount, 4 * sizeof(unsigned long long)));
+    C6_CUDA(cudaMalloc(&D.gcounts, 2 * sizeof(int)));
+    C6_CUDA(cudaMallocHost(&d_->h_counts, 2 * sizeof(int)));
+    C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
+    if (cfg_.evaluator == EVAL_CALLBACK) {
+        size_t nb = G * 8 * CELLS * sizeof(float), nv = G * 8 * sizeof(float);
+        C6_CUDA(cudaMalloc(&D.bboards, nb));
+        C6_CUDA(cudaMalloc(&D.bvalues, nv));
+        C6_CUDA(cudaMallocHost(&d_->h_boards, nb));
+        C6_CUDA(cudaMallocHost(&d_->h_values, nv));
+    }
+    cudaDeviceProp prop;
+    C6_CUDA(cudaGetDeviceProperties(&prop, cfg_.device));
+    d_->sm_count = prop.multiProcessorCount;
+    C6_CUDA(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+    if (!d_) return;
+    Dev& D = d_->dev;
+    cudaStreamSynchronize(stream_);
+    cudaFree(D.rec), cudaFree(D.lnk), cudaFree(D.idx), cudaFree(D.expB), cudaFree(D.exp_rec), cudaFree(D.exp_key);
+    cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gcounts);
+    cudaFree(D.records), cudaFree(D.bboards), cudaFree(D.bvalues), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
+    cudaFreeHost(d_->h_boards), cudaFreeHost(d_->h_values), cudaFreeHost(d_->h_counts), cudaFreeHost(d_->h_gcount);
+    cudaStreamDestroy(stream_);
+    delete d_;
+}
+
+static inline int warps_grid(int G) { return (G * 32 + 127) / 128; }
+
+void Engine::start(uint32_t first_id, int64_t total_games) {
+    Dev& D = d_->dev;
+    C6_CUDA(cudaSetDevice(cfg_.device));
+    sync();
+    total_games_ = total_games, first_id_ = first_id;
+    D.total_games = total_games, D.first_id = first_id;
+    cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
+    D.records = nullptr, D.tr_visits = nullptr, D.tr_n = nullptr, D.tr_w = nullptr;
+    C6_CUDA(cudaMalloc(&D.records, std::max<int64_t>(total_games, 1) * sizeof(GameRecord)));
+    C6_CUDA(cudaMemsetAsync(D.records, 0, std::max<int64_t>(total_games, 1) * sizeof(GameRecord), stream_));
+    if (cfg_.trace) {
+        size_t n = (size_t)total_games * CELLS;
+        C6_CUDA(cudaMalloc(&D.tr_visits, n * CELLS * 4));
+        C6_CUDA(cudaMalloc(&D.tr_n, n * 4));
+        C6_CUDA(cudaMalloc(&D.tr_w, n * 4));
+        C6_CUDA(cudaMemsetAsync(D.tr_visits, 0xFF, n * CELLS * 4, stream_));
+        C6_CUDA(cudaMemsetAsync(D.tr_n, 0, n * 4, stream_));
+        C6_CUDA(cudaMemsetAsync(D.tr_w, 0, n * 4, stream_));
+    }
+    int n_start = (int)std::min<int64_t>(D.G, total_games);
+    unsigned long long gc[4] = {0, (unsigned long long)n_start, 0, 0};
+    C6_CUDA(cudaMemcpyAsync(D.gcount, gc, sizeof gc, cudaMemcpyHostToDevice, stream_));
+    k_start<<<warps_grid(D.G), 128, 0, stream_>>>(D, n_start);
+    launches_ += 1;
+    C6_CUDA(cudaGetLastError());
+    C6_CUDA(cudaStreamSynchronize(stream_));
+}
+
+template <int EVAL>
+static void launch_move(const Dev& D, bool noise, int blocks, cudaStream_t s) {
+    if (noise)
+        k_move_device<EVAL, true><<<blocks, 128, 0, s>>>(D);
+    else
+        k_move_device<EVAL, false><<<blocks, 128, 0, s>>>(D);
+}
+
+void Engine::step_device() {
+    Dev& D = d_->dev;
+    if (cfg_.evaluator == EVAL_CALLBACK) throw std::runtime_error("c6: step_device needs a device evaluator");
+    if (d_->persistent_blocks == 0) {
+        int per_sm = 0;
+        const bool noise = cfg_.epsilon != 0.f;
+        // occupancy of the variant that will run
+        if (cfg_.evaluator == EVAL_PHILOX) {
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_PHILOX, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_PHILOX, false>, 128, 0));
+        } else if (cfg_.evaluator == EVAL_DET) {
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_DET, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_DET, false>, 128, 0));
+        } else {
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_NEG, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_NEG, false>, 128, 0));
+        }
+        if (per_sm < 1) per_sm = 1;
+        d_->persistent_blocks = std::min(d_->sm_count * per_sm, warps_grid(D.G));
+    }
+    C6_CUDA(cudaMemsetAsync(D.cursor, 0, sizeof(int), stream_));
+    if (cfg_.num_simulation <= 0) {
+        k_finish_only<<<warps_grid(D.G), 128, 0, stream_>>>(D);
+    } else {
+        const bool noise = cfg_.epsilon != 0.f;
+        if (cfg_.evaluator == EVAL_PHILOX) launch_move<EVAL_PHILOX>(D, noise, d_->persistent_blocks, stream_);
+        else if (cfg_.evaluator == EVAL_DET) launch_move<EVAL_DET>(D, noise, d_->persistent_blocks, stream_);
+        else launch_move<EVAL_NEG>(D, noise, d_->persistent_blocks, stream_);
+    }
+    launches_ += 1;
+    C6_CUDA(cudaGetLastError());
+}
+
+void Engine::wave_callback(Callback cb) {
+    Dev& D = d_->dev;
+    if (cfg_.evaluator != EVAL_CALLBACK) throw std::runtime_error("c6: engine was not created for the callback path");
+    const int grid = warps_grid(D.G);
+    if (cfg_.num_simulation <= 0) {
+        k_finish_only<<<grid, 128, 0, stream_>>>(D);
+        launches_ += 1;
+        C6_CUDA(cudaGetLastError());
+        return;
+    }
+    if (cfg_.epsilon != 0.f)
+        k_select<true><<<grid, 128, 0, stream_>>>(D);
+    else
+        k_select<false><<<grid, 128, 0, stream_>>>(D);
+    k_rank<<<1, 1024, 0, stream_>>>(D);
+    k_gather<<<grid, 128, 0, stream_>>>(D);
+    launches_ += 3;
+    C6_CUDA(cudaGetLastError());
+    C6_CUDA(cudaMemcpyAsync(d_->h_counts, D.gcounts, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    C6_CUDA(cudaStreamSynchronize(stream_));
+    const int nB = d_->h_counts[0], nW = d_->h_counts[1];
+    const size_t len = (size_t)(nB + nW) * 8;
+    if (len) {
+        C6_CUDA(cudaMemcpyAsync(d_->h_boards, D.bboards, len * CELLS * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        C6_CUDA(cudaStreamSynchronize(stream_));
+        std::memset(d_->h_values, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
+        if (nB) cb(-1, d_->h_values, d_->h_boards, nB * 8);
+        if (nW) cb(1, d_->h_values + (size_t)nB * 8, d_->h_boards + (size_t)nB * 8 * CELLS, nW * 8);
+        C6_CUDA(cudaMemcpyAsync(D.bboards, d_->h_boards, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        C6_CUDA(cudaMemcpyAsync(D.bvalues, d_->h_values, len * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        h2d_bytes_ += (double)len * (CELLS + 1) * sizeof(float);
+        d2h_bytes_ += (double)len * CELLS * sizeof(float) + 8;
+    }
+    k_expand_cb<<<grid, 128, 0, stream_>>>(D);
+    launches_ += 1;
+    C6_CUDA(cudaGetLastError());
+}
+
+void Engine::sync() { C6_CUDA(cudaStreamSynchronize(stream_)); }
+
+static void check_errors(DeviceArrays* d, cudaStream_t s) {
+    C6_CUDA(cudaMemcpyAsync(d->h_gcount, d->dev.gcount, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    C6_CUDA(cudaStreamSynchronize(s));
+    if (d->h_gcount[2]) {
+        std::vector<GameState> gs(d->dev.G);
+        cudaMemcpy(gs.data(), d->dev.gs, gs.size() * sizeof(GameState), cudaMemcpyDeviceToHost);
+        int code = 0, slot = -1;
+        for (int i = 0; i < d->dev.G; ++i)
+            if (gs[i].status == ST_ERROR) {
+                code = gs[i].err, slot = i;
+                break;
+            }
+        char buf[256];
+        std::snprintf(buf, sizeof buf,
+                      "c6: node pool exhausted in game slot %d (%s); raise C6_LOG2_RECORDS (now %u records/game)", slot,
+                      code == ERR_REC_FULL ? "record ring" : code == ERR_LNK_FULL ? "link ring" : "expanded list",
+                      d->dev.R);
+        g_last_error = buf;
+        throw std::runtime_error(buf);
+    }
+}
+
+int64_t Engine::games_done() {
+    check_errors(d_, stream_);
+    return (int64_t)d_->h_gcount[0];
+}
+bool Engine::all_done() { return games_done() >= total_games_; }
+
+void Engine::run_device_to_end() {
+    // a game lasts at most 225 stones; poll every few moves
+    while (!all_done()) {
+        for (int i = 0; i < 4; ++i) step_device();
+    }
+}
+
+GameState Engine::slot_state(int slot) {
+    GameState g;
+    sync();
+    C6_CUDA(cudaMemcpy(&g, d_->dev.gs + slot, sizeof g, cudaMemcpyDeviceToHost));
+    return g;
+}
+
+void Engine::run_callback_to_end(Callback cb, bool debug) {
+    (void)debug;
+    const int per_move = std::max(cfg_.num_simulation, 1);
+    while (!all_done()) {
+        for (int i = 0; i < per_move; ++i) wave_callback(cb);
+    }
+}
+
+float Engine::timed_steps_device(int k) {
+    cudaEvent_t a, b;
+    C6_CUDA(cudaEventCreate(&a));
+    C6_CUDA(cudaEventCreate(&b));
+    C6_CUDA(cudaStreamSynchronize(stream_));
+    C6_CUDA(cudaEventRecord(a, stream_));
+    for (int i = 0; i < k; ++i) step_device();
+    C6_CUDA(cudaEventRecord(b, stream_));
+    C6_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    C6_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    check_errors(d_, stream_);
+    return ms;
+}
+
+float Engine::timed_waves_callback(Callback cb, int k, double* h2d, double* d2h) {
+    cudaEvent_t a, b;
+    C6_CUDA(cudaEventCreate(&a));
+    C6_CUDA(cudaEventCreate(&b));
+    C6_CUDA(cudaStreamSynchronize(stream_));
+    double h0 = h2d_bytes_, d0 = d2h_bytes_;
+    C6_CUDA(cudaEventRecord(a, stream_));
+    for (int i = 0; i < k; ++i) wave_callback(cb);
+    C6_CUDA(cudaEventRecord(b, stream_));
+    C6_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    C6_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    if (h2d) *h2d = h2d_bytes_ - h0;
+    if (d2h) *d2h = d2h_bytes_ - d0;
+    check_errors(d_, stream_);
+    return ms;
+}
+
+Stats Engine::stats() {
+    check_errors(d_, stream_);
+    std::vector<GameState> gs(d_->dev.G);
+    C6_CUDA(cudaMemcpy(gs.data(), d_->dev.gs, gs.size() * sizeof(GameState), cudaMemcpyDeviceToHost));
+    Stats s{};
+    for (auto& g : gs) {
+        s.sims += g.sims, s.sum_ck += g.sum_ck, s.sum_cleaf += g.sum_cleaf, s.sum_depth += g.sum_depth;
+        s.evals += g.evals, s.gc_copied += g.gc_copied;
+        s.peak_rec = std::max(s.peak_rec, g.peak_rec), s.peak_lnk = std::max(s.peak_lnk, g.peak_lnk);
+    }
+    s.games_done = d_->h_gcount[0];
+    return s;
+}
+
+std::vector<GameRecord> Engine::records() {
+    sync();
+    std::vector<GameRecord> r((size_t)total_games_);
+    if (total_games_)
+        C6_CUDA(cudaMemcpy(r.data(), d_->dev.records, r.size() * sizeof(GameRecord), cudaMemcpyDeviceToHost));
+    return r;
+}
+
+void Engine::trace(std::vector<int32_t>& cv, std::vector<int32_t>& rn, std::vector<float>& rw) {
+    sync();
+    if (!cfg_.trace) throw std::runtime_error("c6: trace not enabled");
+    size_t n = (size_t)total_games_ * CELLS;
+    cv.resize(n * CELLS), rn.resize(n), rw.resize(n);
+    C6_CUDA(cudaMemcpy(cv.data(), d_->dev.tr_visits, cv.size() * 4, cudaMemcpyDeviceToHost));
+    C6_CUDA(cudaMemcpy(rn.data(), d_->dev.tr_n, rn.size() * 4, cudaMemcpyDeviceToHost));
+    C6_CUDA(cudaMemcpy(rw.data(), d_->dev.tr_w, rw.size() * 4, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace c6

@@ -1,0 +1,161 @@
+// Batched Connect6 AlphaZero self-play engine for B200 (sm_100a) — host-visible declarations.
+//
+// Replaces, for thousands of concurrent games per GPU (one warp per game):
+//   AlphaZero::{next,search,select,maximum_from,expand,update,policy}   LC/policy/alphazero_policy/mod.rs:218-489
+//   augment_way8 / recover_way8                                          LC/policy/alphazero_policy/augment.rs:60-92
+//   Simulate (board + possible list)                                     LC/policy/simulate/mod.rs:93-302
+//   Game::set turn rule, search() win detector                           LC/game/game_impl/mod.rs:148-169, search_winner/mod.rs:201-246
+//   Agent::play / AsyncAgent::run game loop and records                  LC/agent/agent_impl/mod.rs:121-178, async_agent/mod.rs:100-137
+// (LC = /root/reference/Connect6/libconnect6/src).  See DESIGN.md for the HBM layout.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace c6 {
+
+constexpr int BOARD_SIZE = 15;
+constexpr int CELLS = 225;
+constexpr uint32_t NIL = 0xFFFFFFFFu;  // Rec.link of an unexpanded node
+constexpr uint32_t FWD = 0xFFFFFFFEu;  // Rec.link of a record already moved by the collector
+
+// Node record, 16 B (visit N, value sum W, prior P, offset of the child-link run).
+// q_value of the reference == W / N whenever N > 0 (alphazero_policy/mod.rs:77-79,386-408) and
+// a node has children iff N >= 1 (:353-357), so neither q_value nor next_node.len() is stored.
+struct __align__(16) Rec {
+    int32_t n;
+    float w;
+    float p;
+    uint32_t link;
+};
+// Board-key index slot, 16 B; valid iff epoch == the game's current epoch (O(1) clear).
+struct __align__(16) Slot {
+    uint64_t key;
+    uint32_t idx;
+    uint32_t epoch;
+};
+
+enum Status : int32_t { ST_IDLE = 0, ST_ACTIVE = 1, ST_DONE = 2, ST_ERROR = 3 };
+enum ErrCode : int32_t { ERR_NONE = 0, ERR_REC_FULL = 1, ERR_LNK_FULL = 2, ERR_EXP_FULL = 3 };
+enum EvalKind : int32_t { EVAL_CALLBACK = 0, EVAL_PHILOX = 1, EVAL_DET = 2, EVAL_NEG = 3 };
+
+struct GameState {
+    uint32_t B[8], W[8];  // root bitboards: bit 16*row+col, bit 15 of every row is a zero guard
+    uint64_t key;         // Zobrist key of the root board
+    uint32_t root;        // record index of the root
+    int32_t stones;
+    int32_t status;
+    int32_t winner;
+    int32_t err;
+    uint32_t game_id;
+    uint32_t epoch;
+    uint32_t rec_head, rec_tail;  // ring counters (positions are taken & mask)
+    uint32_t lnk_head, lnk_tail;
+    uint32_t exp_count;
+    uint32_t sim_index;       // simulations started in this game (Philox counter)
+    int32_t sims_this_move;
+    int32_t n_moves;
+    // per-simulation scratch shared by the select / expand kernels of the callback path
+    uint32_t leaf_rec;
+    int32_t depth;
+    int32_t leaf_stones;
+    int32_t need_eval;
+    int32_t batch_pos;
+    int32_t pad0;
+    uint64_t leaf_key;
+    uint32_t leafB[8], leafW[8];
+    // statistics (SURVEY §8d counters)
+    unsigned long long sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied;
+    uint32_t peak_rec, peak_lnk;
+    uint8_t moves[232];
+};
+
+// One finished game, packed (SURVEY §7 "legacy record size": expand to 912 B Paths only at the C-ABI edge)
+struct GameRecord {
+    int8_t winner;
+    uint8_t n_moves;
+    uint8_t finished;
+    uint8_t pad;
+    uint32_t game_id;
+    uint8_t moves[232];  // row*15+col per stone
+};
+
+struct Config {
+    int32_t num_simulation = 800;
+    float epsilon = 0.25f;
+    double dirichlet_alpha = 0.03;
+    float c_puct = 1.f;
+    uint32_t seed = 0xC6;
+    int32_t device = 0;
+    int32_t slots = 1;            // concurrent games (G)
+    int32_t log2_records = 18;    // node-record ring capacity per game
+    int32_t evaluator = EVAL_CALLBACK;
+    int32_t trace = 0;            // record root child visits per move (tests)
+    int32_t max_moves = 0;        // stop games after this many stones (<=0: play to the end)
+};
+
+struct Stats {
+    unsigned long long sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied;
+    unsigned long long games_done;
+    uint32_t peak_rec, peak_lnk;
+};
+
+using Callback = void (*)(int player, float* values, float* policies, int len);
+
+struct DeviceArrays;  // opaque (engine .cu)
+
+class Engine {
+   public:
+    explicit Engine(const Config& cfg);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    // Queue `total_games` games with ids first_id .. first_id+total-1; the first min(slots,total) start now.
+    void start(uint32_t first_id, int64_t total_games);
+    // Device-evaluator path: one move (num_simulation searches + move choice + collection) for every
+    // active slot.  Asynchronous on the engine stream.
+    void step_device();
+    // Host-callback path: one wave = one simulation for every active slot (select kernel -> D2H ->
+    // user Callback per side to move -> H2D -> expand kernel).
+    void wave_callback(Callback cb);
+    void sync();
+    int64_t games_done();       // synchronises
+    bool all_done();            // synchronises
+    void run_device_to_end();
+    void run_callback_to_end(Callback cb, bool debug);
+    // k calls of step_device() bracketed by CUDA events on the engine stream; returns milliseconds.
+    float timed_steps_device(int k);
+    float timed_waves_callback(Callback cb, int k, double* h2d_bytes, double* d2h_bytes);
+    Stats stats();              // synchronises
+    std::vector<GameRecord> records();   // synchronises; index = game id - first_id
+    // trace (cfg.trace): root child visits [game][move][225], root N and W per move
+    void trace(std::vector<int32_t>& child_visits, std::vector<int32_t>& root_n, std::vector<float>& root_w);
+    const Config& config() const { return cfg_; }
+    cudaStream_t stream() const { return stream_; }
+    size_t bytes_per_game() const;
+    long long kernel_launches() const { return launches_; }
+    GameState slot_state(int slot);   // synchronises (debug printing)
+
+   private:
+    Config cfg_;
+    DeviceArrays* d_ = nullptr;
+    cudaStream_t stream_ = nullptr;
+    int64_t total_games_ = 0;
+    uint32_t first_id_ = 0;
+    long long launches_ = 0;
+    double h2d_bytes_ = 0, d2h_bytes_ = 0;
+};
+
+// Stand-alone kernels of the path (config 3 microbenches), host launchers.
+// boards: n x 16 u32 (8 words black, 8 words white); winners: n x i8.
+void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s);
+void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStream_t s);
+// playouts: winner i8, stones u8 (and final boards if d_boards != nullptr)
+void launch_playouts(int64_t first, int64_t n, uint32_t seed, int8_t* d_winner, uint8_t* d_stones,
+                     uint32_t* d_boards, cudaStream_t s);
+
+const char* last_error();
+
+}  // namespace c6

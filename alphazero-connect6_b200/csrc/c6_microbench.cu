@@ -1,0 +1,139 @@
+// Stand-alone kernels of the path (BASELINE.json configs[2]): bit-packed win detection over a batch
+// of boards and random playouts from the empty board.
+//   search()            LC/game/search_winner/mod.rs:201-246
+//   rollout loop        LC/policy/default_policy/mod.rs:186-203
+#include "c6_board.cuh"
+#include "c6_engine.cuh"
+#include "c6_rng.cuh"
+
+namespace c6 {
+
+// One board per thread: 64 B in (two 256-bit loads), 1 B out.  HBM-bound by design: 65 B/board.
+__global__ void __launch_bounds__(256) k_win_check(const uint32_t* __restrict__ boards, int8_t* __restrict__ winners,
+                                                   long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* p = boards + i * 16;
+    uint32_t B[8], W[8];
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(B[0]), "=r"(B[1]), "=r"(B[2]), "=r"(B[3]), "=r"(B[4]), "=r"(B[5]), "=r"(B[6]), "=r"(B[7])
+                 : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(W[0]), "=r"(W[1]), "=r"(W[2]), "=r"(W[3]), "=r"(W[4]), "=r"(W[5]), "=r"(W[6]), "=r"(W[7])
+                 : "l"(p + 8));
+    winners[i] = (int8_t)win_check(B, W);
+}
+
+// Synthetic boards: every cell iid uniform over {Black, None, White} (the reference's own random-board
+// helper, LC/policy/alphazero_policy/augment_tests.rs:126-129), Philox keyed (seed^BRDS, 0),
+// counter (board_lo, board_hi, block, 0), four cells per block.
+__global__ void __launch_bounds__(256) k_random_boards(uint32_t* __restrict__ boards, long long n, uint32_t seed) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t B[8] = {0, 0, 0, 0, 0, 0, 0, 0}, W[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int blk = 0; blk < 57; ++blk) {
+        Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)blk, 0,
+                                  seed ^ DOMAIN_BOARDS, 0);
+        uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int cell = blk * 4 + t;
+            if (cell < CELLS) {
+                uint32_t pick = (uint32_t)(((unsigned long long)v[t] * 3ull) >> 32);
+                uint32_t bit = bit_of_cell(cell);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t m = ((int)(bit >> 5) == j) ? (1u << (bit & 31)) : 0u;
+                    if (pick == 0) B[j] |= m;
+                    if (pick == 2) W[j] |= m;
+                }
+            }
+        }
+    }
+    uint4* out = reinterpret_cast<uint4*>(boards + i * 16);
+    out[0] = make_uint4(B[0], B[1], B[2], B[3]);
+    out[1] = make_uint4(B[4], B[5], B[6], B[7]);
+    out[2] = make_uint4(W[0], W[1], W[2], W[3]);
+    out[3] = make_uint4(W[4], W[5], W[6], W[7]);
+}
+
+// One playout per thread, board in registers.  Stone n takes the ((u32 * remaining) >> 32)-th empty
+// cell in row-major order (IteratorRandom-free twin of `possible.choose`, default_policy/mod.rs:190-199),
+// u32 = lane n%4 of Philox(counter (playout_lo, playout_hi, n/4, 0), key (seed^PLAY, 0)).
+// Only the colour that just moved can newly own a six, so checking that colour after every stone
+// is search() exactly.
+__global__ void __launch_bounds__(128) k_playouts(long long first, long long n, uint32_t seed, int8_t* __restrict__ winner,
+                                                  uint8_t* __restrict__ stones, uint32_t* __restrict__ boards) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long id = (unsigned long long)(first + i);
+    uint32_t B[8] = {0, 0, 0, 0, 0, 0, 0, 0}, W[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int s = 0, win = 0;
+    Philox4 r{0, 0, 0, 0};
+    while (s < CELLS) {
+        if ((s & 3) == 0) r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(s >> 2), 0, seed ^ DOMAIN_PLAYOUT, 0);
+        uint32_t u = (s & 3) == 0 ? r.x : (s & 3) == 1 ? r.y : (s & 3) == 2 ? r.z : r.w;
+        uint32_t pick = (uint32_t)(((unsigned long long)u * (unsigned long long)(CELLS - s)) >> 32);
+        // pick-th empty cell
+        uint32_t bit = 0;
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t e = ~(B[j] | W[j]) & valid_mask(j);
+            uint32_t c = __popc(e);
+            if (!found) {
+                if (pick < c) {
+                    bit = 32u * j + __fns(e, 0, (int)pick + 1);
+                    found = true;
+                } else {
+                    pick -= c;
+                }
+            }
+        }
+        const int turn = turn_of(s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t m = ((int)(bit >> 5) == j) ? (1u << (bit & 31)) : 0u;
+            if (turn < 0) B[j] |= m; else W[j] |= m;
+        }
+        s += 1;
+        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (turn < 0) {
+            run6<1>(B, acc), run6<16>(B, acc), run6<17>(B, acc), run6<15>(B, acc);
+        } else {
+            run6<1>(W, acc), run6<16>(W, acc), run6<17>(W, acc), run6<15>(W, acc);
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) any |= acc[j];
+        if (any) {
+            win = turn;
+            break;
+        }
+    }
+    winner[i] = (int8_t)win;
+    stones[i] = (uint8_t)s;
+    if (boards) {
+        uint4* out = reinterpret_cast<uint4*>(boards + i * 16);
+        out[0] = make_uint4(B[0], B[1], B[2], B[3]);
+        out[1] = make_uint4(B[4], B[5], B[6], B[7]);
+        out[2] = make_uint4(W[0], W[1], W[2], W[3]);
+        out[3] = make_uint4(W[4], W[5], W[6], W[7]);
+    }
+}
+
+void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    k_win_check<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_boards, d_winners, (long long)n);
+}
+void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStream_t s) {
+    if (n <= 0) return;
+    k_random_boards<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_boards, (long long)n, seed);
+}
+void launch_playouts(int64_t first, int64_t n, uint32_t seed, int8_t* d_winner, uint8_t* d_stones, uint32_t* d_boards,
+                     cudaStream_t s) {
+    if (n <= 0) return;
+    k_playouts<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((long long)first, (long long)n, seed, d_winner, d_stones, d_boards);
+}
+
+}  // namespace c6

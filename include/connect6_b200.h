@@ -1,0 +1,172 @@
+/* C-ABI of libcppconnect6 (B200 engine).
+ *
+ * Part 1 is, symbol for symbol and struct for struct, what the reference's C++ header binds
+ * (reference: Connect6/cppbind/headers/connect6.hpp:10-93; Rust side
+ * Connect6/cppbind/libcppconnect6/src/lib.rs:19-169, cppbind/rawobj/mod.rs:29-51,
+ * cppbind/ffi_test/mod.rs).  The reference's own connect6.hpp compiles and links against this
+ * library unchanged.
+ *
+ * Part 2 (c6_*) is the extended interface: explicit engine handles, device-resident evaluators,
+ * packed game records, statistics and the config-3 micro-benchmarks.  Plain pointers and sizes
+ * only; no C++ or torch types cross this boundary.
+ *
+ * There is no CPU fallback: every search runs on the GPU, and calls fail loudly (message on
+ * stderr, abort() for the reference entry points — as the reference's .unwrap() does,
+ * lib.rs:40,107,168 — or a non-zero return + c6_last_error() for c6_*) when no CUDA device or
+ * not enough device memory is available.
+ */
+#ifndef CONNECT6_B200_H
+#define CONNECT6_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1 — reference ABI                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+#define C6_BOARD_SIZE 15
+#define C6_BOARD_CAPACITY 225
+
+/* connect6.hpp:14 — `policies` is in/out: on entry len x 225 boards (-1 black, 0, +1 white), on
+ * exit len x 225 priors; `values` (len, pre-zeroed) out; player = side to move (-1 / +1).       */
+typedef void (*c6_callback)(int player, float* values, float* policies, int len);
+/* connect6.hpp:15 — position pre-set to {-1,-1}; leaving position[0] == -1 ends the game.       */
+typedef void (*c6_policy_callback)(float* board, int* position);
+
+/* connect6.hpp:26-42 (x86-64: 912 B, 24 B, 16 B) */
+typedef struct c6_path {
+    int turn;
+    int board[C6_BOARD_SIZE][C6_BOARD_SIZE];
+    int row;
+    int col;
+} c6_path;
+typedef struct c6_play_result {
+    int winner;
+    c6_path* paths;
+    int len;
+} c6_play_result;
+typedef struct c6_vec {
+    c6_play_result* vec;
+    int len;
+} c6_vec;
+typedef struct c6_vec_int {
+    int* vec;
+    int len;
+} c6_vec_int;
+typedef struct c6_vec_float {
+    float* vec;
+    int len;
+} c6_vec_float;
+
+/* connect6.hpp:17-23 — results are allocated by the caller's allocator (`new T[n]`), never by us */
+typedef c6_path* (*c6_alloc_path)(int size);
+typedef c6_play_result* (*c6_alloc_result)(int size);
+typedef int* (*c6_alloc_int)(int size);
+typedef float* (*c6_alloc_float)(int size);
+
+/* connect6.hpp:44-48 / lib.rs:19-58 — games driven by a user policy callback (host game loop). */
+c6_vec cpp_play(c6_policy_callback callback, c6_alloc_path alloc_path, c6_alloc_result alloc_result, bool debug,
+                int num_game_thread);
+/* connect6.hpp:50-58 / lib.rs:74-126 — AlphaZero self-play; num_game_thread games run concurrently
+ * on the GPU, `callback` is invoked from the calling thread at most twice per simulation wave.  */
+c6_vec cpp_self_play(c6_callback callback, c6_alloc_path alloc_path, c6_alloc_result alloc_result, int num_simulation,
+                     float epsilon, double dirichlet_alpha, float c_puct, bool debug, int num_game_thread);
+/* connect6.hpp:60-65 / lib.rs:139-169 — AlphaZero (Black, GPU) against stdin moves "aB" (White). */
+c6_play_result cpp_play_with(c6_callback callback, c6_alloc_path alloc_path, int num_simulation, float epsilon,
+                             double dirichlet_alpha, float c_puct);
+
+/* connect6.hpp:70-91 / ffi_test/mod.rs — ABI echo helpers used by the reference's Catch2 suite. */
+c6_path test_new_raw_path(void);
+c6_path test_with_raw_path(void);
+c6_path test_echo_raw_path(int turn, int* board, int row, int col);
+c6_play_result test_with_raw_play_result(c6_alloc_path allocator);
+c6_play_result test_echo_raw_play_result(int winner, c6_path* path, int len, c6_alloc_path allocator);
+c6_vec_int test_with_raw_vec(c6_alloc_int allocator);
+c6_vec_int test_echo_raw_vec(int* ptr, int len, c6_alloc_int allocator);
+c6_vec_float test_echo_cppeval(int turn, int* boards, int len, c6_callback callback, c6_alloc_float allocator);
+c6_vec_int test_cpp_policy(float* board, c6_policy_callback callback, c6_alloc_int allocator);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2 — engine interface                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+enum { C6_EVAL_CALLBACK = 0, C6_EVAL_PHILOX_RANDOM = 1, C6_EVAL_DET_HASH = 2, C6_EVAL_NEG_HASH = 3 };
+
+/* HyperParameter (alphazero_policy/mod.rs:90-125) + engine knobs */
+typedef struct c6_config {
+    int32_t num_simulation;  /* 800 */
+    float epsilon;           /* 0.25 */
+    double dirichlet_alpha;  /* 0.03 */
+    float c_puct;            /* 1 */
+    uint32_t seed;           /* Philox key of the noise / random evaluator */
+    int32_t device;          /* CUDA ordinal */
+    int32_t slots;           /* games resident on the GPU at once */
+    int32_t log2_records;    /* node-record ring capacity per game (18 = 262,144) */
+    int32_t evaluator;       /* C6_EVAL_* */
+    int32_t trace;           /* keep root child visits per move */
+    int32_t max_moves;       /* stop each game after this many stones (0 = play out) */
+} c6_config;
+
+/* 240 B per finished game */
+typedef struct c6_record {
+    int8_t winner;
+    uint8_t n_moves;
+    uint8_t finished;
+    uint8_t pad;
+    uint32_t game_id;
+    uint8_t moves[232]; /* row*15+col per stone */
+} c6_record;
+
+typedef struct c6_stats {
+    uint64_t sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied, games_done;
+    uint32_t peak_rec, peak_lnk;
+    uint64_t kernel_launches;
+    uint64_t bytes_per_game;
+} c6_stats;
+
+typedef struct c6_engine c6_engine;
+
+void c6_default_config(c6_config* cfg);
+const char* c6_last_error(void);
+int c6_device_count(void);
+/* NULL on failure (see c6_last_error) */
+c6_engine* c6_engine_create(const c6_config* cfg);
+void c6_engine_destroy(c6_engine* e);
+/* every function below returns 0 on success */
+int c6_engine_start(c6_engine* e, uint32_t first_game_id, int64_t total_games);
+int c6_engine_step_device(c6_engine* e);                  /* one move for every resident game, async */
+int c6_engine_wave_callback(c6_engine* e, c6_callback cb); /* one simulation for every resident game */
+int c6_engine_run_device(c6_engine* e);                   /* until all games are finished */
+int c6_engine_run_callback(c6_engine* e, c6_callback cb);
+int c6_engine_sync(c6_engine* e);
+int c6_engine_timed_steps(c6_engine* e, int steps, float* milliseconds);
+int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* milliseconds, double* h2d_bytes,
+                          double* d2h_bytes);
+int c6_engine_stats(c6_engine* e, c6_stats* out);
+int64_t c6_engine_games_done(c6_engine* e);
+int c6_engine_records(c6_engine* e, c6_record* out, int64_t n); /* n = total_games */
+/* child_visits: total_games x 225 x 225 (i32, -1 = occupied / no entry), root_n / root_w: total_games x 225 */
+int c6_engine_trace(c6_engine* e, int32_t* child_visits, int32_t* root_n, float* root_w);
+
+/* one-shot convenience: n_games of self-play with a device evaluator, packed records out */
+int c6_self_play_device(const c6_config* cfg, uint32_t first_game_id, int64_t n_games, c6_record* out, c6_stats* stats);
+
+/* config 3a: win detection (search(), game/search_winner/mod.rs:201-246) on bit-packed boards.
+ * boards: n x 16 u32 (words 0-7 black, 8-15 white; bit 16*row+col). Host pointers. */
+int c6_win_check_host(const uint32_t* boards, int8_t* winners, int64_t n, int device);
+/* config 3a bench: n random boards generated on the device (cells iid over {B, none, W}), checked
+ * `iters` times; returns the average kernel time; optional copy-out for parity checks. */
+int c6_bench_win_check(int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter, uint32_t* boards_out,
+                       int8_t* winners_out, int64_t n_out);
+/* config 3b: random playouts from the empty board (default_policy/mod.rs:186-203 rollout) */
+int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter,
+                      int8_t* winners_out, uint8_t* stones_out, uint32_t* boards_out, int64_t n_out,
+                      uint64_t* total_stones);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONNECT6_B200_H */

@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): winners, move sequences and visit counts bit-exact; Q/value
+statistics within 1e-5 relative (they come out bit-exact too, which is what is asserted, with the
+1e-5 bound as the documented tolerance).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import c6lib
+from c6lib import EVAL_CALLBACK, EVAL_DET, EVAL_NEG, EVAL_PHILOX
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star tolerance for Q/value statistics
+
+
+def run_engine(n_games, callback_name=None, first_id=0, **cfg_kw):
+    L = c6lib.product()
+    cfg_kw.setdefault("slots", n_games)
+    cfg_kw.setdefault("trace", 1)
+    cfg_kw.setdefault("log2_records", 18)
+    cfg = c6lib.make_config(**cfg_kw)
+    e = L.c6_engine_create(C.byref(cfg))
+    assert e, L.c6_last_error()
+    try:
+        assert L.c6_engine_start(e, first_id, n_games) == 0, L.c6_last_error()
+        if cfg.evaluator == EVAL_CALLBACK:
+            cb = c6lib.CALLBACK(c6lib.oracle_callback(callback_name))
+            assert L.c6_engine_run_callback(e, cb) == 0, L.c6_last_error()
+        else:
+            assert L.c6_engine_run_device(e) == 0, L.c6_last_error()
+        rec = (c6lib.Record * n_games)()
+        assert L.c6_engine_records(e, rec, n_games) == 0, L.c6_last_error()
+        cv = np.zeros((n_games, 225, 225), dtype=np.int32)
+        rn = np.zeros((n_games, 225), dtype=np.int32)
+        rw = np.zeros((n_games, 225), dtype=np.float32)
+        if cfg.trace:
+            assert L.c6_engine_trace(e, cv.ctypes.data_as(C.POINTER(C.c_int32)), rn.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     rw.ctypes.data_as(C.POINTER(C.c_float))) == 0, L.c6_last_error()
+        st = c6lib.Stats()
+        assert L.c6_engine_stats(e, C.byref(st)) == 0
+        return rec, cv, rn, rw, st
+    finally:
+        L.c6_engine_destroy(e)
+
+
+def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0):
+    O = c6lib.oracle()
+    p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, 0, 0, evaluator, max_moves)
+    out = c6lib.OracleGameOut()
+    cv = np.zeros((225, 225), dtype=np.int32)
+    rn = np.zeros(225, dtype=np.int32)
+    rw = np.zeros(225, dtype=np.float32)
+    cb = c6lib.oracle_callback(callback_name) if callback_name else None
+    O.oracle_self_play(cb, C.byref(p), game_id, C.byref(out), cv.ctypes.data_as(C.POINTER(C.c_int32)),
+                       rn.ctypes.data_as(C.POINTER(C.c_int32)), rw.ctypes.data_as(C.POINTER(C.c_float)))
+    return out, cv, rn, rw
+
+
+def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves):
+    for g in range(n_games):
+        out, ocv, orn, orw = run_oracle(first_id + g, callback_name, evaluator, num_simulation, epsilon, seed, max_moves)
+        r = rec[g]
+        where = f"game {first_id + g}"
+        assert r.game_id == first_id + g
+        gm = [r.moves[i] for i in range(r.n_moves)]
+        om = [out.moves[i] for i in range(out.n_moves)]
+        if gm != om:
+            first = next((i for i in range(min(len(gm), len(om))) if gm[i] != om[i]), min(len(gm), len(om)))
+            # locate the divergence for the report
+            raise AssertionError(f"{where}: move sequences diverge at stone {first}: engine {gm[first:first+3]} oracle {om[first:first+3]}; "
+                                 f"visit rows equal before: {np.array_equal(cv[g][:first], ocv[:first])}")
+        assert r.winner == out.winner, where
+        assert r.finished == out.finished, where
+        n = r.n_moves
+        # the engine records a trace row for every next() call, including a final call that returns None
+        assert np.array_equal(cv[g][:n], ocv[:n]), f"{where}: root child visit counts differ"
+        assert np.array_equal(rn[g][:n], orn[:n]), f"{where}: root visits differ"
+        a, b = rw[g][:n], orw[:n]
+        assert np.all(np.abs(a - b) <= REL_TOL * np.maximum(np.abs(b), 1e-30)), f"{where}: root q_sum beyond 1e-5 rel"
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{where}: root q_sum not bit-identical"
+
+
+# ---------------------------------------------------------------------------------------------
+# win detection / playouts (BASELINE configs[2])
+# ---------------------------------------------------------------------------------------------
+def test_win_check_random_boards():
+    L, O = c6lib.product(), c6lib.oracle()
+    n = 1 << 17
+    ms = C.c_float()
+    boards = np.zeros((n, 16), dtype=np.uint32)
+    winners = np.zeros(n, dtype=np.int8)
+    assert L.c6_bench_win_check(n, 0xC6, 1, 0, C.byref(ms), boards.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                winners.ctypes.data_as(C.POINTER(C.c_int8)), n) == 0, L.c6_last_error()
+    cells = c6lib.unpack_boards(boards)
+    # generator sanity: three symbols, roughly uniform
+    frac = [(cells == v).mean() for v in (-1, 0, 1)]
+    assert all(abs(f - 1 / 3) < 0.01 for f in frac), frac
+    ow = np.zeros(n, dtype=np.int8)
+    O.oracle_search_batch(cells.ctypes.data_as(C.POINTER(C.c_int8)), n, ow.ctypes.data_as(C.POINTER(C.c_int8)), 0)
+    assert np.array_equal(winners, ow)
+    assert len(set(ow.tolist())) == 3  # all three outcomes occur
+
+
+def test_win_check_reference_vectors():
+    """search_winner/tests.rs:102-216 replayed through the kernel (incl. the both-colours scan-order case)."""
+    L, O = c6lib.product(), c6lib.oracle()
+    boards = []
+
+    def snap(t):
+        boards.append(np.array(t, dtype=np.int8).reshape(225).copy())
+
+    t = np.zeros((15, 15), dtype=np.int8)
+    for i in range(5):
+        t[0][i] = -1
+    snap(t); t[0][5] = -1; snap(t)
+    for i in range(5):
+        t[5 - i][0] = 1
+    snap(t); t[0][0] = 1; snap(t)
+    for i in range(5):
+        t[5 - i][5 - i] = -1
+    snap(t); t[0][0] = -1; snap(t)
+    for i in range(5):
+        t[5 - i][i] = 1
+    snap(t); t[0][5] = 1; snap(t)
+    expected = [0, -1, -1, 1, 1, -1, -1, 1]
+    for base in (0, 14):
+        for init in (0, 1, 9):
+            for kind in ("row", "col", "rd", "ld"):
+                for upto in (5, 6):
+                    b = np.zeros((15, 15), dtype=np.int8)
+                    for i in range(upto):
+                        if kind == "row":
+                            b[base][init + i] = 1
+                        elif kind == "col":
+                            b[init + i][base] = -1
+                        elif kind == "rd":
+                            b[init + i][init + i] = 1
+                        else:
+                            b[init + i][14 - init - i] = -1
+                    snap(b)
+                    expected.append(0 if upto == 5 else (1 if kind in ("row", "rd") else -1))
+    # overline (7) and a full board without runs are also decided like the oracle
+    b = np.zeros((15, 15), dtype=np.int8)
+    b[7][3:10] = -1
+    snap(b); expected.append(-1)
+    cells = np.stack(boards)
+    n = cells.shape[0]
+    packed = c6lib.pack_boards(cells)
+    w = np.zeros(n, dtype=np.int8)
+    assert L.c6_win_check_host(packed.ctypes.data_as(C.POINTER(C.c_uint32)), w.ctypes.data_as(C.POINTER(C.c_int8)), n, 0) == 0
+    ow = np.array([O.oracle_search(cells[i].ctypes.data_as(C.POINTER(C.c_int8))) for i in range(n)], dtype=np.int8)
+    assert w.tolist() == expected
+    assert ow.tolist() == expected
+
+
+def test_win_check_empty_batch():
+    L = c6lib.product()
+    assert L.c6_win_check_host(None, None, 0, 0) == 0
+
+
+def test_playouts_match_oracle():
+    L, O = c6lib.product(), c6lib.oracle()
+    n, first = 4096, 123456789012
+    ms = C.c_float()
+    w = np.zeros(n, dtype=np.int8)
+    s = np.zeros(n, dtype=np.uint8)
+    b = np.zeros((n, 16), dtype=np.uint32)
+    tot = C.c_uint64()
+    assert L.c6_bench_playouts(first, n, 0xC6, 1, 0, C.byref(ms), w.ctypes.data_as(C.POINTER(C.c_int8)),
+                               s.ctypes.data_as(C.POINTER(C.c_uint8)), b.ctypes.data_as(C.POINTER(C.c_uint32)), n, C.byref(tot)) == 0, L.c6_last_error()
+    assert tot.value == int(s.astype(np.int64).sum())
+    cells = c6lib.unpack_boards(b)
+    for i in range(0, n, 8):
+        ow, os_ = C.c_int(), C.c_int()
+        ob = np.zeros(225, dtype=np.int8)
+        O.oracle_playout(0xC6, first + i, C.byref(ow), C.byref(os_), ob.ctypes.data_as(C.POINTER(C.c_int8)))
+        assert (w[i], s[i]) == (ow.value, os_.value), i
+        assert np.array_equal(cells[i], ob), i
+    # property at scale: the winner is the colour of the last stone, stone counts follow the turn rule
+    for i in range(n):
+        if w[i] != 0:
+            last = s[i] - 1
+            turn = -1 if last == 0 else (1 if ((last - 1) // 2) % 2 == 0 else -1)
+            assert w[i] == turn
+
+
+# ---------------------------------------------------------------------------------------------
+# self-play: callback path (C-ABI evaluator contract) and device evaluators
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cbname,sims,eps,n_games,max_moves", [
+    ("const_eval_callback", 4, 0.0, 1, 12),     # SURVEY B.1 hand trace
+    ("det_eval_callback", 2, 0.0, 6, 0),        # reference sample budget, full games
+    ("neg_eval_callback", 2, 0.25, 6, 0),       # light_weight() defaults incl. noise
+    ("det_eval_callback", 48, 0.0, 4, 30),
+    ("neg_eval_callback", 48, 0.0, 4, 30),
+    ("neg_eval_callback", 32, 0.25, 4, 24),
+])
+def test_selfplay_callback_path(cbname, sims, eps, n_games, max_moves):
+    seed = 0xC6
+    rec, cv, rn, rw, st = run_engine(n_games, cbname, first_id=10, num_simulation=sims, epsilon=eps, seed=seed,
+                                     evaluator=EVAL_CALLBACK, max_moves=max_moves)
+    compare_games(n_games, rec, cv, rn, rw, 10, cbname, 0, sims, eps, seed, max_moves)
+    if cbname == "const_eval_callback":
+        assert [rec[0].moves[i] for i in range(7)] == [2, 4, 5, 6, 7, 8, 9]  # (0,2),(0,4),(0,5),... as derived by hand
+
+
+@pytest.mark.parametrize("evaluator,cbname,sims,eps,n_games,max_moves", [
+    (EVAL_PHILOX, None, 2, 0.0, 8, 0),
+    (EVAL_PHILOX, None, 2, 0.25, 8, 0),
+    (EVAL_PHILOX, None, 64, 0.0, 4, 24),
+    (EVAL_PHILOX, None, 64, 0.25, 4, 24),
+    (EVAL_DET, "det_eval_callback", 40, 0.0, 4, 24),
+    (EVAL_NEG, "neg_eval_callback", 40, 0.25, 4, 24),
+])
+def test_selfplay_device_path(evaluator, cbname, sims, eps, n_games, max_moves):
+    seed = 0xC6
+    rec, cv, rn, rw, st = run_engine(n_games, None, first_id=77, num_simulation=sims, epsilon=eps, seed=seed,
+                                     evaluator=evaluator, max_moves=max_moves)
+    compare_games(n_games, rec, cv, rn, rw, 77, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, max_moves)
+
+
+def test_selfplay_800_sims_reference_default():
+    """Reference default budget (800 simulations, eps .25, alpha .03) for the first stones of two games."""
+    seed, sims, eps, mm = 0xC6, 800, 0.25, 6
+    rec, cv, rn, rw, st = run_engine(2, None, first_id=0, num_simulation=sims, epsilon=eps, seed=seed, evaluator=EVAL_PHILOX, max_moves=mm)
+    compare_games(2, rec, cv, rn, rw, 0, None, 1, sims, eps, seed, mm)
+    assert st.sims == 2 * sims * mm
+
+
+def test_slot_refill_and_game_order():
+    """More games than resident slots: finished slots are refilled, records come back by game id."""
+    seed, sims = 3, 2
+    rec, cv, rn, rw, st = run_engine(10, None, first_id=5, slots=3, num_simulation=sims, epsilon=0.0, seed=seed, evaluator=EVAL_PHILOX)
+    compare_games(10, rec, cv, rn, rw, 5, None, 1, sims, 0.0, seed, 0)
+    assert st.games_done == 10
+    for g in range(10):
+        r = rec[g]
+        if r.winner != 0:  # path.last().turn == winner (alphazero_policy/tests.rs:198-202)
+            last = r.n_moves - 1
+            turn = -1 if last == 0 else (1 if ((last - 1) // 2) % 2 == 0 else -1)
+            assert r.winner == turn
+
+
+def test_zero_simulations():
+    rec, *_ = run_engine(2, None, num_simulation=0, epsilon=0.0, evaluator=EVAL_PHILOX)
+    assert all(rec[g].n_moves == 0 and rec[g].winner == 0 for g in range(2))
+
+
+def test_node_pool_overflow_is_loud():
+    L = c6lib.product()
+    cfg = c6lib.make_config(num_simulation=64, epsilon=0.0, evaluator=EVAL_PHILOX, slots=1, log2_records=10)
+    e = L.c6_engine_create(C.byref(cfg))
+    assert e
+    try:
+        assert L.c6_engine_start(e, 0, 1) == 0
+        assert L.c6_engine_run_device(e) != 0
+        assert b"node pool exhausted" in L.c6_last_error()
+    finally:
+        L.c6_engine_destroy(e)
+
+
+def test_legacy_cpp_self_play_matches_oracle(monkeypatch):
+    """cpp_self_play (connect6.hpp:50-58) end to end: host evaluator buffers, Path[] records."""
+    L = c6lib.product()
+    os.environ["C6_SEED"] = "198"
+    try:
+        cb = c6lib.CALLBACK(c6lib.oracle_callback("neg_eval_callback"))
+        v = L.cpp_self_play(cb, c6lib.alloc_path, c6lib.alloc_result, 3, 0.25, 0.03, 1.0, False, 4)
+    finally:
+        del os.environ["C6_SEED"]
+    assert v.len == 4
+    for g in range(4):
+        out, *_ = run_oracle(g, "neg_eval_callback", 0, 3, 0.25, 198, 0)
+        r = v.vec[g]
+        assert r.winner == out.winner and r.len == out.n_moves
+        board = np.zeros((15, 15), dtype=np.int32)
+        for m in range(r.len):
+            p = r.paths[m]
+            assert (p.row * 15 + p.col, p.turn) == (out.moves[m], out.turns[m])
+            assert np.array_equal(np.ctypeslib.as_array(p.board), board)  # board BEFORE the stone
+            board[p.row][p.col] = p.turn
