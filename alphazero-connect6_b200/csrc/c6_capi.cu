@@ -305,6 +305,22 @@ int c6_engine_trace(c6_engine* e, int32_t* cv, int32_t* rn, float* rw) {
            std::memcpy(cv, a.data(), a.size() * 4); std::memcpy(rn, b.data(), b.size() * 4);
            std::memcpy(rw, c.data(), c.size() * 4))
 }
+long long c6_engine_validate(c6_engine* e, unsigned long long* detail) {
+    try {
+        return e->eng->validate(detail);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
+long long c6_engine_debug_read(c6_engine* e, int what, int slot, void* out, long long max_bytes) {
+    try {
+        return (long long)e->eng->debug_read(what, slot, out, (size_t)max_bytes);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return -1;
+    }
+}
 int c6_self_play_device(const c6_config* cfg, uint32_t first, int64_t n_games, c6_record* out, c6_stats* stats) {
     c6_engine* e = c6_engine_create(cfg);
     if (!e) return 1;

@@ -313,6 +313,7 @@ __device__ inline void expand_leaf(const Dev& D, Warp& w, const Leaf& L, const f
     const uint32_t epoch = g.epoch;
     const uint32_t link_base = g.lnk_head;
     const uint32_t rec_base = g.rec_head;
+    const uint32_t ec = g.exp_count;  // read before any lane can reach the tail that bumps it
     if (g.lnk_head - g.lnk_tail + (uint32_t)C > D.L) return set_error(w, D, ERR_LNK_FULL);
     if (g.rec_head - g.rec_tail + (uint32_t)C > D.R) return set_error(w, D, ERR_REC_FULL);
     if (g.exp_count + 1 > D.E) return set_error(w, D, ERR_EXP_FULL);
@@ -374,8 +375,8 @@ __device__ inline void expand_leaf(const Dev& D, Warp& w, const Leaf& L, const f
         }
         pre += __popc(e[j]);
     }
+    __syncwarp();  // the insert loops above diverge; nothing below may overtake a lane still probing
     // the leaf itself: visit += 1, children attached (:353-357,374-377); remember its board for the collector
-    const uint32_t ec = g.exp_count;
     if (lane < 16) {
         uint32_t word = 0;
 #pragma unroll

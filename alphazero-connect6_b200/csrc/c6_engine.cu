@@ -214,6 +214,88 @@ __global__ void __launch_bounds__(128) k_finish_only(Dev D) {
     if (w.gs->status == ST_ACTIVE) finish_move(D, w);
 }
 
+
+// Invariant checker (tests / debugging): for every resident game, every entry of the expanded list must
+// (1) carry the Zobrist key of its board, (2) own an expanded record (N >= 1, real link run), whose
+// (3) children are unforwarded records that (4) the board-key index maps back to, and (5) no record
+// is listed twice.  Violations are counted in viol[0]; the first few are described in viol[1..].
+__global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* viol) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    GameState& gs = *w.gs;
+    if (gs.status != ST_ACTIVE) return;
+    const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
+    auto report = [&](int code, uint32_t a, uint32_t b, uint32_t c) {
+        unsigned long long n = atomicAdd(viol, 1ull);
+        if (n < 16) {
+            viol[1 + n * 4 + 0] = ((unsigned long long)g << 32) | (unsigned)code;
+            viol[1 + n * 4 + 1] = a, viol[1 + n * 4 + 2] = b, viol[1 + n * 4 + 3] = c;
+        }
+    };
+    auto lookup = [&](uint64_t key, uint32_t& val) {
+        uint32_t pos = hash_slot(key) & Im;
+        Slot seen = load_slot(&w.idx[pos]);
+        return index_find(w.idx, Im, gs.epoch, key, pos, seen, val);
+    };
+    if (lane == 0) {
+        uint32_t val = 0;
+        if (!lookup(gs.key, val) || val != gs.root) report(1, gs.root, val, 0);
+        uint32_t used = gs.rec_head - gs.rec_tail;
+        if (((gs.root - gs.rec_tail) & Rm) >= used) report(9, gs.root, gs.rec_tail, gs.rec_head);
+    }
+    const uint32_t n_exp = gs.exp_count;
+    for (uint32_t ei = 0; ei < n_exp; ++ei) {
+        uint32_t eb[8], ew[8];
+        int est = 0;
+        uint64_t key = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            eb[j] = w.expB[(size_t)ei * 16 + j], ew[j] = w.expB[(size_t)ei * 16 + 8 + j];
+            est += __popc(eb[j]) + __popc(ew[j]);
+            if ((eb[j] >> lane) & 1u) key ^= Zs[32 * j + lane];
+            if ((ew[j] >> lane) & 1u) key ^= Zs[256 + 32 * j + lane];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) key ^= __shfl_xor_sync(FULL, key, off);
+        const uint32_t erec = w.exp_rec[ei];
+        const uint64_t ekey = w.exp_key[ei];
+        Rec r = load_rec(&w.rec[erec & Rm]);
+        if (lane == 0) {
+            if (key != ekey) {
+                report(2, ei, erec, (uint32_t)est);
+                report(20, (uint32_t)(key ^ ekey), (uint32_t)((key ^ ekey) >> 32), 0);
+            }
+            if (r.n < 1 || r.link == NIL || r.link == FWD) report(3, ei, erec, (uint32_t)r.n);
+            uint32_t val = 0;
+            if (!lookup(ekey, val) || val != erec) report(4, ei, erec, val);
+            if (((erec - gs.rec_tail) & Rm) >= gs.rec_head - gs.rec_tail) report(8, ei, erec, gs.rec_tail);
+        }
+        for (uint32_t e2 = ei + 1 + lane; e2 < n_exp; e2 += 32)
+            if (w.exp_rec[e2] == erec) report(5, ei, e2, erec);
+        if (r.n < 1 || r.link == NIL || r.link == FWD) continue;
+        const int turn = turn_of(est);
+        int pre = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t e = ~(eb[j] | ew[j]) & valid_mask(j);
+            if ((e >> lane) & 1u) {
+                int k = pre + __popc(e & ((1u << lane) - 1u));
+                uint32_t ci = w.lnk[(r.link + (uint32_t)k) & Lm];
+                Rec ch = load_rec(&w.rec[ci & Rm]);
+                if (ch.link == FWD) report(6, ei, ci, (uint32_t)k);
+                uint32_t val = 0;
+                if (!lookup(ekey ^ Zs[(turn > 0 ? 256 : 0) + 32 * j + lane], val) || val != ci) report(7, ei, ci, val);
+                if (((ci - gs.rec_tail) & Rm) >= gs.rec_head - gs.rec_tail) report(10, ei, ci, gs.rec_tail);
+            }
+            pre += __popc(e);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -520,6 +602,39 @@ float Engine::timed_waves_callback(Callback cb, int k, double* h2d, double* d2h)
     if (d2h) *d2h = d2h_bytes_ - d0;
     check_errors(d_, stream_);
     return ms;
+}
+
+
+long long Engine::validate(unsigned long long* detail) {
+    Dev& D = d_->dev;
+    unsigned long long* dv = nullptr;
+    C6_CUDA(cudaMalloc(&dv, 65 * sizeof(unsigned long long)));
+    C6_CUDA(cudaMemsetAsync(dv, 0, 65 * sizeof(unsigned long long), stream_));
+    k_validate<<<warps_grid(D.G), 128, 0, stream_>>>(D, dv);
+    C6_CUDA(cudaGetLastError());
+    unsigned long long h[65];
+    C6_CUDA(cudaMemcpyAsync(h, dv, sizeof h, cudaMemcpyDeviceToHost, stream_));
+    C6_CUDA(cudaStreamSynchronize(stream_));
+    cudaFree(dv);
+    if (detail) std::memcpy(detail, h + 1, 64 * sizeof(unsigned long long));
+    return (long long)h[0];
+}
+
+// debug accessor (tests): copy raw per-slot arrays to the host.  what: 0 GameState, 1 expanded boards,
+// 2 expanded keys, 3 expanded record indices.  Returns bytes copied.
+size_t Engine::debug_read(int what, int slot, void* out, size_t max_bytes) {
+    sync();
+    Dev& D = d_->dev;
+    const void* src = nullptr;
+    size_t n = 0;
+    if (what == 0) src = D.gs + slot, n = sizeof(GameState);
+    else if (what == 1) src = D.expB + (size_t)slot * D.E * 16, n = (size_t)D.E * 64;
+    else if (what == 2) src = D.exp_key + (size_t)slot * D.E, n = (size_t)D.E * 8;
+    else if (what == 3) src = D.exp_rec + (size_t)slot * D.E, n = (size_t)D.E * 4;
+    if (!src) return 0;
+    n = std::min(n, max_bytes);
+    C6_CUDA(cudaMemcpy(out, src, n, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 Stats Engine::stats() {

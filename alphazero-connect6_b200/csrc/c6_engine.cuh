@@ -129,6 +129,10 @@ class Engine {
     float timed_steps_device(int k);
     float timed_waves_callback(Callback cb, int k, double* h2d_bytes, double* d2h_bytes);
     Stats stats();              // synchronises
+    // invariant check of every resident game's node pool; returns the number of violations
+    // (detail: 16 x {game<<32|code, a, b, c}); synchronises
+    long long validate(unsigned long long* detail);
+    size_t debug_read(int what, int slot, void* out, size_t max_bytes);
     std::vector<GameRecord> records();   // synchronises; index = game id - first_id
     // trace (cfg.trace): root child visits [game][move][225], root N and W per move
     void trace(std::vector<int32_t>& child_visits, std::vector<int32_t>& root_n, std::vector<float>& root_w);

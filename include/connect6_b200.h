@@ -150,6 +150,11 @@ int64_t c6_engine_games_done(c6_engine* e);
 int c6_engine_records(c6_engine* e, c6_record* out, int64_t n); /* n = total_games */
 /* child_visits: total_games x 225 x 225 (i32, -1 = occupied / no entry), root_n / root_w: total_games x 225 */
 int c6_engine_trace(c6_engine* e, int32_t* child_visits, int32_t* root_n, float* root_w);
+/* node-pool invariant check of every resident game; returns the number of violations (-1 on error);
+ * detail (may be NULL): 16 x {game<<32|code, a, b, c} */
+long long c6_engine_validate(c6_engine* e, unsigned long long* detail);
+/* raw per-slot state for tests: what = 0 game state, 1 expanded boards, 2 expanded keys, 3 expanded record ids */
+long long c6_engine_debug_read(c6_engine* e, int what, int slot, void* out, long long max_bytes);
 
 /* one-shot convenience: n_games of self-play with a device evaluator, packed records out */
 int c6_self_play_device(const c6_config* cfg, uint32_t first_game_id, int64_t n_games, c6_record* out, c6_stats* stats);
