@@ -12,6 +12,7 @@
 #include "../../include/connect6_b200.h"
 #include "c6_board.cuh"
 #include "c6_engine.cuh"
+#include "c6_rng.cuh"
 #include "connect6_host.hpp"
 
 using namespace c6;
@@ -387,3 +388,32 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Sample host evaluator (the twin of Connect6/sample/cpp/main.cpp:6-28's random `callback`), used by
+// bench.py's end-to-end leg and the samples: U(-1,1) values and policies.  Host code on purpose —
+// it stands for the user's evaluator on the far side of the C-ABI.
+// ------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <thread>
+extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
+    static std::atomic<uint64_t> call_no{0};
+    const uint64_t base = call_no.fetch_add(1) * 0x9E3779B97F4A7C15ull + (uint64_t)(player + 2);
+    auto fill = [&](int lo, int hi) {
+        for (int n = lo; n < hi; ++n) {
+            uint64_t s = splitmix64(base ^ ((uint64_t)n << 20));
+            values[n] = (float)(uint32_t)(s >> 40) * (1.0f / 8388608.0f) - 1.0f;
+            float* p = policies + (size_t)n * 225;
+            for (int i = 0; i < 225; i += 2) {
+                s = s * 6364136223846793005ull + 1442695040888963407ull;
+                p[i] = (float)(uint32_t)(s >> 40) * (1.0f / 8388608.0f) - 1.0f;
+                if (i + 1 < 225) p[i + 1] = (float)(uint32_t)((s >> 16) & 0xFFFFFF) * (1.0f / 8388608.0f) - 1.0f;
+            }
+        }
+    };
+    int nt = (int)std::min<unsigned>(std::thread::hardware_concurrency(), 16u);
+    if (len < 2048 || nt <= 1) return fill(0, len);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(fill, (int)((long long)len * t / nt), (int)((long long)len * (t + 1) / nt));
+    for (auto& x : th) x.join();
+}

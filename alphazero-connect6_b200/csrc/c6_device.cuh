@@ -94,6 +94,21 @@ __device__ __forceinline__ void index_insert(Slot* idx, uint32_t Imask, uint32_t
         }
     }
 }
+// continuation of an insert whose first CAS found the slot `pos` taken by another key of this epoch
+__device__ __noinline__ void index_insert_after_conflict(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val,
+                                                         uint32_t pos) {
+    Slot want;
+    want.key = key, want.idx = val, want.epoch = epoch;
+    for (;;) {
+        Slot seen;
+        do {
+            pos = (pos + 1) & Imask;
+            seen = load_slot(&idx[pos]);
+        } while (seen.epoch == epoch);
+        Slot old = cas_slot(&idx[pos], seen, want);
+        if (old.epoch != epoch) return;  // a stale slot only ever changes by being claimed, so old == seen
+    }
+}
 // lookup; returns true and idx if present, else false with (pos, seen) = the free slot reached
 __device__ __forceinline__ bool index_find(const Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t& pos,
                                            Slot& seen, uint32_t& val) {
@@ -151,264 +166,6 @@ __device__ __forceinline__ void set_error(Warp& w, const Dev& D, int code) {
         atomicAdd(D.gcount + 2, 1ull);
     }
     __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------
-// select: AlphaZero::select / maximum_from, LC/policy/alphazero_policy/mod.rs:243-323, looped as in
-// search() :417-420.  Returns with L describing the leaf (a node with N == 0).
-// ------------------------------------------------------------------------------------------------
-template <bool NOISE>
-__device__ void descend(const Dev& D, Warp& w, Leaf& L) {
-    GameState& g = *w.gs;
-    const int lane = w.lane;
-    const uint32_t Rm = D.R - 1, Lm = D.L - 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) L.B[j] = g.B[j], L.W[j] = g.W[j];
-    L.key = g.key;
-    L.stones = g.stones;
-    uint32_t cur = g.root;
-    int depth = 0;
-    unsigned long long ck_sum = 0;
-    const float eps = D.eps, one_m_eps = 1.f - D.eps, cpuct = D.cpuct;
-    for (;;) {
-        Rec r = load_rec(&w.rec[cur]);
-        if (r.n == 0) break;  // no children: leaf (:251-253)
-        if (lane == 0) w.path[depth] = cur;
-        const int C = CELLS - L.stones;
-        const int turn = turn_of(L.stones);
-        ck_sum += (unsigned)C;
-        uint32_t chosen_bit = 0, child = 0;
-        uint32_t e[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
-        if (C == 1) {  // single child: taken without scoring (:254-257)
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (e[j]) chosen_bit = 32 * j + (__ffs((int)e[j]) - 1);
-            child = w.lnk[r.link & Lm];
-        } else {
-            uint32_t ci[8];
-            int cn[8];
-            float cw[8], cp[8];
-            int pre = 0, s_local = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                ci[j] = NIL;
-                if ((e[j] >> lane) & 1u) {
-                    int k = pre + __popc(e[j] & ((1u << lane) - 1u));
-                    ci[j] = w.lnk[(r.link + (uint32_t)k) & Lm];
-                }
-                pre += __popc(e[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                cn[j] = 0, cw[j] = 0.f, cp[j] = 0.f;
-                if (ci[j] != NIL) {
-                    Rec ch = load_rec(&w.rec[ci[j] & Rm]);
-                    cn[j] = ch.n, cw[j] = ch.w, cp[j] = ch.p;
-                    s_local += ch.n;
-                }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
-            const float visit_sum = (float)s_local;  // :265
-            float nz[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) nz[j] = 0.f;
-            if (NOISE) {
-                // Dirichlet(alpha; C) drawn at every node with C >= 2 (:262,283): Gamma draws keyed
-                // (sim, depth, child k), summed lane-partial then butterfly (fixed order), scaled.
-                double gl[8];
-                double part = 0.0;
-                int pre2 = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    gl[j] = 0.0;
-                    if ((e[j] >> lane) & 1u) {
-                        int k = pre2 + __popc(e[j] & ((1u << lane) - 1u));
-                        PhiloxStream st(g.sim_index, (uint32_t)depth, (uint32_t)k, D.seed ^ DOMAIN_NOISE, g.game_id);
-                        gl[j] = gamma_sample(st, D.alpha);
-                        part = part + gl[j];
-                    }
-                    pre2 += __popc(e[j]);
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(FULL, part, off);
-                if (!(part > 0.0)) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) nz[j] = (float)(1.0 / (double)C);
-                } else {
-                    double inv = 1.0 / part;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) nz[j] = (float)(gl[j] * inv);
-                }
-            }
-            float bs = 0.f;
-            uint32_t bb = NIL, bc = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (ci[j] != NIL) {
-                    float visit = (float)cn[j];
-                    float q = cn[j] > 0 ? cw[j] / visit : 0.f;              // q_value (:77-79)
-                    float prob = eps * nz[j] + one_m_eps * cp[j];           // :269
-                    float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
-                    float sc = (turn < 0 ? -q : q) + cpuct * u;             // :272-280
-                    if (bb == NIL || sc > bs) bs = sc, bb = 32u * j + lane, bc = ci[j];
-                }
-            }
-            // maximum; exact ties -> lowest row-major index (the reference picks uniformly, :291-295)
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                float os = __shfl_xor_sync(FULL, bs, off);
-                uint32_t ob = __shfl_xor_sync(FULL, bb, off), oc = __shfl_xor_sync(FULL, bc, off);
-                bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
-                if (take) bs = os, bb = ob, bc = oc;
-            }
-            chosen_bit = bb, child = bc;
-        }
-        // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
-        const uint32_t wj = chosen_bit >> 5, m = 1u << (chosen_bit & 31);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t mm = (j == (int)wj) ? m : 0u;
-            if (turn < 0) L.B[j] |= mm; else L.W[j] |= mm;
-        }
-        L.key ^= w.Z[(turn > 0 ? 256 : 0) + chosen_bit];
-        L.stones += 1;
-        cur = child & Rm;
-        depth += 1;
-    }
-    L.rec = cur;
-    L.depth = depth;
-    if (lane == 0) {
-        g.sum_ck += ck_sum;
-        g.sum_depth += (unsigned)depth;
-        g.sims += 1;
-    }
-    __syncwarp();
-}
-
-// update(): LC/policy/alphazero_policy/mod.rs:386-408 — only the leaf's parent takes the value,
-// every ancestor (leaf excluded) gets visit += 1.
-__device__ __forceinline__ void backup(const Dev& D, Warp& w, int depth, float v) {
-    __syncwarp();
-    for (int i = w.lane; i < depth; i += 32) {
-        uint32_t a = w.path[i];
-        Rec r = load_rec(&w.rec[a]);
-        r.n += 1;
-        if (i == depth - 1) r.w = r.w + v;
-        store_rec(&w.rec[a], r);
-    }
-    __syncwarp();
-}
-
-// expand(): LC/policy/alphazero_policy/mod.rs:350-377 for a non-full leaf, given value and masked
-// priors pr[j] (this lane's cells), followed by update().
-__device__ inline void expand_leaf(const Dev& D, Warp& w, const Leaf& L, const float (&pr)[8], float v) {
-    GameState& g = *w.gs;
-    const int lane = w.lane;
-    const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
-    const int C = CELLS - L.stones;
-    const int turn = turn_of(L.stones);
-    const uint32_t epoch = g.epoch;
-    const uint32_t link_base = g.lnk_head;
-    const uint32_t rec_base = g.rec_head;
-    const uint32_t ec = g.exp_count;  // read before any lane can reach the tail that bumps it
-    if (g.lnk_head - g.lnk_tail + (uint32_t)C > D.L) return set_error(w, D, ERR_LNK_FULL);
-    if (g.rec_head - g.rec_tail + (uint32_t)C > D.R) return set_error(w, D, ERR_REC_FULL);
-    if (g.exp_count + 1 > D.E) return set_error(w, D, ERR_EXP_FULL);
-    uint32_t e[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
-    // phase A: first probe of every child key, all loads in flight together
-    uint64_t ck[8];
-    uint32_t pos[8];
-    Slot seen[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        ck[j] = 0, pos[j] = 0;
-        seen[j].key = 0, seen[j].idx = 0, seen[j].epoch = 0;
-        if ((e[j] >> lane) & 1u) {
-            ck[j] = L.key ^ w.Z[(turn > 0 ? 256 : 0) + 32 * j + lane];
-            pos[j] = hash_slot(ck[j]) & Im;
-            seen[j] = load_slot(&w.idx[pos[j]]);
-        }
-    }
-    // phase B: resolve (entry(hash).or_insert, :367-370)
-    uint32_t child[8];
-    unsigned newmask = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        child[j] = NIL;
-        if ((e[j] >> lane) & 1u) {
-            uint32_t val;
-            if (index_find(w.idx, Im, epoch, ck[j], pos[j], seen[j], val))
-                child[j] = val;
-            else
-                newmask |= 1u << j;
-        }
-    }
-    __syncwarp();
-    // new records are laid out contiguously in row-major child order
-    uint32_t base = rec_base;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        unsigned bal = __ballot_sync(FULL, (newmask >> j) & 1u);
-        if ((newmask >> j) & 1u) child[j] = (base + __popc(bal & ((1u << lane) - 1u))) & Rm;
-        base += __popc(bal);
-    }
-    // phase C: write records / priors, publish keys, write the link run
-    int pre = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if ((e[j] >> lane) & 1u) {
-            if ((newmask >> j) & 1u) {
-                Rec nr;
-                nr.n = 0, nr.w = 0.f, nr.p = pr[j], nr.link = NIL;
-                store_rec(&w.rec[child[j]], nr);
-                index_insert(w.idx, Im, epoch, ck[j], child[j], pos[j], seen[j]);
-            } else {
-                w.rec[child[j]].p = pr[j];  // n_prob is overwritten by the last expanding parent (:371)
-            }
-            int k = pre + __popc(e[j] & ((1u << lane) - 1u));
-            w.lnk[(link_base + (uint32_t)k) & Lm] = child[j];
-        }
-        pre += __popc(e[j]);
-    }
-    __syncwarp();  // the insert loops above diverge; nothing below may overtake a lane still probing
-    // the leaf itself: visit += 1, children attached (:353-357,374-377); remember its board for the collector
-    if (lane < 16) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (lane == j) word = L.B[j];
-            if (lane == j + 8) word = L.W[j];
-        }
-        w.expB[(size_t)ec * 16 + lane] = word;
-    }
-    if (lane == 0) {
-        Rec lr = load_rec(&w.rec[L.rec]);
-        lr.n += 1;
-        lr.link = link_base & Lm;
-        store_rec(&w.rec[L.rec], lr);
-        w.exp_rec[ec] = L.rec;
-        w.exp_key[ec] = L.key;
-        g.exp_count = ec + 1;
-        g.lnk_head = link_base + (uint32_t)C;
-        g.rec_head = base;
-        g.sum_cleaf += (unsigned)C;
-        g.evals += 1;
-        uint32_t ur = base - g.rec_tail, ul = g.lnk_head - g.lnk_tail;
-        if (ur > g.peak_rec) g.peak_rec = ur;
-        if (ul > g.peak_lnk) g.peak_lnk = ul;
-    }
-    backup(D, w, L.depth, v);
-}
-
-// full-board leaf: LC/policy/alphazero_policy/mod.rs:338-348 (no evaluator call, no visit increment)
-__device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, const Leaf& L) {
-    float v = (float)win_check(L.B, L.W);
-    backup(D, w, L.depth, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,117 +458,6 @@ __device__ inline void finish_move(const Dev& D, Warp& w) {
     collect(D, w);
 }
 
-// ------------------------------------------------------------------------------------------------
-// device evaluators (twins of the oracle's; each yields value and this lane's masked priors)
-// ------------------------------------------------------------------------------------------------
-// RandomEvaluator (LC/policy/alphazero_policy/mod.rs:137-169) on Philox, fused with get_from (:218-234)
-// and recover_way8 (augment.rs:75-92): draw s of original cell (r,c) is what plane s shows at its
-// image of (r,c), so the recovered prior needs exactly the 8 draws of its own cell.
-__device__ __forceinline__ float eval_philox(const Dev& D, Warp& w, const Leaf& L, float (&pr)[8]) {
-    const GameState& g = *w.gs;
-    const uint32_t k0 = D.seed ^ DOMAIN_EVAL, k1 = g.game_id, sim = g.sim_index;
-    Philox4 va = philox4x32_10(sim, CELLS, 0, 0, k0, k1), vb = philox4x32_10(sim, CELLS, 1, 0, k0, k1);
-    float sum = 0.f;
-    sum = sum + u32_to_pm1(va.x), sum = sum + u32_to_pm1(va.y), sum = sum + u32_to_pm1(va.z), sum = sum + u32_to_pm1(va.w);
-    sum = sum + u32_to_pm1(vb.x), sum = sum + u32_to_pm1(vb.y), sum = sum + u32_to_pm1(vb.z), sum = sum + u32_to_pm1(vb.w);
-    const float value = sum / 8.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        pr[j] = 0.f;
-        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
-        if ((ej >> w.lane) & 1u) {
-            uint32_t cell = (uint32_t)cell_of_bit(32u * j + w.lane);
-            Philox4 a = philox4x32_10(sim, cell, 0, 0, k0, k1), b = philox4x32_10(sim, cell, 1, 0, k0, k1);
-            float t0 = u32_to_pm1(a.x) + u32_to_pm1(a.y), t1 = u32_to_pm1(a.z) + u32_to_pm1(a.w);
-            float t2 = u32_to_pm1(b.x) + u32_to_pm1(b.y), t3 = u32_to_pm1(b.z) + u32_to_pm1(b.w);
-            float total = 0.f;
-            total = total + t0, total = total + t1, total = total + t2, total = total + t3;
-            pr[j] = total / 8.f;
-        }
-    }
-    return value;
-}
-
-// DetEval / NegEval: hash of the oriented board, evaluated on each of the 8 planes.
-template <bool NEG>
-__device__ __forceinline__ float eval_hash(const Dev& D, Warp& w, const Leaf& L, float (&pr)[8]) {
-    const int lane = w.lane;
-    const int turn = turn_of(L.stones);
-    uint64_t h[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        uint64_t k = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t bit = 32u * j + lane;
-            int r = (int)(bit >> 4), c = (int)(bit & 15), rr, cc;
-            sym_fwd(s, r, c, rr, cc);
-            if ((L.B[j] >> lane) & 1u) k ^= w.Z[rr * 16 + cc];
-            if ((L.W[j] >> lane) & 1u) k ^= w.Z[256 + rr * 16 + cc];
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) k ^= __shfl_xor_sync(FULL, k, off);
-        h[s] = splitmix64(k ^ (turn < 0 ? 0xB1ACull : 0x3417Eull));
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) sum = sum + ((float)(uint32_t)(h[s] >> 40) * (1.0f / 8388608.0f) - 1.0f);
-    const float value = sum / 8.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        pr[j] = 0.f;
-        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
-        if ((ej >> lane) & 1u) {
-            uint32_t bit = 32u * j + lane;
-            int r = (int)(bit >> 4), c = (int)(bit & 15);
-            float pv[8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                int rr, cc;
-                sym_fwd(s, r, c, rr, cc);
-                uint32_t x = (uint32_t)(splitmix64(h[s] + (uint64_t)(rr * 15 + cc) + 1) >> 40);
-                pv[s] = NEG ? ((float)x * (1.0f / 8388608.0f) - 1.0f) : ((float)x * (1.0f / 16777216.0f));
-            }
-            float total = 0.f;
-            total = total + (pv[0] + pv[1]), total = total + (pv[2] + pv[3]);
-            total = total + (pv[4] + pv[5]), total = total + (pv[6] + pv[7]);
-            pr[j] = total / 8.f;
-        }
-    }
-    return value;
-}
-
-// get_from() on an evaluator batch in the API layout (values[8], policies[8][225]) for this leaf.
-__device__ __forceinline__ float eval_from_batch(const float* __restrict__ values, const float* __restrict__ pol,
-                                                 Warp& w, const Leaf& L, float (&pr)[8]) {
-    const int lane = w.lane;
-    float myv = lane < 8 ? values[lane] : 0.f;
-    float sum = 0.f;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) sum = sum + __shfl_sync(FULL, myv, s);  // iter().sum::<f32>() order (:224)
-    const float value = sum / 8.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        pr[j] = 0.f;
-        uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
-        if ((ej >> lane) & 1u) {
-            uint32_t bit = 32u * j + lane;
-            int r = (int)(bit >> 4), c = (int)(bit & 15);
-            float pv[8];
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                int rr, cc;
-                sym_fwd(s, r, c, rr, cc);
-                pv[s] = pol[s * CELLS + rr * 15 + cc];
-            }
-            float total = 0.f;  // recover_way8 order: ((((0+t0)+t1)+t2)+t3)/8, t_i = p[2i] + flip(p[2i+1])
-            total = total + (pv[0] + pv[1]), total = total + (pv[2] + pv[3]);
-            total = total + (pv[4] + pv[5]), total = total + (pv[6] + pv[7]);
-            pr[j] = (total / 8.f) * 1.0f;  // * (cell empty) mask (:227-232)
-        }
-    }
-    return value;
-}
 #endif  // __CUDACC__
 
 }  // namespace c6

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <stdexcept>
 
-#include "c6_device.cuh"
+#include "c6_search.cuh"
 
 namespace c6 {
 
@@ -44,13 +44,19 @@ __global__ void k_start(Dev D, int n_start) {
         w.gs->status = ST_DONE;
 }
 
-// Device-evaluator path: one whole move (num_sim searches, move choice, collection) per game.
-// Persistent warps pull game slots from a counter, so unequal game lengths balance themselves.
+// Device-evaluator path, kernel 1: num_sim searches for every resident game.  Persistent warps pull
+// game slots from a counter, so unequal game lengths balance themselves.  Register-capped for
+// occupancy: the path is latency-bound, resident warps are what hides HBM latency.
+#ifndef C6_SIM_BLOCKS_PER_SM
+#define C6_SIM_BLOCKS_PER_SM 5
+#endif
 template <int EVAL, bool NOISE>
-__global__ void __launch_bounds__(128) k_move_device(Dev D) {
+__global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D) {
     __shared__ uint64_t Zs[512];
+    __shared__ double gl_all[NOISE ? 4 * 256 : 1];
     load_zobrist(D, Zs);
     const int lane = threadIdx.x & 31;
+    double* gl = gl_all + (NOISE ? (threadIdx.x >> 5) * 256 : 0);
     for (;;) {
         int g = 0;
         if (lane == 0) g = atomicAdd(D.cursor, 1);
@@ -58,36 +64,52 @@ __global__ void __launch_bounds__(128) k_move_device(Dev D) {
         if (g >= D.G) break;
         Warp w = make_warp(D, g, Zs, lane);
         if (w.gs->status != ST_ACTIVE) continue;
-        for (int s = 0; s < D.num_sim; ++s) {
+        Cursor cs;
+        load_cursor(*w.gs, cs);
+        for (int s = 0; s < D.num_sim && !cs.err; ++s) {
             Leaf L;
-            descend<NOISE>(D, w, L);
+            descend<NOISE>(D, w, cs, L, gl);
             if (L.stones == CELLS) {
-                terminal_leaf(D, w, L);
+                terminal_leaf(w, L);
+            } else if (EVAL == EVAL_PHILOX) {
+                EvPhilox ev;
+                ev.init(D, cs, lane);
+                expand_leaf(D, w, cs, L, ev, ev.value());
+            } else if (EVAL == EVAL_DET) {
+                EvHash<false> ev;
+                ev.init(L, Zs, lane);
+                expand_leaf(D, w, cs, L, ev, ev.value());
             } else {
-                float pr[8];
-                float v;
-                if (EVAL == EVAL_PHILOX)
-                    v = eval_philox(D, w, L, pr);
-                else if (EVAL == EVAL_DET)
-                    v = eval_hash<false>(D, w, L, pr);
-                else
-                    v = eval_hash<true>(D, w, L, pr);
-                expand_leaf(D, w, L, pr, v);
+                EvHash<true> ev;
+                ev.init(L, Zs, lane);
+                expand_leaf(D, w, cs, L, ev, ev.value());
             }
-            if (lane == 0) w.gs->sim_index += 1;
-            __syncwarp();
-            if (w.gs->status != ST_ACTIVE) break;
+            cs.sim_index += 1;
         }
-        if (w.gs->status == ST_ACTIVE) finish_move(D, w);
+        store_cursor(D, *w.gs, cs, lane);
     }
+}
+
+// Device-evaluator path, kernel 2 (also the tail of the callback path): move choice, stone, win
+// check, record, node collection / slot refill for every resident game.
+__global__ void __launch_bounds__(128) k_move_end(Dev D) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    const int lane = threadIdx.x & 31;
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= D.G) return;
+    Warp w = make_warp(D, g, Zs, lane);
+    if (w.gs->status == ST_ACTIVE) finish_move(D, w);
 }
 
 // Callback path, kernel 1: descend to the leaf and park it in the game state.
 template <bool NOISE>
 __global__ void __launch_bounds__(128) k_select(Dev D) {
     __shared__ uint64_t Zs[512];
+    __shared__ double gl_all[NOISE ? 4 * 256 : 1];
     load_zobrist(D, Zs);
     const int lane = threadIdx.x & 31;
+    double* gl = gl_all + (NOISE ? (threadIdx.x >> 5) * 256 : 0);
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= D.G) return;
     Warp w = make_warp(D, g, Zs, lane);
@@ -96,11 +118,13 @@ __global__ void __launch_bounds__(128) k_select(Dev D) {
         if (lane == 0) gs.need_eval = 0;
         return;
     }
+    Cursor cs;
+    load_cursor(gs, cs);
     Leaf L;
-    descend<NOISE>(D, w, L);
+    descend<NOISE>(D, w, cs, L, gl);
     int need = 1;
     if (L.stones == CELLS) {
-        terminal_leaf(D, w, L);
+        terminal_leaf(w, L);
         need = 0;
     }
 #pragma unroll
@@ -110,6 +134,7 @@ __global__ void __launch_bounds__(128) k_select(Dev D) {
         gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key;
         gs.need_eval = need;
     }
+    store_cursor(D, gs, cs, lane);
 }
 
 // Callback path, kernel 2: order the leaves into a Black-to-move group followed by a White-to-move
@@ -170,7 +195,7 @@ __global__ void __launch_bounds__(128) k_gather(Dev D) {
     if (lane < 8) D.bvalues[(size_t)gs.batch_pos * 8 + lane] = 0.f;
 }
 
-// Callback path, kernel 4: recover_way8 + expansion + backup, then the move if the budget is spent.
+// Callback path, kernel 4: recover_way8 + expansion + backup (k_move_end follows every num_sim waves).
 __global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
     __shared__ uint64_t Zs[512];
     load_zobrist(D, Zs);
@@ -180,40 +205,27 @@ __global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
     Warp w = make_warp(D, g, Zs, lane);
     GameState& gs = *w.gs;
     if (gs.status != ST_ACTIVE) return;
+    Cursor cs;
+    load_cursor(gs, cs);
     if (gs.need_eval) {
         Leaf L;
 #pragma unroll
         for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
         L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
-        float pr[8];
-        float v = eval_from_batch(D.bvalues + (size_t)gs.batch_pos * 8, D.bboards + (size_t)gs.batch_pos * 8 * CELLS,
-                                  w, L, pr);
-        expand_leaf(D, w, L, pr, v);
+        EvBatch ev;
+        ev.values = D.bvalues + (size_t)gs.batch_pos * 8;
+        ev.pol = D.bboards + (size_t)gs.batch_pos * 8 * CELLS;
+        ev.lane = lane;
+        expand_leaf(D, w, cs, L, ev, ev.value());
     }
-    __syncwarp();
+    cs.sim_index += 1;
+    store_cursor(D, gs, cs, lane);
     if (gs.status != ST_ACTIVE) return;
-    int done = 0;
     if (lane == 0) {
-        gs.sim_index += 1;
         gs.sims_this_move += 1;
         gs.need_eval = 0;
-        done = gs.sims_this_move >= D.num_sim;
     }
-    done = __shfl_sync(FULL, done, 0);
-    if (done) finish_move(D, w);
 }
-
-// num_simulation == 0: policy() sees an unexpanded root -> None -> the game ends at once.
-__global__ void __launch_bounds__(128) k_finish_only(Dev D) {
-    __shared__ uint64_t Zs[512];
-    load_zobrist(D, Zs);
-    const int lane = threadIdx.x & 31;
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= D.G) return;
-    Warp w = make_warp(D, g, Zs, lane);
-    if (w.gs->status == ST_ACTIVE) finish_move(D, w);
-}
-
 
 // Invariant checker (tests / debugging): for every resident game, every entry of the expanded list must
 // (1) carry the Zobrist key of its board, (2) own an expanded record (N >= 1, real link run), whose
@@ -441,9 +453,9 @@ void Engine::start(uint32_t first_id, int64_t total_games) {
 template <int EVAL>
 static void launch_move(const Dev& D, bool noise, int blocks, cudaStream_t s) {
     if (noise)
-        k_move_device<EVAL, true><<<blocks, 128, 0, s>>>(D);
+        k_sims_device<EVAL, true><<<blocks, 128, 0, s>>>(D);
     else
-        k_move_device<EVAL, false><<<blocks, 128, 0, s>>>(D);
+        k_sims_device<EVAL, false><<<blocks, 128, 0, s>>>(D);
 }
 
 void Engine::step_device() {
@@ -454,26 +466,28 @@ void Engine::step_device() {
         const bool noise = cfg_.epsilon != 0.f;
         // occupancy of the variant that will run
         if (cfg_.evaluator == EVAL_PHILOX) {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_PHILOX, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_PHILOX, false>, 128, 0));
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_PHILOX, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_PHILOX, false>, 128, 0));
         } else if (cfg_.evaluator == EVAL_DET) {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_DET, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_DET, false>, 128, 0));
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_DET, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_DET, false>, 128, 0));
         } else {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_NEG, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_move_device<EVAL_NEG, false>, 128, 0));
+            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_NEG, true>, 128, 0));
+            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_NEG, false>, 128, 0));
         }
         if (per_sm < 1) per_sm = 1;
         d_->persistent_blocks = std::min(d_->sm_count * per_sm, warps_grid(D.G));
     }
     C6_CUDA(cudaMemsetAsync(D.cursor, 0, sizeof(int), stream_));
     if (cfg_.num_simulation <= 0) {
-        k_finish_only<<<warps_grid(D.G), 128, 0, stream_>>>(D);
+        k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
     } else {
         const bool noise = cfg_.epsilon != 0.f;
         if (cfg_.evaluator == EVAL_PHILOX) launch_move<EVAL_PHILOX>(D, noise, d_->persistent_blocks, stream_);
         else if (cfg_.evaluator == EVAL_DET) launch_move<EVAL_DET>(D, noise, d_->persistent_blocks, stream_);
         else launch_move<EVAL_NEG>(D, noise, d_->persistent_blocks, stream_);
+        k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
+        launches_ += 1;
     }
     launches_ += 1;
     C6_CUDA(cudaGetLastError());
@@ -484,7 +498,7 @@ void Engine::wave_callback(Callback cb) {
     if (cfg_.evaluator != EVAL_CALLBACK) throw std::runtime_error("c6: engine was not created for the callback path");
     const int grid = warps_grid(D.G);
     if (cfg_.num_simulation <= 0) {
-        k_finish_only<<<grid, 128, 0, stream_>>>(D);
+        k_move_end<<<grid, 128, 0, stream_>>>(D);
         launches_ += 1;
         C6_CUDA(cudaGetLastError());
         return;
@@ -514,6 +528,11 @@ void Engine::wave_callback(Callback cb) {
     }
     k_expand_cb<<<grid, 128, 0, stream_>>>(D);
     launches_ += 1;
+    if (++waves_this_move_ >= cfg_.num_simulation) {  // every resident game has spent its budget: all slots are in lockstep
+        waves_this_move_ = 0;
+        k_move_end<<<grid, 128, 0, stream_>>>(D);
+        launches_ += 1;
+    }
     C6_CUDA(cudaGetLastError());
 }
 

@@ -150,6 +150,7 @@ class Engine {
     uint32_t first_id_ = 0;
     long long launches_ = 0;
     double h2d_bytes_ = 0, d2h_bytes_ = 0;
+    int waves_this_move_ = 0;
 };
 
 // Stand-alone kernels of the path (config 3 microbenches), host launchers.

@@ -199,4 +199,12 @@ __host__ __device__ inline double gamma_sample(PhiloxStream& st, double shape) {
     return gamma_large(st, shape);
 }
 
+// One Gamma(shape) draw from the stream with counter (a, b, c).  Kept out of line: eight inlined
+// copies per select step thrash the instruction cache (ncu: stall_no_instruction dominated).
+__host__ __device__ __noinline__ inline double gamma_draw(uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1,
+                                                         double shape) {
+    PhiloxStream st(a, b, c, k0, k1);
+    return gamma_sample(st, shape);
+}
+
 }  // namespace c6

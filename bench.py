@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py — MCTS simulations/sec of batched Connect6 AlphaZero self-play (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload: 4,096 concurrent self-play games per GPU, AlphaZero policy, RandomEvaluator, 800
+simulations per stone, reference default hyper-parameters (epsilon .25, alpha .03, c_puct 1).
+A step is one stone for every resident game (= 4,096 x 800 simulations incl. move choice and node
+collection).  `value` = simulations/s with everything resident in HBM (device RandomEvaluator fused
+into expansion); `e2e` = the same search driven through the reference C-ABI evaluator contract
+(host Callback, host buffers, D2H + H2D inside the timed region).  Games shard by game id across
+GPUs with no collective on the data path (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GAMES_PER_GPU = 4096
+SIMS = 800
+EPS, ALPHA, CPUCT, SEED = 0.25, 0.03, 1.0, 0xC6
+METRIC = "mcts_simulations_per_sec"
+UNIT = "simulations/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def algorithmic_bytes(st0, st1, materialised_batch):
+    """16*sum C_k + 28*sum C_leaf + 16*(D+1) per simulation (+14,432 B per
+    evaluated leaf only when an evaluator batch is materialised in global memory)."""
+    d = {k: getattr(st1, k) - getattr(st0, k) for k in ("sims", "sum_ck", "sum_cleaf", "sum_depth", "evals")}
+    b = 16 * d["sum_ck"] + 28 * d["sum_cleaf"] + 16 * (d["sum_depth"] + d["sims"])
+    if materialised_batch:
+        b += 14432 * d["evals"]
+    return b, d
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the restated reference (oracle, reference cost model) on the host cores."""
+    if rank != 0:
+        return
+    import c6lib
+    O = c6lib.oracle()
+    cores = O.oracle_hardware_concurrency()
+    moves = 2  # stones per game per step: bounded sample
+    p = c6lib.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 0, 1, 1, moves)
+    outs = (c6lib.OracleGameOut * cores)()
+    for w in range(max(args.warmup, 0)):
+        if w >= 1:
+            break  # one warm-up pass is enough for a CPU job; keeps the run within minutes
+        O.oracle_self_play_many(None, C.byref(p), 10_000_000, cores, cores, outs)
+    sims, secs = 0, 0.0
+    for k in range(args.steps):
+        secs += O.oracle_self_play_many(None, C.byref(p), 20_000_000 + k * cores, cores, cores, outs)
+        sims += sum(o.sims for o in outs)
+    v = sims / secs
+    sample = f"{args.steps} x ({cores} games x first {moves} stones x {SIMS} sims), one OS thread per game"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "4096 concurrent self-play games per GPU, AlphaZero policy + RandomEvaluator, 800 simulations/stone "
+                        "(BASELINE.json configs[1]); reference default hyper-parameters epsilon=0.25 alpha=0.03 c_puct=1",
+            "games_per_gpu": GAMES_PER_GPU, "num_simulation": SIMS, "epsilon": EPS, "dirichlet_alpha": ALPHA,
+            "step": "one stone for every resident game (4096 x 800 simulations + move choice + node collection)",
+            "sharding": f"game id -> rank, {n_gpus} rank(s), no data-path collective",
+            "l2": "working set >> L2 (node pool of 4096 games is tens of GB); no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--log2-records", type=int, default=18)
+    ap.add_argument("--epsilon", type=float, default=None, help="override epsilon (0 disables Dirichlet noise)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    global EPS
+    if args.epsilon is not None:
+        EPS = args.epsilon
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import c6lib
+    L = c6lib.product()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    games = args.games
+    cfg = c6lib.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
+                            slots=games, log2_records=args.log2_records, evaluator=c6lib.EVAL_PHILOX)
+    e = L.c6_engine_create(C.byref(cfg))
+    if not e:
+        raise RuntimeError(L.c6_last_error().decode())
+    # many more games queued than will finish: slots refill, the batch stays full
+    assert L.c6_engine_start(e, rank * 100_000_000, 50_000_000) == 0, L.c6_last_error()
+    ms = C.c_float()
+    assert L.c6_engine_timed_steps(e, args.warmup, C.byref(ms)) == 0, L.c6_last_error()
+    st0, st1 = c6lib.Stats(), c6lib.Stats()
+    L.c6_engine_stats(e, C.byref(st0))
+    if dist is not None:
+        dist.barrier()
+    with ClockSampler(local) as clk:
+        assert L.c6_engine_timed_steps(e, args.steps, C.byref(ms)) == 0, L.c6_last_error()
+    L.c6_engine_stats(e, C.byref(st1))
+    elapsed_ms = float(ms.value)
+    sims = st1.sims - st0.sims
+    launches = st1.kernel_launches - st0.kernel_launches
+    if dist is not None:
+        import torch
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        s = torch.tensor([float(sims), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        total_sims, total_launches = float(s[0].item()), int(s[1].item())
+    else:
+        total_sims, total_launches = float(sims), int(launches)
+    value = total_sims / (elapsed_ms * 1e-3)
+
+    # roofline of the dominant kernel (k_move_device: one launch per step) on this rank
+    bytes_alg, d = algorithmic_bytes(st0, st1, materialised_batch=False)
+    peak, peak_src = measured_peak_gbs()
+    achieved = bytes_alg / (float(ms.value) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_move_device<philox,noise> (1 launch/step)", "peak_source": peak_src,
+                "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
+                "avg_depth": d["sum_depth"] / max(d["sims"], 1), "avg_sum_ck": d["sum_ck"] / max(d["sims"], 1),
+                "avg_cleaf": d["sum_cleaf"] / max(d["evals"], 1)}
+    L.c6_engine_destroy(e)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
+           "gpu_launches": total_launches, "clocks": clk.summary(),
+           "peak_records_per_game": int(st1.peak_rec), "bytes_per_game": int(st1.bytes_per_game)}
+
+    # end to end through the reference-facing evaluator contract: host callback, host buffers
+    if not args.no_e2e:
+        cfg2 = c6lib.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
+                                 slots=games, log2_records=args.log2_records, evaluator=c6lib.EVAL_CALLBACK)
+        e2 = L.c6_engine_create(C.byref(cfg2))
+        if not e2:
+            raise RuntimeError(L.c6_last_error().decode())
+        assert L.c6_engine_start(e2, rank * 100_000_000, 50_000_000) == 0
+        cb = C.cast(L.c6_sample_random_callback, c6lib.CALLBACK)
+        h2d, d2h = C.c_double(), C.c_double()
+        waves_w, waves = 8, 48
+        assert L.c6_engine_timed_waves(e2, cb, waves_w, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
+        s0, s1 = c6lib.Stats(), c6lib.Stats()
+        L.c6_engine_stats(e2, C.byref(s0))
+        if dist is not None:
+            dist.barrier()
+        assert L.c6_engine_timed_waves(e2, cb, waves, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
+        L.c6_engine_stats(e2, C.byref(s1))
+        e2e_ms, e2e_sims = float(ms.value), float(s1.sims - s0.sims)
+        if dist is not None:
+            import torch
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+            s = torch.tensor([e2e_sims], device="cuda", dtype=torch.float64)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            e2e_sims = float(s.item())
+        out["e2e"] = {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d.value / waves,
+                      "d2h_bytes_per_step": d2h.value / waves,
+                      "step": f"one wave = one simulation for each of {games} games through the C-ABI Callback "
+                              f"(host buffers, sample host RandomEvaluator); {waves} waves timed",
+                      "ms_per_wave": e2e_ms / waves}
+        L.c6_engine_destroy(e2)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O = c6lib.oracle()
+        cores = O.oracle_hardware_concurrency()
+        moves = 3
+        p = c6lib.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 0, 1, 1, moves)
+        outs = (c6lib.OracleGameOut * cores)()
+        secs = O.oracle_self_play_many(None, C.byref(p), 30_000_000, cores, cores, outs)
+        csims = sum(o.sims for o in outs)
+        out["cpu_baseline"] = {"value": csims / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{cores} games x first {moves} stones x {SIMS} sims, oracle in the reference's cost model "
+                                         f"(SipHash board keys, full nodes), one OS thread per game like AsyncAgent; {secs:.1f} s"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,9 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
                       int8_t* winners_out, uint8_t* stones_out, uint32_t* boards_out, int64_t n_out,
                       uint64_t* total_stones);
 
+/* sample host evaluator (random values/policies), the twin of Connect6/sample/cpp/main.cpp:6-28 */
+void c6_sample_random_callback(int player, float* values, float* policies, int len);
+
 #ifdef __cplusplus
 }
 #endif
