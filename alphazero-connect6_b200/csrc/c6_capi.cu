@@ -279,6 +279,7 @@ int c6_engine_wave_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->wave_
 int c6_engine_run_device(c6_engine* e) { C6_TRY(e->eng->run_device_to_end()) }
 int c6_engine_run_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->run_callback_to_end(cb, false)) }
 int c6_engine_sync(c6_engine* e) { C6_TRY(e->eng->sync()) }
+void c6_engine_cancel(c6_engine* e) { e->eng->cancel(); }
 int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { C6_TRY(*ms = e->eng->timed_steps_device(steps)) }
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, double* h2d, double* d2h) {
     C6_TRY(*ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h))

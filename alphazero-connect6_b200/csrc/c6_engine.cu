@@ -569,6 +569,7 @@ bool Engine::all_done() { return games_done() >= total_games_; }
 void Engine::run_device_to_end() {
     // a game lasts at most 225 stones; poll every few moves
     while (!all_done()) {
+        if (cancel_.load()) throw std::runtime_error("c6: cancelled");
         for (int i = 0; i < 4; ++i) step_device();
     }
 }
@@ -584,7 +585,10 @@ void Engine::run_callback_to_end(Callback cb, bool debug) {
     (void)debug;
     const int per_move = std::max(cfg_.num_simulation, 1);
     while (!all_done()) {
-        for (int i = 0; i < per_move; ++i) wave_callback(cb);
+        for (int i = 0; i < per_move; ++i) {
+            wave_callback(cb);
+            if (cancel_.load()) throw std::runtime_error("c6: cancelled");
+        }
     }
 }
 

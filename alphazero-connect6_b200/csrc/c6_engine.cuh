@@ -8,6 +8,7 @@
 //   Agent::play / AsyncAgent::run game loop and records                  LC/agent/agent_impl/mod.rs:121-178, async_agent/mod.rs:100-137
 // (LC = /root/reference/Connect6/libconnect6/src).  See DESIGN.md for the HBM layout.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <string>
@@ -141,6 +142,9 @@ class Engine {
     size_t bytes_per_game() const;
     long long kernel_launches() const { return launches_; }
     GameState slot_state(int slot);   // synchronises (debug printing)
+    // May be called from inside the evaluator callback (or another thread): the run_*_to_end loops stop
+    // at the next wave / poll and throw "cancelled".
+    void cancel() { cancel_.store(true); }
 
    private:
     Config cfg_;
@@ -151,6 +155,7 @@ class Engine {
     long long launches_ = 0;
     double h2d_bytes_ = 0, d2h_bytes_ = 0;
     int waves_this_move_ = 0;
+    std::atomic<bool> cancel_{false};
 };
 
 // Stand-alone kernels of the path (config 3 microbenches), host launchers.

@@ -142,6 +142,8 @@ int c6_engine_wave_callback(c6_engine* e, c6_callback cb); /* one simulation for
 int c6_engine_run_device(c6_engine* e);                   /* until all games are finished */
 int c6_engine_run_callback(c6_engine* e, c6_callback cb);
 int c6_engine_sync(c6_engine* e);
+/* callable from inside the evaluator callback: c6_engine_run_* return non-zero ("cancelled") at the next wave */
+void c6_engine_cancel(c6_engine* e);
 int c6_engine_timed_steps(c6_engine* e, int steps, float* milliseconds);
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* milliseconds, double* h2d_bytes,
                           double* d2h_bytes);

@@ -72,6 +72,28 @@ void oracle_recover_way8(const float* in, float* out) {
     FBoard r = recover_way8(p);
     std::memcpy(out, &r[0][0], sizeof(FBoard));
 }
+// kind: 0 rotate_left, 1 rotate_right, 2 flip_vertical, 3 flip_horizontal (augment.rs:8-51)
+void oracle_transform(int kind, const int8_t* board, int8_t* out) {
+    Board b = board_from_i8(board);
+    if (kind == 0) rotate_left(b);
+    else if (kind == 1) rotate_right(b);
+    else if (kind == 2) flip_vertical(b);
+    else flip_horizontal(b);
+    for (int r = 0; r < BOARD_SIZE; ++r)
+        for (int c = 0; c < BOARD_SIZE; ++c) out[r * BOARD_SIZE + c] = (int8_t)b[r][c];
+}
+// Game::set replay (game_impl/mod.rs:148-169): per position code 0 ok / 1 "invalid position" /
+// 2 "already set position", the SetResult fields, and the game's turn / num_remain after the call.
+void oracle_game_replay(const int* pos, int n, int* code, int* player, int* remain, int* turn_after, int* remain_after) {
+    Game g;
+    for (int i = 0; i < n; ++i) {
+        SetResult sr;
+        std::string err = g.set(Pos(pos[2 * i], pos[2 * i + 1]), &sr);
+        code[i] = err.empty() ? 0 : (err == "invalid position" ? 1 : (err == "already set position" ? 2 : 3));
+        player[i] = (int)sr.player, remain[i] = sr.num_remain;
+        turn_after[i] = (int)g.turn, remain_after[i] = g.num_remain;
+    }
+}
 uint64_t oracle_zobrist(int white, int cell) { return zobrist().z[white ? 1 : 0][cell]; }
 void oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);

@@ -1,0 +1,187 @@
+"""CPU suite, part 1: the oracle against the reference's known-answer vectors (tests/golden/, transcribed
+from the reference's own tests with file:line) and against its own committed self-play traces.
+
+The reference is Rust and cannot run here; these vectors are what pins the oracle.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import c6lib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def i8(a):
+    return np.ascontiguousarray(a, dtype=np.int8).ctypes.data_as(C.POINTER(C.c_int8))
+
+
+def test_reference_test_ports_pass():
+    """oracle/oracle_tests.cpp: C++ ports of every deterministic reference test on the path."""
+    c6lib.build_oracle()
+    r = subprocess.run([c6lib.ORACLE_TESTS], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 failures" in r.stdout
+
+
+def test_win_detection_known_answers(oracle):
+    vec = load("reference_known_answers.json")["win_detection"]
+    assert len(vec) == 8 + 24 + 12
+    for v in vec:
+        assert oracle.oracle_search(i8(v["board"])) == v["winner"], v["cite"]
+
+
+def test_symmetry_known_answers(oracle):
+    s = load("reference_known_answers.json")["symmetries"]
+    for kind, name in enumerate(["rotate_left", "rotate_right", "flip_vertical", "flip_horizontal"]):
+        out = np.zeros(225, dtype=np.int8)
+        oracle.oracle_transform(kind, i8(s["board"]), i8(out) if False else out.ctypes.data_as(C.POINTER(C.c_int8)))
+        for r, c, want in s[name]:
+            assert out[r * 15 + c] == want, (name, r, c)
+
+
+def test_augment_recover_round_trip(oracle):
+    """augment_tests.rs:115-142 on seeded random boards: 8 distinct planes, recover(augment(x)) == x."""
+    rng = np.random.default_rng(6)
+    for _ in range(20):
+        b = rng.integers(-1, 2, size=225).astype(np.int8)
+        planes = np.zeros((8, 225), dtype=np.int8)
+        oracle.oracle_augment_way8(i8(b), planes.ctypes.data_as(C.POINTER(C.c_int8)))
+        assert len({p.tobytes() for p in planes}) == 8
+        f = planes.astype(np.float32)
+        rec = np.zeros(225, dtype=np.float32)
+        oracle.oracle_recover_way8(f.ctypes.data_as(C.POINTER(C.c_float)), rec.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(rec, b.astype(np.float32))
+
+
+def test_rules_known_answers(oracle):
+    steps = load("reference_known_answers.json")["rules"]["steps"]
+    n = len(steps)
+    pos = (C.c_int * (2 * n))(*[x for s in steps for x in s["pos"]])
+    code, player, remain, ta, ra = [(C.c_int * n)() for _ in range(5)]
+    oracle.oracle_game_replay(pos, n, code, player, remain, ta, ra)
+    for i, s in enumerate(steps):
+        if s["ok"]:
+            assert code[i] == 0 and player[i] == s["player"] and remain[i] == s["num_remain"]
+            assert (ta[i], ra[i]) == (s["turn_after"], s["remain_after"])
+        else:
+            assert code[i] == {"invalid position": 1, "already set position": 2}[s["err"]]
+
+
+def test_scripted_game_known_answer(oracle):
+    g = load("reference_known_answers.json")["scripted_game"]
+    n = len(g["moves"])
+    moves = (C.c_int * (2 * n))(*[x for m in g["moves"] for x in m])
+    winner = C.c_int()
+    paths = (C.c_int * (228 * 225))()
+    err = C.create_string_buffer(64)
+    ln = oracle.oracle_script_game(moves, n, C.byref(winner), paths, err)
+    assert ln == g["path_len"] and winner.value == g["winner"]
+    board = [0] * 225
+    for k in range(ln):
+        p = paths[k * 228:(k + 1) * 228]
+        assert p[0] == g["turns"][k]
+        assert list(p[1:226]) == board  # board BEFORE the stone (agent_impl/mod.rs:139-143)
+        assert [p[226], p[227]] == list(g["moves"][k])
+        board[p[226] * 15 + p[227]] = p[0]
+    # error propagation (agent_impl/tests.rs:37-63): replaying a stone is Err("already set position")
+    bad = (C.c_int * 4)(0, 0, 0, 0)
+    assert oracle.oracle_script_game(bad, 2, C.byref(winner), paths, err) == -1
+    assert err.value == b"already set position"
+
+
+def run_oracle_case(case, g, faithful=0):
+    O = c6lib.oracle()
+    p = c6lib.OracleParams(case["num_simulation"], case["epsilon"], case["dirichlet_alpha"], case["c_puct"], case["seed"],
+                           1 if case["epsilon"] != 0 else 0, 0, faithful, case["evaluator"], case["max_moves"])
+    out = c6lib.OracleGameOut()
+    cv = np.zeros((225, 225), dtype=np.int32)
+    rn = np.zeros(225, dtype=np.int32)
+    rw = np.zeros(225, dtype=np.float32)
+    cb = c6lib.oracle_callback(case["callback"]) if case["callback"] else None
+    O.oracle_self_play(cb, C.byref(p), g["game_id"], C.byref(out), cv.ctypes.data_as(C.POINTER(C.c_int32)),
+                       rn.ctypes.data_as(C.POINTER(C.c_int32)), rw.ctypes.data_as(C.POINTER(C.c_float)))
+    return out, cv, rn, rw
+
+
+def check_against_trace(g, winner, finished, moves, cv, rn, rw):
+    assert moves == g["moves"]
+    assert (winner, finished) == (g["winner"], g["finished"])
+    m = len(moves)
+    assert rn[:m].tolist() == g["root_visit"]
+    assert rw[:m].view(np.uint32).tolist() == g["root_qsum_bits"]
+    assert [int((cv[i].astype(np.int64) * np.arange(1, 226)).sum()) for i in range(m)] == g["child_visit_checksum"]
+
+
+@pytest.mark.parametrize("case", load("selfplay_traces.json"), ids=lambda c: c["name"])
+def test_oracle_reproduces_committed_traces(case):
+    if case["num_simulation"] >= 800:
+        pytest.skip("800-simulation trace is replayed by the GPU suite; too slow for the CPU suite budget")
+    for g in case["games"]:
+        out, cv, rn, rw = run_oracle_case(case, g)
+        check_against_trace(g, out.winner, out.finished, [out.moves[i] for i in range(out.n_moves)], cv, rn, rw)
+        assert (out.sims, out.sum_ck, out.sum_cleaf, out.sum_depth) == (g["sims"], g["sum_ck"], g["sum_cleaf"], g["sum_depth"])
+
+
+def test_lean_cost_model_equals_reference_cost_model():
+    """The oracle's fast mode (Zobrist keys, superset GC) must give the results of the reference's own
+    data structures (SipHash over the whole board, nothing freed)."""
+    case = [c for c in load("selfplay_traces.json") if c["name"] == "philox_64sims_noise"][0]
+    case = dict(case, max_moves=8)
+    g = case["games"][0]
+    a = run_oracle_case(case, g, faithful=0)
+    b = run_oracle_case(case, g, faithful=1)
+    assert [a[0].moves[i] for i in range(a[0].n_moves)] == [b[0].moves[i] for i in range(b[0].n_moves)]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
+
+
+def test_b1_hand_trace(oracle):
+    """derived by hand from the reference source, independent of any code here."""
+    b1 = load("b1_hand_trace.json")
+    case = {"num_simulation": 4, "epsilon": 0.0, "dirichlet_alpha": 0.03, "c_puct": 1.0, "seed": 1, "evaluator": 0,
+            "callback": "const_eval_callback", "max_moves": 7}
+    out, cv, rn, rw = run_oracle_case(case, {"game_id": 0})
+    assert [[out.moves[i] // 15, out.moves[i] % 15] for i in range(7)] == b1["moves_rc"]
+    assert (rn[0], rw[0]) == (b1["move1_root"]["visit"], b1["move1_root"]["q_sum"])
+    assert (rn[1], rw[1]) == (b1["move2_root"]["visit"], b1["move2_root"]["q_sum"])
+
+
+def test_philox_known_answer(oracle):
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): zero, all-ones and the pi digits."""
+    def run(ctr, key):
+        out = (C.c_uint32 * 4)()
+        oracle.oracle_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        return list(out)
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_deterministic_log_exp(oracle):
+    """The noise sampler's own log/exp (no libm, so CPU and GPU agree bit for bit) are accurate."""
+    import math
+    for x in [1e-300, 1e-10, 0.03, 0.5, 1.0, 2.0, 7.25, 1e10]:
+        assert abs(oracle.oracle_det_log(x) - math.log(x)) <= 1e-13 * max(1.0, abs(math.log(x)))
+    for x in [-700.0, -30.0, -1.0, -1e-9, 0.0, 0.3, 1.0, 20.0]:
+        assert abs(oracle.oracle_det_exp(x) - math.exp(x)) <= 1e-13 * math.exp(x)
+
+
+def test_gamma_sampler_distribution(oracle):
+    """Gamma(alpha=0.03) twin of rand 0.6's Dirichlet building block: mean/variance = alpha."""
+    n = 40000
+    xs = np.array([oracle.oracle_gamma(i, 0, 0, 123, 7, 0.03) for i in range(n)])
+    assert np.all(xs >= 0)
+    assert abs(xs.mean() - 0.03) < 0.006
+    assert abs(xs.var() - 0.03) < 0.02
+    xs1 = np.array([oracle.oracle_gamma(i, 1, 2, 123, 7, 1.5) for i in range(n)])
+    assert abs(xs1.mean() - 1.5) < 0.03 and abs(xs1.var() - 1.5) < 0.1

@@ -284,3 +284,137 @@ def test_legacy_cpp_self_play_matches_oracle(monkeypatch):
             assert (p.row * 15 + p.col, p.turn) == (out.moves[m], out.turns[m])
             assert np.array_equal(np.ctypeslib.as_array(p.board), board)  # board BEFORE the stone
             board[p.row][p.col] = p.turn
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden traces (tests/golden/selfplay_traces.json, made by the pinned oracle): no oracle
+# needed at run time
+# ---------------------------------------------------------------------------------------------
+import json  # noqa: E402
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_TRACES = json.load(open(os.path.join(_GOLDEN, "selfplay_traces.json")))
+
+
+@pytest.mark.parametrize("case", _TRACES, ids=lambda c: c["name"])
+def test_engine_reproduces_golden_traces(case):
+    n = len(case["games"])
+    first = case["first_id"]
+    kw = dict(num_simulation=case["num_simulation"], epsilon=case["epsilon"], seed=case["seed"], max_moves=case["max_moves"])
+    if case["evaluator"] == 1:
+        rec, cv, rn, rw, st = run_engine(n, None, first_id=first, evaluator=EVAL_PHILOX, **kw)
+    else:
+        rec, cv, rn, rw, st = run_engine(n, case["callback"], first_id=first, evaluator=EVAL_CALLBACK, **kw)
+    tot = dict(sims=0, sum_ck=0, sum_cleaf=0, sum_depth=0)
+    for g, want in enumerate(case["games"]):
+        r = rec[g]
+        m = r.n_moves
+        assert [r.moves[i] for i in range(m)] == want["moves"], want["game_id"]
+        assert (r.winner, r.finished) == (want["winner"], want["finished"])
+        assert rn[g][:m].tolist() == want["root_visit"]
+        assert rw[g][:m].view(np.uint32).tolist() == want["root_qsum_bits"]
+        assert [int((cv[g][i].astype(np.int64) * np.arange(1, 226)).sum()) for i in range(m)] == want["child_visit_checksum"]
+        for k in tot:
+            tot[k] += want[k]
+    # the device counters behind the roofline's algorithmic-bytes formula equal the oracle's
+    assert (st.sims, st.sum_ck, st.sum_cleaf, st.sum_depth) == (tot["sims"], tot["sum_ck"], tot["sum_cleaf"], tot["sum_depth"])
+
+
+def test_sharded_equals_unsharded():
+    """Records are a pure function of (seed, game id): two half-shards == one run."""
+    from pyconnect6 import sharded
+    kw = dict(num_simulation=8, epsilon=0.25, seed=11, max_moves=20)
+    whole, _ = sharded.play_shard_device(0, 6, **kw)
+    parts = []
+    for r in range(2):
+        lo, n = sharded.shard_range(6, r, 2)
+        parts.append(sharded.play_shard_device(lo, n, **kw)[0])
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert [r["game_id"] for r in sharded.records_from_bytes(whole)] == list(range(6))
+
+
+def test_full_games_properties_at_scale():
+    """Size-independent properties on many full games (2 simulations, noise on): every record is a legal
+    game — distinct cells, stone count == path length, winner == colour of the last stone and a six
+    exists exactly when a winner is reported (checked with the win-check kernel itself)."""
+    L = c6lib.product()
+    n = 2048
+    cfg = c6lib.make_config(num_simulation=2, epsilon=0.25, seed=5, evaluator=EVAL_PHILOX, slots=512, log2_records=12)
+    rec = (c6lib.Record * n)()
+    st = c6lib.Stats()
+    assert L.c6_self_play_device(C.byref(cfg), 1000, n, rec, C.byref(st)) == 0, L.c6_last_error()
+    assert st.games_done == n
+    cells = np.zeros((n, 225), dtype=np.int8)
+    prev = np.zeros((n, 225), dtype=np.int8)
+    for g in range(n):
+        r = rec[g]
+        assert r.finished == 1 and r.game_id == 1000 + g
+        mv = [r.moves[i] for i in range(r.n_moves)]
+        assert len(set(mv)) == len(mv) and all(0 <= m < 225 for m in mv)
+        for i, m in enumerate(mv):
+            turn = -1 if i == 0 else (1 if ((i - 1) // 2) % 2 == 0 else -1)
+            cells[g, m] = turn
+            if i < len(mv) - 1:
+                prev[g, m] = turn
+        if r.winner != 0:
+            last = r.n_moves - 1
+            assert r.winner == (-1 if last == 0 else (1 if ((last - 1) // 2) % 2 == 0 else -1))
+        else:
+            assert r.n_moves == 225
+    w = np.zeros(n, dtype=np.int8)
+    wp = np.zeros(n, dtype=np.int8)
+    pk, pkp = c6lib.pack_boards(cells), c6lib.pack_boards(prev)
+    assert L.c6_win_check_host(pk.ctypes.data_as(C.POINTER(C.c_uint32)), w.ctypes.data_as(C.POINTER(C.c_int8)), n, 0) == 0
+    assert L.c6_win_check_host(pkp.ctypes.data_as(C.POINTER(C.c_uint32)), wp.ctypes.data_as(C.POINTER(C.c_int8)), n, 0) == 0
+    assert np.array_equal(w, np.array([rec[g].winner for g in range(n)], dtype=np.int8))
+    assert not wp.any()  # no six before the last stone: the game stopped at the first win
+
+
+def test_pyconnect6_self_play():
+    """Connect6/pybind/test_pybind/test_pybind.py:16-24 and sample/python/random_policy.py."""
+    import pyconnect6
+
+    class RandomPolicy:
+        def __call__(self, turn, board):
+            size = len(board)
+            assert turn in (-1, 1) and size % 8 == 0 and len(board[0]) == 225
+            return np.random.rand(size), np.random.rand(size, 225)
+
+    param = pyconnect6.default_param()
+    param["num_simulation"] = 2
+    param["num_game_thread"] = 2
+    result = pyconnect6.self_play(RandomPolicy(), param)
+    assert len(result) == 2
+    for winner, path in result:
+        assert winner in (-1, 0, 1) and len(path) >= 11
+        if winner != 0:
+            assert path[-1][0] == winner
+    param["num_game_thread"] = 1
+    winner, path = pyconnect6.self_play(RandomPolicy(), param)
+    turn, board, (row, col) = path[0]
+    assert turn == -1 and board == [0] * 225 and 0 <= row < 15 and 0 <= col < 15
+
+
+def test_pyconnect6_evaluator_error_is_raised():
+    import pyconnect6
+
+    def bad(turn, board):
+        raise KeyError("boom")
+
+    param = pyconnect6.default_param()
+    param["num_simulation"] = 2
+    with pytest.raises(pyconnect6.pyconnect6.EvaluatorError):
+        pyconnect6.self_play(bad, param)
+
+
+def test_reference_catch2_suite_full():
+    """The reference's Catch2 acceptance suite (test_cppbind, incl. Connect6::self_play 2 sims x 2 games and
+    Connect6::play), prebuilt by __graft_entry__.build() from the reference's sources in place, linked
+    against this library."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "test_cppbind")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/test_cppbind not prebuilt (reference tree was not mounted at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "All tests passed" in r.stdout
