@@ -388,6 +388,18 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
            cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db))
 }
 
+int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device) {
+    C6_TRY(CK(cudaSetDevice(device)); double* d = nullptr; CK(cudaMalloc(&d, (size_t)n * 8)); launch_probe_gamma(shape, k0, k1, d, n, 0);
+           CK(cudaGetLastError()); CK(cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost)); cudaFree(d))
+}
+int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device) {
+    C6_TRY(CK(cudaSetDevice(device)); double *dx = nullptr, *dl = nullptr, *de = nullptr; CK(cudaMalloc(&dx, (size_t)n * 8));
+           CK(cudaMalloc(&dl, (size_t)n * 8)); CK(cudaMalloc(&de, (size_t)n * 8));
+           CK(cudaMemcpy(dx, xs, (size_t)n * 8, cudaMemcpyHostToDevice)); launch_probe_math(dx, dl, de, n, 0); CK(cudaGetLastError());
+           CK(cudaMemcpy(logs, dl, (size_t)n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(exps, de, (size_t)n * 8, cudaMemcpyDeviceToHost));
+           cudaFree(dx), cudaFree(dl), cudaFree(de))
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ struct Dev {
     uint32_t first_id;
     int num_sim;
     float eps;
-    double alpha;
+    GammaParams gp;  // Dirichlet alpha and the sampler constants derived from it
     float cpuct;
     uint32_t seed;
     int trace;
@@ -131,17 +131,18 @@ struct Leaf {
     int depth;
 };
 
-struct Warp {  // per-warp view of one game slot
+struct Warp {  // per-warp view of one game slot: hot bases as pointers, the rest derived from the slot number on use
     Rec* rec;
     uint32_t* lnk;
     Slot* idx;
-    uint32_t* expB;
-    uint32_t* exp_rec;
-    uint64_t* exp_key;
-    uint32_t* path;
     GameState* gs;
     const uint64_t* Z;  // shared-memory copy
     int lane;
+    int g;
+    __device__ __forceinline__ uint32_t* expB(const Dev& D) const { return D.expB + (size_t)g * D.E * 16; }
+    __device__ __forceinline__ uint32_t* exp_rec(const Dev& D) const { return D.exp_rec + (size_t)g * D.E; }
+    __device__ __forceinline__ uint64_t* exp_key(const Dev& D) const { return D.exp_key + (size_t)g * D.E; }
+    __device__ __forceinline__ uint32_t* path(const Dev& D) const { return D.path + (size_t)g * 232; }
 };
 
 __device__ __forceinline__ Warp make_warp(const Dev& D, int g, const uint64_t* Zs, int lane) {
@@ -149,13 +150,10 @@ __device__ __forceinline__ Warp make_warp(const Dev& D, int g, const uint64_t* Z
     w.rec = D.rec + (size_t)g * D.R;
     w.lnk = D.lnk + (size_t)g * D.L;
     w.idx = D.idx + (size_t)g * D.I;
-    w.expB = D.expB + (size_t)g * D.E * 16;
-    w.exp_rec = D.exp_rec + (size_t)g * D.E;
-    w.exp_key = D.exp_key + (size_t)g * D.E;
-    w.path = D.path + (size_t)g * 232;
     w.gs = D.gs + g;
     w.Z = Zs;
     w.lane = lane;
+    w.g = g;
     return w;
 }
 
@@ -218,14 +216,14 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         int est = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            eb[j] = w.expB[(size_t)ei * 16 + j];
-            ew[j] = w.expB[(size_t)ei * 16 + 8 + j];
+            eb[j] = w.expB(D)[(size_t)ei * 16 + j];
+            ew[j] = w.expB(D)[(size_t)ei * 16 + 8 + j];
             sup = sup && ((eb[j] & rootB[j]) == rootB[j]) && ((ew[j] & rootW[j]) == rootW[j]);
             est += __popc(eb[j]) + __popc(ew[j]);
         }
         if (!sup) continue;
-        const uint32_t erec = w.exp_rec[ei];
-        const uint64_t ekey = w.exp_key[ei];
+        const uint32_t erec = w.exp_rec(D)[ei];
+        const uint64_t ekey = w.exp_key(D)[ei];
         const int C = CELLS - est;
         const int turn = turn_of(est);
         if (rec_head - old_rec_tail + (uint32_t)C + 1 > D.R || lnk_head - old_lnk_tail + (uint32_t)C > D.L) {
@@ -307,8 +305,8 @@ __device__ inline void collect(const Dev& D, Warp& w) {
             pre += __popc(e[j]);
         }
         // keep the entry (in-place compaction of the expanded list: wcur <= ei)
-        if (lane < 16) w.expB[(size_t)wcur * 16 + lane] = w.expB[(size_t)ei * 16 + lane];
-        if (lane == 0) w.exp_rec[wcur] = new_e, w.exp_key[wcur] = ekey;
+        if (lane < 16) w.expB(D)[(size_t)wcur * 16 + lane] = w.expB(D)[(size_t)ei * 16 + lane];
+        if (lane == 0) w.exp_rec(D)[wcur] = new_e, w.exp_key(D)[wcur] = ekey;
         wcur += 1;
         __syncwarp();
     }

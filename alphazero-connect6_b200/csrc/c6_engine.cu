@@ -48,15 +48,19 @@ __global__ void k_start(Dev D, int n_start) {
 // game slots from a counter, so unequal game lengths balance themselves.  Register-capped for
 // occupancy: the path is latency-bound, resident warps are what hides HBM latency.
 #ifndef C6_SIM_BLOCKS_PER_SM
-#define C6_SIM_BLOCKS_PER_SM 5
+#define C6_SIM_BLOCKS_PER_SM 8
 #endif
-template <int EVAL, bool NOISE>
+template <int EVAL, int NOISE>
 __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D) {
-    __shared__ uint64_t Zs[512];
-    __shared__ double gl_all[NOISE ? 4 * 256 : 1];
-    load_zobrist(D, Zs);
+    // Zobrist keys are read straight from global memory (__ldg: 4 KB, L1-resident) so that eight blocks
+    // of per-warp stages fit the shared memory of an SM.
+    const uint64_t* Zs = D.Z;
+    __shared__ WarpStage<NOISE> stage[4];
+    __shared__ MathTab mt;
+    if (NOISE) load_math_tab(mt);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    double* gl = gl_all + (NOISE ? (threadIdx.x >> 5) * 256 : 0);
+    WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
     for (;;) {
         int g = 0;
         if (lane == 0) g = atomicAdd(D.cursor, 1);
@@ -68,21 +72,21 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
         load_cursor(*w.gs, cs);
         for (int s = 0; s < D.num_sim && !cs.err; ++s) {
             Leaf L;
-            descend<NOISE>(D, w, cs, L, gl);
+            descend<NOISE>(D, w, cs, L, st, mt);
             if (L.stones == CELLS) {
-                terminal_leaf(w, L);
+                terminal_leaf(D, w, L);
             } else if (EVAL == EVAL_PHILOX) {
                 EvPhilox ev;
                 ev.init(D, cs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value());
+                expand_leaf(D, w, cs, L, ev, ev.value(), st);
             } else if (EVAL == EVAL_DET) {
                 EvHash<false> ev;
                 ev.init(L, Zs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value());
+                expand_leaf(D, w, cs, L, ev, ev.value(), st);
             } else {
                 EvHash<true> ev;
                 ev.init(L, Zs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value());
+                expand_leaf(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
         }
@@ -103,13 +107,15 @@ __global__ void __launch_bounds__(128) k_move_end(Dev D) {
 }
 
 // Callback path, kernel 1: descend to the leaf and park it in the game state.
-template <bool NOISE>
+template <int NOISE>
 __global__ void __launch_bounds__(128) k_select(Dev D) {
-    __shared__ uint64_t Zs[512];
-    __shared__ double gl_all[NOISE ? 4 * 256 : 1];
-    load_zobrist(D, Zs);
+    const uint64_t* Zs = D.Z;  // global (__ldg in descend)
+    __shared__ WarpStage<NOISE> stage[4];
+    __shared__ MathTab mt;
+    if (NOISE) load_math_tab(mt);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    double* gl = gl_all + (NOISE ? (threadIdx.x >> 5) * 256 : 0);
+    WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= D.G) return;
     Warp w = make_warp(D, g, Zs, lane);
@@ -121,10 +127,10 @@ __global__ void __launch_bounds__(128) k_select(Dev D) {
     Cursor cs;
     load_cursor(gs, cs);
     Leaf L;
-    descend<NOISE>(D, w, cs, L, gl);
+    descend<NOISE>(D, w, cs, L, st, mt);
     int need = 1;
     if (L.stones == CELLS) {
-        terminal_leaf(w, L);
+        terminal_leaf(D, w, L);
         need = 0;
     }
 #pragma unroll
@@ -197,9 +203,10 @@ __global__ void __launch_bounds__(128) k_gather(Dev D) {
 
 // Callback path, kernel 4: recover_way8 + expansion + backup (k_move_end follows every num_sim waves).
 __global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
-    __shared__ uint64_t Zs[512];
-    load_zobrist(D, Zs);
+    const uint64_t* Zs = D.Z;  // global (__ldg in expand_leaf)
+    __shared__ WarpStage<0> stage[4];
     const int lane = threadIdx.x & 31;
+    WarpStage<0>& st = stage[threadIdx.x >> 5];
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= D.G) return;
     Warp w = make_warp(D, g, Zs, lane);
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
         ev.values = D.bvalues + (size_t)gs.batch_pos * 8;
         ev.pol = D.bboards + (size_t)gs.batch_pos * 8 * CELLS;
         ev.lane = lane;
-        expand_leaf(D, w, cs, L, ev, ev.value());
+        expand_leaf(D, w, cs, L, ev, ev.value(), st);
     }
     cs.sim_index += 1;
     store_cursor(D, gs, cs, lane);
@@ -266,15 +273,15 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
         uint64_t key = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            eb[j] = w.expB[(size_t)ei * 16 + j], ew[j] = w.expB[(size_t)ei * 16 + 8 + j];
+            eb[j] = w.expB(D)[(size_t)ei * 16 + j], ew[j] = w.expB(D)[(size_t)ei * 16 + 8 + j];
             est += __popc(eb[j]) + __popc(ew[j]);
             if ((eb[j] >> lane) & 1u) key ^= Zs[32 * j + lane];
             if ((ew[j] >> lane) & 1u) key ^= Zs[256 + 32 * j + lane];
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) key ^= __shfl_xor_sync(FULL, key, off);
-        const uint32_t erec = w.exp_rec[ei];
-        const uint64_t ekey = w.exp_key[ei];
+        const uint32_t erec = w.exp_rec(D)[ei];
+        const uint64_t ekey = w.exp_key(D)[ei];
         Rec r = load_rec(&w.rec[erec & Rm]);
         if (lane == 0) {
             if (key != ekey) {
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
             if (((erec - gs.rec_tail) & Rm) >= gs.rec_head - gs.rec_tail) report(8, ei, erec, gs.rec_tail);
         }
         for (uint32_t e2 = ei + 1 + lane; e2 < n_exp; e2 += 32)
-            if (w.exp_rec[e2] == erec) report(5, ei, e2, erec);
+            if (w.exp_rec(D)[e2] == erec) report(5, ei, e2, erec);
         if (r.n < 1 || r.link == NIL || r.link == FWD) continue;
         const int turn = turn_of(est);
         int pre = 0;
@@ -348,6 +355,10 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         throw std::runtime_error(g_last_error);
     }
     C6_CUDA(cudaSetDevice(cfg_.device));
+    if (const char* fg = std::getenv("C6_L2_FETCH")) {  // tuning knob: 32 / 64 / 128 B L2 fetch granularity
+        cudaError_t fe = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(fg));
+        if (fe != cudaSuccess) cudaGetLastError();
+    }
     C6_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     d_ = new DeviceArrays();
     Dev& D = d_->dev;
@@ -356,7 +367,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.L = D.R * 2;
     D.I = D.R * 2;
     D.E = 4096;
-    D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.alpha = cfg_.dirichlet_alpha, D.cpuct = cfg_.c_puct;
+    D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
     D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves;
     const size_t G = (size_t)D.G;
     d_->rec_bytes = G * D.R * sizeof(Rec);
@@ -450,45 +461,34 @@ void Engine::start(uint32_t first_id, int64_t total_games) {
     C6_CUDA(cudaStreamSynchronize(stream_));
 }
 
-template <int EVAL>
-static void launch_move(const Dev& D, bool noise, int blocks, cudaStream_t s) {
-    if (noise)
-        k_sims_device<EVAL, true><<<blocks, 128, 0, s>>>(D);
-    else
-        k_sims_device<EVAL, false><<<blocks, 128, 0, s>>>(D);
+static int noise_mode(const Config& c) { return c.epsilon == 0.f ? 0 : (c.dirichlet_alpha < 1.0 ? 1 : 2); }
+
+// the one (evaluator, noise) variant of the fused kernel this engine runs
+using SimKernel = void (*)(Dev);
+static SimKernel sim_kernel(int evaluator, int noise) {
+    static const SimKernel table[3][3] = {
+        {k_sims_device<EVAL_PHILOX, 0>, k_sims_device<EVAL_PHILOX, 1>, k_sims_device<EVAL_PHILOX, 2>},
+        {k_sims_device<EVAL_DET, 0>, k_sims_device<EVAL_DET, 1>, k_sims_device<EVAL_DET, 2>},
+        {k_sims_device<EVAL_NEG, 0>, k_sims_device<EVAL_NEG, 1>, k_sims_device<EVAL_NEG, 2>}};
+    return table[evaluator - EVAL_PHILOX][noise];
 }
 
 void Engine::step_device() {
     Dev& D = d_->dev;
     if (cfg_.evaluator == EVAL_CALLBACK) throw std::runtime_error("c6: step_device needs a device evaluator");
+    const SimKernel kern = sim_kernel(cfg_.evaluator, noise_mode(cfg_));
     if (d_->persistent_blocks == 0) {
         int per_sm = 0;
-        const bool noise = cfg_.epsilon != 0.f;
-        // occupancy of the variant that will run
-        if (cfg_.evaluator == EVAL_PHILOX) {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_PHILOX, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_PHILOX, false>, 128, 0));
-        } else if (cfg_.evaluator == EVAL_DET) {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_DET, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_DET, false>, 128, 0));
-        } else {
-            if (noise) C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_NEG, true>, 128, 0));
-            else C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sims_device<EVAL_NEG, false>, 128, 0));
-        }
+        C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
         if (per_sm < 1) per_sm = 1;
         d_->persistent_blocks = std::min(d_->sm_count * per_sm, warps_grid(D.G));
     }
     C6_CUDA(cudaMemsetAsync(D.cursor, 0, sizeof(int), stream_));
-    if (cfg_.num_simulation <= 0) {
-        k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
-    } else {
-        const bool noise = cfg_.epsilon != 0.f;
-        if (cfg_.evaluator == EVAL_PHILOX) launch_move<EVAL_PHILOX>(D, noise, d_->persistent_blocks, stream_);
-        else if (cfg_.evaluator == EVAL_DET) launch_move<EVAL_DET>(D, noise, d_->persistent_blocks, stream_);
-        else launch_move<EVAL_NEG>(D, noise, d_->persistent_blocks, stream_);
-        k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
+    if (cfg_.num_simulation > 0) {
+        kern<<<d_->persistent_blocks, 128, 0, stream_>>>(D);
         launches_ += 1;
     }
+    k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
     launches_ += 1;
     C6_CUDA(cudaGetLastError());
 }
@@ -503,10 +503,13 @@ void Engine::wave_callback(Callback cb) {
         C6_CUDA(cudaGetLastError());
         return;
     }
-    if (cfg_.epsilon != 0.f)
-        k_select<true><<<grid, 128, 0, stream_>>>(D);
+    const int noise = noise_mode(cfg_);
+    if (noise == 1)
+        k_select<1><<<grid, 128, 0, stream_>>>(D);
+    else if (noise == 2)
+        k_select<2><<<grid, 128, 0, stream_>>>(D);
     else
-        k_select<false><<<grid, 128, 0, stream_>>>(D);
+        k_select<0><<<grid, 128, 0, stream_>>>(D);
     k_rank<<<1, 1024, 0, stream_>>>(D);
     k_gather<<<grid, 128, 0, stream_>>>(D);
     launches_ += 3;

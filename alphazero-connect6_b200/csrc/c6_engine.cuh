@@ -166,6 +166,9 @@ void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStre
 void launch_playouts(int64_t first, int64_t n, uint32_t seed, int8_t* d_winner, uint8_t* d_stones,
                      uint32_t* d_boards, cudaStream_t s);
 
+void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* d_out, int n, cudaStream_t s);
+void launch_probe_math(const double* d_xs, double* d_logs, double* d_exps, int n, cudaStream_t s);
+
 const char* last_error();
 
 }  // namespace c6

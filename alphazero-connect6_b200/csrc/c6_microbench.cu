@@ -122,6 +122,41 @@ __global__ void __launch_bounds__(128) k_playouts(long long first, long long n, 
     }
 }
 
+// Parity probes for the noise sampler (tests only): draw i of stream (i, 7, 9) keyed (k0, k1), and the
+// deterministic log / exp on given inputs, so that every bit can be compared with the oracle.
+__global__ void k_probe_gamma(double shape, double inv_shape, double bb, uint32_t k0, uint32_t k1, double* out, int n) {
+    __shared__ MathTab mt;
+    load_math_tab(mt);
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GammaParams gp;
+    gp.shape = shape, gp.inv_shape = inv_shape, gp.b = bb;
+    double x;
+    if (shape < 1.0) {
+        if (!gamma_small_fast(mt, gp, (uint32_t)i, 7u, 9u, k0, k1, x)) x = gamma_small(mt, shape, inv_shape, bb, (uint32_t)i, 7u, 9u, k0, k1);
+    } else {
+        x = gamma_large(mt, shape, (uint32_t)i, 7u, 9u, k0, k1);
+    }
+    out[i] = x;
+}
+__global__ void k_probe_math(const double* xs, double* logs, double* exps, int n) {
+    __shared__ MathTab mt;
+    load_math_tab(mt);
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    logs[i] = xs[i] > 0.0 ? det_log(mt, xs[i]) : 0.0;
+    exps[i] = det_exp(mt, xs[i]);
+}
+void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* d_out, int n, cudaStream_t s) {
+    GammaParams gp = gamma_params(shape);
+    k_probe_gamma<<<(n + 127) / 128, 128, 0, s>>>(gp.shape, gp.inv_shape, gp.b, k0, k1, d_out, n);
+}
+void launch_probe_math(const double* d_xs, double* d_logs, double* d_exps, int n, cudaStream_t s) {
+    k_probe_math<<<(n + 127) / 128, 128, 0, s>>>(d_xs, d_logs, d_exps, n);
+}
+
 void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s) {
     if (n <= 0) return;
     k_win_check<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_boards, d_winners, (long long)n);

@@ -4,14 +4,20 @@
 //   Dirichlet noise at every select step   LC/policy/alphazero_policy/mod.rs:262,283
 //   RandomEvaluator                        LC/policy/alphazero_policy/mod.rs:137-169
 // with Philox4x32-10 streams keyed by (seed, game) and counted by (simulation, depth, child), so a
-// game's search is a pure function of its id.  The Gamma sampler is rand 0.6's algorithm
-// (Marsaglia–Tsang + U^(1/alpha) boost for alpha < 1) on normals from the Marsaglia polar method;
-// log/exp are fixed polynomials over IEEE + - * / only, and this translation unit is compiled with
-// -fmad=false, so every value is reproducible bit for bit on a CPU (tests/ compare against the
-// oracle's independent restatement).
+// game's search is a pure function of its id.  Dirichlet(alpha; C) = C independent Gamma(alpha, 1)
+// draws normalised by their sum in f64, as rand 0.6 builds it.  The Gamma draws use exact rejection
+// samplers chosen for the GPU: Ahrens–Dieter GS for alpha < 1 (the default 0.03; ~175 instructions a
+// draw against ~700 for Marsaglia–Tsang + boost — the first ncu profile had the sampler at two thirds
+// of all instructions), Marsaglia–Tsang on polar normals for alpha >= 1.  log/exp are fixed
+// polynomials over IEEE + - * / fma only, and this translation unit is compiled with -fmad=false, so
+// every value is reproducible bit for bit on a CPU (tests/ compare against the oracle's independent
+// restatement).  rand's own stream is unseedable (thread_rng) and unpinned by any reference test, so
+// only the distribution is contractual.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+
+#include "c6_tables.cuh"
 
 namespace c6 {
 
@@ -24,15 +30,9 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-#else
-        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-#endif
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;  // one IMAD.WIDE each
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0, c1 = (uint32_t)p1, c2 = n2, c3 = (uint32_t)p0;
         k0 += W0, k1 += W1;
     }
     return Philox4{c0, c1, c2, c3};
@@ -53,11 +53,6 @@ constexpr uint32_t DOMAIN_BOARDS = 0x42524453u;
 __host__ __device__ __forceinline__ float u32_to_pm1(uint32_t x) {
     return (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;
 }
-__host__ __device__ __forceinline__ double u64_to_open01(uint32_t lo, uint32_t hi) {
-    uint64_t x = ((uint64_t)hi << 32) | lo;
-    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-}
-
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ double bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ uint64_t double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
@@ -74,7 +69,33 @@ inline uint64_t double_to_bits(double d) {
 }
 #endif
 
-__host__ __device__ inline double det_log(double x) {
+// 52 random bits -> uniform on (0,1): mantissa of a double in [1,2), minus 1, plus half a step, all exact
+// (no 64-bit integer -> double conversion, which is slow on the GPU).
+__host__ __device__ __forceinline__ double u64_to_open01(uint32_t lo, uint32_t hi) {
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (bits_to_double(0x3FF0000000000000ull | (x >> 12)) - 1.0) + 1.1102230246251565e-16;
+}
+
+#ifdef __CUDACC__
+// IEEE fused multiply-add, explicit (the translation unit is compiled with -fmad=false, so nothing else
+// contracts): one rounding, identical on sm_100a and x86-64 FMA3 (the oracle uses __builtin_fma).
+__device__ __forceinline__ double det_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// Tables of the log / exp below, staged in shared memory by every kernel that samples noise (per-lane
+// indices would serialise in the constant cache).
+struct MathTab {
+    double2 logt[64];  // {1/c_i, ln c_i}, c_i = 1 + (2i+1)/128
+    double expt[32];   // 2^(j/32)
+};
+__device__ __forceinline__ void load_math_tab(MathTab& T) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) T.logt[i] = LOG_TAB_C[i];
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) T.expt[i] = EXP_TAB_C[i];
+}
+
+// natural log of a positive finite double, division-free: x = 2^e m, m in [1,2) falls in one of 64
+// intervals with centre c_i; r = m/c_i - 1 (|r| < 2^-7) by one fma with the tabulated reciprocal;
+// ln x = e ln2 + ln c_i + log1p(r), log1p as a degree-8 alternating series.  Absolute error ~1e-16.
+__device__ __forceinline__ double det_log(const MathTab& T, double x) {
     int e = 0;
     uint64_t b = double_to_bits(x);
     if ((b >> 52) == 0) {
@@ -83,128 +104,124 @@ __host__ __device__ inline double det_log(double x) {
         e = -54;
     }
     e += (int)((b >> 52) & 0x7FF) - 1023;
-    double m = bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-    if (m > 1.4142135623730951) {
-        m = m * 0.5;
-        e += 1;
-    }
-    double f = m - 1.0;
-    double s = f / (2.0 + f);
-    double z = s * s;
-    double p = 1.0 / 23.0;
-    p = p * z + 1.0 / 21.0;
-    p = p * z + 1.0 / 19.0;
-    p = p * z + 1.0 / 17.0;
-    p = p * z + 1.0 / 15.0;
-    p = p * z + 1.0 / 13.0;
-    p = p * z + 1.0 / 11.0;
-    p = p * z + 1.0 / 9.0;
-    p = p * z + 1.0 / 7.0;
-    p = p * z + 1.0 / 5.0;
-    p = p * z + 1.0 / 3.0;
-    p = p * z + 1.0;
-    double lm = 2.0 * s * p;
-    return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lm);
+    const double m = bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    const double2 t = T.logt[(uint32_t)(b >> 46) & 63u];
+    const double r = det_fma(m, t.x, -1.0);
+    double p = -1.0 / 8.0;
+    p = det_fma(p, r, 1.0 / 7.0);
+    p = det_fma(p, r, -1.0 / 6.0);
+    p = det_fma(p, r, 1.0 / 5.0);
+    p = det_fma(p, r, -1.0 / 4.0);
+    p = det_fma(p, r, 1.0 / 3.0);
+    p = det_fma(p, r, -0.5);
+    p = det_fma(p, r * r, r);  // r + r^2 (-1/2 + r/3 - ...)
+    const double ed = (double)e;
+    return det_fma(ed, 0.6931471803691238, t.y + det_fma(ed, 1.9082149292705877e-10, p));
 }
 
-__host__ __device__ __forceinline__ double det_floor(double x) {
-    double t = (double)(long long)x;
-    return (t > x) ? t - 1.0 : t;
-}
-
-__host__ __device__ inline double det_exp(double x) {
+// e^x: x = (32 q + j) ln2/32 + r, |r| <= ln2/64; e^x = 2^q 2^(j/32) (1 + expm1(r)), expm1 to r^6;
+// scaled by 2^q in two exact steps (subnormal results round once).
+__device__ __forceinline__ double det_exp(const MathTab& T, double x) {
     if (x < -745.2) return 0.0;
     if (x > 709.0) x = 709.0;
-    double kd = det_floor(x * 1.4426950408889634 + 0.5);
-    double r = (x - kd * 0.6931471803691238) - kd * 1.9082149292705877e-10;
-    double p = 1.0 / 6227020800.0;
-    p = p * r + 1.0 / 479001600.0;
-    p = p * r + 1.0 / 39916800.0;
-    p = p * r + 1.0 / 3628800.0;
-    p = p * r + 1.0 / 362880.0;
-    p = p * r + 1.0 / 40320.0;
-    p = p * r + 1.0 / 5040.0;
-    p = p * r + 1.0 / 720.0;
-    p = p * r + 1.0 / 120.0;
-    p = p * r + 1.0 / 24.0;
-    p = p * r + 1.0 / 6.0;
-    p = p * r + 0.5;
-    p = p * r + 1.0;
-    p = p * r + 1.0;
-    int k = (int)kd;
-    int k1 = k / 2, k2 = k - k1;
-    double s1 = bits_to_double((uint64_t)(k1 + 1023) << 52);
-    double s2 = bits_to_double((uint64_t)(k2 + 1023) << 52);
-    return (p * s1) * s2;
+    const double kd = (double)__double2ll_rd(det_fma(x, 46.16624130844683, 0.5));  // floor(x 32/ln2 + 1/2)
+    const double r = det_fma(-kd, 5.9631716539705866e-12, det_fma(-kd, 0.02166084938653512, x));
+    double p = 1.0 / 720.0;
+    p = det_fma(p, r, 1.0 / 120.0);
+    p = det_fma(p, r, 1.0 / 24.0);
+    p = det_fma(p, r, 1.0 / 6.0);
+    p = det_fma(p, r, 0.5);
+    p = det_fma(p, r, 1.0);
+    p = p * r;  // expm1(r)
+    const int k = (int)kd;
+    const double tj = T.expt[k & 31];
+    const double y = det_fma(tj, p, tj);
+    const int q = k >> 5;
+    const int q1 = q / 2, q2 = q - q1;
+    const double s1 = bits_to_double((uint64_t)(q1 + 1023) << 52);
+    const double s2 = bits_to_double((uint64_t)(q2 + 1023) << 52);
+    return (y * s1) * s2;
 }
 
-__host__ __device__ __forceinline__ double det_sqrt(double x) {
-#ifdef __CUDA_ARCH__
-    return __dsqrt_rn(x);
-#else
-    return __builtin_sqrt(x);
-#endif
-}
+__device__ __forceinline__ double det_sqrt(double x) { return __dsqrt_rn(x); }
 
-struct PhiloxStream {
-    uint32_t c0, c1, c2, blk, k0, k1;
-    uint32_t b0, b1, b2, b3;
-    int pos;
-    __host__ __device__ PhiloxStream(uint32_t a, uint32_t b, uint32_t c, uint32_t key0, uint32_t key1)
-        : c0(a), c1(b), c2(c), blk(0), k0(key0), k1(key1), b0(0), b1(0), b2(0), b3(0), pos(4) {}
-    __host__ __device__ double next_open01() {
-        if (pos >= 4) {
-            Philox4 r = philox4x32_10(c0, c1, c2, blk++, k0, k1);
-            b0 = r.x, b1 = r.y, b2 = r.z, b3 = r.w;
-            pos = 0;
-        }
-        double u = (pos == 0) ? u64_to_open01(b0, b1) : u64_to_open01(b2, b3);
-        pos += 2;
-        return u;
-    }
+// ------------------------------------------------------------------------------------------------
+// Gamma(shape, 1) draw number (a, b, c) of the stream keyed (k0, k1): Philox block `trial` of counter
+// (a, b, c, trial) feeds trial number `trial` of a rejection sampler, so a draw is a pure function of
+// its coordinates and costs one Philox call per trial.
+// ------------------------------------------------------------------------------------------------
+#endif  // __CUDACC__
+struct GammaParams {  // per-run constants, computed once on the host (IEEE ops only)
+    double shape, inv_shape, b;  // b = (e + shape) / e
 };
+inline GammaParams gamma_params(double shape) {
+    GammaParams g;
+    g.shape = shape;
+    g.inv_shape = 1.0 / shape;
+    g.b = (2.718281828459045 + shape) / 2.718281828459045;
+    return g;
+}
+#ifdef __CUDACC__
 
-__host__ __device__ inline double normal_polar(PhiloxStream& st) {
-    for (;;) {
-        double a = 2.0 * st.next_open01() - 1.0;
-        double b = 2.0 * st.next_open01() - 1.0;
-        double s = a * a + b * b;
+// shape < 1 (the reference default is 0.03): Ahrens–Dieter GS rejection sampler — exact for every
+// 0 < shape < 1, acceptance > 98% at 0.03.  With P = b U:
+//   P <= 1 : X = P^(1/shape),           accept iff V <= e^-X   (squeeze: e^-X >= 1 - X + X^2/2 - X^3/6)
+//   P >  1 : X = -ln((b - P)/shape),    accept iff V <= X^(shape-1)
+// gamma_small_fast tries trial 0 on the hot branch only and reports failure; gamma_small is the full loop.
+__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, uint32_t a, uint32_t b, uint32_t c,
+                                                 uint32_t k0, uint32_t k1, double& x) {
+    const Philox4 r = philox4x32_10(a, b, c, 0u, k0, k1);
+    const double u = u64_to_open01(r.x, r.y), v = u64_to_open01(r.z, r.w);
+    const double p = gp.b * u;
+    x = 0.0;
+    if (p > 1.0) return false;
+    x = det_exp(T, det_log(T, p) * gp.inv_shape);
+    return v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0);
+}
+static __device__ __noinline__ double gamma_small(const MathTab& T, double shape, double inv_shape, double bb, uint32_t a, uint32_t b,
+                                           uint32_t c, uint32_t k0, uint32_t k1) {
+    double x = 0.0;
+    for (uint32_t trial = 0; trial < 64u; ++trial) {
+        const Philox4 r = philox4x32_10(a, b, c, trial, k0, k1);
+        const double u = u64_to_open01(r.x, r.y), v = u64_to_open01(r.z, r.w);
+        const double p = bb * u;
+        if (p <= 1.0) {
+            x = det_exp(T, det_log(T, p) * inv_shape);
+            if (v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0)) break;
+            if (v <= det_exp(T, -x)) break;
+        } else {
+            x = -det_log(T, (bb - p) * inv_shape);
+            if (v <= det_exp(T, (shape - 1.0) * det_log(T, x))) break;
+        }
+    }
+    return x;
+}
+
+// shape >= 1: Marsaglia–Tsang (2000) on normals from the Marsaglia polar method; trial t reads blocks
+// 2t (polar pair) and 2t+1 (acceptance uniform).  Not on the default path; kept out of line.
+static __device__ __noinline__ double gamma_large(const MathTab& T, double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0,
+                                           uint32_t k1) {
+    const double d = shape - 1.0 / 3.0;
+    const double cc = 1.0 / det_sqrt(9.0 * d);
+    double out = d;
+    for (uint32_t trial = 0; trial < 64u; ++trial) {
+        const Philox4 r = philox4x32_10(a, b, c, 2u * trial, k0, k1);
+        const double p = 2.0 * u64_to_open01(r.x, r.y) - 1.0, q = 2.0 * u64_to_open01(r.z, r.w) - 1.0;
+        const double s = p * p + q * q;
         if (s >= 1.0 || s == 0.0) continue;
-        double f = det_sqrt(-2.0 * det_log(s) / s);
-        return a * f;
-    }
-}
-
-__host__ __device__ inline double gamma_large(PhiloxStream& st, double shape) {
-    double d = shape - 1.0 / 3.0;
-    double c = 1.0 / det_sqrt(9.0 * d);
-    for (;;) {
-        double x = normal_polar(st);
-        double vc = 1.0 + c * x;
+        const double x = p * det_sqrt(-2.0 * det_log(T, s) / s);
+        const double vc = 1.0 + cc * x;
         if (vc <= 0.0) continue;
-        double v = vc * vc * vc;
-        double u = st.next_open01();
-        double x2 = x * x;
-        if (u < 1.0 - 0.0331 * x2 * x2) return d * v;
-        if (det_log(u) < 0.5 * x2 + d * (1.0 - v + det_log(v))) return d * v;
+        const double v = vc * vc * vc;
+        const Philox4 r2 = philox4x32_10(a, b, c, 2u * trial + 1u, k0, k1);
+        const double u = u64_to_open01(r2.x, r2.y);
+        const double x2 = x * x;
+        out = d * v;
+        if (u < 1.0 - 0.0331 * x2 * x2) break;
+        if (det_log(T, u) < 0.5 * x2 + d * (1.0 - v + det_log(T, v))) break;
     }
+    return out;
 }
-
-__host__ __device__ inline double gamma_sample(PhiloxStream& st, double shape) {
-    if (shape < 1.0) {
-        double g = gamma_large(st, shape + 1.0);
-        double u = st.next_open01();
-        return g * det_exp(det_log(u) / shape);
-    }
-    return gamma_large(st, shape);
-}
-
-// One Gamma(shape) draw from the stream with counter (a, b, c).  Kept out of line: eight inlined
-// copies per select step thrash the instruction cache (ncu: stall_no_instruction dominated).
-__host__ __device__ __noinline__ inline double gamma_draw(uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1,
-                                                         double shape) {
-    PhiloxStream st(a, b, c, k0, k1);
-    return gamma_sample(st, shape);
-}
+#endif  // __CUDACC__
 
 }  // namespace c6

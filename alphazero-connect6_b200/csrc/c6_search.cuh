@@ -2,12 +2,18 @@
 //   select / maximum_from   LC/policy/alphazero_policy/mod.rs:243-323  (looped as in search() :417-420)
 //   expand / get_from       LC/policy/alphazero_policy/mod.rs:218-234,331-381, augment.rs:60-92
 //   update                  LC/policy/alphazero_policy/mod.rs:386-408
-// Shaped by the ncu profile of the first version (profiles/r01_*): latency-bound on HBM round trips,
-// so (1) everything a move needs from the game state lives in registers (`Cursor`) instead of being
-// re-read and re-written in global memory every simulation, (2) the board-key inserts of an expansion
-// are issued back to back and only their returned epochs are inspected, (3) expansion runs in two
-// half-batches so that the live state fits the register budget of 5 blocks/SM without spills, and the
-// priors of a batch are computed while its index probes are in flight.
+//
+// Shaped by two rounds of ncu evidence (profiles/r01a_*): the first fused kernel was 105 KB of SASS with
+// `stall_no_instruction` as its top stall (instruction-cache thrash: 20 warps at unrelated places of an
+// unrolled body), spent two thirds of its instructions in the f64 Gamma sampler and pushed 100+ GB per
+// launch through local memory.  Hence:
+//   (1) memory phases stay unrolled (eight independent loads in flight per lane), arithmetic phases
+//       are ROLLED loops over the eight board words that read their operands from a per-warp
+//       shared-memory stage filled by cp.async — one copy of the PUCT, Gamma and Philox code each;
+//   (2) everything a move needs from the game state lives in registers (`Cursor`);
+//   (3) the board-key inserts of an expansion are issued back to back, four children per lane in
+//       flight, with the priors of the batch computed under the probe latency;
+//   (4) no stack frame: every helper on the default path is inlined into a single call site.
 #pragma once
 #include "c6_device.cuh"
 
@@ -43,14 +49,34 @@ __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const C
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-warp shared-memory stage
+// ------------------------------------------------------------------------------------------------
+// NOISE: 0 = epsilon == 0 (the draw is multiplied by 0: skipped), 1 = Dirichlet alpha < 1, 2 = alpha >= 1
+template <int NOISE>
+struct WarpStage {
+    uint4 child[8][32];  // select: {N, W, P, record index} of this lane's child in board word j
+    union {
+        double gamma[NOISE ? 8 : 1][32];  // select: Gamma draws of one step
+        float prior[8][32];               // expand: priors of the new children (select's stage is dead by then)
+    };
+    uint32_t empty[8];  // empty-cell mask of the current node, one board word each
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // select
 // ------------------------------------------------------------------------------------------------
-// `gl` = per-warp shared scratch for the Gamma draws of one select step ([8][32] doubles), NOISE only.
-template <bool NOISE>
-__device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf& L, double* gl) {
+template <int NOISE>
+__device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf& L, WarpStage<NOISE>& st, const MathTab& mt) {
     const GameState& g = *w.gs;
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1;
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) L.B[j] = g.B[j], L.W[j] = g.W[j];
     L.key = g.key;
@@ -61,40 +87,83 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     for (;;) {
         const Rec r = load_rec(&w.rec[cur]);
         if (r.n == 0) break;  // no children: leaf (:251-253)
-        if (lane == 0) w.path[depth] = cur;
+        if (lane == 0) w.path(D)[depth] = cur;
         const int C = CELLS - L.stones;
         const int turn = turn_of(L.stones);
         cs.sum_ck += (uint32_t)C;
         uint32_t chosen_bit = 0, child = 0;
-        uint32_t e[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
         if (C == 1) {  // single child: taken without scoring (:254-257)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (e[j]) chosen_bit = 32 * j + (__ffs((int)e[j]) - 1);
+            for (int j = 0; j < 8; ++j) {
+                uint32_t e = ~(L.B[j] | L.W[j]) & valid_mask(j);
+                if (e) chosen_bit = 32 * j + (__ffs((int)e) - 1);
+            }
             child = w.lnk[r.link & Lm];
         } else {
+            // memory phase: this lane's child of every board word, links then records, all in flight
             uint32_t ci[8];
-            int cn[8];
-            float cw[8], cp[8];
-            int pre = 0, s_local = 0;
+            int pre = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+                const uint32_t e = ~(L.B[j] | L.W[j]) & valid_mask(j);
                 ci[j] = NIL;
-                if ((e[j] >> lane) & 1u) {
-                    int k = pre + __popc(e[j] & ((1u << lane) - 1u));
-                    ci[j] = w.lnk[(r.link + (uint32_t)k) & Lm];
-                }
-                pre += __popc(e[j]);
+                if ((e >> lane) & 1u) ci[j] = w.lnk[(r.link + (uint32_t)(pre + __popc(e & lt))) & Lm];
+                pre += __popc(e);
+                if (lane == j) st.empty[j] = e;
             }
 #pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ci[j] != NIL) cp_async16(&st.child[j][lane], &w.rec[ci[j] & Rm]);
+            cp_async_wait_all();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ci[j] != NIL) st.child[j][lane].w = ci[j];  // the link field is not needed here
+            __syncwarp();
+            // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
+            // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
+            // sampler for every child; the ~1-3% of draws that need the other branch or another trial are
+            // finished together in pass B (one diverged excursion per step instead of one per board word);
+            // pass C sums in a fixed order: lane-partials in word order, then a butterfly.
+            int s_local = 0;
+            double part = 0.0;
+            if (NOISE) {
+                const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
+                unsigned pend = 0;
+                pre = 0;
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t e = st.empty[j];
+                    if ((e >> lane) & 1u) {
+                        const uint32_t k = (uint32_t)(pre + __popc(e & lt));
+                        double gj;
+                        if (NOISE == 1) {
+                            if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, k, nk0, cs.game_id, gj)) pend |= 1u << j;
+                        } else {
+                            gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, k, nk0, cs.game_id);
+                        }
+                        st.gamma[j][lane] = gj;
+                    }
+                    pre += __popc(e);
+                }
+                if (NOISE == 1) {
+                    while (__any_sync(FULL, pend != 0)) {
+                        if (pend) {
+                            const int j = __ffs((int)pend) - 1;
+                            pend &= pend - 1;
+                            int before = 0;
+                            for (int jj = 0; jj < j; ++jj) before += __popc(st.empty[jj]);
+                            const uint32_t k = (uint32_t)(before + __popc(st.empty[j] & lt));
+                            st.gamma[j][lane] = gamma_small(mt, D.gp.shape, D.gp.inv_shape, D.gp.b, cs.sim_index, (uint32_t)depth, k,
+                                                            nk0, cs.game_id);
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
             for (int j = 0; j < 8; ++j) {
-                cn[j] = 0, cw[j] = 0.f, cp[j] = 0.f;
-                if (ci[j] != NIL) {
-                    Rec ch = load_rec(&w.rec[ci[j] & Rm]);
-                    cn[j] = ch.n, cw[j] = ch.w, cp[j] = ch.p;
-                    s_local += ch.n;
+                if ((st.empty[j] >> lane) & 1u) {
+                    s_local += (int)st.child[j][lane].x;
+                    if (NOISE) part = part + st.gamma[j][lane];
                 }
             }
 #pragma unroll
@@ -103,60 +172,50 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             double inv = 0.0;
             bool flat = false;
             if (NOISE) {
-                // Dirichlet(alpha; C) drawn at every node with C >= 2 (:262,283): Gamma draws keyed
-                // (sim, depth, child k), summed lane-partial then butterfly (fixed order), scaled.
-                double part = 0.0;
-                int pre2 = 0;
-#pragma unroll 1
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t ej = ~(L.B[j] | L.W[j]) & valid_mask(j);
-                    double gj = 0.0;
-                    if ((ej >> lane) & 1u) {
-                        int k = pre2 + __popc(ej & ((1u << lane) - 1u));
-                        gj = gamma_draw(cs.sim_index, (uint32_t)depth, (uint32_t)k, D.seed ^ DOMAIN_NOISE, cs.game_id, D.alpha);
-                        part = part + gj;
-                    }
-                    gl[j * 32 + lane] = gj;
-                    pre2 += __popc(ej);
-                }
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(FULL, part, off);
                 flat = !(part > 0.0);
                 inv = flat ? 0.0 : 1.0 / part;
             }
+            // arithmetic phase 2: PUCT (:266-280)
             float bs = 0.f;
-            uint32_t bb = NIL, bc = 0;
-#pragma unroll
+            uint32_t bb = NIL;
+#pragma unroll 1
             for (int j = 0; j < 8; ++j) {
-                if (ci[j] != NIL) {
+                if ((st.empty[j] >> lane) & 1u) {
+                    const uint4 ch = st.child[j][lane];
+                    const int cn = (int)ch.x;
+                    const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
                     float nz = 0.f;
-                    if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(gl[j * 32 + lane] * inv);
-                    float visit = (float)cn[j];
-                    float q = cn[j] > 0 ? cw[j] / visit : 0.f;                  // q_value (:77-79)
-                    float prob = eps * nz + one_m_eps * cp[j];                  // :269
-                    float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
-                    float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
-                    if (bb == NIL || sc > bs) bs = sc, bb = 32u * j + lane, bc = ci[j];
+                    if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[j][lane] * inv);
+                    const float visit = (float)cn;
+                    const float q = cn > 0 ? cw / visit : 0.f;                        // q_value (:77-79)
+                    const float prob = eps * nz + one_m_eps * cp;                     // :269
+                    const float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
+                    const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
+                    if (bb == NIL || sc > bs) bs = sc, bb = 32u * j + lane;
                 }
             }
             // maximum; exact ties -> lowest row-major index (the reference picks uniformly, :291-295)
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
-                float os = __shfl_xor_sync(FULL, bs, off);
-                uint32_t ob = __shfl_xor_sync(FULL, bb, off), oc = __shfl_xor_sync(FULL, bc, off);
-                bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
-                if (take) bs = os, bb = ob, bc = oc;
+                const float os = __shfl_xor_sync(FULL, bs, off);
+                const uint32_t ob = __shfl_xor_sync(FULL, bb, off);
+                const bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
+                if (take) bs = os, bb = ob;
             }
-            chosen_bit = bb, child = bc;
+            chosen_bit = bb;
+            child = st.child[bb >> 5][bb & 31].w;
+            __syncwarp();  // the stage is rewritten by the next step
         }
         // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
         const uint32_t wj = chosen_bit >> 5, m = 1u << (chosen_bit & 31);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            uint32_t mm = (j == (int)wj) ? m : 0u;
+            const uint32_t mm = (j == (int)wj) ? m : 0u;
             if (turn < 0) L.B[j] |= mm; else L.W[j] |= mm;
         }
-        L.key ^= w.Z[(turn > 0 ? 256 : 0) + chosen_bit];
+        L.key ^= __ldg(&w.Z[(turn > 0 ? 256 : 0) + chosen_bit]);
         L.stones += 1;
         cur = child & Rm;
         depth += 1;
@@ -169,10 +228,10 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
 }
 
 // update(): only the leaf's parent takes the value, every ancestor (leaf excluded) gets visit += 1.
-__device__ __forceinline__ void backup(Warp& w, int depth, float v) {
+__device__ __forceinline__ void backup(const Dev& D, Warp& w, int depth, float v) {
     __syncwarp();
     for (int i = w.lane; i < depth; i += 32) {
-        uint32_t a = w.path[i];
+        uint32_t a = w.path(D)[i];
         Rec r = load_rec(&w.rec[a]);
         r.n += 1;
         if (i == depth - 1) r.w = r.w + v;
@@ -181,10 +240,18 @@ __device__ __forceinline__ void backup(Warp& w, int depth, float v) {
     __syncwarp();
 }
 
-// full-board leaf (:338-348): no evaluator call, no visit increment
-__device__ __forceinline__ void terminal_leaf(Warp& w, const Leaf& L) {
-    float v = (float)win_check(L.B, L.W);
-    backup(w, L.depth, v);
+// full-board leaf (:338-348): no evaluator call, no visit increment, value = winner.  Reached a handful
+// of times per game at most: the win check is kept out of line (arguments by value, so nothing of the
+// caller is forced onto the stack) and out of the hot instruction stream.
+__device__ __noinline__ float terminal_value(uint4 b0, uint4 b1, uint4 w0, uint4 w1) {
+    const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint32_t W[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    return (float)win_check(B, W);
+}
+__device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, const Leaf& L) {
+    const float v = terminal_value(make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]), make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]),
+                                   make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]), make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]));
+    backup(D, w, L.depth, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -200,20 +267,29 @@ struct EvPhilox {
     __device__ __forceinline__ void init(const Dev& D, const Cursor& cs, int lane_) {
         k0 = D.seed ^ DOMAIN_EVAL, k1 = cs.game_id, sim = cs.sim_index, lane = lane_;
     }
-    __device__ __forceinline__ float value() const {
-        Philox4 va = philox4x32_10(sim, CELLS, 0, 0, k0, k1), vb = philox4x32_10(sim, CELLS, 1, 0, k0, k1);
+    // eight U[-1,1) draws of `cell` folded pairwise in plane order: {d0+d1, d2+d3, d4+d5, d6+d7}
+    __device__ __forceinline__ void pairs(uint32_t cell, float (&t)[4]) const {
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+            Philox4 a = philox4x32_10(sim, cell, half, 0, k0, k1);
+            const float lo = u32_to_pm1(a.x) + u32_to_pm1(a.y), hi = u32_to_pm1(a.z) + u32_to_pm1(a.w);
+            if (half == 0) t[0] = lo, t[1] = hi; else t[2] = lo, t[3] = hi;
+        }
+    }
+    __device__ __forceinline__ float value() const {  // ((((((((0+v0)+v1)+..)+v7)/8 (:224)
         float sum = 0.f;
-        sum = sum + u32_to_pm1(va.x), sum = sum + u32_to_pm1(va.y), sum = sum + u32_to_pm1(va.z), sum = sum + u32_to_pm1(va.w);
-        sum = sum + u32_to_pm1(vb.x), sum = sum + u32_to_pm1(vb.y), sum = sum + u32_to_pm1(vb.z), sum = sum + u32_to_pm1(vb.w);
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+            Philox4 a = philox4x32_10(sim, CELLS, half, 0, k0, k1);
+            sum = sum + u32_to_pm1(a.x), sum = sum + u32_to_pm1(a.y), sum = sum + u32_to_pm1(a.z), sum = sum + u32_to_pm1(a.w);
+        }
         return sum / 8.f;
     }
     __device__ __forceinline__ float prior(int j) const {
-        uint32_t cell = (uint32_t)cell_of_bit(32u * j + lane);
-        Philox4 a = philox4x32_10(sim, cell, 0, 0, k0, k1), b = philox4x32_10(sim, cell, 1, 0, k0, k1);
-        float t0 = u32_to_pm1(a.x) + u32_to_pm1(a.y), t1 = u32_to_pm1(a.z) + u32_to_pm1(a.w);
-        float t2 = u32_to_pm1(b.x) + u32_to_pm1(b.y), t3 = u32_to_pm1(b.z) + u32_to_pm1(b.w);
+        float t[4];
+        pairs((uint32_t)cell_of_bit(32u * j + lane), t);
         float total = 0.f;
-        total = total + t0, total = total + t1, total = total + t2, total = total + t3;
+        total = total + t[0], total = total + t[1], total = total + t[2], total = total + t[3];
         return total / 8.f;
     }
 };
@@ -298,10 +374,12 @@ struct EvBatch {
 // ------------------------------------------------------------------------------------------------
 // expand (:350-377) for a non-full leaf, then update()
 // ------------------------------------------------------------------------------------------------
-template <class Ev>
-__device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, const Leaf& L, const Ev& ev, float v) {
+template <class Ev, int NOISE>
+__device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, const Leaf& L, const Ev& ev, float v,
+                                            WarpStage<NOISE>& st) {
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
+    const uint32_t lt = (1u << lane) - 1u;
     const int C = CELLS - L.stones;
     const uint32_t zoff = turn_of(L.stones) > 0 ? 256u : 0u;
     const uint32_t epoch = cs.epoch;
@@ -319,42 +397,47 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
             if (lane == j) word = L.B[j];
             if (lane == j + 8) word = L.W[j];
         }
-        w.expB[(size_t)ec * 16 + lane] = word;
+        w.expB(D)[(size_t)ec * 16 + lane] = word;
     }
-    uint32_t e[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
+    for (int j = 0; j < 8; ++j)
+        if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
+    __syncwarp();
     const uint64_t key = L.key;
     uint32_t base = cs.rec_head;
     int pre = 0;
-#pragma unroll
+#pragma unroll 1
     for (int h = 0; h < 2; ++h) {
         uint64_t ck[4];
         uint32_t pos[4];
         Slot seen[4];
+        uint32_t e4[4];
         // A: first probe of every child key of this half, all loads in flight together
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int j = 4 * h + t;
+            e4[t] = st.empty[j];
             ck[t] = 0, pos[t] = 0;
             seen[t].key = 0, seen[t].idx = 0, seen[t].epoch = 0;
-            if ((e[j] >> lane) & 1u) {
-                ck[t] = key ^ w.Z[zoff + 32 * j + lane];
+            if ((e4[t] >> lane) & 1u) {
+                ck[t] = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
                 pos[t] = hash_slot(ck[t]) & Im;
                 seen[t] = load_slot(&w.idx[pos[t]]);
             }
         }
-        // priors of this half: arithmetic under the probe latency
-        float pr[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) pr[t] = ((e[4 * h + t] >> lane) & 1u) ? ev.prior(4 * h + t) : 0.f;
+        // priors of this half: arithmetic under the probe latency (one copy of the evaluator code)
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+            const int j = 4 * h + t;
+            if ((st.empty[j] >> lane) & 1u) st.prior[j][lane] = ev.prior(j);
+        }
         // B: resolve (entry(hash).or_insert, :367-370)
         uint32_t child[4];
         unsigned newmask = 0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             child[t] = NIL;
-            if ((e[4 * h + t] >> lane) & 1u) {
+            if ((e4[t] >> lane) & 1u) {
                 uint32_t val;
                 if (index_find(w.idx, Im, epoch, ck[t], pos[t], seen[t], val))
                     child[t] = val;
@@ -366,7 +449,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             unsigned bal = __ballot_sync(FULL, (newmask >> t) & 1u);
-            if ((newmask >> t) & 1u) child[t] = (base + __popc(bal & ((1u << lane) - 1u))) & Rm;
+            if ((newmask >> t) & 1u) child[t] = (base + __popc(bal & lt)) & Rm;
             base += __popc(bal);
         }
         // C: records / priors / link run; the key inserts are issued back to back
@@ -375,21 +458,21 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         for (int t = 0; t < 4; ++t) {
             const int j = 4 * h + t;
             got[t] = 0;
-            if ((e[j] >> lane) & 1u) {
+            if ((e4[t] >> lane) & 1u) {
+                const float pr = st.prior[j][lane];
                 if ((newmask >> t) & 1u) {
                     Rec nr;
-                    nr.n = 0, nr.w = 0.f, nr.p = pr[t], nr.link = NIL;
+                    nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
                     store_rec(&w.rec[child[t]], nr);
                     Slot want;
                     want.key = ck[t], want.idx = child[t], want.epoch = epoch;
                     got[t] = cas_slot(&w.idx[pos[t]], seen[t], want).epoch;
                 } else {
-                    w.rec[child[t]].p = pr[t];  // n_prob is overwritten by the last expanding parent (:371)
+                    w.rec[child[t]].p = pr;  // n_prob is overwritten by the last expanding parent (:371)
                 }
-                int k = pre + __popc(e[j] & ((1u << lane) - 1u));
-                w.lnk[(link_base + (uint32_t)k) & Lm] = child[t];
+                w.lnk[(link_base + (uint32_t)(pre + __popc(e4[t] & lt))) & Lm] = child[t];
             }
-            pre += __popc(e[j]);
+            pre += __popc(e4[t]);
         }
         // a returned current epoch means another lane claimed the slot first: keep probing (rare)
 #pragma unroll
@@ -404,8 +487,8 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         lr.n += 1;
         lr.link = link_base & Lm;
         store_rec(&w.rec[L.rec], lr);
-        w.exp_rec[ec] = L.rec;
-        w.exp_key[ec] = key;
+        w.exp_rec(D)[ec] = L.rec;
+        w.exp_key(D)[ec] = key;
     }
     cs.exp_count = ec + 1;
     cs.lnk_head = link_base + (uint32_t)C;
@@ -414,7 +497,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     cs.evals += 1;
     cs.peak_rec = max(cs.peak_rec, base - cs.rec_tail);
     cs.peak_lnk = max(cs.peak_lnk, cs.lnk_head - cs.lnk_tail);
-    backup(w, L.depth, v);
+    backup(D, w, L.depth, v);
 }
 
 }  // namespace c6

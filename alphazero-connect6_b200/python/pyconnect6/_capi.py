@@ -116,6 +116,8 @@ def product():
         L.c6_bench_win_check.argtypes = [C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_int64]
         L.c6_bench_playouts.argtypes = [C.c_int64, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int8),
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
+        L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.c6_probe_math.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]
         _product = L
     return _product
 

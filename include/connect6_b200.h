@@ -173,6 +173,11 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
                       int8_t* winners_out, uint8_t* stones_out, uint32_t* boards_out, int64_t n_out,
                       uint64_t* total_stones);
 
+/* parity probes of the Dirichlet-noise sampler (tests): Gamma(shape) draw i of stream (i, 7, 9) keyed
+ * (k0, k1); the engine's deterministic f64 log / exp on xs (log only where xs > 0) */
+int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device);
+int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device);
+
 /* sample host evaluator (random values/policies), the twin of Connect6/sample/cpp/main.cpp:6-28 */
 void c6_sample_random_callback(int player, float* values, float* policies, int len);
 

@@ -483,8 +483,8 @@ struct AlphaZero {
         double partial[32];
         for (auto& p : partial) p = 0.0;
         for (size_t k = 0; k < n; ++k) {
-            PhiloxStream st(ctx.sim_index, (uint32_t)depth, (uint32_t)k, ctx.seed ^ DOMAIN_NOISE, ctx.game_id);
-            g[k] = gamma_sample(st, param.dirichlet_alpha);
+            g[k] = gamma_sample(param.dirichlet_alpha, ctx.sim_index, (uint32_t)depth, (uint32_t)k, ctx.seed ^ DOMAIN_NOISE,
+                                ctx.game_id);
             Pos p = *diff_board(child[k]->board, parent);
             int bit = 16 * p.first + p.second;
             partial[bit & 31] = partial[bit & 31] + g[k];

@@ -8,17 +8,21 @@
 //   * RandomEvaluator        — alphazero_policy/mod.rs:137-169
 // The published algorithms restated here:
 //   * Philox4x32-10 (Salmon et al., SC'11 "Parallel random numbers: as easy as 1, 2, 3").
-//   * rand 0.6 `Gamma` for shape < 1 (GammaSmallShape): Marsaglia–Tsang (2000) sample of
-//     Gamma(shape+1) times U^(1/shape); `Dirichlet` = n independent Gamma(alpha,1) normalised
-//     by their sum, in f64 (rand 0.6.x is a caret dependency, no lockfile: LC/Cargo.toml:12).
-//     rand draws its normal deviates from a ziggurat table; here they come from the Marsaglia
-//     polar method so that only + - * / sqrt and the fixed-polynomial log/exp below are needed
-//     (bit-identical on x86-64 and on the GPU when neither side contracts FMAs).
+//   * rand 0.6 `Dirichlet::new_with_param(alpha, n)` = n independent Gamma(alpha, 1) draws
+//     normalised by their sum, in f64 (rand 0.6.x is a caret dependency, no lockfile:
+//     LC/Cargo.toml:12).  rand's own Gamma uses Marsaglia–Tsang (+ U^(1/shape) for shape < 1) on
+//     ziggurat normals from an unseedable thread_rng, so no stream can be matched; what is
+//     contractual is the distribution.  The exact samplers used here are the ones the engine
+//     runs: Ahrens–Dieter GS (1974) for shape < 1, Marsaglia–Tsang (2000) on polar-method
+//     normals for shape >= 1 — only + - * / sqrt fma and the fixed-polynomial log/exp below,
+//     hence bit-identical on x86-64 and on the GPU (no implicit FMA contraction on either side).
 // Everything in this header must stay bit-for-bit equal to the device twin in
 // alphazero-connect6_b200/csrc/c6_rng.cuh; tests/test_rng_parity.py checks that on the GPU.
 #pragma once
 #include <cstdint>
 #include <cstring>
+
+#include "c6_tables.hpp"
 
 namespace c6o {
 
@@ -59,14 +63,17 @@ constexpr uint32_t DOMAIN_BOARDS = 0x42524453u;   // "BRDS"
 
 // u32 -> f32 uniform on [-1, 1): 24-bit integer, exact in f32 (SURVEY B.4 style).
 inline float u32_to_pm1(uint32_t x) { return (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f; }
-// two u32 -> f64 uniform on (0, 1): 53 bits, never 0 or 1.
+// two u32 -> f64 uniform on (0, 1): the top 52 bits become the mantissa of a double in [1, 2);
+// subtracting 1 and adding 2^-53 is exact, so the result is (2k + 1) / 2^53, never 0 or 1.
+inline double bits_to_double(uint64_t b);
 inline double u64_to_open01(uint32_t lo, uint32_t hi) {
     uint64_t x = ((uint64_t)hi << 32) | lo;
-    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    double one_two = bits_to_double(0x3FF0000000000000ull | (x >> 12));
+    return (one_two - 1.0) + 1.1102230246251565e-16;
 }
 
 // ----------------------------------------------------------------------------------------------
-// Fixed-polynomial log / exp in f64 (only IEEE + - * / and bit moves: same bits on CPU and GPU).
+// Table + fixed-polynomial log / exp in f64 (only IEEE + - * fma and bit moves: same bits on CPU and GPU).
 // ----------------------------------------------------------------------------------------------
 inline double bits_to_double(uint64_t b) {
     double d;
@@ -79,8 +86,20 @@ inline uint64_t double_to_bits(double d) {
     return b;
 }
 
+inline double fma1(double a, double b, double c) { return __builtin_fma(a, b, c); }  // one rounding (FMA3 / libm)
+
+// Horner evaluation with one fused multiply-add per coefficient, highest degree first.
+template <int N>
+inline double horner_fma(const double (&coef)[N], double t) {
+    double acc = coef[0];
+    for (int i = 1; i < N; ++i) acc = fma1(acc, t, coef[i]);
+    return acc;
+}
+
+// ln x for positive finite x, division-free (tables: c6_tables.hpp).  x = 2^e * m with m in [1, 2);
+// the top six mantissa bits pick the interval centre c; r = m / c - 1 through the tabulated 1/c;
+// ln x = e ln2 + ln c + log1p(r) with log1p(r) = r + r^2 (-1/2 + r/3 - ... - r^6/8).
 inline double det_log(double x) {
-    // x > 0, finite.
     int e = 0;
     uint64_t b = double_to_bits(x);
     if ((b >> 52) == 0) {  // subnormal: scale by 2^54
@@ -90,128 +109,101 @@ inline double det_log(double x) {
     }
     e += (int)((b >> 52) & 0x7FF) - 1023;
     double m = bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);  // [1,2)
-    if (m > 1.4142135623730951) {
-        m = m * 0.5;
-        e += 1;
-    }
-    double f = m - 1.0;
-    double s = f / (2.0 + f);
-    double z = s * s;
-    // 2*atanh(s) = 2s(1 + z/3 + z^2/5 + ...), |s| <= 0.1716
-    double p = 1.0 / 23.0;
-    p = p * z + 1.0 / 21.0;
-    p = p * z + 1.0 / 19.0;
-    p = p * z + 1.0 / 17.0;
-    p = p * z + 1.0 / 15.0;
-    p = p * z + 1.0 / 13.0;
-    p = p * z + 1.0 / 11.0;
-    p = p * z + 1.0 / 9.0;
-    p = p * z + 1.0 / 7.0;
-    p = p * z + 1.0 / 5.0;
-    p = p * z + 1.0 / 3.0;
-    p = p * z + 1.0;
-    double lm = 2.0 * s * p;
-    return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lm);
+    const double* row = LOG_TABLE[(b >> 46) & 63];
+    double r = fma1(m, row[0], -1.0);
+    static const double C[7] = {-1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
+    double log1p_r = fma1(horner_fma(C, r), r * r, r);
+    double ed = (double)e;
+    return fma1(ed, 0.6931471803691238, row[1] + fma1(ed, 1.9082149292705877e-10, log1p_r));
 }
 
-inline double det_floor(double x) {
-    // |x| < 2^31 here.  Truncate then fix up; avoids relying on libm/device floor.
-    double t = (double)(int64_t)x;
-    return (t > x) ? t - 1.0 : t;
-}
-
+// e^x.  k = floor(x * 32/ln2 + 1/2) = 32 q + j; r = x - k ln2/32 (two-part ln2); e^x = 2^q * 2^(j/32) *
+// (1 + expm1(r)) with expm1 to r^6; the 2^q scaling is done in two exact steps so that subnormal
+// results round once.
 inline double det_exp(double x) {
     if (x < -745.2) return 0.0;
     if (x > 709.0) x = 709.0;
-    double kd = det_floor(x * 1.4426950408889634 + 0.5);
-    double r = (x - kd * 0.6931471803691238) - kd * 1.9082149292705877e-10;  // |r| <= 0.3466
-    double p = 1.0 / 6227020800.0;  // 1/13!
-    p = p * r + 1.0 / 479001600.0;
-    p = p * r + 1.0 / 39916800.0;
-    p = p * r + 1.0 / 3628800.0;
-    p = p * r + 1.0 / 362880.0;
-    p = p * r + 1.0 / 40320.0;
-    p = p * r + 1.0 / 5040.0;
-    p = p * r + 1.0 / 720.0;
-    p = p * r + 1.0 / 120.0;
-    p = p * r + 1.0 / 24.0;
-    p = p * r + 1.0 / 6.0;
-    p = p * r + 0.5;
-    p = p * r + 1.0;
-    p = p * r + 1.0;
+    double kd = (double)(int64_t)__builtin_floor(fma1(x, 46.16624130844683, 0.5));
+    double r = fma1(-kd, 5.9631716539705866e-12, fma1(-kd, 0.02166084938653512, x));
+    static const double C[6] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+    double expm1_r = horner_fma(C, r) * r;
     int k = (int)kd;
-    // scale by 2^k in two exact-power steps so that subnormal results round once, identically.
-    int k1 = k / 2, k2 = k - k1;
-    double s1 = bits_to_double((uint64_t)(k1 + 1023) << 52);
-    double s2 = bits_to_double((uint64_t)(k2 + 1023) << 52);
-    return (p * s1) * s2;
-}
-
-// ----------------------------------------------------------------------------------------------
-// Gamma(alpha < 1 or >= 1, scale 1) from a counter-based stream.
-// Stream = Philox blocks (c0,c1,c2, blk=0,1,2,...) consumed two u32 at a time.
-// ----------------------------------------------------------------------------------------------
-struct PhiloxStream {
-    uint32_t c0, c1, c2, blk, k0, k1;
-    uint32_t buf[4];
-    int pos;
-    PhiloxStream(uint32_t a, uint32_t b, uint32_t c, uint32_t key0, uint32_t key1)
-        : c0(a), c1(b), c2(c), blk(0), k0(key0), k1(key1), pos(4) {}
-    double next_open01() {
-        if (pos >= 4) {
-            Philox4 r = philox4x32_10(c0, c1, c2, blk++, k0, k1);
-            buf[0] = r.v[0], buf[1] = r.v[1], buf[2] = r.v[2], buf[3] = r.v[3];
-            pos = 0;
-        }
-        double u = u64_to_open01(buf[pos], buf[pos + 1]);
-        pos += 2;
-        return u;
-    }
-};
-
-inline double det_sqrt(double x);  // IEEE sqrt; defined below via <cmath> (correctly rounded)
-
-inline double normal_polar(PhiloxStream& st) {
-    for (;;) {
-        double a = 2.0 * st.next_open01() - 1.0;
-        double b = 2.0 * st.next_open01() - 1.0;
-        double s = a * a + b * b;
-        if (s >= 1.0 || s == 0.0) continue;
-        double f = det_sqrt(-2.0 * det_log(s) / s);
-        return a * f;
-    }
-}
-
-// Marsaglia–Tsang for shape >= 1 (rand 0.6 GammaLargeShape).
-inline double gamma_large(PhiloxStream& st, double shape) {
-    double d = shape - 1.0 / 3.0;
-    double c = 1.0 / det_sqrt(9.0 * d);
-    for (;;) {
-        double x = normal_polar(st);
-        double vc = 1.0 + c * x;
-        if (vc <= 0.0) continue;
-        double v = vc * vc * vc;
-        double u = st.next_open01();
-        double x2 = x * x;
-        if (u < 1.0 - 0.0331 * x2 * x2) return d * v;
-        if (det_log(u) < 0.5 * x2 + d * (1.0 - v + det_log(v))) return d * v;
-    }
-}
-
-// rand 0.6 Gamma::new(shape, 1.0): shape < 1 -> GammaSmallShape, else large (shape == 1 is
-// Exp(1) in rand; Marsaglia–Tsang is used here for it too — same distribution).
-inline double gamma_sample(PhiloxStream& st, double shape) {
-    if (shape < 1.0) {
-        double g = gamma_large(st, shape + 1.0);
-        double u = st.next_open01();
-        return g * det_exp(det_log(u) / shape);
-    }
-    return gamma_large(st, shape);
+    double tj = EXP_TABLE[k & 31];
+    double y = fma1(tj, expm1_r, tj);
+    int q = k >> 5;  // arithmetic shift: floor division by 32
+    int q1 = q / 2, q2 = q - q1;
+    double s1 = bits_to_double((uint64_t)(q1 + 1023) << 52);
+    double s2 = bits_to_double((uint64_t)(q2 + 1023) << 52);
+    return (y * s1) * s2;
 }
 
 }  // namespace c6o
 
 #include <cmath>
 namespace c6o {
-inline double det_sqrt(double x) { return std::sqrt(x); }
+inline double det_sqrt(double x) { return std::sqrt(x); }  // IEEE sqrt, correctly rounded
+
+// ----------------------------------------------------------------------------------------------
+// Gamma(shape, 1), draw (a, b, c) of the stream keyed (k0, k1).  Trial t of the rejection loop
+// reads Philox block(s) of counter (a, b, c, t) — two 53-bit uniforms per block.
+//   shape <  1 : Ahrens & Dieter (1974) algorithm GS.  With b = (e + shape)/e and P = b*U:
+//                  P <= 1 : X = P^(1/shape), accept iff V <= e^(-X)   (cubic lower bound tried first)
+//                  P >  1 : X = -ln((b - P)/shape), accept iff V <= X^(shape-1)
+//   shape >= 1 : Marsaglia & Tsang (2000), normal deviate from the Marsaglia polar method
+//                (blocks 2t and 2t+1 of trial t).
+// ----------------------------------------------------------------------------------------------
+struct Uniform2 {
+    double first, second;
+};
+inline Uniform2 uniforms(uint32_t a, uint32_t b, uint32_t c, uint32_t block, uint32_t k0, uint32_t k1) {
+    Philox4 r = philox4x32_10(a, b, c, block, k0, k1);
+    return Uniform2{u64_to_open01(r.v[0], r.v[1]), u64_to_open01(r.v[2], r.v[3])};
+}
+
+inline double gamma_small_shape(double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1) {
+    const double inv_shape = 1.0 / shape;
+    const double bb = (2.718281828459045 + shape) / 2.718281828459045;
+    double x = 0.0;
+    for (uint32_t t = 0; t < 64; ++t) {
+        Uniform2 uv = uniforms(a, b, c, t, k0, k1);
+        double p = bb * uv.first;
+        if (p <= 1.0) {
+            x = det_exp(det_log(p) * inv_shape);
+            // squeeze first (e^-x >= 1 - x + x^2/2 - x^3/6 for x >= 0), then the exact test
+            double lower = fma1(x, fma1(x, fma1(x, -1.0 / 6.0, 0.5), -1.0), 1.0);
+            if (uv.second <= lower || uv.second <= det_exp(-x)) return x;
+        } else {
+            x = -det_log((bb - p) * inv_shape);
+            if (uv.second <= det_exp((shape - 1.0) * det_log(x))) return x;
+        }
+    }
+    return x;  // 64 rejections in a row: probability < 1e-100
+}
+
+inline double gamma_large_shape(double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1) {
+    const double d = shape - 1.0 / 3.0;
+    const double cc = 1.0 / det_sqrt(9.0 * d);
+    double out = d;
+    for (uint32_t t = 0; t < 64; ++t) {
+        Uniform2 pq = uniforms(a, b, c, 2 * t, k0, k1);
+        double p = 2.0 * pq.first - 1.0, q = 2.0 * pq.second - 1.0;
+        double s = p * p + q * q;
+        if (s >= 1.0 || s == 0.0) continue;
+        double x = p * det_sqrt(-2.0 * det_log(s) / s);
+        double vc = 1.0 + cc * x;
+        if (vc <= 0.0) continue;
+        double v = vc * vc * vc;
+        double u = uniforms(a, b, c, 2 * t + 1, k0, k1).first;
+        double x2 = x * x;
+        out = d * v;
+        if (u < 1.0 - 0.0331 * x2 * x2) return out;
+        if (det_log(u) < 0.5 * x2 + d * (1.0 - v + det_log(v))) return out;
+    }
+    return out;
+}
+
+inline double gamma_sample(double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1) {
+    return shape < 1.0 ? gamma_small_shape(shape, a, b, c, k0, k1) : gamma_large_shape(shape, a, b, c, k0, k1);
+}
+
 }  // namespace c6o

@@ -102,8 +102,7 @@ void oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
 double oracle_det_log(double x) { return det_log(x); }
 double oracle_det_exp(double x) { return det_exp(x); }
 double oracle_gamma(uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1, double shape) {
-    PhiloxStream st(a, b, c, k0, k1);
-    return gamma_sample(st, shape);
+    return gamma_sample(shape, a, b, c, k0, k1);
 }
 
 // Random playout (default_policy/mod.rs:186-203 rollout loop) from the empty board with the

@@ -408,15 +408,23 @@ static void test_rng() {
     for (double x : es) CHECK(std::fabs(det_exp(x) - std::exp(x)) <= 1e-14 * std::exp(x) + 1e-320);
     CHECK(det_exp(-800.0) == 0.0);
     // Gamma(0.03): mean alpha; Gamma(2.5): mean 2.5 (loose Monte-Carlo check of the sampler)
-    double m1 = 0, m2 = 0;
-    const int NS = 200000;
+    // and of the shape of the distribution: E[X] = Var[X] = shape, E[X^2] = shape (shape + 1),
+    // P(X <= x) for Gamma(0.03) at x = 1e-30 is 1e-0.9 / Gamma(1.03) ~ 0.1274 (x^a / Gamma(a+1) for tiny x)
+    double m1 = 0, m2 = 0, q1 = 0, q2 = 0, m3 = 0, q3 = 0;
+    int tiny = 0;
+    const int NS = 400000;
     for (int i = 0; i < NS; ++i) {
-        PhiloxStream s1(i, 0, 0, 1, 2), s2(i, 1, 0, 1, 2);
-        m1 += gamma_sample(s1, 0.03);
-        m2 += gamma_sample(s2, 2.5);
+        double g1 = gamma_sample(0.03, i, 0, 0, 1, 2), g2 = gamma_sample(2.5, i, 1, 0, 1, 2), g3 = gamma_sample(0.7, i, 2, 0, 1, 2);
+        m1 += g1, q1 += g1 * g1, m2 += g2, q2 += g2 * g2, m3 += g3, q3 += g3 * g3;
+        tiny += g1 <= 1e-30;
     }
-    CHECK(std::fabs(m1 / NS - 0.03) < 0.003);
-    CHECK(std::fabs(m2 / NS - 2.5) < 0.03);
+    CHECK(std::fabs(m1 / NS - 0.03) < 0.002);
+    CHECK(std::fabs(q1 / NS - 0.03 * 1.03) < 0.004);
+    CHECK(std::fabs((double)tiny / NS - 0.1274) < 0.003);
+    CHECK(std::fabs(m2 / NS - 2.5) < 0.02);
+    CHECK(std::fabs(q2 / NS - 2.5 * 3.5) < 0.15);
+    CHECK(std::fabs(m3 / NS - 0.7) < 0.008);
+    CHECK(std::fabs(q3 / NS - 0.7 * 1.7) < 0.03);
 }
 
 int main() {

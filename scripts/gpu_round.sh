@@ -12,6 +12,8 @@ tail -5 $OUT/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/smoke.log
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err
 cat $OUT/bench.json
+timeout 600 python bench.py --epsilon 0 --no-e2e --no-cpu-baseline > $OUT/bench_eps0.json 2> $OUT/bench_eps0.err
+cat $OUT/bench_eps0.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
 cat $OUT/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
