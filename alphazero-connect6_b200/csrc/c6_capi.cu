@@ -408,25 +408,96 @@ int c6_probe_math(const double* xs, double* logs, double* exps, int n, int devic
 // it stands for the user's evaluator on the far side of the C-ABI.
 // ------------------------------------------------------------------------------------------------
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
-extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
-    static std::atomic<uint64_t> call_no{0};
-    const uint64_t base = call_no.fetch_add(1) * 0x9E3779B97F4A7C15ull + (uint64_t)(player + 2);
-    auto fill = [&](int lo, int hi) {
-        for (int n = lo; n < hi; ++n) {
-            uint64_t s = splitmix64(base ^ ((uint64_t)n << 20));
-            values[n] = (float)(uint32_t)(s >> 40) * (1.0f / 8388608.0f) - 1.0f;
-            float* p = policies + (size_t)n * 225;
-            for (int i = 0; i < 225; i += 2) {
-                s = s * 6364136223846793005ull + 1442695040888963407ull;
-                p[i] = (float)(uint32_t)(s >> 40) * (1.0f / 8388608.0f) - 1.0f;
-                if (i + 1 < 225) p[i + 1] = (float)(uint32_t)((s >> 16) & 0xFFFFFF) * (1.0f / 8388608.0f) - 1.0f;
-            }
+
+namespace {
+// Minimal persistent fork-join pool for the sample evaluator (a user evaluator would bring its own).
+class ForkJoin {
+   public:
+    explicit ForkJoin(int n) : n_(n) {
+        for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~ForkJoin() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+            ++gen_;
         }
-    };
-    int nt = (int)std::min<unsigned>(std::thread::hardware_concurrency(), 16u);
-    if (len < 2048 || nt <= 1) return fill(0, len);
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; ++t) th.emplace_back(fill, (int)((long long)len * t / nt), (int)((long long)len * (t + 1) / nt));
-    for (auto& x : th) x.join();
+        cv_.notify_all();
+        for (auto& x : th_) x.join();
+    }
+    int size() const { return n_; }
+    void run(const std::function<void(int)>& f) {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            f_ = &f;
+            left_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return left_ == 0; });
+    }
+
+   private:
+    void loop(int t) {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                f = f_;
+            }
+            (*f)(t);
+            std::lock_guard<std::mutex> l(m_);
+            if (--left_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* f_ = nullptr;
+    unsigned long gen_ = 0;
+    int left_ = 0;
+    bool stop_ = false;
+};
+}  // namespace
+
+// U[-1,1) values and policies from a counter hash (two 32-bit multiplies per float; the loop has no carried
+// dependence, so gcc vectorises it 8-wide).
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((optimize("O3"), target("avx2")))
+#endif
+static void sample_fill(uint32_t base, float* values, float* policies, int lo, int hi) {
+    for (int n = lo; n < hi; ++n) {
+        const uint32_t seed = (base ^ (uint32_t)n) * 0x9E3779B1u;
+        uint32_t v = seed ^ 0x5bd1e995u;
+        v ^= v >> 15, v *= 0x85EBCA77u, v ^= v >> 13;
+        values[n] = (float)(int)(v >> 8) * (1.0f / 8388608.0f) - 1.0f;
+        float* p = policies + (size_t)n * 225;
+        for (int i = 0; i < 225; ++i) {
+            uint32_t x = (seed + (uint32_t)i) * 0xC2B2AE3Du;
+            x ^= x >> 15, x *= 0x85EBCA77u, x ^= x >> 13;
+            p[i] = (float)(int)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;
+        }
+    }
+}
+
+extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
+    static std::atomic<uint32_t> call_no{0};
+    const uint32_t base = (call_no.fetch_add(1) * 0x9E3779B9u) ^ ((uint32_t)(player + 2) << 28);
+    if (len < 2048) return sample_fill(base, values, policies, 0, len);
+    static ForkJoin pool((int)std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)));
+    static std::mutex one_at_a_time;  // the pool is shared: callers from several engines take turns
+    std::lock_guard<std::mutex> l(one_at_a_time);
+    const int nt = pool.size();
+    pool.run([&](int t) { sample_fill(base, values, policies, (int)((long long)len * t / nt), (int)((long long)len * (t + 1) / nt)); });
 }

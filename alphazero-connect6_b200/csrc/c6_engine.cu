@@ -96,19 +96,19 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
 
 // Device-evaluator path, kernel 2 (also the tail of the callback path): move choice, stone, win
 // check, record, node collection / slot refill for every resident game.
-__global__ void __launch_bounds__(128) k_move_end(Dev D) {
+__global__ void __launch_bounds__(128) k_move_end(Dev D, int g0, int g1) {
     __shared__ uint64_t Zs[512];
     load_zobrist(D, Zs);
     const int lane = threadIdx.x & 31;
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= D.G) return;
+    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= g1) return;
     Warp w = make_warp(D, g, Zs, lane);
     if (w.gs->status == ST_ACTIVE) finish_move(D, w);
 }
 
 // Callback path, kernel 1: descend to the leaf and park it in the game state.
 template <int NOISE>
-__global__ void __launch_bounds__(128) k_select(Dev D) {
+__global__ void __launch_bounds__(128) k_select(Dev D, int g0, int g1) {
     const uint64_t* Zs = D.Z;  // global (__ldg in descend)
     __shared__ WarpStage<NOISE> stage[4];
     __shared__ MathTab mt;
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(128) k_select(Dev D) {
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= D.G) return;
+    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= g1) return;
     Warp w = make_warp(D, g, Zs, lane);
     GameState& gs = *w.gs;
     if (gs.status != ST_ACTIVE) {
@@ -143,15 +143,17 @@ __global__ void __launch_bounds__(128) k_select(Dev D) {
     store_cursor(D, gs, cs, lane);
 }
 
-// Callback path, kernel 2: order the leaves into a Black-to-move group followed by a White-to-move
-// group (the Callback ABI takes one `player` per call, CB/libcppconnect6/src/cppbind/cppeval/mod.rs:8-13).
-__global__ void k_rank(Dev D) {
+// Callback path, kernel 2: order the leaves of one pipeline group (slots g0..g1) into a Black-to-move
+// run followed by a White-to-move run (the Callback ABI takes one `player` per call,
+// CB/libcppconnect6/src/cppbind/cppeval/mod.rs:8-13).  Positions are relative to the group's region of
+// the batch buffers; counts go to gcounts[2*group ..].
+__global__ void k_rank(Dev D, int g0, int g1, int group) {
     __shared__ int sB[1024], sW[1024];
-    const int t = threadIdx.x, per = (D.G + 1023) / 1024;
+    const int t = threadIdx.x, n = g1 - g0, per = (n + 1023) / 1024;
     int nb = 0, nw = 0;
     for (int i = 0; i < per; ++i) {
-        int g = t * per + i;
-        if (g < D.G && D.gs[g].need_eval) (turn_of(D.gs[g].leaf_stones) < 0 ? nb : nw) += 1;
+        int g = g0 + t * per + i;
+        if (g < g1 && D.gs[g].need_eval) (turn_of(D.gs[g].leaf_stones) < 0 ? nb : nw) += 1;
     }
     sB[t] = nb, sW[t] = nw;
     __syncthreads();
@@ -164,29 +166,30 @@ __global__ void k_rank(Dev D) {
     const int totalB = sB[1023], totalW = sW[1023];
     int ob = sB[t] - nb, ow = sW[t] - nw;
     for (int i = 0; i < per; ++i) {
-        int g = t * per + i;
-        if (g < D.G && D.gs[g].need_eval) {
+        int g = g0 + t * per + i;
+        if (g < g1 && D.gs[g].need_eval) {
             if (turn_of(D.gs[g].leaf_stones) < 0)
                 D.gs[g].batch_pos = ob++;
             else
                 D.gs[g].batch_pos = totalB + ow++;
         }
     }
-    if (t == 0) D.gcounts[0] = totalB, D.gcounts[1] = totalW;
+    if (t == 0) D.gcounts[2 * group] = totalB, D.gcounts[2 * group + 1] = totalW;
 }
 
 // Callback path, kernel 3: augment_way8 + board_to_float for every leaf, written in the API layout
 // float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73, CB/.../cpp_support.rs:10-18).
-__global__ void __launch_bounds__(128) k_gather(Dev D) {
+__global__ void __launch_bounds__(128) k_gather(Dev D, int g0, int g1) {
     const int lane = threadIdx.x & 31;
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= D.G) return;
+    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= g1) return;
     const GameState& gs = D.gs[g];
     if (!gs.need_eval) return;
     uint32_t B[8], W[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) B[j] = gs.leafB[j], W[j] = gs.leafW[j];
-    float* out = D.bboards + (size_t)gs.batch_pos * 8 * CELLS;
+    const size_t slot = (size_t)g0 + (size_t)gs.batch_pos;
+    float* out = D.bboards + slot * 8 * CELLS;
     for (int i = lane; i < 8 * CELLS; i += 32) {
         int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
         sym_inv(s, rr, cc, r, c);
@@ -198,17 +201,17 @@ __global__ void __launch_bounds__(128) k_gather(Dev D) {
         float v = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
         out[i] = v;
     }
-    if (lane < 8) D.bvalues[(size_t)gs.batch_pos * 8 + lane] = 0.f;
+    if (lane < 8) D.bvalues[slot * 8 + lane] = 0.f;
 }
 
 // Callback path, kernel 4: recover_way8 + expansion + backup (k_move_end follows every num_sim waves).
-__global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
+__global__ void __launch_bounds__(128) k_expand_cb(Dev D, int g0, int g1) {
     const uint64_t* Zs = D.Z;  // global (__ldg in expand_leaf)
     __shared__ WarpStage<0> stage[4];
     const int lane = threadIdx.x & 31;
     WarpStage<0>& st = stage[threadIdx.x >> 5];
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= D.G) return;
+    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= g1) return;
     Warp w = make_warp(D, g, Zs, lane);
     GameState& gs = *w.gs;
     if (gs.status != ST_ACTIVE) return;
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(128) k_expand_cb(Dev D) {
         for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
         L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
         EvBatch ev;
-        ev.values = D.bvalues + (size_t)gs.batch_pos * 8;
-        ev.pol = D.bboards + (size_t)gs.batch_pos * 8 * CELLS;
+        ev.values = D.bvalues + ((size_t)g0 + (size_t)gs.batch_pos) * 8;
+        ev.pol = D.bboards + ((size_t)g0 + (size_t)gs.batch_pos) * 8 * CELLS;
         ev.lane = lane;
         expand_leaf(D, w, cs, L, ev, ev.value(), st);
     }
@@ -318,11 +321,25 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// One pipeline group of the callback path: a contiguous range of game slots with its own stream, its own
+// region of the batch buffers (device and pinned host) and its own position in the simulation budget.
+struct Group {
+    int g0 = 0, g1 = 0;
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev = nullptr;
+    int* h_counts = nullptr;  // pinned [2]
+    int waves_this_move = 0;
+    int last_count = -1;      // leaves evaluated in the previous wave (-1: unknown)
+    bool front_pending = false;
+    bool exact = false;
+};
+
 struct DeviceArrays {
     Dev dev{};
     float* h_boards = nullptr;  // pinned
     float* h_values = nullptr;
     int* h_counts = nullptr;
+    std::vector<Group> groups;
     unsigned long long* h_gcount = nullptr;
     size_t rec_bytes = 0, lnk_bytes = 0, idx_bytes = 0;
     int sm_count = 0;
@@ -403,8 +420,28 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.Z = dz;
     C6_CUDA(cudaMalloc(&D.cursor, sizeof(int)));
     C6_CUDA(cudaMalloc(&D.gcount, 4 * sizeof(unsigned long long)));
-    C6_CUDA(cudaMalloc(&D.gcounts, 2 * sizeof(int)));
-    C6_CUDA(cudaMallocHost(&d_->h_counts, 2 * sizeof(int)));
+    int n_groups = 1;
+    if (cfg_.evaluator == EVAL_CALLBACK) {
+        // pipeline depth of the callback path: while the host evaluates one group, the others run their
+        // kernels and copies.  Small batches are not worth splitting.
+        const char* pe = std::getenv("C6_PIPELINE");
+        n_groups = pe && *pe ? std::atoi(pe) : (D.G >= 2048 ? 4 : (D.G >= 512 ? 2 : 1));
+        n_groups = std::max(1, std::min(n_groups, std::min(D.G, 16)));
+    }
+    C6_CUDA(cudaMalloc(&D.gcounts, 2 * n_groups * sizeof(int)));
+    C6_CUDA(cudaMallocHost(&d_->h_counts, 2 * n_groups * sizeof(int)));
+    d_->groups.resize(n_groups);
+    for (int p = 0; p < n_groups; ++p) {
+        Group& gr = d_->groups[p];
+        gr.g0 = (int)((long long)D.G * p / n_groups), gr.g1 = (int)((long long)D.G * (p + 1) / n_groups);
+        gr.h_counts = d_->h_counts + 2 * p;
+        if (n_groups == 1) {
+            gr.s = stream_;
+        } else {
+            C6_CUDA(cudaStreamCreateWithFlags(&gr.s, cudaStreamNonBlocking));
+        }
+        C6_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming));
+    }
     C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
     if (cfg_.evaluator == EVAL_CALLBACK) {
         size_t nb = G * 8 * CELLS * sizeof(float), nv = G * 8 * sizeof(float);
@@ -427,6 +464,10 @@ Engine::~Engine() {
     cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gcounts);
     cudaFree(D.records), cudaFree(D.bboards), cudaFree(D.bvalues), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
     cudaFreeHost(d_->h_boards), cudaFreeHost(d_->h_values), cudaFreeHost(d_->h_counts), cudaFreeHost(d_->h_gcount);
+    for (Group& gr : d_->groups) {
+        if (gr.s && gr.s != stream_) cudaStreamSynchronize(gr.s), cudaStreamDestroy(gr.s);
+        if (gr.ev) cudaEventDestroy(gr.ev);
+    }
     cudaStreamDestroy(stream_);
     delete d_;
 }
@@ -488,58 +529,112 @@ void Engine::step_device() {
         kern<<<d_->persistent_blocks, 128, 0, stream_>>>(D);
         launches_ += 1;
     }
-    k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D);
+    k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D, 0, D.G);
     launches_ += 1;
     C6_CUDA(cudaGetLastError());
 }
 
-void Engine::wave_callback(Callback cb) {
+// ---- callback path ------------------------------------------------------------------------------
+// One wave of one group is split in a front half (select -> rank -> gather -> D2H of the leaf boards in
+// the API layout) and a back half (user Callback per side to move -> H2D of policies and values ->
+// expand/backup, plus the move-end kernel once the group has spent its simulation budget).  Groups run
+// on their own streams: while the calling thread sits in the Callback of one group, the kernels and
+// copies of the others proceed, and PCIe carries both directions at once.
+void Engine::group_front(int p) {
     Dev& D = d_->dev;
-    if (cfg_.evaluator != EVAL_CALLBACK) throw std::runtime_error("c6: engine was not created for the callback path");
-    const int grid = warps_grid(D.G);
+    Group& gr = d_->groups[p];
+    const int n = gr.g1 - gr.g0, grid = warps_grid(n);
+    if (cfg_.num_simulation > 0) {
+        const int noise = noise_mode(cfg_);
+        if (noise == 1)
+            k_select<1><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+        else if (noise == 2)
+            k_select<2><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+        else
+            k_select<0><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+        k_rank<<<1, 1024, 0, gr.s>>>(D, gr.g0, gr.g1, p);
+        k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+        launches_ += 3;
+        C6_CUDA(cudaGetLastError());
+        C6_CUDA(cudaMemcpyAsync(gr.h_counts, D.gcounts + 2 * p, 2 * sizeof(int), cudaMemcpyDeviceToHost, gr.s));
+        // Nearly every resident game needs an evaluation in a wave, so the whole region of the group is
+        // copied without waiting for the count; when most slots are idle (tail of a run) the copy
+        // waits for the exact count instead.
+        gr.exact = gr.last_count >= 0 && gr.last_count < n / 2;
+        if (!gr.exact) {
+            const size_t off = (size_t)gr.g0 * 8 * CELLS;
+            C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
+            d2h_bytes_ += (double)n * 8 * CELLS * sizeof(float) + 8;
+        }
+    }
+    C6_CUDA(cudaEventRecord(gr.ev, gr.s));
+    gr.front_pending = true;
+}
+
+void Engine::group_back(int p, Callback cb) {
+    Dev& D = d_->dev;
+    Group& gr = d_->groups[p];
+    const int n = gr.g1 - gr.g0, grid = warps_grid(n);
+    gr.front_pending = false;
     if (cfg_.num_simulation <= 0) {
-        k_move_end<<<grid, 128, 0, stream_>>>(D);
+        k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
         launches_ += 1;
         C6_CUDA(cudaGetLastError());
         return;
     }
-    const int noise = noise_mode(cfg_);
-    if (noise == 1)
-        k_select<1><<<grid, 128, 0, stream_>>>(D);
-    else if (noise == 2)
-        k_select<2><<<grid, 128, 0, stream_>>>(D);
-    else
-        k_select<0><<<grid, 128, 0, stream_>>>(D);
-    k_rank<<<1, 1024, 0, stream_>>>(D);
-    k_gather<<<grid, 128, 0, stream_>>>(D);
-    launches_ += 3;
-    C6_CUDA(cudaGetLastError());
-    C6_CUDA(cudaMemcpyAsync(d_->h_counts, D.gcounts, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    C6_CUDA(cudaStreamSynchronize(stream_));
-    const int nB = d_->h_counts[0], nW = d_->h_counts[1];
-    const size_t len = (size_t)(nB + nW) * 8;
+    C6_CUDA(cudaEventSynchronize(gr.ev));
+    const int nB = gr.h_counts[0], nW = gr.h_counts[1];
+    const size_t len = (size_t)(nB + nW) * 8, off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
+    gr.last_count = nB + nW;
     if (len) {
-        C6_CUDA(cudaMemcpyAsync(d_->h_boards, D.bboards, len * CELLS * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-        C6_CUDA(cudaStreamSynchronize(stream_));
-        std::memset(d_->h_values, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
-        if (nB) cb(-1, d_->h_values, d_->h_boards, nB * 8);
-        if (nW) cb(1, d_->h_values + (size_t)nB * 8, d_->h_boards + (size_t)nB * 8 * CELLS, nW * 8);
-        C6_CUDA(cudaMemcpyAsync(D.bboards, d_->h_boards, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, stream_));
-        C6_CUDA(cudaMemcpyAsync(D.bvalues, d_->h_values, len * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        if (gr.exact) {
+            C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, len * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
+            C6_CUDA(cudaStreamSynchronize(gr.s));
+            d2h_bytes_ += (double)len * CELLS * sizeof(float) + 8;
+        }
+        float* hb = d_->h_boards + off;
+        float* hv = d_->h_values + voff;
+        std::memset(hv, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
+        if (nB) cb(-1, hv, hb, nB * 8);
+        if (nW) cb(1, hv + (size_t)nB * 8, hb + (size_t)nB * 8 * CELLS, nW * 8);
+        C6_CUDA(cudaMemcpyAsync(D.bboards + off, hb, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, gr.s));
+        C6_CUDA(cudaMemcpyAsync(D.bvalues + voff, hv, len * sizeof(float), cudaMemcpyHostToDevice, gr.s));
         h2d_bytes_ += (double)len * (CELLS + 1) * sizeof(float);
-        d2h_bytes_ += (double)len * CELLS * sizeof(float) + 8;
     }
-    k_expand_cb<<<grid, 128, 0, stream_>>>(D);
+    k_expand_cb<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
     launches_ += 1;
-    if (++waves_this_move_ >= cfg_.num_simulation) {  // every resident game has spent its budget: all slots are in lockstep
-        waves_this_move_ = 0;
-        k_move_end<<<grid, 128, 0, stream_>>>(D);
+    if (++gr.waves_this_move >= cfg_.num_simulation) {  // every game of the group has spent its budget: they are in lockstep
+        gr.waves_this_move = 0;
+        k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
         launches_ += 1;
     }
     C6_CUDA(cudaGetLastError());
 }
 
-void Engine::sync() { C6_CUDA(cudaStreamSynchronize(stream_)); }
+// `waves` simulations for every resident game, software-pipelined over the groups.
+void Engine::waves_callback(Callback cb, int waves) {
+    if (cfg_.evaluator != EVAL_CALLBACK) throw std::runtime_error("c6: engine was not created for the callback path");
+    const int P = (int)d_->groups.size();
+    if (waves <= 0) return;
+    for (int p = 0; p < P; ++p) group_front(p);
+    for (int wv = 0; wv < waves; ++wv)
+        for (int p = 0; p < P; ++p) {
+            group_back(p, cb);
+            if (wv + 1 < waves) group_front(p);
+            if (cancel_.load()) {
+                sync();
+                throw std::runtime_error("c6: cancelled");
+            }
+        }
+}
+
+void Engine::wave_callback(Callback cb) { waves_callback(cb, 1); }
+
+void Engine::sync() {
+    for (Group& gr : d_->groups)
+        if (gr.s && gr.s != stream_) C6_CUDA(cudaStreamSynchronize(gr.s));
+    C6_CUDA(cudaStreamSynchronize(stream_));
+}
 
 static void check_errors(DeviceArrays* d, cudaStream_t s) {
     C6_CUDA(cudaMemcpyAsync(d->h_gcount, d->dev.gcount, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -564,6 +659,7 @@ static void check_errors(DeviceArrays* d, cudaStream_t s) {
 }
 
 int64_t Engine::games_done() {
+    sync();
     check_errors(d_, stream_);
     return (int64_t)d_->h_gcount[0];
 }
@@ -587,12 +683,7 @@ GameState Engine::slot_state(int slot) {
 void Engine::run_callback_to_end(Callback cb, bool debug) {
     (void)debug;
     const int per_move = std::max(cfg_.num_simulation, 1);
-    while (!all_done()) {
-        for (int i = 0; i < per_move; ++i) {
-            wave_callback(cb);
-            if (cancel_.load()) throw std::runtime_error("c6: cancelled");
-        }
-    }
+    while (!all_done()) waves_callback(cb, per_move);
 }
 
 float Engine::timed_steps_device(int k) {
@@ -615,10 +706,18 @@ float Engine::timed_waves_callback(Callback cb, int k, double* h2d, double* d2h)
     cudaEvent_t a, b;
     C6_CUDA(cudaEventCreate(&a));
     C6_CUDA(cudaEventCreate(&b));
-    C6_CUDA(cudaStreamSynchronize(stream_));
+    sync();
     double h0 = h2d_bytes_, d0 = d2h_bytes_;
+    // the timed region spans every group stream: the start event gates them all, the end event waits for them all
     C6_CUDA(cudaEventRecord(a, stream_));
-    for (int i = 0; i < k; ++i) wave_callback(cb);
+    for (Group& gr : d_->groups)
+        if (gr.s != stream_) C6_CUDA(cudaStreamWaitEvent(gr.s, a, 0));
+    waves_callback(cb, k);
+    for (Group& gr : d_->groups)
+        if (gr.s != stream_) {
+            C6_CUDA(cudaEventRecord(gr.ev, gr.s));
+            C6_CUDA(cudaStreamWaitEvent(stream_, gr.ev, 0));
+        }
     C6_CUDA(cudaEventRecord(b, stream_));
     C6_CUDA(cudaEventSynchronize(b));
     float ms = 0;
@@ -664,6 +763,7 @@ size_t Engine::debug_read(int what, int slot, void* out, size_t max_bytes) {
 }
 
 Stats Engine::stats() {
+    sync();
     check_errors(d_, stream_);
     std::vector<GameState> gs(d_->dev.G);
     C6_CUDA(cudaMemcpy(gs.data(), d_->dev.gs, gs.size() * sizeof(GameState), cudaMemcpyDeviceToHost));

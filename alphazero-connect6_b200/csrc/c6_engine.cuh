@@ -121,6 +121,8 @@ class Engine {
     // Host-callback path: one wave = one simulation for every active slot (select kernel -> D2H ->
     // user Callback per side to move -> H2D -> expand kernel).
     void wave_callback(Callback cb);
+    // `waves` simulations for every resident game, pipelined over the groups (see c6_engine.cu)
+    void waves_callback(Callback cb, int waves);
     void sync();
     int64_t games_done();       // synchronises
     bool all_done();            // synchronises
@@ -147,6 +149,8 @@ class Engine {
     void cancel() { cancel_.store(true); }
 
    private:
+    void group_front(int p);
+    void group_back(int p, Callback cb);
     Config cfg_;
     DeviceArrays* d_ = nullptr;
     cudaStream_t stream_ = nullptr;
@@ -154,7 +158,6 @@ class Engine {
     uint32_t first_id_ = 0;
     long long launches_ = 0;
     double h2d_bytes_ = 0, d2h_bytes_ = 0;
-    int waves_this_move_ = 0;
     std::atomic<bool> cancel_{false};
 };
 

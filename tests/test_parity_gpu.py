@@ -442,3 +442,15 @@ def test_noise_sampler_bitwise_vs_oracle():
     assert np.array_equal(exps.view(np.uint64), we.view(np.uint64))
     pos = xs > 0
     assert np.all(np.abs(logs[pos] - np.log(xs[pos])) <= 4e-16 * np.maximum(1.0, np.abs(np.log(xs[pos]))))
+
+
+@pytest.mark.parametrize("pipeline", ["1", "3", "7"])
+def test_callback_pipeline_groups_do_not_change_results(pipeline, monkeypatch):
+    """The callback path splits the resident games into pipeline groups (own stream, own batch region);
+    records must not depend on the split, and slot refill must work across groups."""
+    monkeypatch.setenv("C6_PIPELINE", pipeline)
+    seed, sims, eps, n = 0xC6, 6, 0.25, 12
+    rec, cv, rn, rw, st = run_engine(n, "neg_eval_callback", first_id=300, slots=7, num_simulation=sims, epsilon=eps, seed=seed,
+                                     evaluator=EVAL_CALLBACK, max_moves=14)
+    compare_games(n, rec, cv, rn, rw, 300, "neg_eval_callback", 0, sims, eps, seed, 14)
+    assert st.games_done == n
