@@ -284,6 +284,9 @@ int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { C6_TRY(*ms = e->
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, double* h2d, double* d2h) {
     C6_TRY(*ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h))
 }
+int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_seconds) {
+    C6_TRY(*wait_seconds = e->eng->host_wait_seconds(); *callback_seconds = e->eng->host_callback_seconds())
+}
 int c6_engine_stats(c6_engine* e, c6_stats* out) {
     C6_TRY(Stats s = e->eng->stats(); out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf,
            out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,
@@ -388,6 +391,36 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
            cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db))
 }
 
+// Host<->device copy bandwidth of this box with pinned buffers (GB/s): H2D alone, D2H alone, and both at
+// once on two streams (per direction).  This is the ceiling of the host-callback evaluator path.
+int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs) {
+    C6_TRY(CK(cudaSetDevice(device)); void *h1 = nullptr, *h2 = nullptr, *d1 = nullptr, *d2 = nullptr;
+           CK(cudaMallocHost(&h1, (size_t)bytes)); CK(cudaMallocHost(&h2, (size_t)bytes)); CK(cudaMalloc(&d1, (size_t)bytes));
+           CK(cudaMalloc(&d2, (size_t)bytes)); std::memset(h1, 1, (size_t)bytes); std::memset(h2, 2, (size_t)bytes);
+           cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2)); cudaEvent_t a, b, c;
+           CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventCreate(&c));
+           auto timed = [&](int mode) {
+               float ms = 0;
+               for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+                   CK(cudaDeviceSynchronize());
+                   CK(cudaEventRecord(a, s1));
+                   CK(cudaStreamWaitEvent(s2, a, 0));
+                   for (int i = 0; i < iters; ++i) {
+                       if (mode != 1) CK(cudaMemcpyAsync(d1, h1, (size_t)bytes, cudaMemcpyHostToDevice, s1));
+                       if (mode != 0) CK(cudaMemcpyAsync(h2, d2, (size_t)bytes, cudaMemcpyDeviceToHost, s2));
+                   }
+                   CK(cudaEventRecord(c, s2));
+                   CK(cudaStreamWaitEvent(s1, c, 0));
+                   CK(cudaEventRecord(b, s1));
+                   CK(cudaEventSynchronize(b));
+                   CK(cudaEventElapsedTime(&ms, a, b));
+               }
+               return (double)bytes * iters / (ms * 1e-3) / 1e9;
+           };
+           *h2d_gbs = timed(0); *d2h_gbs = timed(1); *both_gbs = timed(2);
+           cudaEventDestroy(a), cudaEventDestroy(b), cudaEventDestroy(c), cudaStreamDestroy(s1), cudaStreamDestroy(s2);
+           cudaFreeHost(h1), cudaFreeHost(h2), cudaFree(d1), cudaFree(d2))
+}
 int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device) {
     C6_TRY(CK(cudaSetDevice(device)); double* d = nullptr; CK(cudaMalloc(&d, (size_t)n * 8)); launch_probe_gamma(shape, k0, k1, d, n, 0);
            CK(cudaGetLastError()); CK(cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost)); cudaFree(d))
@@ -415,58 +448,68 @@ int c6_probe_math(const double* xs, double* logs, double* exps, int n, int devic
 
 namespace {
 // Minimal persistent fork-join pool for the sample evaluator (a user evaluator would bring its own).
+// Workers spin briefly on the generation counter before sleeping: the engine calls the evaluator every
+// few tens of microseconds in steady state, and a futex wake-up per call would cost more than the fill.
 class ForkJoin {
    public:
-    explicit ForkJoin(int n) : n_(n) {
+    explicit ForkJoin(int n) : n_(n), spin_limit_(env_int("C6_SAMPLE_SPIN", 20000)) {
         for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
     }
     ~ForkJoin() {
         {
             std::lock_guard<std::mutex> l(m_);
             stop_ = true;
-            ++gen_;
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto& x : th_) x.join();
     }
     int size() const { return n_; }
     void run(const std::function<void(int)>& f) {
+        f_ = &f;
+        left_.store(n_ - 1, std::memory_order_relaxed);
         {
             std::lock_guard<std::mutex> l(m_);
-            f_ = &f;
-            left_ = n_ - 1;
-            ++gen_;
+            gen_.fetch_add(1, std::memory_order_release);
         }
-        cv_.notify_all();
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         f(0);
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return left_ == 0; });
+        while (left_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 
    private:
+    static void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
     void loop(int t) {
         unsigned long seen = 0;
         for (;;) {
-            const std::function<void(int)>* f;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                f = f_;
+            int spins = 0;
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                if (++spins < spin_limit_) {
+                    cpu_relax();
+                } else {
+                    std::unique_lock<std::mutex> l(m_);
+                    sleepers_.fetch_add(1, std::memory_order_release);
+                    cv_.wait(l, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                    sleepers_.fetch_sub(1, std::memory_order_release);
+                }
             }
-            (*f)(t);
-            std::lock_guard<std::mutex> l(m_);
-            if (--left_ == 0) done_.notify_one();
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_) return;
+            (*f_)(t);
+            left_.fetch_sub(1, std::memory_order_release);
         }
     }
-    int n_;
+    int n_, spin_limit_;
     std::vector<std::thread> th_;
     std::mutex m_;
-    std::condition_variable cv_, done_;
+    std::condition_variable cv_;
     const std::function<void(int)>* f_ = nullptr;
-    unsigned long gen_ = 0;
-    int left_ = 0;
+    std::atomic<unsigned long> gen_{0};
+    std::atomic<int> left_{0}, sleepers_{0};
     bool stop_ = false;
 };
 }  // namespace
@@ -495,7 +538,9 @@ extern "C" void c6_sample_random_callback(int player, float* values, float* poli
     static std::atomic<uint32_t> call_no{0};
     const uint32_t base = (call_no.fetch_add(1) * 0x9E3779B9u) ^ ((uint32_t)(player + 2) << 28);
     if (len < 2048) return sample_fill(base, values, policies, 0, len);
-    static ForkJoin pool((int)std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)));
+    // four workers: measured best on the 16-vCPU B200 box (more threads compete with the engine's calling
+    // thread and the CUDA driver's own threads; profiles/e2e4)
+    static ForkJoin pool(env_int("C6_SAMPLE_THREADS", (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 4u))));
     static std::mutex one_at_a_time;  // the pool is shared: callers from several engines take turns
     std::lock_guard<std::mutex> l(one_at_a_time);
     const int nt = pool.size();

@@ -1,5 +1,6 @@
 // Kernels + host driver of the batched self-play engine.  See c6_engine.cuh / DESIGN.md.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -332,6 +333,9 @@ struct Group {
     int last_count = -1;      // leaves evaluated in the previous wave (-1: unknown)
     bool front_pending = false;
     bool exact = false;
+    // the fixed-shape halves of a wave as CUDA graphs (one launch call instead of six): front = select,
+    // rank, gather, D2H counts + whole region; back = H2D whole region, expand [, move end]
+    cudaGraphExec_t front_graph = nullptr, back_graph = nullptr, back_move_graph = nullptr;
 };
 
 struct DeviceArrays {
@@ -425,11 +429,12 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         // pipeline depth of the callback path: while the host evaluates one group, the others run their
         // kernels and copies.  Small batches are not worth splitting.
         const char* pe = std::getenv("C6_PIPELINE");
-        n_groups = pe && *pe ? std::atoi(pe) : (D.G >= 2048 ? 4 : (D.G >= 512 ? 2 : 1));
+        n_groups = pe && *pe ? std::atoi(pe) : std::max(1, std::min(16, D.G / 256));  // 16 groups of 256 games at G = 4096: profiles/e2e3-4
         n_groups = std::max(1, std::min(n_groups, std::min(D.G, 16)));
     }
     C6_CUDA(cudaMalloc(&D.gcounts, 2 * n_groups * sizeof(int)));
     C6_CUDA(cudaMallocHost(&d_->h_counts, 2 * n_groups * sizeof(int)));
+    if (const char* ug = std::getenv("C6_GRAPHS")) use_graphs_ = std::atoi(ug) != 0;
     d_->groups.resize(n_groups);
     for (int p = 0; p < n_groups; ++p) {
         Group& gr = d_->groups[p];
@@ -464,6 +469,7 @@ Engine::~Engine() {
     cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gcounts);
     cudaFree(D.records), cudaFree(D.bboards), cudaFree(D.bvalues), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
     cudaFreeHost(d_->h_boards), cudaFreeHost(d_->h_values), cudaFreeHost(d_->h_counts), cudaFreeHost(d_->h_gcount);
+    drop_graphs();
     for (Group& gr : d_->groups) {
         if (gr.s && gr.s != stream_) cudaStreamSynchronize(gr.s), cudaStreamDestroy(gr.s);
         if (gr.ev) cudaEventDestroy(gr.ev);
@@ -478,6 +484,8 @@ void Engine::start(uint32_t first_id, int64_t total_games) {
     Dev& D = d_->dev;
     C6_CUDA(cudaSetDevice(cfg_.device));
     sync();
+    drop_graphs();  // kernel arguments (record / trace pointers, game ids) are baked into the graphs
+    for (Group& gr : d_->groups) gr.waves_this_move = 0, gr.last_count = -1, gr.front_pending = false;
     total_games_ = total_games, first_id_ = first_id;
     D.total_games = total_games, D.first_id = first_id;
     cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
@@ -540,42 +548,95 @@ void Engine::step_device() {
 // expand/backup, plus the move-end kernel once the group has spent its simulation budget).  Groups run
 // on their own streams: while the calling thread sits in the Callback of one group, the kernels and
 // copies of the others proceed, and PCIe carries both directions at once.
-void Engine::group_front(int p) {
+void Engine::front_ops(int p, bool whole_region) {
     Dev& D = d_->dev;
     Group& gr = d_->groups[p];
     const int n = gr.g1 - gr.g0, grid = warps_grid(n);
+    const int noise = noise_mode(cfg_);
+    if (noise == 1)
+        k_select<1><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    else if (noise == 2)
+        k_select<2><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    else
+        k_select<0><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    k_rank<<<1, 1024, 0, gr.s>>>(D, gr.g0, gr.g1, p);
+    k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    C6_CUDA(cudaGetLastError());
+    C6_CUDA(cudaMemcpyAsync(gr.h_counts, D.gcounts + 2 * p, 2 * sizeof(int), cudaMemcpyDeviceToHost, gr.s));
+    if (whole_region) {
+        const size_t off = (size_t)gr.g0 * 8 * CELLS;
+        C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
+    }
+}
+
+void Engine::back_ops(int p, size_t len, bool move_end) {
+    Dev& D = d_->dev;
+    Group& gr = d_->groups[p];
+    const int n = gr.g1 - gr.g0, grid = warps_grid(n);
+    const size_t off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
+    if (len) {
+        C6_CUDA(cudaMemcpyAsync(D.bboards + off, d_->h_boards + off, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, gr.s));
+        C6_CUDA(cudaMemcpyAsync(D.bvalues + voff, d_->h_values + voff, len * sizeof(float), cudaMemcpyHostToDevice, gr.s));
+    }
+    k_expand_cb<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    if (move_end) k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
+    C6_CUDA(cudaGetLastError());
+}
+
+void Engine::build_graphs(int p) {
+    Group& gr = d_->groups[p];
+    const size_t whole = (size_t)(gr.g1 - gr.g0) * 8;
+    auto capture = [&](cudaGraphExec_t& exec, auto&& ops) {
+        cudaGraph_t graph = nullptr;
+        C6_CUDA(cudaStreamBeginCapture(gr.s, cudaStreamCaptureModeThreadLocal));
+        ops();
+        C6_CUDA(cudaStreamEndCapture(gr.s, &graph));
+        C6_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+    };
+    capture(gr.front_graph, [&] { front_ops(p, true); });
+    capture(gr.back_graph, [&] { back_ops(p, whole, false); });
+    capture(gr.back_move_graph, [&] { back_ops(p, whole, true); });
+}
+
+void Engine::drop_graphs() {
+    for (Group& gr : d_->groups) {
+        if (gr.front_graph) cudaGraphExecDestroy(gr.front_graph);
+        if (gr.back_graph) cudaGraphExecDestroy(gr.back_graph);
+        if (gr.back_move_graph) cudaGraphExecDestroy(gr.back_move_graph);
+        gr.front_graph = gr.back_graph = gr.back_move_graph = nullptr;
+    }
+}
+
+void Engine::group_front(int p) {
+    Group& gr = d_->groups[p];
+    const int n = gr.g1 - gr.g0;
     if (cfg_.num_simulation > 0) {
-        const int noise = noise_mode(cfg_);
-        if (noise == 1)
-            k_select<1><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        else if (noise == 2)
-            k_select<2><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        else
-            k_select<0><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        k_rank<<<1, 1024, 0, gr.s>>>(D, gr.g0, gr.g1, p);
-        k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        launches_ += 3;
-        C6_CUDA(cudaGetLastError());
-        C6_CUDA(cudaMemcpyAsync(gr.h_counts, D.gcounts + 2 * p, 2 * sizeof(int), cudaMemcpyDeviceToHost, gr.s));
         // Nearly every resident game needs an evaluation in a wave, so the whole region of the group is
         // copied without waiting for the count; when most slots are idle (tail of a run) the copy
         // waits for the exact count instead.
         gr.exact = gr.last_count >= 0 && gr.last_count < n / 2;
-        if (!gr.exact) {
-            const size_t off = (size_t)gr.g0 * 8 * CELLS;
-            C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
-            d2h_bytes_ += (double)n * 8 * CELLS * sizeof(float) + 8;
+        if (!gr.exact && use_graphs_) {
+            if (!gr.front_graph) build_graphs(p);
+            C6_CUDA(cudaGraphLaunch(gr.front_graph, gr.s));
+        } else {
+            front_ops(p, !gr.exact);
         }
+        launches_ += 3;
+        if (!gr.exact) d2h_bytes_ += (double)n * 8 * CELLS * sizeof(float) + 8;
     }
     C6_CUDA(cudaEventRecord(gr.ev, gr.s));
     gr.front_pending = true;
 }
+
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void Engine::group_back(int p, Callback cb) {
     Dev& D = d_->dev;
     Group& gr = d_->groups[p];
     const int n = gr.g1 - gr.g0, grid = warps_grid(n);
     gr.front_pending = false;
+    const double t0 = now_s();
     if (cfg_.num_simulation <= 0) {
         k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
         launches_ += 1;
@@ -583,6 +644,8 @@ void Engine::group_back(int p, Callback cb) {
         return;
     }
     C6_CUDA(cudaEventSynchronize(gr.ev));
+    const double t1 = now_s();
+    host_wait_s_ += t1 - t0;
     const int nB = gr.h_counts[0], nW = gr.h_counts[1];
     const size_t len = (size_t)(nB + nW) * 8, off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
     gr.last_count = nB + nW;
@@ -595,20 +658,22 @@ void Engine::group_back(int p, Callback cb) {
         float* hb = d_->h_boards + off;
         float* hv = d_->h_values + voff;
         std::memset(hv, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
+        const double t2 = now_s();
         if (nB) cb(-1, hv, hb, nB * 8);
         if (nW) cb(1, hv + (size_t)nB * 8, hb + (size_t)nB * 8 * CELLS, nW * 8);
-        C6_CUDA(cudaMemcpyAsync(D.bboards + off, hb, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, gr.s));
-        C6_CUDA(cudaMemcpyAsync(D.bvalues + voff, hv, len * sizeof(float), cudaMemcpyHostToDevice, gr.s));
+        host_callback_s_ += now_s() - t2;
+    }
+    const bool move_end = gr.waves_this_move + 1 >= cfg_.num_simulation;  // the group has spent its budget: its games are in lockstep
+    gr.waves_this_move = move_end ? 0 : gr.waves_this_move + 1;
+    if (!gr.exact && use_graphs_ && len) {
+        if (!gr.back_graph) build_graphs(p);
+        C6_CUDA(cudaGraphLaunch(move_end ? gr.back_move_graph : gr.back_graph, gr.s));
+        h2d_bytes_ += (double)n * 8 * (CELLS + 1) * sizeof(float);
+    } else {
+        back_ops(p, len, move_end);
         h2d_bytes_ += (double)len * (CELLS + 1) * sizeof(float);
     }
-    k_expand_cb<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    launches_ += 1;
-    if (++gr.waves_this_move >= cfg_.num_simulation) {  // every game of the group has spent its budget: they are in lockstep
-        gr.waves_this_move = 0;
-        k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        launches_ += 1;
-    }
-    C6_CUDA(cudaGetLastError());
+    launches_ += move_end ? 2 : 1;
 }
 
 // `waves` simulations for every resident game, software-pipelined over the groups.

@@ -143,6 +143,8 @@ class Engine {
     cudaStream_t stream() const { return stream_; }
     size_t bytes_per_game() const;
     long long kernel_launches() const { return launches_; }
+    double host_wait_seconds() const { return host_wait_s_; }
+    double host_callback_seconds() const { return host_callback_s_; }
     GameState slot_state(int slot);   // synchronises (debug printing)
     // May be called from inside the evaluator callback (or another thread): the run_*_to_end loops stop
     // at the next wave / poll and throw "cancelled".
@@ -151,6 +153,11 @@ class Engine {
    private:
     void group_front(int p);
     void group_back(int p, Callback cb);
+    void front_ops(int p, bool whole_region);
+    void back_ops(int p, size_t len, bool move_end);
+    void build_graphs(int p);
+    void drop_graphs();
+    bool use_graphs_ = false;  // C6_GRAPHS=1: measured no gain over plain launches on the B200 box (profiles/e2e4)
     Config cfg_;
     DeviceArrays* d_ = nullptr;
     cudaStream_t stream_ = nullptr;
@@ -158,6 +165,7 @@ class Engine {
     uint32_t first_id_ = 0;
     long long launches_ = 0;
     double h2d_bytes_ = 0, d2h_bytes_ = 0;
+    double host_wait_s_ = 0, host_callback_s_ = 0;  // callback path: time blocked on the GPU / inside the user Callback
     std::atomic<bool> cancel_{false};
 };
 

@@ -105,6 +105,7 @@ def product():
         L.c6_engine_timed_steps.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.c6_engine_timed_waves.argtypes = [C.c_void_p, CALLBACK, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.c6_engine_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.c6_engine_host_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.c6_engine_games_done.restype = C.c_int64
         L.c6_engine_games_done.argtypes = [C.c_void_p]
         L.c6_engine_records.argtypes = [C.c_void_p, C.POINTER(Record), C.c_int64]
@@ -118,6 +119,7 @@ def product():
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
         L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_int, C.c_int]
         L.c6_probe_math.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.c6_probe_pcie.argtypes = [C.c_int64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
         _product = L
     return _product
 

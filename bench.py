@@ -223,8 +223,12 @@ def main():
         L.c6_engine_stats(e2, C.byref(s0))
         if dist is not None:
             dist.barrier()
+        hw0, hc0 = C.c_double(), C.c_double()
+        L.c6_engine_host_times(e2, C.byref(hw0), C.byref(hc0))
         assert L.c6_engine_timed_waves(e2, cb, waves, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
         L.c6_engine_stats(e2, C.byref(s1))
+        hw1, hc1 = C.c_double(), C.c_double()
+        L.c6_engine_host_times(e2, C.byref(hw1), C.byref(hc1))
         e2e_ms, e2e_sims = float(ms.value), float(s1.sims - s0.sims)
         if dist is not None:
             import torch
@@ -238,7 +242,9 @@ def main():
                       "d2h_bytes_per_step": d2h.value / waves,
                       "step": f"one wave = one simulation for each of {games} games through the C-ABI Callback "
                               f"(host buffers, sample host RandomEvaluator); {waves} waves timed",
-                      "ms_per_wave": e2e_ms / waves}
+                      "ms_per_wave": e2e_ms / waves,
+                      "host_ms_per_wave": {"in_callback": 1e3 * (hc1.value - hc0.value) / waves,
+                                           "blocked_on_gpu": 1e3 * (hw1.value - hw0.value) / waves}}
         L.c6_engine_destroy(e2)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -148,6 +148,8 @@ int c6_engine_timed_steps(c6_engine* e, int steps, float* milliseconds);
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* milliseconds, double* h2d_bytes,
                           double* d2h_bytes);
 int c6_engine_stats(c6_engine* e, c6_stats* out);
+/* callback path, cumulative: seconds the calling thread was blocked on the GPU / spent inside the user Callback */
+int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_seconds);
 int64_t c6_engine_games_done(c6_engine* e);
 int c6_engine_records(c6_engine* e, c6_record* out, int64_t n); /* n = total_games */
 /* child_visits: total_games x 225 x 225 (i32, -1 = occupied / no entry), root_n / root_w: total_games x 225 */
@@ -177,6 +179,9 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
  * (k0, k1); the engine's deterministic f64 log / exp on xs (log only where xs > 0) */
 int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device);
 int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device);
+
+/* pinned host<->device copy bandwidth in GB/s: H2D alone, D2H alone, both at once (per direction) */
+int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs);
 
 /* sample host evaluator (random values/policies), the twin of Connect6/sample/cpp/main.cpp:6-28 */
 void c6_sample_random_callback(int player, float* values, float* policies, int len);
