@@ -13,6 +13,7 @@
 #include "c6_board.cuh"
 #include "c6_engine.cuh"
 #include "c6_rng.cuh"
+#include "connect6_alphazero.hpp"
 #include "connect6_host.hpp"
 
 using namespace c6;
@@ -143,8 +144,37 @@ c6_vec cpp_play(c6_policy_callback callback, c6_alloc_path alloc_path, c6_alloc_
     return out;
 }
 
-c6_play_result cpp_play_with(c6_callback, c6_alloc_path, int, float, double, float) {
-    die("cpp_play_with", "interactive play is not built yet (SURVEY.md §8f rank 3)");
+// MultiPolicy(AlphaZero as Black on the GPU, IoPolicy on stdin as White) under Agent::debug (lib.rs:140-169)
+c6_play_result cpp_play_with(c6_callback callback, c6_alloc_path alloc_path, int num_simulation, float epsilon,
+                             double dirichlet_alpha, float c_puct) {
+    if (!callback) die("cpp_play_with", "null evaluator callback");
+    c6_play_result r;
+    r.winner = 0, r.len = 0, r.paths = nullptr;
+    try {
+        connect6::HyperParameter hp;
+        hp.num_simulation = num_simulation, hp.epsilon = epsilon, hp.dirichlet_alpha = dirichlet_alpha, hp.c_puct = c_puct;
+        connect6::AlphaZero black(std::unique_ptr<connect6::Evaluator>(new connect6::CppEval(callback)), hp, env_seed(),
+                                  env_int("C6_DEVICE", 0), env_int("C6_LOG2_RECORDS", 18));
+        connect6::IoPolicy white(stdin, stdout);
+        connect6::MultiPolicy multi(black, white);
+        connect6::Agent agent(multi, true);
+        connect6::PlayResult res;
+        std::string err = agent.play(res);
+        if (!err.empty()) die("cpp_play_with", err.c_str());
+        r.winner = (int)res.winner;
+        r.len = (int)res.path.size();
+        r.paths = alloc_path(r.len);
+        for (int m = 0; m < r.len; ++m) {
+            c6_path& p = r.paths[m];
+            p.turn = (int)res.path[m].turn;
+            for (int a = 0; a < 15; ++a)
+                for (int b = 0; b < 15; ++b) p.board[a][b] = (int)res.path[m].board[a][b];
+            p.row = (int)res.path[m].pos.first, p.col = (int)res.path[m].pos.second;
+        }
+    } catch (const std::exception& e) {
+        die("cpp_play_with", e.what());
+    }
+    return r;
 }
 
 c6_path test_new_raw_path(void) {  // ffi_test/mod.rs:13-15
@@ -280,6 +310,8 @@ int c6_engine_run_device(c6_engine* e) { C6_TRY(e->eng->run_device_to_end()) }
 int c6_engine_run_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->run_callback_to_end(cb, false)) }
 int c6_engine_sync(c6_engine* e) { C6_TRY(e->eng->sync()) }
 void c6_engine_cancel(c6_engine* e) { e->eng->cancel(); }
+int c6_engine_external_move(c6_engine* e, int slot, int row, int col) { C6_TRY(e->eng->external_move(slot, row, col)) }
+int c6_engine_waves_callback(c6_engine* e, c6_callback cb, int waves) { C6_TRY(e->eng->waves_callback(cb, waves)) }
 int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { C6_TRY(*ms = e->eng->timed_steps_device(steps)) }
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, double* h2d, double* d2h) {
     C6_TRY(*ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h))

@@ -456,6 +456,59 @@ __device__ inline void finish_move(const Dev& D, Warp& w) {
     collect(D, w);
 }
 
+// A stone placed by somebody else (the White side of cpp_play_with, or any caller of AlphaZero::next with
+// a game that moved on): Game::set, then what `init` does on the next search (alphazero_policy/mod.rs:
+// 302-306: the node of the new board is reused with its statistics if the table has it, else created),
+// then the same collection as after an own move.
+__device__ inline void external_move(const Dev& D, Warp& w, uint32_t bit) {
+    GameState& g = *w.gs;
+    const int lane = w.lane;
+    const uint32_t Rm = D.R - 1, Im = D.I - 1;
+    uint32_t B[8], W[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) B[j] = g.B[j], W[j] = g.W[j];
+    const int stones = g.stones;
+    const int turn = turn_of(stones);
+    const uint32_t wj = bit >> 5, m = 1u << (bit & 31);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t mm = (j == (int)wj) ? m : 0u;
+        if (turn < 0) B[j] |= mm; else W[j] |= mm;
+    }
+    const int winner = win_check(B, W);
+    const uint64_t key = g.key ^ w.Z[(turn > 0 ? 256 : 0) + bit];
+    if (g.rec_head - g.rec_tail + 1 > D.R) return set_error(w, D, ERR_REC_FULL);
+    uint32_t root = 0;
+    if (lane == 0) {
+        uint32_t pos = hash_slot(key) & Im;
+        Slot seen = load_slot(&w.idx[pos]);
+        uint32_t val;
+        if (index_find(w.idx, Im, g.epoch, key, pos, seen, val)) {
+            root = val;
+        } else {
+            root = g.rec_head & Rm;
+            g.rec_head += 1;
+            Rec r;
+            r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
+            store_rec(&w.rec[root], r);
+            index_insert(w.idx, Im, g.epoch, key, root, pos, seen);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.B[j] = B[j], g.W[j] = W[j];
+        g.key = key;
+        g.stones = stones + 1;
+        g.moves[g.n_moves] = (uint8_t)cell_of_bit(bit);
+        g.n_moves += 1;
+        g.root = root;
+        g.sims_this_move = 0;
+    }
+    __syncwarp();
+    if (winner != 0) return finish_game(D, w, winner, 1);
+    if (stones + 1 == CELLS) return finish_game(D, w, 0, 1);
+    if (D.max_moves > 0 && g.n_moves >= D.max_moves) return finish_game(D, w, 0, 0);
+    collect(D, w);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace c6

@@ -107,6 +107,14 @@ __global__ void __launch_bounds__(128) k_move_end(Dev D, int g0, int g1) {
     if (w.gs->status == ST_ACTIVE) finish_move(D, w);
 }
 
+// A stone decided outside the engine for the game in `slot` (interactive play, external game drivers).
+__global__ void __launch_bounds__(32) k_external_move(Dev D, int slot, int cell) {
+    __shared__ uint64_t Zs[512];
+    load_zobrist(D, Zs);
+    Warp w = make_warp(D, slot, Zs, threadIdx.x & 31);
+    if (w.gs->status == ST_ACTIVE) external_move(D, w, bit_of_cell(cell));
+}
+
 // Callback path, kernel 1: descend to the leaf and park it in the game state.
 template <int NOISE>
 __global__ void __launch_bounds__(128) k_select(Dev D, int g0, int g1) {
@@ -694,6 +702,22 @@ void Engine::waves_callback(Callback cb, int waves) {
 }
 
 void Engine::wave_callback(Callback cb) { waves_callback(cb, 1); }
+
+void Engine::external_move(int slot, int row, int col) {
+    Dev& D = d_->dev;
+    if (slot < 0 || slot >= D.G || row < 0 || row >= BOARD_SIZE || col < 0 || col >= BOARD_SIZE) throw std::runtime_error("c6: external_move out of range");
+    sync();
+    GameState gs = slot_state(slot);
+    const uint32_t bit = bit_of_cell(row * BOARD_SIZE + col);
+    if (gs.status != ST_ACTIVE) throw std::runtime_error("c6: external_move on a slot without an active game");
+    if (((gs.B[bit >> 5] | gs.W[bit >> 5]) >> (bit & 31)) & 1u) throw std::runtime_error("already set position");
+    for (Group& gr : d_->groups)
+        if (slot >= gr.g0 && slot < gr.g1) gr.waves_this_move = 0;
+    k_external_move<<<1, 32, 0, stream_>>>(D, slot, row * BOARD_SIZE + col);
+    launches_ += 1;
+    C6_CUDA(cudaGetLastError());
+    C6_CUDA(cudaStreamSynchronize(stream_));
+}
 
 void Engine::sync() {
     for (Group& gr : d_->groups)

@@ -123,6 +123,9 @@ class Engine {
     void wave_callback(Callback cb);
     // `waves` simulations for every resident game, pipelined over the groups (see c6_engine.cu)
     void waves_callback(Callback cb, int waves);
+    // A stone chosen outside the engine for the game in `slot` (rules as Game::set; throws "already set
+    // position" like the reference's error text).  The node of the new board is reused if the table has it.
+    void external_move(int slot, int row, int col);
     void sync();
     int64_t games_done();       // synchronises
     bool all_done();            // synchronises

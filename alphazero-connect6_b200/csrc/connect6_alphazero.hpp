@@ -1,0 +1,147 @@
+// Host-side mirror of the reference's search-policy API, served by the GPU engine:
+//   HyperParameter          LC/policy/alphazero_policy/mod.rs:90-125
+//   Evaluator (trait)       LC/policy/alphazero_policy/mod.rs:128-134
+//   AlphaZero: Policy       LC/policy/alphazero_policy/mod.rs:186-209,464-489   (new / with_param / next)
+//   CppEval                 CB/libcppconnect6/src/cppbind/cppeval/mod.rs:8-55
+// `AlphaZero::next(&game)` runs num_simulation searches for that game on the GPU (an engine with one
+// resident game) and returns the chosen position.  Stones that were placed by somebody else since the last
+// call are fed to the engine first, so the tree is reused exactly as the reference's `init` reuses it.
+#pragma once
+#include <array>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "c6_engine.cuh"
+#include "connect6_host.hpp"
+
+namespace connect6 {
+
+struct HyperParameter {
+    int num_simulation = 800;
+    float epsilon = 0.25f;
+    double dirichlet_alpha = 0.03;
+    float c_puct = 1.f;
+    static HyperParameter light_weight() {
+        HyperParameter p;
+        p.num_simulation = 2;
+        return p;
+    }
+};
+
+using FBoard = std::array<std::array<float, BOARD_SIZE>, BOARD_SIZE>;
+
+struct Evaluator {
+    virtual ~Evaluator() {}
+    // None -> the search aborts ("couldn't get value, prob", alphazero_policy/mod.rs:378-380)
+    virtual std::optional<std::pair<std::vector<float>, std::vector<FBoard>>> eval(Player turn, const std::vector<Board>& boards) = 0;
+    // Batched form used by the engine (one call per side to move and wave): boards arrive as len x 225 floats
+    // (-1/0/+1) in `policies`, which is overwritten with the priors.  The default adapts to eval() above.
+    virtual void eval_raw(int player, float* values, float* policies, int len) {
+        std::vector<Board> boards((size_t)len);
+        for (int n = 0; n < len; ++n)
+            for (size_t i = 0; i < BOARD_SIZE; ++i)
+                for (size_t j = 0; j < BOARD_SIZE; ++j) boards[n][i][j] = player_from((int)policies[(size_t)n * BOARD_CAPACITY + i * BOARD_SIZE + j]);
+        auto res = eval(player_from(player), boards);
+        if (!res || (int)res->first.size() != len || (int)res->second.size() != len)
+            throw std::runtime_error("alpha_zero::expand couldn't get value, prob");
+        for (int n = 0; n < len; ++n) {
+            values[n] = res->first[n];
+            for (size_t i = 0; i < BOARD_SIZE; ++i)
+                for (size_t j = 0; j < BOARD_SIZE; ++j) policies[(size_t)n * BOARD_CAPACITY + i * BOARD_SIZE + j] = res->second[n][i][j];
+        }
+    }
+};
+
+using Callback = void (*)(int player, float* values, float* policies, int len);
+class CppEval : public Evaluator {
+   public:
+    explicit CppEval(Callback cb) : cb_(cb) {}
+    std::optional<std::pair<std::vector<float>, std::vector<FBoard>>> eval(Player turn, const std::vector<Board>& boards) override {
+        const int len = (int)boards.size();
+        std::vector<float> values((size_t)len, 0.f);
+        std::vector<FBoard> pol((size_t)len);
+        for (int n = 0; n < len; ++n)
+            for (size_t i = 0; i < BOARD_SIZE; ++i)
+                for (size_t j = 0; j < BOARD_SIZE; ++j) pol[n][i][j] = (float)(int)boards[n][i][j];
+        cb_((int)turn, values.data(), len ? &pol[0][0][0] : nullptr, len);
+        return std::make_pair(std::move(values), std::move(pol));
+    }
+    void eval_raw(int player, float* values, float* policies, int len) override { cb_(player, values, policies, len); }
+
+   private:
+    Callback cb_;
+};
+
+class AlphaZero : public Policy {
+   public:
+    explicit AlphaZero(std::unique_ptr<Evaluator> evaluator) : AlphaZero(std::move(evaluator), HyperParameter()) {}  // AlphaZero::new
+    AlphaZero(std::unique_ptr<Evaluator> evaluator, HyperParameter param, uint32_t seed = 0xC6, int device = 0, int log2_records = 18)
+        : evaluator_(std::move(evaluator)), param_(param) {  // AlphaZero::with_param
+        c6::Config cfg;
+        cfg.num_simulation = param.num_simulation, cfg.epsilon = param.epsilon, cfg.dirichlet_alpha = param.dirichlet_alpha;
+        cfg.c_puct = param.c_puct, cfg.seed = seed, cfg.device = device, cfg.slots = 1, cfg.log2_records = log2_records;
+        cfg.evaluator = c6::EVAL_CALLBACK;
+        engine_.reset(new c6::Engine(cfg));
+        for (auto& r : seen_) r.fill(Player::None);
+    }
+
+    std::optional<Pos> next(const Game& game) override {
+        if (!started_) {
+            engine_->start(0, 1);
+            started_ = true;
+        }
+        // stones the engine has not seen yet (placed by another policy): Game::set order within one colour
+        // does not matter for the tree, colours follow the stone count
+        const Board& b = game.get_board();
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t i = 0; i < BOARD_SIZE; ++i)
+                for (size_t j = 0; j < BOARD_SIZE; ++j)
+                    if (b[i][j] != seen_[i][j]) {
+                        if (seen_[i][j] != Player::None) throw std::runtime_error("AlphaZero::next: the game went backwards");
+                        if ((int)b[i][j] != c6::turn_of(stones_)) continue;  // the other colour's stone comes first
+                        engine_->external_move(0, (int)i, (int)j);
+                        seen_[i][j] = b[i][j];
+                        stones_ += 1;
+                    }
+        for (size_t i = 0; i < BOARD_SIZE; ++i)
+            for (size_t j = 0; j < BOARD_SIZE; ++j)
+                if (b[i][j] != seen_[i][j]) throw std::runtime_error("AlphaZero::next: board does not follow the turn rule");
+        c6::GameState before = engine_->slot_state(0);
+        if (before.status != c6::ST_ACTIVE) return std::nullopt;
+        current() = evaluator_.get();
+        engine_->waves_callback(&AlphaZero::trampoline, std::max(param_.num_simulation, 1));
+        current() = nullptr;
+        std::vector<c6::GameRecord> rec;
+        c6::GameState after = engine_->slot_state(0);
+        int n_moves = after.n_moves;
+        const uint8_t* moves = after.moves;
+        if (after.status != c6::ST_ACTIVE) {  // the game ended with this stone: the slot was retired, the record has it
+            rec = engine_->records();
+            n_moves = rec[0].n_moves, moves = rec[0].moves;
+        }
+        if (n_moves <= stones_) return std::nullopt;  // no children: policy() -> None (:433-452)
+        const int cell = moves[n_moves - 1];
+        seen_[cell / 15][cell % 15] = player_from(c6::turn_of(stones_));
+        stones_ += 1;
+        return Pos((size_t)(cell / 15), (size_t)(cell % 15));
+    }
+
+    c6::Engine& engine() { return *engine_; }
+
+   private:
+    static Evaluator*& current() {
+        static thread_local Evaluator* e = nullptr;
+        return e;
+    }
+    static void trampoline(int player, float* values, float* policies, int len) { current()->eval_raw(player, values, policies, len); }
+
+    std::unique_ptr<Evaluator> evaluator_;
+    HyperParameter param_;
+    std::unique_ptr<c6::Engine> engine_;
+    Board seen_;
+    int stones_ = 0;
+    bool started_ = false;
+};
+
+}  // namespace connect6

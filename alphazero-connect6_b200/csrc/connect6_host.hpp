@@ -114,6 +114,51 @@ class CppPolicy : public Policy {
     PolicyCallback cb_;
 };
 
+// LC/policy/multi_policy/mod.rs:61-71 — one policy per colour
+class MultiPolicy : public Policy {
+   public:
+    MultiPolicy(Policy& black, Policy& white) : black_(black), white_(white) {}
+    std::optional<Pos> next(const Game& game) override {
+        return game.get_turn() == Player::Black ? black_.next(game) : white_.next(game);
+    }
+
+   private:
+    Policy &black_, &white_;
+};
+
+// LC/policy/io_policy/mod.rs:68-107 — a move typed as "aB" (row 'a'.., column 'A'..): up to 10 bytes per read, the
+// alphabetic characters must be exactly two and in range, else "invalid input, retry".  End of input returns
+// no move (the reference would spin on an exhausted reader).
+class IoPolicy : public Policy {
+   public:
+    IoPolicy(FILE* in, FILE* out) : in_(in), out_(out) {}
+    std::optional<Pos> next(const Game&) override {
+        for (;;) {
+            char buf[10];
+            size_t got = 0;
+            int c;
+            while (got < sizeof buf && (c = std::fgetc(in_)) != EOF) {  // one line-buffered read() of at most 10 bytes
+                buf[got++] = (char)c;
+                if (c == '\n') break;
+            }
+            if (got == 0) return std::nullopt;
+            char q[10];
+            size_t n = 0;
+            for (size_t i = 0; i < got; ++i)
+                if ((buf[i] >= 'a' && buf[i] <= 'z') || (buf[i] >= 'A' && buf[i] <= 'Z')) q[n++] = buf[i];
+            if (n == 2) {
+                size_t row = (size_t)(unsigned char)q[0] - 0x61, col = (size_t)(unsigned char)q[1] - 0x41;  // wraps like usize
+                if (row < BOARD_SIZE && col < BOARD_SIZE) return Pos(row, col);
+            }
+            std::fputs("invalid input, retry\n", out_);
+            std::fflush(out_);
+        }
+    }
+
+   private:
+    FILE *in_, *out_;
+};
+
 struct Path {
     Player turn;
     Board board;

@@ -97,6 +97,8 @@ def product():
         L.c6_engine_start.argtypes = [C.c_void_p, C.c_uint32, C.c_int64]
         L.c6_engine_step_device.argtypes = [C.c_void_p]
         L.c6_engine_wave_callback.argtypes = [C.c_void_p, CALLBACK]
+        L.c6_engine_waves_callback.argtypes = [C.c_void_p, CALLBACK, C.c_int]
+        L.c6_engine_external_move.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.c6_engine_run_device.argtypes = [C.c_void_p]
         L.c6_engine_run_callback.argtypes = [C.c_void_p, CALLBACK]
         L.c6_engine_sync.argtypes = [C.c_void_p]

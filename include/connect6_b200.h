@@ -139,6 +139,10 @@ void c6_engine_destroy(c6_engine* e);
 int c6_engine_start(c6_engine* e, uint32_t first_game_id, int64_t total_games);
 int c6_engine_step_device(c6_engine* e);                  /* one move for every resident game, async */
 int c6_engine_wave_callback(c6_engine* e, c6_callback cb); /* one simulation for every resident game */
+int c6_engine_waves_callback(c6_engine* e, c6_callback cb, int waves); /* `waves` simulations per game, pipelined */
+/* a stone chosen outside the engine for the game in `slot` (Game::set rules; the node of the new board is
+ * reused if the table has it, as AlphaZero::init does, alphazero_policy/mod.rs:302-306) */
+int c6_engine_external_move(c6_engine* e, int slot, int row, int col);
 int c6_engine_run_device(c6_engine* e);                   /* until all games are finished */
 int c6_engine_run_callback(c6_engine* e, c6_callback cb);
 int c6_engine_sync(c6_engine* e);

@@ -264,6 +264,40 @@ double oracle_self_play_many(Callback cb, const OracleParams* p, uint32_t first_
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// MultiPolicy(AlphaZero as Black, scripted White) under Agent::play — the shape of cpp_play_with
+// (cppbind/libcppconnect6/src/lib.rs:140-169, policy/multi_policy/mod.rs:61-71) with the stdin policy
+// replaced by a move list.  White running out of moves ends the game (next() -> None).
+void oracle_play_with(Callback cb, const OracleParams* p, uint32_t game_id, const int* white_moves, int n_white,
+                      OracleGameOut* out) {
+    HyperParameter hp;
+    hp.num_simulation = p->num_simulation, hp.epsilon = p->epsilon, hp.dirichlet_alpha = p->dirichlet_alpha, hp.c_puct = p->c_puct;
+    std::unique_ptr<Evaluator> ev;
+    if (p->evaluator == 1)
+        ev.reset(new PhiloxRandomEvaluator());
+    else
+        ev.reset(new CppEval(cb));
+    AlphaZeroPolicy black(ev.get(), hp);
+    black.az.tie = TieBreak::LowestIndex;
+    black.az.noise = p->noise_mode ? NoiseMode::Philox : NoiseMode::None;
+    black.az.faithful = p->faithful != 0;
+    black.az.ctx.seed = p->seed, black.az.ctx.game_id = game_id;
+    ScriptPolicy white(white_moves, n_white);
+    struct Multi : Policy {
+        Policy &b, &w;
+        Multi(Policy& b_, Policy& w_) : b(b_), w(w_) {}
+        std::optional<Pos> next(const Game& g) override { return g.turn == Player::Black ? b.next(g) : w.next(g); }
+    } multi(black, white);
+    PlayResult r = agent_play(multi);
+    out->winner = (int)r.winner, out->n_moves = (int)r.path.size(), out->finished = r.error.empty() ? 1 : 0;
+    for (size_t k = 0; k < r.path.size(); ++k) {
+        out->moves[k] = r.path[k].pos.first * BOARD_SIZE + r.path[k].pos.second;
+        out->turns[k] = (int)r.path[k].turn;
+    }
+    const SearchStats& st = black.az.stats;
+    out->sims = st.sims, out->sum_ck = st.sum_ck, out->sum_cleaf = st.sum_cleaf, out->sum_depth = st.sum_depth, out->evals = st.evals,
+    out->max_nodes = st.max_nodes;
+}
+
 int oracle_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 // 16M-board style batch win check (config 3a): boards as int8 [n][225]

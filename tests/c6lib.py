@@ -66,6 +66,7 @@ def oracle():
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.oracle_self_play_many.restype = C.c_double
         L.oracle_self_play_many.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.c_int, C.c_int, C.POINTER(OracleGameOut)]
+        L.oracle_play_with.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(OracleGameOut)]
         L.oracle_search_batch.argtypes = [C.POINTER(C.c_int8), C.c_int64, C.POINTER(C.c_int8), C.c_int]
         _oracle = L
     return _oracle

@@ -454,3 +454,53 @@ def test_callback_pipeline_groups_do_not_change_results(pipeline, monkeypatch):
                                      evaluator=EVAL_CALLBACK, max_moves=14)
     compare_games(n, rec, cv, rn, rw, 300, "neg_eval_callback", 0, sims, eps, seed, 14)
     assert st.games_done == n
+
+
+def test_cpp_play_with_matches_oracle():
+    """cpp_play_with (connect6.hpp:60-65): AlphaZero as Black on the GPU against White moves typed on stdin.
+    The tree must be reused across White's stones exactly as the reference's `init` reuses it; checked against
+    the oracle's MultiPolicy(AlphaZero, scripted White) with the same evaluator, seed and tie-break."""
+    import subprocess
+    import sys
+    white = [(14, 0), (14, 2), (13, 5), (12, 9), (14, 14), (11, 1), (13, 13), (10, 10), (14, 7), (12, 3)]
+    sims, eps, seed = 24, 0.25, 4242
+    O = c6lib.oracle()
+    p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1, 0, 0, 0, 0)
+    out = c6lib.OracleGameOut()
+    wm = (C.c_int * (2 * len(white)))(*[x for m in white for x in m])
+    O.oracle_play_with(c6lib.oracle_callback("neg_eval_callback"), C.byref(p), 0, wm, len(white), C.byref(out))
+    assert out.finished == 1  # the script does not collide with Black's stones
+    want = [out.moves[i] for i in range(out.n_moves)]
+    code = (
+        "import ctypes as C, c6lib\n"
+        "L = c6lib.product()\n"
+        "L.cpp_play_with.restype = c6lib.PlayResult\n"
+        "L.cpp_play_with.argtypes = [c6lib.CALLBACK, c6lib.ALLOC_PATH, C.c_int, C.c_float, C.c_double, C.c_float]\n"
+        "cb = c6lib.CALLBACK(c6lib.oracle_callback('neg_eval_callback'))\n"
+        f"r = L.cpp_play_with(cb, c6lib.alloc_path, {sims}, {eps}, 0.03, 1.0)\n"
+        "import sys; sys.stdout.flush()\n"
+        "print('RESULT', r.winner, ' '.join(str(r.paths[i].row * 15 + r.paths[i].col) for i in range(r.len)))\n"
+    )
+    stdin = "zz\n" + "".join(f"{chr(0x61 + r)}{chr(0x41 + c)}\n" for r, c in white)  # first line is rejected: "invalid input, retry"
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.abspath(__file__)), C6_SEED=str(seed))
+    r = subprocess.run([sys.executable, "-c", code], input=stdin, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert int(line[1]) == out.winner
+    assert [int(x) for x in line[2:]] == want
+    assert "invalid input, retry" in r.stdout and "0 A B C D E F G H I J K L M N O" in r.stdout  # IoPolicy + Agent::debug transcript
+
+
+def test_host_alphazero_policy_single_game_equals_batched_engine():
+    """cpp_self_play with one game (the reference's n == 1 path) and with several give the same game 0."""
+    L = c6lib.product()
+    os.environ["C6_SEED"] = "77"
+    try:
+        cb = c6lib.CALLBACK(c6lib.oracle_callback("det_eval_callback"))
+        one = L.cpp_self_play(cb, c6lib.alloc_path, c6lib.alloc_result, 5, 0.25, 0.03, 1.0, False, 1)
+        many = L.cpp_self_play(cb, c6lib.alloc_path, c6lib.alloc_result, 5, 0.25, 0.03, 1.0, False, 3)
+    finally:
+        del os.environ["C6_SEED"]
+    a, b = one.vec[0], many.vec[0]
+    assert (a.winner, a.len) == (b.winner, b.len)
+    assert all((a.paths[i].row, a.paths[i].col) == (b.paths[i].row, b.paths[i].col) for i in range(a.len))
