@@ -258,3 +258,25 @@ def build_reference_catch2():
            "-L", os.path.dirname(c6lib.LIB_PATH), "-lcppconnect6", "-Wl,-rpath,$ORIGIN/../../alphazero-connect6_b200/lib", "-pthread", "-ldl"]
     subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
     return exe
+
+
+SAMPLE_EXE = os.path.join(ROOT, "tests", "_build", "sample_cpp")
+
+
+def build_reference_sample():
+    """Connect6/sample/cpp/main.cpp (config 1 of BASELINE.json in its C++ form), compiled in place against the
+    reference's header and linked with our library."""
+    ref = "/root/reference"
+    os.makedirs(os.path.dirname(SAMPLE_EXE), exist_ok=True)
+    if os.path.exists(SAMPLE_EXE) and os.path.getmtime(SAMPLE_EXE) >= os.path.getmtime(c6lib.LIB_PATH):
+        return SAMPLE_EXE
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ref, "Connect6/cppbind/headers"), os.path.join(ref, "Connect6/sample/cpp/main.cpp"),
+           "-o", SAMPLE_EXE, "-L", os.path.dirname(c6lib.LIB_PATH), "-lcppconnect6", "-Wl,-rpath,$ORIGIN/../../alphazero-connect6_b200/lib",
+           "-pthread", "-ldl"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
+    return SAMPLE_EXE
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6/sample/cpp"), reason="reference tree not mounted")
+def test_reference_cpp_sample_links_against_our_library():
+    assert os.path.exists(build_reference_sample())

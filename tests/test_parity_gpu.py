@@ -462,7 +462,7 @@ def test_cpp_play_with_matches_oracle():
     the oracle's MultiPolicy(AlphaZero, scripted White) with the same evaluator, seed and tie-break."""
     import subprocess
     import sys
-    white = [(14, 0), (14, 2), (13, 5), (12, 9), (14, 14), (11, 1), (13, 13), (10, 10), (14, 7), (12, 3)]
+    white = [(2, 4), (9, 10), (14, 6), (13, 10), (13, 0), (1, 1), (4, 5), (2, 0), (8, 6), (12, 14)]  # collides with no Black stone (checked below)
     sims, eps, seed = 24, 0.25, 4242
     O = c6lib.oracle()
     p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1, 0, 0, 0, 0)
@@ -504,3 +504,16 @@ def test_host_alphazero_policy_single_game_equals_batched_engine():
     a, b = one.vec[0], many.vec[0]
     assert (a.winner, a.len) == (b.winner, b.len)
     assert all((a.paths[i].row, a.paths[i].col) == (b.paths[i].row, b.paths[i].col) for i in range(a.len))
+
+
+def test_reference_cpp_sample_runs():
+    """Connect6/sample/cpp/main.cpp unchanged (BASELINE configs[0] in its C++ form: one game, random evaluator,
+    2 simulations, debug transcript), prebuilt by build() against the reference's header."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "sample_cpp")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/sample_cpp not prebuilt (reference tree was not mounted at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Winner : " in r.stdout and "0 A B C D E F G H I J K L M N O" in r.stdout
+    assert any(l.startswith(("Black (", "White (")) and "remain" in l for l in r.stdout.splitlines())
