@@ -6,7 +6,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <random>
+#include <string>
+#include <thread>
+#include <vector>
 #include <stdexcept>
 
 #include "../../include/connect6_b200.h"
@@ -62,6 +66,58 @@ static c6_play_result expand_record(const GameRecord& r, c6_alloc_path alloc) {
     return out;
 }
 
+// C6_DEVICES = "0,1,2,3" | "all": shard the games of one cpp_self_play call over several GPUs of the box by
+// game id (one host thread + engine per GPU, no exchange between them).  Default: one GPU
+// (C6_DEVICE), callbacks from the calling thread only.
+static std::vector<int> env_devices() {
+    std::vector<int> devs;
+    const char* v = std::getenv("C6_DEVICES");
+    if (!v || !*v) return {env_int("C6_DEVICE", 0)};
+    if (std::string(v) == "all") {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) n = 1;
+        for (int i = 0; i < n; ++i) devs.push_back(i);
+        return devs;
+    }
+    for (const char* q = v; *q;) {
+        char* end = nullptr;
+        long d = std::strtol(q, &end, 10);
+        if (end == q) break;
+        devs.push_back((int)d);
+        q = (*end == ',') ? end + 1 : end;
+    }
+    if (devs.empty()) devs.push_back(0);
+    return devs;
+}
+
+// contiguous block of game ids for shard r of w: sizes differ by at most one (pyconnect6.sharded.shard_range)
+static void shard_range(int64_t n, int r, int w, int64_t& lo, int64_t& cnt) {
+    const int64_t base = n / w, extra = n % w;
+    lo = r * base + std::min<int64_t>(r, extra);
+    cnt = base + (r < extra ? 1 : 0);
+}
+
+template <class Run>  // Run(device, first_id, count, GameRecord* out) on one thread per shard; rethrows the first failure
+static void run_sharded(const std::vector<int>& devices, uint32_t first, int64_t n, GameRecord* out, Run&& run) {
+    const int w = (int)std::min<int64_t>((int64_t)devices.size(), std::max<int64_t>(n, 1));
+    if (w <= 1) return run(devices[0], first, n, out);
+    std::vector<std::thread> th;
+    std::vector<std::string> errs((size_t)w);
+    for (int r = 0; r < w; ++r)
+        th.emplace_back([&, r] {
+            int64_t lo, cnt;
+            shard_range(n, r, w, lo, cnt);
+            try {
+                if (cnt > 0) run(devices[r], first + (uint32_t)lo, cnt, out + lo);
+            } catch (const std::exception& e) {
+                errs[r] = e.what();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+}
+
 static void print_game_debug(const GameRecord& r) {
     // Agent::debug transcript (agent_impl/mod.rs:127-129,147-161,173-175); per-move time is not
     // observable for a batched search, printed as 0.0.
@@ -91,18 +147,24 @@ c6_vec cpp_self_play(c6_callback callback, c6_alloc_path alloc_path, c6_alloc_re
     out.vec = alloc_result(out.len);
     if (n <= 0) return out;
     try {
-        Config cfg;
-        cfg.num_simulation = num_simulation, cfg.epsilon = epsilon, cfg.dirichlet_alpha = dirichlet_alpha, cfg.c_puct = c_puct;
-        cfg.seed = env_seed();
-        cfg.device = env_int("C6_DEVICE", 0);
-        cfg.slots = std::min(n, env_int("C6_MAX_CONCURRENT", 8192));
-        cfg.log2_records = env_int("C6_LOG2_RECORDS", 18);
-        cfg.evaluator = EVAL_CALLBACK;
-        Engine eng(cfg);
+        Config base;
+        base.num_simulation = num_simulation, base.epsilon = epsilon, base.dirichlet_alpha = dirichlet_alpha, base.c_puct = c_puct;
+        base.seed = env_seed();
+        base.log2_records = env_int("C6_LOG2_RECORDS", 18);
+        base.evaluator = EVAL_CALLBACK;
+        const int max_conc = env_int("C6_MAX_CONCURRENT", 8192);
+        std::vector<GameRecord> rec((size_t)n);
         auto t0 = std::chrono::steady_clock::now();
-        eng.start(0, n);
-        eng.run_callback_to_end(callback, debug);
-        std::vector<GameRecord> rec = eng.records();
+        run_sharded(env_devices(), 0, n, rec.data(), [&](int device, uint32_t first, int64_t cnt, GameRecord* dst) {
+            Config cfg = base;
+            cfg.device = device;
+            cfg.slots = (int)std::min<int64_t>(cnt, max_conc);
+            Engine eng(cfg);
+            eng.start(first, cnt);
+            eng.run_callback_to_end(callback, debug);
+            std::vector<GameRecord> r = eng.records();
+            std::copy(r.begin(), r.end(), dst);
+        });
         double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         for (int i = 0; i < n; ++i) {
             if (debug && n == 1) print_game_debug(rec[i]);
@@ -306,6 +368,10 @@ void c6_engine_destroy(c6_engine* e) { delete e; }
 int c6_engine_start(c6_engine* e, uint32_t first, int64_t total) { C6_TRY(e->total = total; e->eng->start(first, total)) }
 int c6_engine_step_device(c6_engine* e) { C6_TRY(e->eng->step_device()) }
 int c6_engine_wave_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->wave_callback(cb)) }
+int c6_engine_waves_device_callback(c6_engine* e, c6_device_callback cb, void* user, int waves) {
+    C6_TRY(e->eng->waves_device_callback(cb, user, waves))
+}
+int c6_engine_run_device_callback(c6_engine* e, c6_device_callback cb, void* user) { C6_TRY(e->eng->run_device_callback_to_end(cb, user)) }
 int c6_engine_run_device(c6_engine* e) { C6_TRY(e->eng->run_device_to_end()) }
 int c6_engine_run_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->run_callback_to_end(cb, false)) }
 int c6_engine_sync(c6_engine* e) { C6_TRY(e->eng->sync()) }
@@ -367,6 +433,30 @@ int c6_self_play_device(const c6_config* cfg, uint32_t first, int64_t n_games, c
     if (!rc && stats) rc = c6_engine_stats(e, stats);
     c6_engine_destroy(e);
     return rc;
+}
+
+// n_games of self-play with a device evaluator, sharded by game id over `devices` (one host thread + engine per GPU)
+int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_devices, uint32_t first, int64_t n_games,
+                                c6_record* out, c6_stats* stats) {
+    C6_TRY(std::vector<int> devs(devices, devices + std::max(n_devices, 0)); if (devs.empty()) devs.push_back(cfg->device);
+           std::vector<GameRecord> rec((size_t)std::max<int64_t>(n_games, 0)); std::mutex m; c6_stats tot; std::memset(&tot, 0, sizeof tot);
+           run_sharded(devs, first, n_games, rec.data(), [&](int device, uint32_t f, int64_t cnt, GameRecord* dst) {
+               Config c = to_config(cfg);
+               c.device = device;
+               c.slots = (int)std::min<int64_t>(std::max<int64_t>(cnt, 1), cfg->slots > 0 ? cfg->slots : cnt);
+               Engine eng(c);
+               eng.start(f, cnt);
+               eng.run_device_to_end();
+               std::vector<GameRecord> r = eng.records();
+               std::copy(r.begin(), r.end(), dst);
+               Stats s = eng.stats();
+               std::lock_guard<std::mutex> l(m);
+               tot.sims += s.sims, tot.sum_ck += s.sum_ck, tot.sum_cleaf += s.sum_cleaf, tot.sum_depth += s.sum_depth, tot.evals += s.evals;
+               tot.gc_copied += s.gc_copied, tot.games_done += s.games_done, tot.kernel_launches += (uint64_t)eng.kernel_launches();
+               tot.peak_rec = std::max(tot.peak_rec, s.peak_rec), tot.peak_lnk = std::max(tot.peak_lnk, s.peak_lnk);
+               tot.bytes_per_game = eng.bytes_per_game();
+           });
+           if (out && n_games > 0) std::memcpy(out, rec.data(), (size_t)n_games * sizeof(GameRecord)); if (stats) *stats = tot)
 }
 
 #define CK(call)                                                                  \

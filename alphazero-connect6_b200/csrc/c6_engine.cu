@@ -433,7 +433,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     C6_CUDA(cudaMalloc(&D.cursor, sizeof(int)));
     C6_CUDA(cudaMalloc(&D.gcount, 4 * sizeof(unsigned long long)));
     int n_groups = 1;
-    if (cfg_.evaluator == EVAL_CALLBACK) {
+    if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
         // pipeline depth of the callback path: while the host evaluates one group, the others run their
         // kernels and copies.  Small batches are not worth splitting.
         const char* pe = std::getenv("C6_PIPELINE");
@@ -456,12 +456,14 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         C6_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming));
     }
     C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
-    if (cfg_.evaluator == EVAL_CALLBACK) {
+    if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
         size_t nb = G * 8 * CELLS * sizeof(float), nv = G * 8 * sizeof(float);
         C6_CUDA(cudaMalloc(&D.bboards, nb));
         C6_CUDA(cudaMalloc(&D.bvalues, nv));
-        C6_CUDA(cudaMallocHost(&d_->h_boards, nb));
-        C6_CUDA(cudaMallocHost(&d_->h_values, nv));
+        if (cfg_.evaluator == EVAL_CALLBACK) {
+            C6_CUDA(cudaMallocHost(&d_->h_boards, nb));
+            C6_CUDA(cudaMallocHost(&d_->h_values, nv));
+        }
     }
     cudaDeviceProp prop;
     C6_CUDA(cudaGetDeviceProperties(&prop, cfg_.device));
@@ -532,7 +534,7 @@ static SimKernel sim_kernel(int evaluator, int noise) {
 
 void Engine::step_device() {
     Dev& D = d_->dev;
-    if (cfg_.evaluator == EVAL_CALLBACK) throw std::runtime_error("c6: step_device needs a device evaluator");
+    if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) throw std::runtime_error("c6: step_device needs a built-in device evaluator");
     const SimKernel kern = sim_kernel(cfg_.evaluator, noise_mode(cfg_));
     if (d_->persistent_blocks == 0) {
         int per_sm = 0;
@@ -623,7 +625,7 @@ void Engine::group_front(int p) {
         // Nearly every resident game needs an evaluation in a wave, so the whole region of the group is
         // copied without waiting for the count; when most slots are idle (tail of a run) the copy
         // waits for the exact count instead.
-        gr.exact = gr.last_count >= 0 && gr.last_count < n / 2;
+        gr.exact = (gr.last_count >= 0 && gr.last_count < n / 2) || cfg_.evaluator == EVAL_DEVICE_CALLBACK;  // device evaluator: counts only
         if (!gr.exact && use_graphs_) {
             if (!gr.front_graph) build_graphs(p);
             C6_CUDA(cudaGraphLaunch(gr.front_graph, gr.s));
@@ -657,6 +659,21 @@ void Engine::group_back(int p, Callback cb) {
     const int nB = gr.h_counts[0], nW = gr.h_counts[1];
     const size_t len = (size_t)(nB + nW) * 8, off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
     gr.last_count = nB + nW;
+    if (cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
+        if (len) {
+            float* db = D.bboards + off;
+            float* dv = D.bvalues + voff;  // zeroed by k_gather
+            const double t2 = now_s();
+            if (nB) dcb_(-1, dv, db, nB * 8, (void*)gr.s, dcb_user_);
+            if (nW) dcb_(1, dv + (size_t)nB * 8, db + (size_t)nB * 8 * CELLS, nW * 8, (void*)gr.s, dcb_user_);
+            host_callback_s_ += now_s() - t2;
+        }
+        const bool move_end = gr.waves_this_move + 1 >= cfg_.num_simulation;
+        gr.waves_this_move = move_end ? 0 : gr.waves_this_move + 1;
+        back_ops(p, 0, move_end);
+        launches_ += move_end ? 2 : 1;
+        return;
+    }
     if (len) {
         if (gr.exact) {
             C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, len * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
@@ -702,6 +719,28 @@ void Engine::waves_callback(Callback cb, int waves) {
 }
 
 void Engine::wave_callback(Callback cb) { waves_callback(cb, 1); }
+
+void Engine::waves_device_callback(DeviceCallback cb, void* user, int waves) {
+    if (cfg_.evaluator != EVAL_DEVICE_CALLBACK) throw std::runtime_error("c6: engine was not created for the device-callback path");
+    dcb_ = cb, dcb_user_ = user;
+    const int P = (int)d_->groups.size();
+    if (waves <= 0) return;
+    for (int p = 0; p < P; ++p) group_front(p);
+    for (int wv = 0; wv < waves; ++wv)
+        for (int p = 0; p < P; ++p) {
+            group_back(p, nullptr);
+            if (wv + 1 < waves) group_front(p);
+            if (cancel_.load()) {
+                sync();
+                throw std::runtime_error("c6: cancelled");
+            }
+        }
+}
+
+void Engine::run_device_callback_to_end(DeviceCallback cb, void* user) {
+    const int per_move = std::max(cfg_.num_simulation, 1);
+    while (!all_done()) waves_device_callback(cb, user, per_move);
+}
 
 void Engine::external_move(int slot, int row, int col) {
     Dev& D = d_->dev;

@@ -39,7 +39,7 @@ struct __align__(16) Slot {
 
 enum Status : int32_t { ST_IDLE = 0, ST_ACTIVE = 1, ST_DONE = 2, ST_ERROR = 3 };
 enum ErrCode : int32_t { ERR_NONE = 0, ERR_REC_FULL = 1, ERR_LNK_FULL = 2, ERR_EXP_FULL = 3 };
-enum EvalKind : int32_t { EVAL_CALLBACK = 0, EVAL_PHILOX = 1, EVAL_DET = 2, EVAL_NEG = 3 };
+enum EvalKind : int32_t { EVAL_CALLBACK = 0, EVAL_PHILOX = 1, EVAL_DET = 2, EVAL_NEG = 3, EVAL_DEVICE_CALLBACK = 4 };
 
 struct GameState {
     uint32_t B[8], W[8];  // root bitboards: bit 16*row+col, bit 15 of every row is a zero guard
@@ -103,6 +103,10 @@ struct Stats {
 };
 
 using Callback = void (*)(int player, float* values, float* policies, int len);
+// The same contract with DEVICE pointers: the leaf batch stays in HBM (API layout float[len][15][15] in
+// `d_policies`, overwritten with the priors; `d_values` pre-zeroed), `stream` is the CUDA stream the engine's
+// kernels of this group are ordered on — the evaluator enqueues its work there (or synchronises itself).
+using DeviceCallback = void (*)(int player, float* d_values, float* d_policies, int len, void* stream, void* user);
 
 struct DeviceArrays;  // opaque (engine .cu)
 
@@ -123,6 +127,9 @@ class Engine {
     void wave_callback(Callback cb);
     // `waves` simulations for every resident game, pipelined over the groups (see c6_engine.cu)
     void waves_callback(Callback cb, int waves);
+    // device-pointer evaluator (engine created with EVAL_DEVICE_CALLBACK): no host copies of the batch
+    void waves_device_callback(DeviceCallback cb, void* user, int waves);
+    void run_device_callback_to_end(DeviceCallback cb, void* user);
     // A stone chosen outside the engine for the game in `slot` (rules as Game::set; throws "already set
     // position" like the reference's error text).  The node of the new board is reused if the table has it.
     void external_move(int slot, int row, int col);
@@ -160,6 +167,8 @@ class Engine {
     void back_ops(int p, size_t len, bool move_end);
     void build_graphs(int p);
     void drop_graphs();
+    DeviceCallback dcb_ = nullptr;
+    void* dcb_user_ = nullptr;
     bool use_graphs_ = false;  // C6_GRAPHS=1: measured no gain over plain launches on the B200 box (profiles/e2e4)
     Config cfg_;
     DeviceArrays* d_ = nullptr;

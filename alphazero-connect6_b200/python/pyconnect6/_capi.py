@@ -53,7 +53,8 @@ class Stats(C.Structure):
                [("peak_rec", C.c_uint32), ("peak_lnk", C.c_uint32), ("kernel_launches", C.c_uint64), ("bytes_per_game", C.c_uint64)]
 
 
-EVAL_CALLBACK, EVAL_PHILOX, EVAL_DET, EVAL_NEG = 0, 1, 2, 3
+EVAL_CALLBACK, EVAL_PHILOX, EVAL_DET, EVAL_NEG, EVAL_DEVICE_CALLBACK = 0, 1, 2, 3, 4
+DEVICE_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 
 # symbols of the reference ABI (connect6.hpp:44-91)
 REFERENCE_SYMBOLS = ["cpp_play", "cpp_self_play", "cpp_play_with", "test_new_raw_path", "test_with_raw_path",
@@ -99,6 +100,8 @@ def product():
         L.c6_engine_wave_callback.argtypes = [C.c_void_p, CALLBACK]
         L.c6_engine_waves_callback.argtypes = [C.c_void_p, CALLBACK, C.c_int]
         L.c6_engine_external_move.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.c6_engine_waves_device_callback.argtypes = [C.c_void_p, DEVICE_CALLBACK, C.c_void_p, C.c_int]
+        L.c6_engine_run_device_callback.argtypes = [C.c_void_p, DEVICE_CALLBACK, C.c_void_p]
         L.c6_engine_run_device.argtypes = [C.c_void_p]
         L.c6_engine_run_callback.argtypes = [C.c_void_p, CALLBACK]
         L.c6_engine_sync.argtypes = [C.c_void_p]
@@ -115,6 +118,7 @@ def product():
         L.c6_engine_validate.restype = C.c_longlong
         L.c6_engine_validate.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.c6_self_play_device.argtypes = [C.POINTER(Config), C.c_uint32, C.c_int64, C.POINTER(Record), C.POINTER(Stats)]
+        L.c6_self_play_device_sharded.argtypes = [C.POINTER(Config), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.c_int64, C.POINTER(Record), C.POINTER(Stats)]
         L.c6_win_check_host.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_int64, C.c_int]
         L.c6_bench_win_check.argtypes = [C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_int64]
         L.c6_bench_playouts.argtypes = [C.c_int64, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int8),

@@ -89,7 +89,7 @@ def algorithmic_bytes(st0, st1, materialised_batch):
 def run_reference(args, rank, world):
     """--impl reference: the restated reference (oracle, reference cost model) on the host cores."""
     if rank != 0:
-        return
+        return None
     import c6lib
     O = c6lib.oracle()
     cores = O.oracle_hardware_concurrency()
@@ -106,7 +106,7 @@ def run_reference(args, rank, world):
         sims += sum(o.sims for o in outs)
     v = sims / secs
     sample = f"{args.steps} x ({cores} games x first {moves} stones x {SIMS} sims), one OS thread per game"
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -114,7 +114,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def workload_config(n_gpus):
@@ -126,7 +126,30 @@ def workload_config(n_gpus):
             "l2": "working set >> L2 (node pool of 4096 games is tens of GB); no flush needed"}
 
 
+class StdoutToStderr:
+    """Everything written to fd 1 while the benchmark runs (NCCL's version banner, library chatter) goes to
+    stderr, so that stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
+    with StdoutToStderr():
+        line = run()
+    if line is not None:
+        print(line, flush=True)
+
+
+def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
@@ -261,8 +284,7 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(out))
+    return json.dumps(out) if rank == 0 else None
 
 
 if __name__ == "__main__":

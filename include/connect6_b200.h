@@ -93,7 +93,14 @@ c6_vec_int test_cpp_policy(float* board, c6_policy_callback callback, c6_alloc_i
 /* ------------------------------------------------------------------------------------------ */
 /* Part 2 — engine interface                                                                   */
 /* ------------------------------------------------------------------------------------------ */
-enum { C6_EVAL_CALLBACK = 0, C6_EVAL_PHILOX_RANDOM = 1, C6_EVAL_DET_HASH = 2, C6_EVAL_NEG_HASH = 3 };
+enum { C6_EVAL_CALLBACK = 0, C6_EVAL_PHILOX_RANDOM = 1, C6_EVAL_DET_HASH = 2, C6_EVAL_NEG_HASH = 3, C6_EVAL_DEVICE_CALLBACK = 4 };
+
+/* connect6.hpp:14 with DEVICE pointers: the leaf batch stays in HBM (float[len][15][15] boards in `d_policies`,
+ * overwritten with the priors; `d_values` pre-zeroed).  `stream` is the cudaStream_t the engine's kernels of this
+ * pipeline group are ordered on: enqueue the evaluation there (or synchronise before returning).  This is the
+ * zero-copy path for a network that lives on the same GPU (AlphaZero/cpp_weighted/main.cpp:16-37 copies through
+ * the host twice per leaf). */
+typedef void (*c6_device_callback)(int player, float* d_values, float* d_policies, int len, void* stream, void* user);
 
 /* HyperParameter (alphazero_policy/mod.rs:90-125) + engine knobs */
 typedef struct c6_config {
@@ -143,6 +150,8 @@ int c6_engine_waves_callback(c6_engine* e, c6_callback cb, int waves); /* `waves
 /* a stone chosen outside the engine for the game in `slot` (Game::set rules; the node of the new board is
  * reused if the table has it, as AlphaZero::init does, alphazero_policy/mod.rs:302-306) */
 int c6_engine_external_move(c6_engine* e, int slot, int row, int col);
+int c6_engine_waves_device_callback(c6_engine* e, c6_device_callback cb, void* user, int waves);
+int c6_engine_run_device_callback(c6_engine* e, c6_device_callback cb, void* user); /* until all games are finished */
 int c6_engine_run_device(c6_engine* e);                   /* until all games are finished */
 int c6_engine_run_callback(c6_engine* e, c6_callback cb);
 int c6_engine_sync(c6_engine* e);
@@ -166,6 +175,10 @@ long long c6_engine_debug_read(c6_engine* e, int what, int slot, void* out, long
 
 /* one-shot convenience: n_games of self-play with a device evaluator, packed records out */
 int c6_self_play_device(const c6_config* cfg, uint32_t first_game_id, int64_t n_games, c6_record* out, c6_stats* stats);
+
+/* the same, sharded by game id over several GPUs of the box (one host thread + engine each, no exchange) */
+int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_devices, uint32_t first_game_id,
+                                int64_t n_games, c6_record* out, c6_stats* stats);
 
 /* config 3a: win detection (search(), game/search_winner/mod.rs:201-246) on bit-packed boards.
  * boards: n x 16 u32 (words 0-7 black, 8-15 white; bit 16*row+col). Host pointers. */
