@@ -14,7 +14,7 @@ per side to move, so `len` is 8 x (number of games whose leaf has that side to m
 import json
 
 from . import pyconnect6  # noqa: F401  (the native-module namespace of the reference)
-from . import sharded  # noqa: F401
+from . import replay, sharded  # noqa: F401
 
 _PARAM_ORDER = ("num_simulation", "epsilon", "dirichlet_alpha", "c_puct", "debug", "num_game_thread")
 
