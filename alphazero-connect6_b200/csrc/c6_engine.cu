@@ -49,7 +49,7 @@ __global__ void k_start(Dev D, int n_start) {
 // game slots from a counter, so unequal game lengths balance themselves.  Register-capped for
 // occupancy: the path is latency-bound, resident warps are what hides HBM latency.
 #ifndef C6_SIM_BLOCKS_PER_SM
-#define C6_SIM_BLOCKS_PER_SM 8
+#define C6_SIM_BLOCKS_PER_SM 7
 #endif
 template <int EVAL, int NOISE>
 __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D) {

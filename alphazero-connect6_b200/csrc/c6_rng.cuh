@@ -88,8 +88,8 @@ struct MathTab {
     double expt[32];   // 2^(j/32)
 };
 __device__ __forceinline__ void load_math_tab(MathTab& T) {
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) T.logt[i] = LOG_TAB_C[i];
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) T.expt[i] = EXP_TAB_C[i];
+    if (threadIdx.x < 64) T.logt[threadIdx.x] = LOG_TAB_C[threadIdx.x];  // blocks have at least 64 threads
+    if (threadIdx.x < 32) T.expt[threadIdx.x] = EXP_TAB_C[threadIdx.x];
 }
 
 // natural log of a positive finite double, division-free: x = 2^e m, m in [1,2) falls in one of 64

@@ -52,19 +52,38 @@ __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const C
 // per-warp shared-memory stage
 // ------------------------------------------------------------------------------------------------
 // NOISE: 0 = epsilon == 0 (the draw is multiplied by 0: skipped), 1 = Dirichlet alpha < 1, 2 = alpha >= 1
+// One stage per warp.  Both memory phases fill it with cp.async from ROLLED loops (every request of a lane is
+// in flight before the first is waited for), so neither the addresses nor the results occupy registers and
+// the code of a phase exists once.
 template <int NOISE>
 struct WarpStage {
-    uint4 child[8][32];  // select: {N, W, P, record index} of this lane's child in board word j
     union {
-        double gamma[NOISE ? 8 : 1][32];  // select: Gamma draws of one step
-        float prior[8][32];               // expand: priors of the new children (select's stage is dead by then)
+        uint4 child[8][32];  // select: {N, W, P, link} of this lane's child in board word j
+        uint4 slot[8][32];   // expand: the index slot last probed for this lane's child of word j, then its verdict
+    };
+    union {
+        uint32_t ci[8][32];  // select: record index of that child
+        float prior[8][32];  // expand: priors of the new children
+    };
+    union {
+        double gamma[NOISE ? 8 : 4][32];  // select: Gamma draws of one step
+        uint32_t pos[8][32];              // expand: index position being probed
     };
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
 };
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// L2 only: index slots are claimed with atomics, an L1 copy could be stale
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -100,25 +119,24 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             }
             child = w.lnk[r.link & Lm];
         } else {
-            // memory phase: this lane's child of every board word, links then records, all in flight
-            uint32_t ci[8];
-            int pre = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t e = ~(L.B[j] | L.W[j]) & valid_mask(j);
-                ci[j] = NIL;
-                if ((e >> lane) & 1u) ci[j] = w.lnk[(r.link + (uint32_t)(pre + __popc(e & lt))) & Lm];
-                pre += __popc(e);
-                if (lane == j) st.empty[j] = e;
-            }
+            // memory phase: this lane's child of every board word — links, then records, eight requests of
+            // each kind in flight per lane
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (ci[j] != NIL) cp_async16(&st.child[j][lane], &w.rec[ci[j] & Rm]);
-            cp_async_wait_all();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (ci[j] != NIL) st.child[j][lane].w = ci[j];  // the link field is not needed here
+                if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
             __syncwarp();
+            int pre = 0;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t e = st.empty[j];
+                if ((e >> lane) & 1u) cp_async4(&st.ci[j][lane], &w.lnk[(r.link + (uint32_t)(pre + __popc(e & lt))) & Lm]);
+                pre += __popc(e);
+            }
+            cp_async_wait_all();
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j)
+                if ((st.empty[j] >> lane) & 1u) cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+            cp_async_wait_all();
             // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
             // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
             // sampler for every child; the ~1-3% of draws that need the other branch or another trial are
@@ -205,7 +223,8 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 if (take) bs = os, bb = ob;
             }
             chosen_bit = bb;
-            child = st.child[bb >> 5][bb & 31].w;
+            __syncwarp();  // cp.async results of the other lanes
+            child = st.ci[bb >> 5][bb & 31];
             __syncwarp();  // the stage is rewritten by the next step
         }
         // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
@@ -374,6 +393,19 @@ struct EvBatch {
 // ------------------------------------------------------------------------------------------------
 // expand (:350-377) for a non-full leaf, then update()
 // ------------------------------------------------------------------------------------------------
+// Continuation of a claim whose slot was taken by another key of this epoch in the meantime (two children
+// of one expansion hashing to the same free slot): keep probing for a free slot and claim it.  Rare.
+__device__ __noinline__ uint32_t index_claim_after_conflict(Slot* idx, uint32_t Imask, uint32_t epoch, uint32_t pos) {
+    for (;;) {
+        uint32_t seen_epoch;
+        do {
+            pos = (pos + 1) & Imask;
+            seen_epoch = __ldcg(&idx[pos].epoch);
+        } while (seen_epoch == epoch);
+        if (atomicCAS(&idx[pos].epoch, seen_epoch, epoch) != epoch) return pos;
+    }
+}
+
 template <class Ev, int NOISE>
 __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, const Leaf& L, const Ev& ev, float v,
                                             WarpStage<NOISE>& st) {
@@ -404,83 +436,89 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
     __syncwarp();
     const uint64_t key = L.key;
+    unsigned mine = 0;  // bit j: this lane has a child in board word j
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) mine |= ((st.empty[j] >> lane) & 1u) << j;
+    // A: first probe of every child key (entry(hash), :367-370), all in flight; priors computed under the latency
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j)
+        if ((mine >> j) & 1u) {
+            const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+            const uint32_t pos = hash_slot(ck) & Im;
+            st.pos[j][lane] = pos;
+            cp_async16_cg(&st.slot[j][lane], &w.idx[pos]);
+        }
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j)
+        if ((mine >> j) & 1u) st.prior[j][lane] = ev.prior(j);
+    // B: resolve in rounds — every child still walking its probe chain issues its next probe, then ONE wait
+    // serves them all (a lane-by-lane walk would pay a memory round trip per hop and per board word)
+    unsigned todo = mine, isnew = 0;
+    for (;;) {
+        cp_async_wait_all();
+        unsigned again = 0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j)
+            if ((todo >> j) & 1u) {
+                const uint4 sv = st.slot[j][lane];  // {key lo, key hi, idx, epoch}
+                const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+                if (sv.w != epoch) {  // free: the child is new; its verdict = {position, epoch seen there, -, -}
+                    isnew |= 1u << j;
+                } else if ((((uint64_t)sv.y << 32) | sv.x) == ck) {  // present: or_insert keeps it
+                    st.slot[j][lane] = make_uint4(0u, 0u, sv.z, 0u);
+                } else {
+                    const uint32_t pos = (st.pos[j][lane] + 1) & Im;
+                    st.pos[j][lane] = pos;
+                    cp_async16_cg(&st.slot[j][lane], &w.idx[pos]);
+                    again |= 1u << j;
+                }
+            }
+        todo = again;
+        if (!__any_sync(FULL, todo != 0)) break;
+    }
+    // new records are laid out contiguously in row-major child order
     uint32_t base = cs.rec_head;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const bool nw = (isnew >> j) & 1u;
+        const unsigned bal = __ballot_sync(FULL, nw);
+        if (nw) st.slot[j][lane].z = (base + __popc(bal & lt)) & Rm;
+        base += __popc(bal);
+    }
+    // C1: claim the free slots — a 32-bit CAS on the epoch word (only this warp writes this game's index, and
+    // nothing reads a key between the claim and the key store below); the eight claims are in flight together
+    uint32_t got[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        got[j] = 0;
+        if ((isnew >> j) & 1u) got[j] = atomicCAS(&w.idx[st.pos[j][lane]].epoch, st.slot[j][lane].w, epoch);
+    }
+    // a returned current epoch means another child of this expansion claimed the slot first: keep probing (rare)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (((isnew >> j) & 1u) && got[j] == epoch) st.pos[j][lane] = index_claim_after_conflict(w.idx, Im, epoch, st.pos[j][lane]);
+    // C2: keys, records, priors, link run
     int pre = 0;
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        uint64_t ck[4];
-        uint32_t pos[4];
-        Slot seen[4];
-        uint32_t e4[4];
-        // A: first probe of every child key of this half, all loads in flight together
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int j = 4 * h + t;
-            e4[t] = st.empty[j];
-            ck[t] = 0, pos[t] = 0;
-            seen[t].key = 0, seen[t].idx = 0, seen[t].epoch = 0;
-            if ((e4[t] >> lane) & 1u) {
-                ck[t] = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
-                pos[t] = hash_slot(ck[t]) & Im;
-                seen[t] = load_slot(&w.idx[pos[t]]);
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = st.empty[j];
+        if ((mine >> j) & 1u) {
+            const uint32_t child = st.slot[j][lane].z;
+            const float pr = st.prior[j][lane];
+            if ((isnew >> j) & 1u) {
+                const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+                *reinterpret_cast<uint4*>(&w.idx[st.pos[j][lane]]) = make_uint4((uint32_t)ck, (uint32_t)(ck >> 32), child, epoch);
+                Rec nr;
+                nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
+                store_rec(&w.rec[child], nr);
+            } else {
+                w.rec[child].p = pr;  // n_prob is overwritten by the last expanding parent (:371)
             }
+            w.lnk[(link_base + (uint32_t)(pre + __popc(e & lt))) & Lm] = child;
         }
-        // priors of this half: arithmetic under the probe latency (one copy of the evaluator code)
-#pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-            const int j = 4 * h + t;
-            if ((st.empty[j] >> lane) & 1u) st.prior[j][lane] = ev.prior(j);
-        }
-        // B: resolve (entry(hash).or_insert, :367-370)
-        uint32_t child[4];
-        unsigned newmask = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            child[t] = NIL;
-            if ((e4[t] >> lane) & 1u) {
-                uint32_t val;
-                if (index_find(w.idx, Im, epoch, ck[t], pos[t], seen[t], val))
-                    child[t] = val;
-                else
-                    newmask |= 1u << t;
-            }
-        }
-        // new records are laid out contiguously in row-major child order
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            unsigned bal = __ballot_sync(FULL, (newmask >> t) & 1u);
-            if ((newmask >> t) & 1u) child[t] = (base + __popc(bal & lt)) & Rm;
-            base += __popc(bal);
-        }
-        // C: records / priors / link run; the key inserts are issued back to back
-        uint32_t got[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int j = 4 * h + t;
-            got[t] = 0;
-            if ((e4[t] >> lane) & 1u) {
-                const float pr = st.prior[j][lane];
-                if ((newmask >> t) & 1u) {
-                    Rec nr;
-                    nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
-                    store_rec(&w.rec[child[t]], nr);
-                    Slot want;
-                    want.key = ck[t], want.idx = child[t], want.epoch = epoch;
-                    got[t] = cas_slot(&w.idx[pos[t]], seen[t], want).epoch;
-                } else {
-                    w.rec[child[t]].p = pr;  // n_prob is overwritten by the last expanding parent (:371)
-                }
-                w.lnk[(link_base + (uint32_t)(pre + __popc(e4[t] & lt))) & Lm] = child[t];
-            }
-            pre += __popc(e4[t]);
-        }
-        // a returned current epoch means another lane claimed the slot first: keep probing (rare)
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (((newmask >> t) & 1u) && got[t] == epoch)
-                index_insert_after_conflict(w.idx, Im, epoch, ck[t], child[t], pos[t]);
+        pre += __popc(e);
     }
-    __syncwarp();  // the insert paths above diverge; nothing below may overtake a lane still probing
+    __syncwarp();  // the claim paths above diverge; nothing below may overtake a lane still probing
     // the leaf itself: visit += 1, children attached (:353-357,374-377)
     if (lane == 0) {
         Rec lr = load_rec(&w.rec[L.rec]);

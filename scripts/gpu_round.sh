@@ -21,5 +21,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sims_device -s 3 -c 1 -o $OUT/prof_sims \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" >> $OUT/ncu_full.log
 tail -3 $OUT/ncu_full.log
+timeout 300 python scripts/micro.py > $OUT/micro.jsonl 2> $OUT/micro.err; cat $OUT/micro.jsonl
 kill $SMI
 ls -la $OUT
