@@ -385,6 +385,9 @@ int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, do
 int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_seconds) {
     C6_TRY(*wait_seconds = e->eng->host_wait_seconds(); *callback_seconds = e->eng->host_callback_seconds())
 }
+int c6_engine_kernel_times(c6_engine* e, double* sims_kernel_ms, long long* sims_kernel_launches) {
+    C6_TRY(*sims_kernel_ms = e->eng->sims_kernel_ms(); *sims_kernel_launches = e->eng->sims_kernel_launches())
+}
 int c6_engine_stats(c6_engine* e, c6_stats* out) {
     C6_TRY(Stats s = e->eng->stats(); out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf,
            out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,

@@ -544,7 +544,17 @@ void Engine::step_device() {
     }
     C6_CUDA(cudaMemsetAsync(D.cursor, 0, sizeof(int), stream_));
     if (cfg_.num_simulation > 0) {
+        cudaEvent_t k0 = nullptr, k1 = nullptr;
+        if (time_kernels_) {
+            C6_CUDA(cudaEventCreate(&k0));
+            C6_CUDA(cudaEventCreate(&k1));
+            C6_CUDA(cudaEventRecord(k0, stream_));
+        }
         kern<<<d_->persistent_blocks, 128, 0, stream_>>>(D);
+        if (time_kernels_) {
+            C6_CUDA(cudaEventRecord(k1, stream_));
+            kev_.push_back(k0), kev_.push_back(k1);
+        }
         launches_ += 1;
     }
     k_move_end<<<warps_grid(D.G), 128, 0, stream_>>>(D, 0, D.G);
@@ -820,12 +830,21 @@ float Engine::timed_steps_device(int k) {
     C6_CUDA(cudaEventCreate(&b));
     C6_CUDA(cudaStreamSynchronize(stream_));
     C6_CUDA(cudaEventRecord(a, stream_));
+    time_kernels_ = true;
     for (int i = 0; i < k; ++i) step_device();
+    time_kernels_ = false;
     C6_CUDA(cudaEventRecord(b, stream_));
     C6_CUDA(cudaEventSynchronize(b));
     float ms = 0;
     C6_CUDA(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a), cudaEventDestroy(b);
+    for (size_t i = 0; i + 1 < kev_.size(); i += 2) {
+        float kms = 0;
+        C6_CUDA(cudaEventElapsedTime(&kms, kev_[i], kev_[i + 1]));
+        sims_kernel_ms_ += kms, sims_kernel_launches_ += 1;
+        cudaEventDestroy(kev_[i]), cudaEventDestroy(kev_[i + 1]);
+    }
+    kev_.clear();
     check_errors(d_, stream_);
     return ms;
 }

@@ -155,6 +155,10 @@ class Engine {
     long long kernel_launches() const { return launches_; }
     double host_wait_seconds() const { return host_wait_s_; }
     double host_callback_seconds() const { return host_callback_s_; }
+    // timed_steps_device() brackets every launch of the fused search kernel with its own pair of CUDA events on
+    // the engine stream: cumulative milliseconds and launch count (bench.py's roofline denominator)
+    double sims_kernel_ms() const { return sims_kernel_ms_; }
+    long long sims_kernel_launches() const { return sims_kernel_launches_; }
     GameState slot_state(int slot);   // synchronises (debug printing)
     // May be called from inside the evaluator callback (or another thread): the run_*_to_end loops stop
     // at the next wave / poll and throw "cancelled".
@@ -177,6 +181,10 @@ class Engine {
     uint32_t first_id_ = 0;
     long long launches_ = 0;
     double h2d_bytes_ = 0, d2h_bytes_ = 0;
+    double sims_kernel_ms_ = 0;
+    long long sims_kernel_launches_ = 0;
+    std::vector<cudaEvent_t> kev_;  // event pairs of the timed region in flight
+    bool time_kernels_ = false;
     double host_wait_s_ = 0, host_callback_s_ = 0;  // callback path: time blocked on the GPU / inside the user Callback
     std::atomic<bool> cancel_{false};
 };

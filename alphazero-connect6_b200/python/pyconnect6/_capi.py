@@ -111,6 +111,7 @@ def product():
         L.c6_engine_timed_waves.argtypes = [C.c_void_p, CALLBACK, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.c6_engine_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.c6_engine_host_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.c6_engine_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.c6_engine_games_done.restype = C.c_int64
         L.c6_engine_games_done.argtypes = [C.c_void_p]
         L.c6_engine_records.argtypes = [C.c_void_p, C.POINTER(Record), C.c_int64]

@@ -76,6 +76,19 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def ncu_traffic(sims_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    workload (profiles/traffic.json, written by scripts/summarize_profile.py); None if the capture is of another shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if int(t["sims_per_launch"]) == int(sims_per_launch):
+            return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def algorithmic_bytes(st0, st1, materialised_batch):
     """16*sum C_k + 28*sum C_leaf + 16*(D+1) per simulation (+14,432 B per
     evaluated leaf only when an evaluator batch is materialised in global memory)."""
@@ -193,11 +206,14 @@ def run():
     assert L.c6_engine_timed_steps(e, args.warmup, C.byref(ms)) == 0, L.c6_last_error()
     st0, st1 = c6lib.Stats(), c6lib.Stats()
     L.c6_engine_stats(e, C.byref(st0))
+    km0, kl0, km1, kl1 = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
+    L.c6_engine_kernel_times(e, C.byref(km0), C.byref(kl0))
     if dist is not None:
         dist.barrier()
     with ClockSampler(local) as clk:
         assert L.c6_engine_timed_steps(e, args.steps, C.byref(ms)) == 0, L.c6_last_error()
     L.c6_engine_stats(e, C.byref(st1))
+    L.c6_engine_kernel_times(e, C.byref(km1), C.byref(kl1))
     elapsed_ms = float(ms.value)
     sims = st1.sims - st0.sims
     launches = st1.kernel_launches - st0.kernel_launches
@@ -213,12 +229,19 @@ def run():
         total_sims, total_launches = float(sims), int(launches)
     value = total_sims / (elapsed_ms * 1e-3)
 
-    # roofline of the dominant kernel (k_move_device: one launch per step) on this rank
+    # roofline of the dominant kernel (k_sims_device: one launch per step) on this rank: algorithmic bytes of the
+    # launches in the timed region / their own durations (one CUDA event pair per launch on the engine stream)
     bytes_alg, d = algorithmic_bytes(st0, st1, materialised_batch=False)
     peak, peak_src = measured_peak_gbs()
-    achieved = bytes_alg / (float(ms.value) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_move_device<philox,noise> (1 launch/step)", "peak_source": peak_src,
+    k_launches = max(kl1.value - kl0.value, 1)
+    k_ms = (km1.value - km0.value) / k_launches
+    achieved = (bytes_alg / k_launches) / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(d["sims"] / k_launches)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "kernel": "k_sims_device<philox,noise> (1 launch/step)", "kernel_ms_per_launch": k_ms,
+                "kernel_share_of_step": k_ms * k_launches / float(ms.value),
+                "algorithmic_bytes_per_launch": bytes_alg / k_launches, "peak_source": peak_src,
                 "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
                 "avg_depth": d["sum_depth"] / max(d["sims"], 1), "avg_sum_ck": d["sum_ck"] / max(d["sims"], 1),
                 "avg_cleaf": d["sum_cleaf"] / max(d["evals"], 1)}
@@ -273,7 +296,7 @@ def run():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         O = c6lib.oracle()
         cores = O.oracle_hardware_concurrency()
-        moves = 3
+        moves = 12  # ~16 core-seconds of CPU work on the 16-core box
         p = c6lib.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 0, 1, 1, moves)
         outs = (c6lib.OracleGameOut * cores)()
         secs = O.oracle_self_play_many(None, C.byref(p), 30_000_000, cores, cores, outs)

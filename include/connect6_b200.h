@@ -163,6 +163,9 @@ int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* millis
 int c6_engine_stats(c6_engine* e, c6_stats* out);
 /* callback path, cumulative: seconds the calling thread was blocked on the GPU / spent inside the user Callback */
 int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_seconds);
+/* device path, cumulative over c6_engine_timed_steps: milliseconds inside the fused search kernel (one CUDA event
+ * pair per launch on the engine stream) and the number of its launches */
+int c6_engine_kernel_times(c6_engine* e, double* sims_kernel_ms, long long* sims_kernel_launches);
 int64_t c6_engine_games_done(c6_engine* e);
 int c6_engine_records(c6_engine* e, c6_record* out, int64_t n); /* n = total_games */
 /* child_visits: total_games x 225 x 225 (i32, -1 = occupied / no entry), root_n / root_w: total_games x 225 */

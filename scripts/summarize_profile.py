@@ -80,6 +80,11 @@ def full(prof):
                 tr = float(d["dram__bytes_read.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u["dram__bytes_read.sum"]]
                 tw = float(d["dram__bytes_write.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u["dram__bytes_write.sum"]]
                 f.write(f"\nDRAM traffic per launch: {tr + tw:.4g} B (read {tr:.4g} + write {tw:.4g})\n\n")
+                if "k_sims_device" in d.get("Kernel Name", ""):
+                    # bench.py's roofline.traffic: the capture is of `bench.py --steps 1 --warmup 3` (4096 games x 800 sims per launch)
+                    json.dump({"source": f"profiles/{tag}_{prof}.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                               "kernel": d["Kernel Name"], "dram_bytes_per_launch": tr + tw, "dram_bytes_read": tr, "dram_bytes_write": tw,
+                               "sims_per_launch": 4096 * 800}, open("profiles/traffic.json", "w"), indent=1)
             except (KeyError, ValueError):
                 pass
     print(open(f"profiles/{tag}_{prof}.md").read())
