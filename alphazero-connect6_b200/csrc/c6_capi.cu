@@ -639,32 +639,52 @@ class ForkJoin {
 };
 }  // namespace
 
-// U[-1,1) values and policies from a counter hash (two 32-bit multiplies per float; the loop has no carried
-// dependence, so gcc vectorises it 8-wide).
+// U[-1,1) values and policies from a counter hash of the flat element index (two 32-bit multiplies per float,
+// no carried dependence).  The policy buffer is write-only for a random evaluator: the 8-wide body uses
+// non-temporal stores, so the fill costs one pass of host memory traffic instead of two (no read for ownership).
+static inline uint32_t sample_mix(uint32_t x) {
+    x *= 0xC2B2AE3Du, x ^= x >> 15, x *= 0x85EBCA77u, x ^= x >> 13;
+    return x;
+}
+static inline float sample_unit(uint32_t x) { return (float)(int)(x >> 8) * (1.0f / 8388608.0f) - 1.0f; }
 #if defined(__GNUC__) && defined(__x86_64__)
-__attribute__((optimize("O3"), target("avx2")))
+#include <immintrin.h>
+__attribute__((target("avx2")))
+static void sample_fill_flat(uint32_t base, float* out, size_t lo, size_t hi) {
+    size_t e = lo;
+    for (; e < hi && ((uintptr_t)(out + e) & 31u); ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+    const __m256i step = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m256i m1 = _mm256_set1_epi32((int)0xC2B2AE3Du), m2 = _mm256_set1_epi32((int)0x85EBCA77u);
+    const __m256 scale = _mm256_set1_ps(1.0f / 8388608.0f), one = _mm256_set1_ps(1.0f);
+    for (; e + 8 <= hi; e += 8) {
+        __m256i x = _mm256_add_epi32(_mm256_set1_epi32((int)(base + (uint32_t)e)), step);
+        x = _mm256_mullo_epi32(x, m1);
+        x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 15));
+        x = _mm256_mullo_epi32(x, m2);
+        x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 13));
+        const __m256 f = _mm256_sub_ps(_mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_srli_epi32(x, 8)), scale), one);
+        _mm256_stream_ps(out + e, f);
+    }
+    for (; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+    _mm_sfence();
+}
+#else
+static void sample_fill_flat(uint32_t base, float* out, size_t lo, size_t hi) {
+    for (size_t e = lo; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+}
 #endif
 static void sample_fill(uint32_t base, float* values, float* policies, int lo, int hi) {
-    for (int n = lo; n < hi; ++n) {
-        const uint32_t seed = (base ^ (uint32_t)n) * 0x9E3779B1u;
-        uint32_t v = seed ^ 0x5bd1e995u;
-        v ^= v >> 15, v *= 0x85EBCA77u, v ^= v >> 13;
-        values[n] = (float)(int)(v >> 8) * (1.0f / 8388608.0f) - 1.0f;
-        float* p = policies + (size_t)n * 225;
-        for (int i = 0; i < 225; ++i) {
-            uint32_t x = (seed + (uint32_t)i) * 0xC2B2AE3Du;
-            x ^= x >> 15, x *= 0x85EBCA77u, x ^= x >> 13;
-            p[i] = (float)(int)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;
-        }
-    }
+    for (int n = lo; n < hi; ++n) values[n] = sample_unit(sample_mix((base ^ 0x5bd1e995u) + (uint32_t)n));
+    sample_fill_flat(base * 0x9E3779B1u, policies, (size_t)lo * 225, (size_t)hi * 225);
 }
 
 extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
     static std::atomic<uint32_t> call_no{0};
     const uint32_t base = (call_no.fetch_add(1) * 0x9E3779B9u) ^ ((uint32_t)(player + 2) << 28);
-    if (len < 2048) return sample_fill(base, values, policies, 0, len);
-    // four workers: measured best on the 16-vCPU B200 box (more threads compete with the engine's calling
-    // thread and the CUDA driver's own threads; profiles/e2e4)
+    static const int pool_min = env_int("C6_SAMPLE_POOL_MIN", 512);
+    if (len < pool_min) return sample_fill(base, values, policies, 0, len);
+    // a few workers: more compete with the engine's two host threads and the CUDA driver's own on the 16-vCPU
+    // B200 box (profiles/e2e4, e2e5)
     static ForkJoin pool(env_int("C6_SAMPLE_THREADS", (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 4u))));
     static std::mutex one_at_a_time;  // the pool is shared: callers from several engines take turns
     std::lock_guard<std::mutex> l(one_at_a_time);

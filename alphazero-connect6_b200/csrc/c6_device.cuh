@@ -22,9 +22,14 @@ struct Dev {
     const uint64_t* Z;  // [2][256] Zobrist keys by bit position
     int* cursor;
     unsigned long long* gcount;  // [0] games finished, [1] next game offset to start, [2] error count
-    float* bboards;              // evaluator batch, API layout float[len][15][15] (in: boards, out: policies)
-    float* bvalues;              // float[len]
-    int* gcounts;                // [0] leaves with Black to move, [1] White
+    // evaluator batch (callback paths): per pipeline group of n slots a region of n*8*226 floats at offset
+    // g0*8*226, laid out [values n*8 | boards n*8*225]; boards in the API layout float[len][15][15] (in: boards,
+    // out: policies)
+    float* batch;                // device copy
+    float* hbatch;               // the same layout in mapped pinned host memory (host-callback path)
+    uint8_t* leaf_flag;          // [G] 0 nothing to evaluate, 1 Black to move at the leaf, 2 White
+    int* gdone;                  // [groups] blocks of the running k_gather that have finished
+    int* hsync;                  // mapped pinned host memory, per group {Black leaves, White leaves, seq, -}
     int32_t* tr_visits;
     int32_t* tr_n;
     float* tr_w;

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
+#include <thread>
 
 #include "c6_search.cuh"
 
@@ -115,136 +117,142 @@ __global__ void __launch_bounds__(32) k_external_move(Dev D, int slot, int cell)
     if (w.gs->status == ST_ACTIVE) external_move(D, w, bit_of_cell(cell));
 }
 
-// Callback path, kernel 1: descend to the leaf and park it in the game state.
+// Callback path, kernel 1 — one wave of one pipeline group (slots g0..g1), one warp per game:
+//   back half  (do_back):  recover_way8 + get_from on the evaluator's answer, expansion, backup; after the
+//                          game's num_sim-th simulation of this stone also policy(), Game::set, win check, node
+//                          collection / slot refill (what k_move_end does on the device-evaluator path);
+//   front half (do_front): descend to the next leaf and park it in the game state; leaf_flag[g] = 0 (nothing
+//                          to evaluate), 1 (Black to move at the leaf) or 2 (White).
+// Both halves of consecutive waves touch only this game's own state, so they share a launch: a wave of a group
+// is k_step -> k_gather -> (evaluator) -> one H2D copy.
 template <int NOISE>
-__global__ void __launch_bounds__(128) k_select(Dev D, int g0, int g1) {
-    const uint64_t* Zs = D.Z;  // global (__ldg in descend)
+__global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back, int do_front) {
+    const uint64_t* Zs = D.Z;  // global (__ldg in descend / expand_leaf)
     __shared__ WarpStage<NOISE> stage[4];
     __shared__ MathTab mt;
     if (NOISE) load_math_tab(mt);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
-    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (g >= g1) return;
     Warp w = make_warp(D, g, Zs, lane);
     GameState& gs = *w.gs;
-    if (gs.status != ST_ACTIVE) {
-        if (lane == 0) gs.need_eval = 0;
-        return;
-    }
-    Cursor cs;
-    load_cursor(gs, cs);
-    Leaf L;
-    descend<NOISE>(D, w, cs, L, st, mt);
-    int need = 1;
-    if (L.stones == CELLS) {
-        terminal_leaf(D, w, L);
-        need = 0;
-    }
+    if (do_back && gs.status == ST_ACTIVE) {
+        if (D.num_sim > 0) {
+            Cursor cs;
+            load_cursor(gs, cs);
+            if (gs.need_eval) {
+                Leaf L;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (lane == j) gs.leafB[j] = L.B[j], gs.leafW[j] = L.W[j];
-    if (lane == 0) {
-        gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key;
-        gs.need_eval = need;
-    }
-    store_cursor(D, gs, cs, lane);
-}
-
-// Callback path, kernel 2: order the leaves of one pipeline group (slots g0..g1) into a Black-to-move
-// run followed by a White-to-move run (the Callback ABI takes one `player` per call,
-// CB/libcppconnect6/src/cppbind/cppeval/mod.rs:8-13).  Positions are relative to the group's region of
-// the batch buffers; counts go to gcounts[2*group ..].
-__global__ void k_rank(Dev D, int g0, int g1, int group) {
-    __shared__ int sB[1024], sW[1024];
-    const int t = threadIdx.x, n = g1 - g0, per = (n + 1023) / 1024;
-    int nb = 0, nw = 0;
-    for (int i = 0; i < per; ++i) {
-        int g = g0 + t * per + i;
-        if (g < g1 && D.gs[g].need_eval) (turn_of(D.gs[g].leaf_stones) < 0 ? nb : nw) += 1;
-    }
-    sB[t] = nb, sW[t] = nw;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        int vb = t >= off ? sB[t - off] : 0, vw = t >= off ? sW[t - off] : 0;
-        __syncthreads();
-        sB[t] += vb, sW[t] += vw;
-        __syncthreads();
-    }
-    const int totalB = sB[1023], totalW = sW[1023];
-    int ob = sB[t] - nb, ow = sW[t] - nw;
-    for (int i = 0; i < per; ++i) {
-        int g = g0 + t * per + i;
-        if (g < g1 && D.gs[g].need_eval) {
-            if (turn_of(D.gs[g].leaf_stones) < 0)
-                D.gs[g].batch_pos = ob++;
-            else
-                D.gs[g].batch_pos = totalB + ow++;
+                for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
+                L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
+                const float* region = D.batch + (size_t)g0 * 8 * (CELLS + 1);
+                EvBatch ev;
+                ev.values = region + (size_t)gs.batch_pos * 8;
+                ev.pol = region + (size_t)(g1 - g0) * 8 + (size_t)gs.batch_pos * 8 * CELLS;
+                ev.lane = lane;
+                expand_leaf(D, w, cs, L, ev, ev.value(), st);
+            }
+            cs.sim_index += 1;
+            store_cursor(D, gs, cs, lane);
+            if (gs.status == ST_ACTIVE && lane == 0) {
+                gs.sims_this_move += 1;
+                gs.need_eval = 0;
+            }
+            __syncwarp();
         }
+        if (gs.status == ST_ACTIVE && gs.sims_this_move >= D.num_sim) finish_move(D, w);
+        __syncwarp();
     }
-    if (t == 0) D.gcounts[2 * group] = totalB, D.gcounts[2 * group + 1] = totalW;
-}
-
-// Callback path, kernel 3: augment_way8 + board_to_float for every leaf, written in the API layout
-// float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73, CB/.../cpp_support.rs:10-18).
-__global__ void __launch_bounds__(128) k_gather(Dev D, int g0, int g1) {
-    const int lane = threadIdx.x & 31;
-    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (g >= g1) return;
-    const GameState& gs = D.gs[g];
-    if (!gs.need_eval) return;
-    uint32_t B[8], W[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) B[j] = gs.leafB[j], W[j] = gs.leafW[j];
-    const size_t slot = (size_t)g0 + (size_t)gs.batch_pos;
-    float* out = D.bboards + slot * 8 * CELLS;
-    for (int i = lane; i < 8 * CELLS; i += 32) {
-        int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
-        sym_inv(s, rr, cc, r, c);
-        uint32_t bit = (uint32_t)(r * 16 + c);
-        uint32_t bw = 0, ww = 0;
+    if (!do_front) return;
+    int flag = 0;
+    if (gs.status == ST_ACTIVE && D.num_sim > 0) {
+        Cursor cs;
+        load_cursor(gs, cs);
+        Leaf L;
+        descend<NOISE>(D, w, cs, L, st, mt);
+        int need = 1;
+        if (L.stones == CELLS) {
+            terminal_leaf(D, w, L);
+            need = 0;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if ((int)(bit >> 5) == j) bw = B[j], ww = W[j];
-        float v = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
-        out[i] = v;
-    }
-    if (lane < 8) D.bvalues[slot * 8 + lane] = 0.f;
-}
-
-// Callback path, kernel 4: recover_way8 + expansion + backup (k_move_end follows every num_sim waves).
-__global__ void __launch_bounds__(128) k_expand_cb(Dev D, int g0, int g1) {
-    const uint64_t* Zs = D.Z;  // global (__ldg in expand_leaf)
-    __shared__ WarpStage<0> stage[4];
-    const int lane = threadIdx.x & 31;
-    WarpStage<0>& st = stage[threadIdx.x >> 5];
-    int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (g >= g1) return;
-    Warp w = make_warp(D, g, Zs, lane);
-    GameState& gs = *w.gs;
-    if (gs.status != ST_ACTIVE) return;
-    Cursor cs;
-    load_cursor(gs, cs);
-    if (gs.need_eval) {
-        Leaf L;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
-        L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
-        EvBatch ev;
-        ev.values = D.bvalues + ((size_t)g0 + (size_t)gs.batch_pos) * 8;
-        ev.pol = D.bboards + ((size_t)g0 + (size_t)gs.batch_pos) * 8 * CELLS;
-        ev.lane = lane;
-        expand_leaf(D, w, cs, L, ev, ev.value(), st);
-    }
-    cs.sim_index += 1;
-    store_cursor(D, gs, cs, lane);
-    if (gs.status != ST_ACTIVE) return;
-    if (lane == 0) {
-        gs.sims_this_move += 1;
+            if (lane == j) gs.leafB[j] = L.B[j], gs.leafW[j] = L.W[j];
+        if (lane == 0) {
+            gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key;
+            gs.need_eval = need;
+        }
+        store_cursor(D, gs, cs, lane);
+        flag = need ? (turn_of(L.stones) < 0 ? 1 : 2) : 0;
+    } else if (lane == 0) {
         gs.need_eval = 0;
     }
+    if (lane == 0) D.leaf_flag[g] = (uint8_t)flag;
 }
+
+// Callback path, kernel 2: the leaves of the group ordered into a Black-to-move run followed by a
+// White-to-move run (the Callback ABI takes one `player` per call, CB/libcppconnect6/src/cppbind/cppeval/
+// mod.rs:8-13; every warp ranks its own leaf from the group's flag bytes), then augment_way8 + board_to_float
+// for every leaf in the API layout float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73,
+// CB/.../cpp_support.rs:10-18).  The batch region of a group is [values n*8 | boards n*8*225] floats.
+// to_host: the boards go straight to the mapped pinned host buffer the user Callback reads (no copy call);
+// the last block to finish publishes {Black leaves, White leaves, seq} to the host, which polls seq.
+__global__ void __launch_bounds__(128) k_gather(Dev D, int g0, int g1, int group, int seq, int to_host, int publish) {
+    const int lane = threadIdx.x & 31;
+    const int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int n = g1 - g0;
+    const int myflag = g < g1 ? (int)D.leaf_flag[g] : 0;
+    int nB = 0, nW = 0, rank = 0;
+    if (myflag || threadIdx.x < 32) {  // warp-uniform
+        for (int base = g0; base < g1; base += 32) {
+            const int i = base + lane;
+            const int f = i < g1 ? (int)D.leaf_flag[i] : 0;
+            const unsigned mb = __ballot_sync(FULL, f == 1), mw = __ballot_sync(FULL, f == 2);
+            nB += __popc(mb), nW += __popc(mw);
+            const unsigned mine = myflag == 1 ? mb : mw;
+            if (base + 32 <= g) rank += __popc(mine);
+            else if (base <= g) rank += __popc(mine & ((1u << (g - base)) - 1u));
+        }
+    }
+    if (myflag) {
+        GameState& gs = D.gs[g];
+        const int slot = myflag == 1 ? rank : nB + rank;
+        if (lane == 0) gs.batch_pos = slot;
+        uint32_t B[8], W[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) B[j] = gs.leafB[j], W[j] = gs.leafW[j];
+        float* region = (to_host ? D.hbatch : D.batch) + (size_t)g0 * 8 * (CELLS + 1);
+        float* out = region + (size_t)n * 8 + (size_t)slot * 8 * CELLS;
+        for (int i = lane; i < 8 * CELLS; i += 32) {
+            int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
+            sym_inv(s, rr, cc, r, c);
+            uint32_t bit = (uint32_t)(r * 16 + c);
+            uint32_t bw = 0, ww = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if ((int)(bit >> 5) == j) bw = B[j], ww = W[j];
+            out[i] = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
+        }
+        if (!to_host && lane < 8) region[(size_t)slot * 8 + lane] = 0.f;  // values pre-zeroed (cppeval/mod.rs:34); the host path zeroes its own
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(D.gdone + group, 1);
+        if (done == (int)gridDim.x - 1) {
+            D.gdone[group] = 0;
+            volatile int* hs = D.hsync + 4 * group;
+            hs[0] = nB, hs[1] = nW;
+            __threadfence_system();
+            if (publish) hs[2] = seq;
+        }
+    }
+}
+
+// D2H-by-copy variant (C6_ZEROCOPY=0): the sequence number follows the copy in stream order
+__global__ void k_publish(Dev D, int group, int seq) { *(volatile int*)(D.hsync + 4 * group + 2) = seq; }
 
 // Invariant checker (tests / debugging): for every resident game, every entry of the expanded list must
 // (1) carry the Zobrist key of its board, (2) own an expanded record (N >= 1, real link run), whose
@@ -336,21 +344,13 @@ struct Group {
     int g0 = 0, g1 = 0;
     cudaStream_t s = nullptr;
     cudaEvent_t ev = nullptr;
-    int* h_counts = nullptr;  // pinned [2]
-    int waves_this_move = 0;
-    int last_count = -1;      // leaves evaluated in the previous wave (-1: unknown)
-    bool front_pending = false;
-    bool exact = false;
-    // the fixed-shape halves of a wave as CUDA graphs (one launch call instead of six): front = select,
-    // rank, gather, D2H counts + whole region; back = H2D whole region, expand [, move end]
-    cudaGraphExec_t front_graph = nullptr, back_graph = nullptr, back_move_graph = nullptr;
+    int seq = 0;  // sequence number of the last leaf batch asked for (k_gather publishes it to hsync when the batch is ready)
 };
 
 struct DeviceArrays {
     Dev dev{};
-    float* h_boards = nullptr;  // pinned
-    float* h_values = nullptr;
-    int* h_counts = nullptr;
+    float* h_batch = nullptr;  // mapped pinned host memory, same layout as Dev::batch
+    int* h_sync = nullptr;     // mapped pinned host memory, per group {Black leaves, White leaves, seq, -}
     std::vector<Group> groups;
     unsigned long long* h_gcount = nullptr;
     size_t rec_bytes = 0, lnk_bytes = 0, idx_bytes = 0;
@@ -395,6 +395,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.R = 1u << cfg_.log2_records;
     D.L = D.R * 2;
     D.I = D.R * 2;
+    if (const char* xf = std::getenv("C6_INDEX_FACTOR")) D.I = D.R * (uint32_t)std::max(1, std::atoi(xf));  // tuning knob (power of two)
     D.E = 4096;
     D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
     D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves;
@@ -404,7 +405,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     d_->idx_bytes = G * D.I * sizeof(Slot);
     size_t free_b = 0, total_b = 0;
     C6_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t need = d_->rec_bytes + d_->lnk_bytes + d_->idx_bytes + G * D.E * 76 + G * (8 * CELLS + 8) * 4 + (64u << 20);
+    size_t need = d_->rec_bytes + d_->lnk_bytes + d_->idx_bytes + G * D.E * 76 + G * 8 * (CELLS + 1) * 4 + (64u << 20);
     if (need > free_b) {
         char buf[256];
         std::snprintf(buf, sizeof buf,
@@ -437,17 +438,22 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         // pipeline depth of the callback path: while the host evaluates one group, the others run their
         // kernels and copies.  Small batches are not worth splitting.
         const char* pe = std::getenv("C6_PIPELINE");
-        n_groups = pe && *pe ? std::atoi(pe) : std::max(1, std::min(16, D.G / 256));  // 16 groups of 256 games at G = 4096: profiles/e2e3-4
+        n_groups = pe && *pe ? std::atoi(pe) : std::max(1, std::min(16, D.G / 1024));  // 4 groups of 1024 games at G = 4096: profiles/e2e/e2e7.md
         n_groups = std::max(1, std::min(n_groups, std::min(D.G, 16)));
     }
-    C6_CUDA(cudaMalloc(&D.gcounts, 2 * n_groups * sizeof(int)));
-    C6_CUDA(cudaMallocHost(&d_->h_counts, 2 * n_groups * sizeof(int)));
-    if (const char* ug = std::getenv("C6_GRAPHS")) use_graphs_ = std::atoi(ug) != 0;
+    C6_CUDA(cudaMalloc(&D.gdone, n_groups * sizeof(int)));
+    C6_CUDA(cudaMemsetAsync(D.gdone, 0, n_groups * sizeof(int), stream_));
+    C6_CUDA(cudaMalloc(&D.leaf_flag, G));
+    C6_CUDA(cudaMemsetAsync(D.leaf_flag, 0, G, stream_));
+    C6_CUDA(cudaHostAlloc(&d_->h_sync, 4 * n_groups * sizeof(int), cudaHostAllocMapped));
+    std::memset(d_->h_sync, 0, 4 * n_groups * sizeof(int));
+    C6_CUDA(cudaHostGetDevicePointer((void**)&D.hsync, d_->h_sync, 0));
+    if (const char* ul = std::getenv("C6_LAUNCHER")) use_launcher_ = std::atoi(ul) != 0;
+    if (const char* uz = std::getenv("C6_ZEROCOPY")) zero_copy_ = std::atoi(uz) != 0;
     d_->groups.resize(n_groups);
     for (int p = 0; p < n_groups; ++p) {
         Group& gr = d_->groups[p];
         gr.g0 = (int)((long long)D.G * p / n_groups), gr.g1 = (int)((long long)D.G * (p + 1) / n_groups);
-        gr.h_counts = d_->h_counts + 2 * p;
         if (n_groups == 1) {
             gr.s = stream_;
         } else {
@@ -457,12 +463,11 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     }
     C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
     if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
-        size_t nb = G * 8 * CELLS * sizeof(float), nv = G * 8 * sizeof(float);
-        C6_CUDA(cudaMalloc(&D.bboards, nb));
-        C6_CUDA(cudaMalloc(&D.bvalues, nv));
+        const size_t nb = G * 8 * (CELLS + 1) * sizeof(float);
+        C6_CUDA(cudaMalloc(&D.batch, nb));
         if (cfg_.evaluator == EVAL_CALLBACK) {
-            C6_CUDA(cudaMallocHost(&d_->h_boards, nb));
-            C6_CUDA(cudaMallocHost(&d_->h_values, nv));
+            C6_CUDA(cudaHostAlloc(&d_->h_batch, nb, cudaHostAllocMapped));
+            C6_CUDA(cudaHostGetDevicePointer((void**)&D.hbatch, d_->h_batch, 0));
         }
     }
     cudaDeviceProp prop;
@@ -476,10 +481,9 @@ Engine::~Engine() {
     Dev& D = d_->dev;
     cudaStreamSynchronize(stream_);
     cudaFree(D.rec), cudaFree(D.lnk), cudaFree(D.idx), cudaFree(D.expB), cudaFree(D.exp_rec), cudaFree(D.exp_key);
-    cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gcounts);
-    cudaFree(D.records), cudaFree(D.bboards), cudaFree(D.bvalues), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
-    cudaFreeHost(d_->h_boards), cudaFreeHost(d_->h_values), cudaFreeHost(d_->h_counts), cudaFreeHost(d_->h_gcount);
-    drop_graphs();
+    cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gdone), cudaFree(D.leaf_flag);
+    cudaFree(D.records), cudaFree(D.batch), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
+    cudaFreeHost(d_->h_batch), cudaFreeHost(d_->h_sync), cudaFreeHost(d_->h_gcount);
     for (Group& gr : d_->groups) {
         if (gr.s && gr.s != stream_) cudaStreamSynchronize(gr.s), cudaStreamDestroy(gr.s);
         if (gr.ev) cudaEventDestroy(gr.ev);
@@ -494,8 +498,6 @@ void Engine::start(uint32_t first_id, int64_t total_games) {
     Dev& D = d_->dev;
     C6_CUDA(cudaSetDevice(cfg_.device));
     sync();
-    drop_graphs();  // kernel arguments (record / trace pointers, game ids) are baked into the graphs
-    for (Group& gr : d_->groups) gr.waves_this_move = 0, gr.last_count = -1, gr.front_pending = false;
     total_games_ = total_games, first_id_ = first_id;
     D.total_games = total_games, D.first_id = first_id;
     cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
@@ -563,152 +565,161 @@ void Engine::step_device() {
 }
 
 // ---- callback path ------------------------------------------------------------------------------
-// One wave of one group is split in a front half (select -> rank -> gather -> D2H of the leaf boards in
-// the API layout) and a back half (user Callback per side to move -> H2D of policies and values ->
-// expand/backup, plus the move-end kernel once the group has spent its simulation budget).  Groups run
-// on their own streams: while the calling thread sits in the Callback of one group, the kernels and
-// copies of the others proceed, and PCIe carries both directions at once.
-void Engine::front_ops(int p, bool whole_region) {
-    Dev& D = d_->dev;
-    Group& gr = d_->groups[p];
-    const int n = gr.g1 - gr.g0, grid = warps_grid(n);
-    const int noise = noise_mode(cfg_);
-    if (noise == 1)
-        k_select<1><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    else if (noise == 2)
-        k_select<2><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    else
-        k_select<0><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    k_rank<<<1, 1024, 0, gr.s>>>(D, gr.g0, gr.g1, p);
-    k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    C6_CUDA(cudaGetLastError());
-    C6_CUDA(cudaMemcpyAsync(gr.h_counts, D.gcounts + 2 * p, 2 * sizeof(int), cudaMemcpyDeviceToHost, gr.s));
-    if (whole_region) {
-        const size_t off = (size_t)gr.g0 * 8 * CELLS;
-        C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
-    }
+// One wave of one group: k_step (expansion + backup for the evaluator's answer to the previous leaf, move end
+// when the stone's budget is spent, descent to the next leaf) -> k_gather (leaf boards in the API layout,
+// written straight into the mapped pinned host buffer; the last block publishes the counts and a sequence
+// number the host polls) -> user Callback per side to move -> one H2D copy of values and policies.  Three
+// driver calls per group and wave, no events.  Groups run on their own streams: while the calling thread sits
+// in the Callback of one group, the kernels and copies of the others proceed, and PCIe carries both directions.
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
 }
-
-void Engine::back_ops(int p, size_t len, bool move_end) {
-    Dev& D = d_->dev;
-    Group& gr = d_->groups[p];
-    const int n = gr.g1 - gr.g0, grid = warps_grid(n);
-    const size_t off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
-    if (len) {
-        C6_CUDA(cudaMemcpyAsync(D.bboards + off, d_->h_boards + off, len * CELLS * sizeof(float), cudaMemcpyHostToDevice, gr.s));
-        C6_CUDA(cudaMemcpyAsync(D.bvalues + voff, d_->h_values + voff, len * sizeof(float), cudaMemcpyHostToDevice, gr.s));
-    }
-    k_expand_cb<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    if (move_end) k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-    C6_CUDA(cudaGetLastError());
-}
-
-void Engine::build_graphs(int p) {
-    Group& gr = d_->groups[p];
-    const size_t whole = (size_t)(gr.g1 - gr.g0) * 8;
-    auto capture = [&](cudaGraphExec_t& exec, auto&& ops) {
-        cudaGraph_t graph = nullptr;
-        C6_CUDA(cudaStreamBeginCapture(gr.s, cudaStreamCaptureModeThreadLocal));
-        ops();
-        C6_CUDA(cudaStreamEndCapture(gr.s, &graph));
-        C6_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-        cudaGraphDestroy(graph);
-    };
-    capture(gr.front_graph, [&] { front_ops(p, true); });
-    capture(gr.back_graph, [&] { back_ops(p, whole, false); });
-    capture(gr.back_move_graph, [&] { back_ops(p, whole, true); });
-}
-
-void Engine::drop_graphs() {
-    for (Group& gr : d_->groups) {
-        if (gr.front_graph) cudaGraphExecDestroy(gr.front_graph);
-        if (gr.back_graph) cudaGraphExecDestroy(gr.back_graph);
-        if (gr.back_move_graph) cudaGraphExecDestroy(gr.back_move_graph);
-        gr.front_graph = gr.back_graph = gr.back_move_graph = nullptr;
-    }
-}
-
-void Engine::group_front(int p) {
-    Group& gr = d_->groups[p];
-    const int n = gr.g1 - gr.g0;
-    if (cfg_.num_simulation > 0) {
-        // Nearly every resident game needs an evaluation in a wave, so the whole region of the group is
-        // copied without waiting for the count; when most slots are idle (tail of a run) the copy
-        // waits for the exact count instead.
-        gr.exact = (gr.last_count >= 0 && gr.last_count < n / 2) || cfg_.evaluator == EVAL_DEVICE_CALLBACK;  // device evaluator: counts only
-        if (!gr.exact && use_graphs_) {
-            if (!gr.front_graph) build_graphs(p);
-            C6_CUDA(cudaGraphLaunch(gr.front_graph, gr.s));
-        } else {
-            front_ops(p, !gr.exact);
-        }
-        launches_ += 3;
-        if (!gr.exact) d2h_bytes_ += (double)n * 8 * CELLS * sizeof(float) + 8;
-    }
-    C6_CUDA(cudaEventRecord(gr.ev, gr.s));
-    gr.front_pending = true;
-}
-
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-void Engine::group_back(int p, Callback cb) {
+// Enqueue for group p: [H2D of `len` evaluated boards] -> k_step(do_back, do_front) [-> k_gather].
+void Engine::group_issue(int p, size_t len, bool do_back, bool do_front) {
     Dev& D = d_->dev;
     Group& gr = d_->groups[p];
     const int n = gr.g1 - gr.g0, grid = warps_grid(n);
-    gr.front_pending = false;
-    const double t0 = now_s();
-    if (cfg_.num_simulation <= 0) {
-        k_move_end<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1);
-        launches_ += 1;
-        C6_CUDA(cudaGetLastError());
-        return;
+    const size_t roff = (size_t)gr.g0 * 8 * (CELLS + 1);
+    const bool host_cb = cfg_.evaluator == EVAL_CALLBACK;
+    if (do_back && len && host_cb) {
+        const size_t bytes = ((size_t)n * 8 + len * CELLS) * sizeof(float);  // all values of the region + the evaluated boards
+        C6_CUDA(cudaMemcpyAsync(D.batch + roff, d_->h_batch + roff, bytes, cudaMemcpyHostToDevice, gr.s));
+        h2d_bytes_ += (double)bytes;
     }
-    C6_CUDA(cudaEventSynchronize(gr.ev));
+    const int noise = noise_mode(cfg_);
+    if (noise == 1)
+        k_step<1><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1, do_back, do_front);
+    else if (noise == 2)
+        k_step<2><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1, do_back, do_front);
+    else
+        k_step<0><<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1, do_back, do_front);
+    launches_ += 1;
+    if (do_front && cfg_.num_simulation > 0) {
+        gr.seq += 1;
+        const bool zc = host_cb && zero_copy_;
+        k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1, p, gr.seq, zc ? 1 : 0, (zc || !host_cb) ? 1 : 0);
+        launches_ += 1;
+        if (host_cb && !zc) {
+            const size_t boff = roff + (size_t)n * 8;
+            C6_CUDA(cudaMemcpyAsync(d_->h_batch + boff, D.batch + boff, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
+            k_publish<<<1, 1, 0, gr.s>>>(D, p, gr.seq);
+            launches_ += 1;
+        }
+    }
+    C6_CUDA(cudaGetLastError());
+}
+
+// The calling thread's half of a wave of one group: wait for the leaf batch, run the user Callback once per
+// side to move (cppeval/mod.rs:8-13).  Returns the number of boards to copy back (8 per evaluated leaf).
+size_t Engine::group_eval(int p, Callback cb) {
+    Dev& D = d_->dev;
+    Group& gr = d_->groups[p];
+    if (cfg_.num_simulation <= 0) return 0;
+    const int n = gr.g1 - gr.g0;
+    const double t0 = now_s();
+    volatile int* hs = d_->h_sync + 4 * p;
+    const int want = gr.seq;
+    for (unsigned spins = 1; hs[2] != want; ++spins) {
+        cpu_relax();
+        if ((spins & 0xFFFFu) == 0) {  // a failed kernel never publishes: look at the stream now and then
+            if (abort_.load(std::memory_order_relaxed)) throw std::runtime_error("c6: wave aborted");
+            cudaError_t q = cudaStreamQuery(gr.s);
+            if (q != cudaSuccess && q != cudaErrorNotReady) C6_CUDA(q);
+            if (q == cudaSuccess && hs[2] != want) throw std::runtime_error("c6: leaf batch was never published");
+        }
+    }
     const double t1 = now_s();
     host_wait_s_ += t1 - t0;
-    const int nB = gr.h_counts[0], nW = gr.h_counts[1];
-    const size_t len = (size_t)(nB + nW) * 8, off = (size_t)gr.g0 * 8 * CELLS, voff = (size_t)gr.g0 * 8;
-    gr.last_count = nB + nW;
+    const int nB = hs[0], nW = hs[1];
+    const size_t len = (size_t)(nB + nW) * 8, roff = (size_t)gr.g0 * 8 * (CELLS + 1);
+    if (!len) return 0;
     if (cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
-        if (len) {
-            float* db = D.bboards + off;
-            float* dv = D.bvalues + voff;  // zeroed by k_gather
-            const double t2 = now_s();
-            if (nB) dcb_(-1, dv, db, nB * 8, (void*)gr.s, dcb_user_);
-            if (nW) dcb_(1, dv + (size_t)nB * 8, db + (size_t)nB * 8 * CELLS, nW * 8, (void*)gr.s, dcb_user_);
-            host_callback_s_ += now_s() - t2;
+        float* dv = D.batch + roff;  // zeroed by k_gather
+        float* db = dv + (size_t)n * 8;
+        if (nB) dcb_(-1, dv, db, nB * 8, (void*)gr.s, dcb_user_);
+        if (nW) dcb_(1, dv + (size_t)nB * 8, db + (size_t)nB * 8 * CELLS, nW * 8, (void*)gr.s, dcb_user_);
+        host_callback_s_ += now_s() - t1;
+        return 0;  // nothing to copy back
+    }
+    float* hv = d_->h_batch + roff;
+    float* hb = hv + (size_t)n * 8;
+    std::memset(hv, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
+    const double t2 = now_s();
+    if (nB) cb(-1, hv, hb, nB * 8);
+    if (nW) cb(1, hv + (size_t)nB * 8, hb + (size_t)nB * 8 * CELLS, nW * 8);
+    host_callback_s_ += now_s() - t2;
+    d2h_bytes_ += (double)(zero_copy_ ? len : (size_t)n * 8) * CELLS * sizeof(float) + 12;
+    return len;
+}
+
+// Per-group hand-over between the calling thread (evaluator callbacks) and the launching thread (every CUDA
+// enqueue of the wave).  A group's stream is only ever touched by the launching thread; issued = w+1 hands
+// wave w to the caller, cb_seq = w+1 hands it back together with the number of boards to copy.
+struct alignas(64) GroupSync {
+    std::atomic<int> issued{0}, cb_seq{0};
+    size_t len = 0;
+};
+
+// `waves` simulations for every resident game with the CUDA enqueues on a second thread: side by side with the
+// evaluator instead of in series with it (profiles/e2e5-7).  The user Callback still runs on the calling thread
+// only, one call at a time — the reference's single-thread contract (lib.rs:98-108) holds.
+void Engine::waves_callback_threaded(Callback cb, int waves) {
+    const int P = (int)d_->groups.size();
+    std::unique_ptr<GroupSync[]> gs(new GroupSync[P]);
+    abort_.store(false);
+    std::exception_ptr launcher_error;
+    auto wait_for = [&](std::atomic<int>& a, int want) {
+        for (int spins = 0; a.load(std::memory_order_acquire) < want; ++spins) {
+            if (abort_.load(std::memory_order_relaxed)) return false;
+            if (spins < 4096) cpu_relax(); else std::this_thread::yield();
         }
-        const bool move_end = gr.waves_this_move + 1 >= cfg_.num_simulation;
-        gr.waves_this_move = move_end ? 0 : gr.waves_this_move + 1;
-        back_ops(p, 0, move_end);
-        launches_ += move_end ? 2 : 1;
-        return;
-    }
-    if (len) {
-        if (gr.exact) {
-            C6_CUDA(cudaMemcpyAsync(d_->h_boards + off, D.bboards + off, len * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
-            C6_CUDA(cudaStreamSynchronize(gr.s));
-            d2h_bytes_ += (double)len * CELLS * sizeof(float) + 8;
+        return true;
+    };
+    std::thread launcher([&] {
+        try {
+            C6_CUDA(cudaSetDevice(cfg_.device));
+            for (int p = 0; p < P; ++p) {
+                group_issue(p, 0, false, true);
+                gs[p].issued.store(1, std::memory_order_release);
+            }
+            for (int wv = 0; wv < waves; ++wv)
+                for (int p = 0; p < P; ++p) {
+                    if (!wait_for(gs[p].cb_seq, wv + 1)) return;
+                    group_issue(p, gs[p].len, true, wv + 1 < waves);
+                    gs[p].issued.store(wv + 2, std::memory_order_release);
+                }
+        } catch (...) {
+            launcher_error = std::current_exception();
+            abort_.store(true);
         }
-        float* hb = d_->h_boards + off;
-        float* hv = d_->h_values + voff;
-        std::memset(hv, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
-        const double t2 = now_s();
-        if (nB) cb(-1, hv, hb, nB * 8);
-        if (nW) cb(1, hv + (size_t)nB * 8, hb + (size_t)nB * 8 * CELLS, nW * 8);
-        host_callback_s_ += now_s() - t2;
+    });
+    bool cancelled = false;
+    std::exception_ptr caller_error;
+    try {
+        for (int wv = 0; wv < waves && !cancelled; ++wv)
+            for (int p = 0; p < P; ++p) {
+                const double t0 = now_s();
+                if (!wait_for(gs[p].issued, wv + 1)) { cancelled = true; break; }
+                host_wait_s_ += now_s() - t0;
+                gs[p].len = group_eval(p, cb);
+                gs[p].cb_seq.store(wv + 1, std::memory_order_release);
+                if (cancel_.load()) { cancelled = true; abort_.store(true); break; }
+            }
+    } catch (...) {
+        caller_error = std::current_exception();
+        abort_.store(true);
     }
-    const bool move_end = gr.waves_this_move + 1 >= cfg_.num_simulation;  // the group has spent its budget: its games are in lockstep
-    gr.waves_this_move = move_end ? 0 : gr.waves_this_move + 1;
-    if (!gr.exact && use_graphs_ && len) {
-        if (!gr.back_graph) build_graphs(p);
-        C6_CUDA(cudaGraphLaunch(move_end ? gr.back_move_graph : gr.back_graph, gr.s));
-        h2d_bytes_ += (double)n * 8 * (CELLS + 1) * sizeof(float);
-    } else {
-        back_ops(p, len, move_end);
-        h2d_bytes_ += (double)len * (CELLS + 1) * sizeof(float);
+    launcher.join();
+    if (launcher_error) std::rethrow_exception(launcher_error);
+    if (caller_error) std::rethrow_exception(caller_error);
+    if (cancelled) {
+        sync();
+        throw std::runtime_error("c6: cancelled");
     }
-    launches_ += move_end ? 2 : 1;
 }
 
 // `waves` simulations for every resident game, software-pipelined over the groups.
@@ -716,11 +727,13 @@ void Engine::waves_callback(Callback cb, int waves) {
     if (cfg_.evaluator != EVAL_CALLBACK) throw std::runtime_error("c6: engine was not created for the callback path");
     const int P = (int)d_->groups.size();
     if (waves <= 0) return;
-    for (int p = 0; p < P; ++p) group_front(p);
+    if (use_launcher_ && P > 1 && cfg_.num_simulation > 0) return waves_callback_threaded(cb, waves);
+    abort_.store(false);
+    for (int p = 0; p < P; ++p) group_issue(p, 0, false, true);
     for (int wv = 0; wv < waves; ++wv)
         for (int p = 0; p < P; ++p) {
-            group_back(p, cb);
-            if (wv + 1 < waves) group_front(p);
+            const size_t len = group_eval(p, cb);
+            group_issue(p, len, true, wv + 1 < waves);
             if (cancel_.load()) {
                 sync();
                 throw std::runtime_error("c6: cancelled");
@@ -735,11 +748,12 @@ void Engine::waves_device_callback(DeviceCallback cb, void* user, int waves) {
     dcb_ = cb, dcb_user_ = user;
     const int P = (int)d_->groups.size();
     if (waves <= 0) return;
-    for (int p = 0; p < P; ++p) group_front(p);
+    abort_.store(false);
+    for (int p = 0; p < P; ++p) group_issue(p, 0, false, true);
     for (int wv = 0; wv < waves; ++wv)
         for (int p = 0; p < P; ++p) {
-            group_back(p, nullptr);
-            if (wv + 1 < waves) group_front(p);
+            group_eval(p, nullptr);
+            group_issue(p, 0, true, wv + 1 < waves);
             if (cancel_.load()) {
                 sync();
                 throw std::runtime_error("c6: cancelled");
@@ -760,8 +774,6 @@ void Engine::external_move(int slot, int row, int col) {
     const uint32_t bit = bit_of_cell(row * BOARD_SIZE + col);
     if (gs.status != ST_ACTIVE) throw std::runtime_error("c6: external_move on a slot without an active game");
     if (((gs.B[bit >> 5] | gs.W[bit >> 5]) >> (bit & 31)) & 1u) throw std::runtime_error("already set position");
-    for (Group& gr : d_->groups)
-        if (slot >= gr.g0 && slot < gr.g1) gr.waves_this_move = 0;
     k_external_move<<<1, 32, 0, stream_>>>(D, slot, row * BOARD_SIZE + col);
     launches_ += 1;
     C6_CUDA(cudaGetLastError());

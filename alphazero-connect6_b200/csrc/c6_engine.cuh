@@ -165,15 +165,18 @@ class Engine {
     void cancel() { cancel_.store(true); }
 
    private:
-    void group_front(int p);
-    void group_back(int p, Callback cb);
-    void front_ops(int p, bool whole_region);
-    void back_ops(int p, size_t len, bool move_end);
-    void build_graphs(int p);
-    void drop_graphs();
+    void group_issue(int p, size_t len, bool do_back, bool do_front);  // launching thread: every CUDA enqueue of a wave
+    size_t group_eval(int p, Callback cb);                             // calling thread: wait for the leaves, run the user Callback(s)
+    void waves_callback_threaded(Callback cb, int waves);
     DeviceCallback dcb_ = nullptr;
     void* dcb_user_ = nullptr;
-    bool use_graphs_ = false;  // C6_GRAPHS=1: measured no gain over plain launches on the B200 box (profiles/e2e4)
+    // Measured on the B200 box (profiles/e2e/e2e7.md): with five driver calls per group and wave the enqueues no
+    // longer bound the wave, so the second thread buys nothing (C6_LAUNCHER=1 turns it on for slow hosts); leaf
+    // boards stored by the kernel straight into mapped host memory reach ~30 GB/s against ~45 GB/s for the copy
+    // engine, so the copy is the default (C6_ZEROCOPY=1 for the store variant).
+    bool use_launcher_ = false;
+    bool zero_copy_ = false;
+    std::atomic<bool> abort_{false};
     Config cfg_;
     DeviceArrays* d_ = nullptr;
     cudaStream_t stream_ = nullptr;

@@ -85,6 +85,31 @@ __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gmem_s
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// Zobrist keys: 4 KB read by every expansion.  The fused kernel leaves ~40 KB of L1 per SM beside its
+// shared-memory stages and streams node records through it, so the table is kept with an evict-last hint.
+#ifndef C6_Z_EVICT_LAST
+#define C6_Z_EVICT_LAST 1
+#endif
+__device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
+#if C6_Z_EVICT_LAST
+    uint64_t v;
+    asm("ld.global.nc.L1::evict_last.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+#ifndef C6_CHILD_CG
+#define C6_CHILD_CG 0
+#endif
+#ifndef C6_NOISE_UNROLL
+#define C6_NOISE_UNROLL 1
+#endif
+#ifndef C6_PRIOR_UNROLL
+#define C6_PRIOR_UNROLL 1
+#endif
+#define C6_PRAGMA_(x) _Pragma(#x)
+#define C6_UNROLL(n) C6_PRAGMA_(unroll n)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +160,13 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             cp_async_wait_all();
 #pragma unroll 1
             for (int j = 0; j < 8; ++j)
-                if ((st.empty[j] >> lane) & 1u) cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+                if ((st.empty[j] >> lane) & 1u) {
+#if C6_CHILD_CG
+                    cp_async16_cg(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+#else
+                    cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+#endif
+                }
             cp_async_wait_all();
             // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
             // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
@@ -148,7 +179,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
                 unsigned pend = 0;
                 pre = 0;
-#pragma unroll 1
+C6_UNROLL(C6_NOISE_UNROLL)
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t e = st.empty[j];
                     if ((e >> lane) & 1u) {
@@ -234,7 +265,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             const uint32_t mm = (j == (int)wj) ? m : 0u;
             if (turn < 0) L.B[j] |= mm; else L.W[j] |= mm;
         }
-        L.key ^= __ldg(&w.Z[(turn > 0 ? 256 : 0) + chosen_bit]);
+        L.key ^= ldz(&w.Z[(turn > 0 ? 256 : 0) + chosen_bit]);
         L.stones += 1;
         cur = child & Rm;
         depth += 1;
@@ -443,12 +474,12 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
 #pragma unroll 1
     for (int j = 0; j < 8; ++j)
         if ((mine >> j) & 1u) {
-            const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+            const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
             const uint32_t pos = hash_slot(ck) & Im;
             st.pos[j][lane] = pos;
             cp_async16_cg(&st.slot[j][lane], &w.idx[pos]);
         }
-#pragma unroll 1
+C6_UNROLL(C6_PRIOR_UNROLL)
     for (int j = 0; j < 8; ++j)
         if ((mine >> j) & 1u) st.prior[j][lane] = ev.prior(j);
     // B: resolve in rounds — every child still walking its probe chain issues its next probe, then ONE wait
@@ -461,7 +492,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         for (int j = 0; j < 8; ++j)
             if ((todo >> j) & 1u) {
                 const uint4 sv = st.slot[j][lane];  // {key lo, key hi, idx, epoch}
-                const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+                const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
                 if (sv.w != epoch) {  // free: the child is new; its verdict = {position, epoch seen there, -, -}
                     isnew |= 1u << j;
                 } else if ((((uint64_t)sv.y << 32) | sv.x) == ck) {  // present: or_insert keeps it
@@ -506,7 +537,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
             const uint32_t child = st.slot[j][lane].z;
             const float pr = st.prior[j][lane];
             if ((isnew >> j) & 1u) {
-                const uint64_t ck = key ^ __ldg(&w.Z[zoff + 32 * j + lane]);
+                const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
                 *reinterpret_cast<uint4*>(&w.idx[st.pos[j][lane]]) = make_uint4((uint32_t)ck, (uint32_t)(ck >> 32), child, epoch);
                 Rec nr;
                 nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
