@@ -12,7 +12,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct Dev {
     Rec* rec;
     uint32_t* lnk;
-    Slot* idx;
+    Slot* idx;       // [G][I] key table of the expanded nodes (key -> record)
     uint32_t* expB;  // [G][Ecap][16] bitboards of expanded nodes (8 words black, 8 white)
     uint32_t* exp_rec;
     uint64_t* exp_key;
@@ -83,6 +83,23 @@ __device__ __forceinline__ void store_rec(Rec* p, const Rec& r) {
 }
 __device__ __forceinline__ uint32_t hash_slot(uint64_t key) { return (uint32_t)(key ^ (key >> 32)); }
 
+// Key table of the expanded nodes of one game.  Only the warp that owns the game touches it, one lane at a
+// time, so plain L2 loads and a 16 B store are enough; the table holds at most E <= I/2 live entries.
+__device__ __forceinline__ uint32_t xh_find(const Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key) {
+    uint32_t pos = hash_slot(key) & Imask;
+    for (;;) {
+        const Slot s = load_slot(&idx[pos]);
+        if (s.epoch != epoch) return NIL;
+        if (s.key == key) return s.idx;
+        pos = (pos + 1) & Imask;
+    }
+}
+__device__ __forceinline__ void xh_insert(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val) {
+    uint32_t pos = hash_slot(key) & Imask;
+    while (__ldcg(&idx[pos].epoch) == epoch) pos = (pos + 1) & Imask;
+    __stcg(reinterpret_cast<uint4*>(&idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), val, epoch));
+}
+
 // insert (key -> idx) for the current epoch; keys inserted concurrently by the lanes of the warp are
 // distinct and not yet present.  `pos`/`seen` = first non-current slot found by a preceding lookup.
 __device__ __forceinline__ void index_insert(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val,
@@ -134,6 +151,7 @@ struct Leaf {
     int stones;
     uint32_t rec;
     int depth;
+    uint32_t last_bit;  // bit position of the last stone on the path (valid when depth >= 1)
 };
 
 struct Warp {  // per-warp view of one game slot: hot bases as pointers, the rest derived from the slot number on use
@@ -187,11 +205,8 @@ __device__ inline void init_game(const Dev& D, Warp& w, uint32_t game_id) {
         Rec r;
         r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
         store_rec(&w.rec[0], r);
-        uint32_t pos = hash_slot(0ull) & (D.I - 1);
-        Slot seen = load_slot(&w.idx[pos]);
-        uint32_t val;
-        if (!index_find(w.idx, D.I - 1, g.epoch, 0ull, pos, seen, val))
-            index_insert(w.idx, D.I - 1, g.epoch, 0ull, 0u, pos, seen);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.orph[j] = 0;
     }
     __syncwarp();
 }
@@ -230,7 +245,6 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         const uint32_t erec = w.exp_rec(D)[ei];
         const uint64_t ekey = w.exp_key(D)[ei];
         const int C = CELLS - est;
-        const int turn = turn_of(est);
         if (rec_head - old_rec_tail + (uint32_t)C + 1 > D.R || lnk_head - old_lnk_tail + (uint32_t)C > D.L) {
             overflow = true;
             break;
@@ -250,13 +264,10 @@ __device__ inline void collect(const Dev& D, Warp& w) {
                 Rec f;
                 f.n = (int32_t)new_e, f.w = 0.f, f.p = 0.f, f.link = FWD;
                 store_rec(&w.rec[erec], f);
-                uint32_t pos = hash_slot(ekey) & Im;
-                Slot seen = load_slot(&w.idx[pos]);
-                while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
-                index_insert(w.idx, Im, epoch, ekey, new_e, pos, seen);
             }
             copied += 1;
         }
+        if (lane == 0) xh_insert(w.idx, Im, epoch, ekey, new_e);  // expanded nodes stay findable by key
         __syncwarp();
         const uint32_t new_link = lnk_head;
         lnk_head += (uint32_t)C;
@@ -294,11 +305,6 @@ __device__ inline void collect(const Dev& D, Warp& w) {
                     Rec f;
                     f.n = (int32_t)ni, f.w = 0.f, f.p = 0.f, f.link = FWD;
                     store_rec(&w.rec[ci[j]], f);
-                    uint64_t key = ekey ^ w.Z[(turn > 0 ? 256 : 0) + 32 * j + lane];
-                    uint32_t pos = hash_slot(key) & Im;
-                    Slot seen = load_slot(&w.idx[pos]);
-                    while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
-                    index_insert(w.idx, Im, epoch, key, ni, pos, seen);
                 } else {
                     ni = (uint32_t)ch[j].n;
                 }
@@ -325,15 +331,35 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         new_root = rec_head & Rm;
         rec_head += 1;
         copied += 1;
-        if (lane == 0) {
-            store_rec(&w.rec[new_root], rr);
-            uint32_t pos = hash_slot(g.key) & Im;
-            Slot seen = load_slot(&w.idx[pos]);
-            while (seen.epoch == epoch) pos = (pos + 1) & Im, seen = load_slot(&w.idx[pos]);
-            index_insert(w.idx, Im, epoch, g.key, new_root, pos, seen);
-        }
+        if (lane == 0) store_rec(&w.rec[new_root], rr);
     }
     __syncwarp();
+    // Orphans: a kept expanded node X (other than the root) is reached by later expansions through one of its
+    // expanded parents X - s (s a stone of the colour placed last, not on the root board).  If none is left —
+    // its former parent lacked the stone just played — flag X's stone count, so that expansions creating
+    // children of that size look them up by key (c6_search.cuh: resolve_rare).
+    uint32_t orph = 0;  // lane j < 8 holds word j
+    for (uint32_t ei = 0; ei < wcur; ++ei) {
+        int est = 0;
+        uint32_t eb[8], ew[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            eb[j] = w.expB(D)[(size_t)ei * 16 + j];
+            ew[j] = w.expB(D)[(size_t)ei * 16 + 8 + j];
+            est += __popc(eb[j]) + __popc(ew[j]);
+        }
+        if (est == g.stones) continue;  // the root itself
+        const uint64_t ekey = w.exp_key(D)[ei];
+        const int m = turn_of(est - 1);  // colour of the stone placed last
+        bool safe = false;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t cand = m < 0 ? (eb[j] & ~rootB[j]) : (ew[j] & ~rootW[j]);
+            if ((cand >> lane) & 1u) safe = safe || xh_find(w.idx, Im, epoch, ekey ^ w.Z[(m > 0 ? 256 : 0) + 32 * j + lane]) != NIL;
+        }
+        if (!__any_sync(FULL, safe) && lane == (est >> 5)) orph |= 1u << (est & 31);
+    }
+    if (lane < 8) g.orph[lane] = orph;
     if (lane == 0) {
         g.root = new_root;
         g.epoch = epoch;
@@ -485,10 +511,23 @@ __device__ inline void external_move(const Dev& D, Warp& w, uint32_t bit) {
     if (g.rec_head - g.rec_tail + 1 > D.R) return set_error(w, D, ERR_REC_FULL);
     uint32_t root = 0;
     if (lane == 0) {
-        uint32_t pos = hash_slot(key) & Im;
-        Slot seen = load_slot(&w.idx[pos]);
-        uint32_t val;
-        if (index_find(w.idx, Im, g.epoch, key, pos, seen, val)) {
+        // an expanded root links the record of every child board; otherwise the new board may still be an
+        // expanded node of an earlier search (key table); otherwise it is new
+        const Rec rr = load_rec(&w.rec[g.root]);
+        uint32_t val = NIL;
+        if (rr.n >= 1) {
+            int k = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t e = ~(g.B[j] | g.W[j]) & valid_mask(j);
+                if (j < (int)wj) k += __popc(e);
+                if (j == (int)wj) k += __popc(e & (m - 1u));
+            }
+            val = w.lnk[(rr.link + (uint32_t)k) & (D.L - 1)] & Rm;
+        } else {
+            val = xh_find(w.idx, Im, g.epoch, key);
+        }
+        if (val != NIL) {
             root = val;
         } else {
             root = g.rec_head & Rm;
@@ -496,7 +535,6 @@ __device__ inline void external_move(const Dev& D, Warp& w, uint32_t bit) {
             Rec r;
             r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
             store_rec(&w.rec[root], r);
-            index_insert(w.idx, Im, g.epoch, key, root, pos, seen);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.B[j] = B[j], g.W[j] = W[j];

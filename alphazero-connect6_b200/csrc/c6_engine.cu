@@ -81,15 +81,15 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
             } else if (EVAL == EVAL_PHILOX) {
                 EvPhilox ev;
                 ev.init(D, cs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value(), st);
+                expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             } else if (EVAL == EVAL_DET) {
                 EvHash<false> ev;
                 ev.init(L, Zs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value(), st);
+                expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             } else {
                 EvHash<true> ev;
                 ev.init(L, Zs, lane);
-                expand_leaf(D, w, cs, L, ev, ev.value(), st);
+                expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
         }
@@ -146,13 +146,13 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
                 Leaf L;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
-                L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth;
+                L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth, L.last_bit = gs.leaf_last;
                 const float* region = D.batch + (size_t)g0 * 8 * (CELLS + 1);
                 EvBatch ev;
                 ev.values = region + (size_t)gs.batch_pos * 8;
                 ev.pol = region + (size_t)(g1 - g0) * 8 + (size_t)gs.batch_pos * 8 * CELLS;
                 ev.lane = lane;
-                expand_leaf(D, w, cs, L, ev, ev.value(), st);
+                expand_leaf<false>(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
             store_cursor(D, gs, cs, lane);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
         for (int j = 0; j < 8; ++j)
             if (lane == j) gs.leafB[j] = L.B[j], gs.leafW[j] = L.W[j];
         if (lane == 0) {
-            gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key;
+            gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key, gs.leaf_last = L.last_bit;
             gs.need_eval = need;
         }
         store_cursor(D, gs, cs, lane);
@@ -255,9 +255,10 @@ __global__ void __launch_bounds__(128) k_gather(Dev D, int g0, int g1, int group
 __global__ void k_publish(Dev D, int group, int seq) { *(volatile int*)(D.hsync + 4 * group + 2) = seq; }
 
 // Invariant checker (tests / debugging): for every resident game, every entry of the expanded list must
-// (1) carry the Zobrist key of its board, (2) own an expanded record (N >= 1, real link run), whose
-// (3) children are unforwarded records that (4) the board-key index maps back to, and (5) no record
-// is listed twice.  Violations are counted in viol[0]; the first few are described in viol[1..].
+// (1) carry the Zobrist key of its board, (2) own an expanded record (N >= 1, real link run) that (3) the key
+// table maps its key to, whose (4) children are unforwarded records inside the live part of the ring, and
+// (5) a child board that is itself expanded is linked to THAT record (one record per board), (6) no record is
+// listed twice.  Violations are counted in viol[0]; the first few are described in viol[1..].
 __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* viol) {
     __shared__ uint64_t Zs[512];
     load_zobrist(D, Zs);
@@ -275,16 +276,11 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
             viol[1 + n * 4 + 1] = a, viol[1 + n * 4 + 2] = b, viol[1 + n * 4 + 3] = c;
         }
     };
-    auto lookup = [&](uint64_t key, uint32_t& val) {
-        uint32_t pos = hash_slot(key) & Im;
-        Slot seen = load_slot(&w.idx[pos]);
-        return index_find(w.idx, Im, gs.epoch, key, pos, seen, val);
-    };
     if (lane == 0) {
-        uint32_t val = 0;
-        if (!lookup(gs.key, val) || val != gs.root) report(1, gs.root, val, 0);
         uint32_t used = gs.rec_head - gs.rec_tail;
         if (((gs.root - gs.rec_tail) & Rm) >= used) report(9, gs.root, gs.rec_tail, gs.rec_head);
+        const Rec rr = load_rec(&w.rec[gs.root & Rm]);
+        if (rr.n >= 1 && xh_find(w.idx, Im, gs.epoch, gs.key) != gs.root) report(1, gs.root, 0, 0);
     }
     const uint32_t n_exp = gs.exp_count;
     for (uint32_t ei = 0; ei < n_exp; ++ei) {
@@ -309,8 +305,8 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
                 report(20, (uint32_t)(key ^ ekey), (uint32_t)((key ^ ekey) >> 32), 0);
             }
             if (r.n < 1 || r.link == NIL || r.link == FWD) report(3, ei, erec, (uint32_t)r.n);
-            uint32_t val = 0;
-            if (!lookup(ekey, val) || val != erec) report(4, ei, erec, val);
+            const uint32_t val = xh_find(w.idx, Im, gs.epoch, ekey);
+            if (val != erec) report(4, ei, erec, val);
             if (((erec - gs.rec_tail) & Rm) >= gs.rec_head - gs.rec_tail) report(8, ei, erec, gs.rec_tail);
         }
         for (uint32_t e2 = ei + 1 + lane; e2 < n_exp; e2 += 32)
@@ -326,8 +322,8 @@ __global__ void __launch_bounds__(128) k_validate(Dev D, unsigned long long* vio
                 uint32_t ci = w.lnk[(r.link + (uint32_t)k) & Lm];
                 Rec ch = load_rec(&w.rec[ci & Rm]);
                 if (ch.link == FWD) report(6, ei, ci, (uint32_t)k);
-                uint32_t val = 0;
-                if (!lookup(ekey ^ Zs[(turn > 0 ? 256 : 0) + 32 * j + lane], val) || val != ci) report(7, ei, ci, val);
+                const uint32_t val = xh_find(w.idx, Im, gs.epoch, ekey ^ Zs[(turn > 0 ? 256 : 0) + 32 * j + lane]);
+                if (val != NIL ? val != ci : ch.n >= 1) report(7, ei, ci, val);
                 if (((ci - gs.rec_tail) & Rm) >= gs.rec_head - gs.rec_tail) report(10, ei, ci, gs.rec_tail);
             }
             pre += __popc(e);
@@ -370,7 +366,7 @@ static void make_zobrist(uint64_t* Zb) {  // same sequence as the test oracle's 
 
 size_t Engine::bytes_per_game() const {
     size_t R = (size_t)1 << cfg_.log2_records;
-    return R * sizeof(Rec) + 2 * R * sizeof(uint32_t) + 2 * R * sizeof(Slot) + d_->dev.E * (64 + 4 + 8) + 232 * 4 +
+    return R * sizeof(Rec) + 2 * R * sizeof(uint32_t) + d_->dev.I * sizeof(Slot) + d_->dev.E * (64 + 4 + 8) + 232 * 4 +
            sizeof(GameState);
 }
 
@@ -394,9 +390,8 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.G = cfg_.slots;
     D.R = 1u << cfg_.log2_records;
     D.L = D.R * 2;
-    D.I = D.R * 2;
-    if (const char* xf = std::getenv("C6_INDEX_FACTOR")) D.I = D.R * (uint32_t)std::max(1, std::atoi(xf));  // tuning knob (power of two)
     D.E = 4096;
+    D.I = 8192;  // key table of expanded nodes: power of two >= 2 * E
     D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
     D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves;
     const size_t G = (size_t)D.G;

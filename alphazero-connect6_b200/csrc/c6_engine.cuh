@@ -30,7 +30,9 @@ struct __align__(16) Rec {
     float p;
     uint32_t link;
 };
-// Board-key index slot, 16 B; valid iff epoch == the game's current epoch (O(1) clear).
+// Key-table slot, 16 B; valid iff epoch == the game's current epoch (O(1) clear).  The table holds the
+// EXPANDED nodes of a game only (one insert per simulation); children are shared through link runs
+// (c6_search.cuh: expand_leaf), so there is no per-child board-key index.
 struct __align__(16) Slot {
     uint64_t key;
     uint32_t idx;
@@ -63,9 +65,12 @@ struct GameState {
     int32_t leaf_stones;
     int32_t need_eval;
     int32_t batch_pos;
-    int32_t pad0;
+    uint32_t leaf_last;       // bit position of the last stone on the path to the parked leaf
     uint64_t leaf_key;
     uint32_t leafB[8], leafW[8];
+    // bit s: some expanded node with s stones kept by the collector has no expanded parent left (its former
+    // parent did not contain the new root); expansions that create children with s stones look those up by key
+    uint32_t orph[8];
     // statistics (SURVEY §8d counters)
     unsigned long long sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied;
     uint32_t peak_rec, peak_lnk;

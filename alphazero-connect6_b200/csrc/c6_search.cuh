@@ -11,8 +11,10 @@
 //       are ROLLED loops over the eight board words that read their operands from a per-warp
 //       shared-memory stage filled by cp.async — one copy of the PUCT, Gamma and Philox code each;
 //   (2) everything a move needs from the game state lives in registers (`Cursor`);
-//   (3) the board-key inserts of an expansion are issued back to back, four children per lane in
-//       flight, with the priors of the batch computed under the probe latency;
+//   (3) an expansion does not hash its children: a child shared with another parent ("transposition",
+//       `entry(hash).or_insert`, :367-370) is found by following the link run of the expanded sibling
+//       the select step has just read (r01d: the per-child board-key index cost 60 KB of DRAM traffic per
+//       simulation against 12.5 KB of algorithmic bytes); only expanded nodes are kept in a key table;
 //   (4) no stack frame: every helper on the default path is inlined into a single call site.
 #pragma once
 #include "c6_device.cuh"
@@ -57,17 +59,14 @@ __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const C
 // the code of a phase exists once.
 template <int NOISE>
 struct WarpStage {
-    union {
-        uint4 child[8][32];  // select: {N, W, P, link} of this lane's child in board word j
-        uint4 slot[8][32];   // expand: the index slot last probed for this lane's child of word j, then its verdict
-    };
+    uint4 child[8][32];  // select: {N, W, P, link} of this lane's child in board word j; expand reads the siblings here
     union {
         uint32_t ci[8][32];  // select: record index of that child
         float prior[8][32];  // expand: priors of the new children
     };
     union {
         double gamma[NOISE ? 8 : 4][32];  // select: Gamma draws of one step
-        uint32_t pos[8][32];              // expand: index position being probed
+        uint32_t pos[8][32];              // expand: record index of the child
     };
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
 };
@@ -112,6 +111,32 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #define C6_UNROLL(n) C6_PRAGMA_(unroll n)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Memory phase of a select step: for the node whose empty-cell masks are in st.empty and whose link run starts
+// at `link`, this lane's child of every board word — record indices into st.ci, then records into st.child,
+// eight requests of each kind in flight per lane.
+template <int NOISE>
+__device__ __forceinline__ void stage_children(const Warp& w, WarpStage<NOISE>& st, uint32_t link, int lane, uint32_t Rm, uint32_t Lm) {
+    const uint32_t lt = (1u << lane) - 1u;
+    int pre = 0;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = st.empty[j];
+        if ((e >> lane) & 1u) cp_async4(&st.ci[j][lane], &w.lnk[(link + (uint32_t)(pre + __popc(e & lt))) & Lm]);
+        pre += __popc(e);
+    }
+    cp_async_wait_all();
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j)
+        if ((st.empty[j] >> lane) & 1u) {
+#if C6_CHILD_CG
+            cp_async16_cg(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+#else
+            cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
+#endif
+        }
+    cp_async_wait_all();
+}
+
 // ------------------------------------------------------------------------------------------------
 // select
 // ------------------------------------------------------------------------------------------------
@@ -125,6 +150,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     for (int j = 0; j < 8; ++j) L.B[j] = g.B[j], L.W[j] = g.W[j];
     L.key = g.key;
     L.stones = g.stones;
+    L.last_bit = 0;
     uint32_t cur = g.root;
     int depth = 0;
     const float eps = D.eps, one_m_eps = 1.f - D.eps, cpuct = D.cpuct;
@@ -151,23 +177,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
             __syncwarp();
             int pre = 0;
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t e = st.empty[j];
-                if ((e >> lane) & 1u) cp_async4(&st.ci[j][lane], &w.lnk[(r.link + (uint32_t)(pre + __popc(e & lt))) & Lm]);
-                pre += __popc(e);
-            }
-            cp_async_wait_all();
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j)
-                if ((st.empty[j] >> lane) & 1u) {
-#if C6_CHILD_CG
-                    cp_async16_cg(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
-#else
-                    cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
-#endif
-                }
-            cp_async_wait_all();
+            stage_children(w, st, r.link, lane, Rm, Lm);
             // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
             // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
             // sampler for every child; the ~1-3% of draws that need the other branch or another trial are
@@ -267,6 +277,7 @@ C6_UNROLL(C6_NOISE_UNROLL)
         }
         L.key ^= ldz(&w.Z[(turn > 0 ? 256 : 0) + chosen_bit]);
         L.stones += 1;
+        L.last_bit = chosen_bit;
         cur = child & Rm;
         depth += 1;
     }
@@ -424,28 +435,76 @@ struct EvBatch {
 // ------------------------------------------------------------------------------------------------
 // expand (:350-377) for a non-full leaf, then update()
 // ------------------------------------------------------------------------------------------------
-// Continuation of a claim whose slot was taken by another key of this epoch in the meantime (two children
-// of one expansion hashing to the same free slot): keep probing for a free slot and claim it.  Rare.
-__device__ __noinline__ uint32_t index_claim_after_conflict(Slot* idx, uint32_t Imask, uint32_t epoch, uint32_t pos) {
-    for (;;) {
-        uint32_t seen_epoch;
-        do {
-            pos = (pos + 1) & Imask;
-            seen_epoch = __ldcg(&idx[pos].epoch);
-        } while (seen_epoch == epoch);
-        if (atomicCAS(&idx[pos].epoch, seen_epoch, epoch) != epoch) return pos;
+// How a child of the leaf B finds the record of its board if another parent made it first
+// (`entry(hash).or_insert`, :367-370; oracle/pool_model.cpp checks these rules against the map-based
+// restatement on the CPU).  Write B = root + a_1 .. a_d, m = colour of the stone B's children add, X = B + c.
+// Every expanded node kept by the collector contains the root, so another expanded parent of X is
+// E = B - s' + c for a path stone s' of colour m:
+//   (F)  s' = a_d (same colour as c): E = P + c is the sibling of B under its parent P, whose record the last
+//        select step left in st.child; if it is expanded, X is entry rank_E(a_d) of its link run.  The common case.
+//   (S1) s' an earlier path stone of colour m (possible from depth 3): E is looked up in the key table of
+//        expanded nodes; X is entry rank_E(s') of its link run.
+//   (S2) X itself expanded with no expanded parent left after a collection (flagged per stone count in
+//        GameState::orph): looked up in the key table.
+// An unexpanded node that nothing links any more carries no state (N = 0, W = 0, its prior is overwritten by
+// the next expanding parent, :371), so a fresh record is equivalent.
+//
+// S1 + S2, out of line: rare (late-game deep paths), kept out of the hot instruction stream.  `cm0/cm1` = the
+// leaf's stones of colour m, `skip` = bit of a_d when rule F covers it (else NIL).  Returns the updated mask
+// of resolved board words; record indices go to pos[j*32 + lane].
+__device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint32_t epoch, const uint32_t* lnk, uint32_t Lm,
+                                              const Rec* rec, uint32_t Rm, const uint64_t* Z, const GameState* gs, uint32_t* pos,
+                                              const uint32_t* empty, uint4 cm0, uint4 cm1, uint64_t key, int stones, uint32_t zoff,
+                                              uint32_t skip, unsigned mine, unsigned res, int lane, int depth) {
+    const uint32_t cm[8] = {cm0.x, cm0.y, cm0.z, cm0.w, cm1.x, cm1.y, cm1.z, cm1.w};
+    if (depth >= 3) {
+        const uint32_t* rootcol = zoff ? gs->W : gs->B;
+        int before = 0;  // empty cells of the leaf in the words below j
+        for (int j = 0; j < 8; ++j) {
+            uint32_t others = cm[j] & ~rootcol[j];
+            if ((skip >> 5) == (uint32_t)j) others &= ~(1u << (skip & 31));
+            while (others) {  // warp-uniform
+                const int b = __ffs((int)others) - 1;
+                others &= others - 1;
+                const uint32_t sp = 32u * j + (uint32_t)b;
+                const uint32_t rsp = (uint32_t)(before + __popc(empty[j] & ((1u << b) - 1u)));
+                const uint64_t ks = key ^ Z[zoff + sp];
+                for (int jj = 0; jj < 8; ++jj)
+                    if (((mine & ~res) >> jj) & 1u) {
+                        const uint32_t cbit = 32u * jj + (uint32_t)lane;
+                        const uint32_t e = xh_find(idx, Im, epoch, ks ^ Z[zoff + cbit]);
+                        if (e != NIL) {
+                            const uint32_t link = rec[e & Rm].link;
+                            pos[jj * 32 + lane] = lnk[(link + rsp - (cbit < sp ? 1u : 0u)) & Lm];
+                            res |= 1u << jj;
+                        }
+                    }
+            }
+            before += __popc(empty[j]);
+        }
     }
+    const uint32_t s1 = (uint32_t)stones + 1u;
+    if ((gs->orph[s1 >> 5] >> (s1 & 31)) & 1u) {
+        for (int jj = 0; jj < 8; ++jj)
+            if (((mine & ~res) >> jj) & 1u) {
+                const uint32_t x = xh_find(idx, Im, epoch, key ^ Z[zoff + 32u * jj + (uint32_t)lane]);
+                if (x != NIL) pos[jj * 32 + lane] = x, res |= 1u << jj;
+            }
+    }
+    return res;
 }
 
-template <class Ev, int NOISE>
+// STAGED: st.child still holds the children of the leaf's parent from the last select step (fused kernel);
+// otherwise (the expansion runs in a later launch than the descent) they are staged again here.
+template <bool STAGED, class Ev, int NOISE>
 __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, const Leaf& L, const Ev& ev, float v,
                                             WarpStage<NOISE>& st) {
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1, Im = D.I - 1;
     const uint32_t lt = (1u << lane) - 1u;
     const int C = CELLS - L.stones;
-    const uint32_t zoff = turn_of(L.stones) > 0 ? 256u : 0u;
-    const uint32_t epoch = cs.epoch;
+    const int turn = turn_of(L.stones);
+    const uint32_t zoff = turn > 0 ? 256u : 0u;
     const uint32_t link_base = cs.lnk_head;
     const uint32_t ec = cs.exp_count;
     if (cs.lnk_head - cs.lnk_tail + (uint32_t)C > D.L) cs.err = ERR_LNK_FULL;
@@ -462,83 +521,78 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         }
         w.expB(D)[(size_t)ec * 16 + lane] = word;
     }
+    // rule F applies when the last path stone has the colour of the stone the children add
+    const bool sib = L.depth >= 1 && turn_of(L.stones - 1) == turn;
+    const uint32_t lj = L.last_bit >> 5, lm = 1u << (L.last_bit & 31);
+    if (!STAGED && sib) {  // the parent's children: its empties are the leaf's plus the last stone
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane == j) st.empty[j] = (~(L.B[j] | L.W[j]) & valid_mask(j)) | (j == (int)lj ? lm : 0u);
+        __syncwarp();
+        const uint32_t prec = w.path(D)[L.depth - 1];
+        stage_children(w, st, w.rec[prec].link, lane, Rm, Lm);
+        __syncwarp();
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
     __syncwarp();
     const uint64_t key = L.key;
     unsigned mine = 0;  // bit j: this lane has a child in board word j
+    uint32_t r0 = 0;    // rank of the last path stone among the empties of a sibling that lacks it (before the c < a_d correction)
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) mine |= ((st.empty[j] >> lane) & 1u) << j;
-    // A: first probe of every child key (entry(hash), :367-370), all in flight; priors computed under the latency
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = st.empty[j];
+        mine |= ((e >> lane) & 1u) << j;
+        r0 += j < (int)lj ? __popc(e) : (j == (int)lj ? __popc(e & (lm - 1u)) : 0);
+    }
+    // A: rule F — the link of every shared child in flight; priors computed under the latency
+    unsigned res = 0;  // bit j: the child of word j already has a record, index in st.pos
+    if (sib) {
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j)
-        if ((mine >> j) & 1u) {
-            const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
-            const uint32_t pos = hash_slot(ck) & Im;
-            st.pos[j][lane] = pos;
-            cp_async16_cg(&st.slot[j][lane], &w.idx[pos]);
-        }
+        for (int j = 0; j < 8; ++j)
+            if ((mine >> j) & 1u) {
+                const uint4 sv = st.child[j][lane];  // the sibling P + c
+                if ((int)sv.x >= 1) {
+                    const uint32_t cbit = 32u * j + (uint32_t)lane;
+                    cp_async4(&st.pos[j][lane], &w.lnk[(sv.w + r0 - (cbit < L.last_bit ? 1u : 0u)) & Lm]);
+                    res |= 1u << j;
+                }
+            }
+    }
 C6_UNROLL(C6_PRIOR_UNROLL)
     for (int j = 0; j < 8; ++j)
         if ((mine >> j) & 1u) st.prior[j][lane] = ev.prior(j);
-    // B: resolve in rounds — every child still walking its probe chain issues its next probe, then ONE wait
-    // serves them all (a lane-by-lane walk would pay a memory round trip per hop and per board word)
-    unsigned todo = mine, isnew = 0;
-    for (;;) {
-        cp_async_wait_all();
-        unsigned again = 0;
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j)
-            if ((todo >> j) & 1u) {
-                const uint4 sv = st.slot[j][lane];  // {key lo, key hi, idx, epoch}
-                const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
-                if (sv.w != epoch) {  // free: the child is new; its verdict = {position, epoch seen there, -, -}
-                    isnew |= 1u << j;
-                } else if ((((uint64_t)sv.y << 32) | sv.x) == ck) {  // present: or_insert keeps it
-                    st.slot[j][lane] = make_uint4(0u, 0u, sv.z, 0u);
-                } else {
-                    const uint32_t pos = (st.pos[j][lane] + 1) & Im;
-                    st.pos[j][lane] = pos;
-                    cp_async16_cg(&st.slot[j][lane], &w.idx[pos]);
-                    again |= 1u << j;
-                }
-            }
-        todo = again;
-        if (!__any_sync(FULL, todo != 0)) break;
+    // rules S1 / S2 (warp-uniform test)
+    {
+        const uint32_t s1 = (uint32_t)L.stones + 1u;
+        if (L.depth >= 3 || ((w.gs->orph[s1 >> 5] >> (s1 & 31)) & 1u)) {
+            const uint4 cm0 = turn < 0 ? make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]) : make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]);
+            const uint4 cm1 = turn < 0 ? make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]) : make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]);
+            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, cm0, cm1, key, L.stones,
+                               zoff, sib ? L.last_bit : NIL, mine, res, lane, L.depth);
+        }
     }
-    // new records are laid out contiguously in row-major child order
+    cp_async_wait_all();
+    // B: new records are laid out contiguously in row-major child order
+    const unsigned isnew = mine & ~res;
     uint32_t base = cs.rec_head;
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
         const bool nw = (isnew >> j) & 1u;
         const unsigned bal = __ballot_sync(FULL, nw);
-        if (nw) st.slot[j][lane].z = (base + __popc(bal & lt)) & Rm;
+        if (nw) st.pos[j][lane] = base + __popc(bal & lt);
         base += __popc(bal);
     }
-    // C1: claim the free slots — a 32-bit CAS on the epoch word (only this warp writes this game's index, and
-    // nothing reads a key between the claim and the key store below); the eight claims are in flight together
-    uint32_t got[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        got[j] = 0;
-        if ((isnew >> j) & 1u) got[j] = atomicCAS(&w.idx[st.pos[j][lane]].epoch, st.slot[j][lane].w, epoch);
-    }
-    // a returned current epoch means another child of this expansion claimed the slot first: keep probing (rare)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (((isnew >> j) & 1u) && got[j] == epoch) st.pos[j][lane] = index_claim_after_conflict(w.idx, Im, epoch, st.pos[j][lane]);
-    // C2: keys, records, priors, link run
+    // C: records, priors, link run
     int pre = 0;
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
         const uint32_t e = st.empty[j];
         if ((mine >> j) & 1u) {
-            const uint32_t child = st.slot[j][lane].z;
+            const uint32_t child = st.pos[j][lane] & Rm;
             const float pr = st.prior[j][lane];
             if ((isnew >> j) & 1u) {
-                const uint64_t ck = key ^ ldz(&w.Z[zoff + 32 * j + lane]);
-                *reinterpret_cast<uint4*>(&w.idx[st.pos[j][lane]]) = make_uint4((uint32_t)ck, (uint32_t)(ck >> 32), child, epoch);
                 Rec nr;
                 nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
                 store_rec(&w.rec[child], nr);
@@ -549,8 +603,8 @@ C6_UNROLL(C6_PRIOR_UNROLL)
         }
         pre += __popc(e);
     }
-    __syncwarp();  // the claim paths above diverge; nothing below may overtake a lane still probing
-    // the leaf itself: visit += 1, children attached (:353-357,374-377)
+    __syncwarp();
+    // the leaf itself: visit += 1, children attached (:353-357,374-377), findable by key from now on
     if (lane == 0) {
         Rec lr = load_rec(&w.rec[L.rec]);
         lr.n += 1;
@@ -558,6 +612,7 @@ C6_UNROLL(C6_PRIOR_UNROLL)
         store_rec(&w.rec[L.rec], lr);
         w.exp_rec(D)[ec] = L.rec;
         w.exp_key(D)[ec] = key;
+        xh_insert(w.idx, Im, cs.epoch, key, L.rec);
     }
     cs.exp_count = ec + 1;
     cs.lnk_head = link_base + (uint32_t)C;

@@ -187,7 +187,7 @@ struct OracleGameOut {
 };
 
 static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, OracleGameOut* out,
-                     int32_t* child_visits, int32_t* root_visit, float* root_qsum) {
+                     int32_t* child_visits, int32_t* root_visit, float* root_qsum, const int* prefix = nullptr, int n_prefix = 0) {
     HyperParameter hp;
     hp.num_simulation = p.num_simulation, hp.epsilon = p.epsilon, hp.dirichlet_alpha = p.dirichlet_alpha,
     hp.c_puct = p.c_puct;
@@ -207,6 +207,13 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
     // Agent::play with an optional stone limit (bounded samples for timing)
     Game game;
     out->winner = 0, out->n_moves = 0, out->finished = 1;
+    // stones placed by somebody else before the policy is asked for the first time (must not end the game)
+    for (int i = 0; i < n_prefix; ++i) {
+        out->moves[out->n_moves] = prefix[i];
+        out->turns[out->n_moves] = (int)game.turn;
+        out->n_moves += 1;
+        if (!game.set(Pos(prefix[i] / BOARD_SIZE, prefix[i] % BOARD_SIZE)).empty() || game.is_game_end() != Player::None) std::abort();
+    }
     for (;;) {
         if (p.max_moves > 0 && out->n_moves >= p.max_moves) {
             out->finished = 0;
@@ -229,10 +236,10 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
     out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf, out->sum_depth = s.sum_depth,
     out->evals = s.evals, out->max_nodes = s.max_nodes;
     if (child_visits) {
-        for (size_t m = 0; m < pol.child_visits.size(); ++m) {
-            std::memcpy(child_visits + m * BOARD_CAPACITY, pol.child_visits[m].data(), BOARD_CAPACITY * 4);
-            root_visit[m] = pol.root_visit[m];
-            root_qsum[m] = pol.root_qsum[m];
+        for (size_t m = 0; m < pol.child_visits.size(); ++m) {  // row = stones on the board when next() was called
+            std::memcpy(child_visits + (m + n_prefix) * BOARD_CAPACITY, pol.child_visits[m].data(), BOARD_CAPACITY * 4);
+            root_visit[m + n_prefix] = pol.root_visit[m];
+            root_qsum[m + n_prefix] = pol.root_qsum[m];
         }
     }
 }
@@ -241,6 +248,12 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
 void oracle_self_play(Callback cb, const OracleParams* p, uint32_t game_id, OracleGameOut* out,
                       int32_t* child_visits, int32_t* root_visit, float* root_qsum) {
     play_one(cb, *p, game_id, out, child_visits, root_visit, root_qsum);
+}
+
+// The same from a given position: `prefix` = cells (row*15+col) of the stones already played, in order.
+void oracle_self_play_from(Callback cb, const OracleParams* p, uint32_t game_id, const int* prefix, int n_prefix, OracleGameOut* out,
+                           int32_t* child_visits, int32_t* root_visit, float* root_qsum) {
+    play_one(cb, *p, game_id, out, child_visits, root_visit, root_qsum, prefix, n_prefix);
 }
 
 // n_games games on n_threads OS threads, one game per task like AsyncAgent::run

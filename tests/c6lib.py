@@ -64,6 +64,8 @@ def oracle():
         L.oracle_script_game.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         L.oracle_self_play.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(OracleGameOut),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.oracle_self_play_from.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(OracleGameOut),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.oracle_self_play_many.restype = C.c_double
         L.oracle_self_play_many.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.c_int, C.c_int, C.POINTER(OracleGameOut)]
         L.oracle_play_with.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(OracleGameOut)]

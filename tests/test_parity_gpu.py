@@ -18,7 +18,26 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5  # north_star tolerance for Q/value statistics
 
 
-def run_engine(n_games, callback_name=None, first_id=0, **cfg_kw):
+def make_prefix(n_stones, seed):
+    """A legal opening of n_stones cells (row*15+col, in playing order) that nobody has won yet."""
+    O = c6lib.oracle()
+    rng = np.random.default_rng(seed)
+    board = np.zeros(225, dtype=np.int8)
+    cells = []
+    while len(cells) < n_stones:
+        c = int(rng.integers(225))
+        if board[c] != 0:
+            continue
+        i = len(cells)
+        board[c] = -1 if i == 0 else (1 if ((i - 1) // 2) % 2 == 0 else -1)
+        if O.oracle_search(board.ctypes.data_as(C.POINTER(C.c_int8))) != 0:
+            board[c] = 0
+            continue
+        cells.append(c)
+    return cells
+
+
+def run_engine(n_games, callback_name=None, first_id=0, prefixes=None, **cfg_kw):
     L = c6lib.product()
     cfg_kw.setdefault("slots", n_games)
     cfg_kw.setdefault("trace", 1)
@@ -28,6 +47,9 @@ def run_engine(n_games, callback_name=None, first_id=0, **cfg_kw):
     assert e, L.c6_last_error()
     try:
         assert L.c6_engine_start(e, first_id, n_games) == 0, L.c6_last_error()
+        for g, cells in enumerate(prefixes or []):  # stones placed from outside before the first search (slot g = game g)
+            for c in cells:
+                assert L.c6_engine_external_move(e, g, c // 15, c % 15) == 0, L.c6_last_error()
         if cfg.evaluator == EVAL_CALLBACK:
             cb = c6lib.CALLBACK(c6lib.oracle_callback(callback_name))
             assert L.c6_engine_run_callback(e, cb) == 0, L.c6_last_error()
@@ -48,7 +70,7 @@ def run_engine(n_games, callback_name=None, first_id=0, **cfg_kw):
         L.c6_engine_destroy(e)
 
 
-def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0):
+def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0, prefix=None):
     O = c6lib.oracle()
     p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, 0, 0, evaluator, max_moves)
     out = c6lib.OracleGameOut()
@@ -56,14 +78,19 @@ def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed,
     rn = np.zeros(225, dtype=np.int32)
     rw = np.zeros(225, dtype=np.float32)
     cb = c6lib.oracle_callback(callback_name) if callback_name else None
-    O.oracle_self_play(cb, C.byref(p), game_id, C.byref(out), cv.ctypes.data_as(C.POINTER(C.c_int32)),
-                       rn.ctypes.data_as(C.POINTER(C.c_int32)), rw.ctypes.data_as(C.POINTER(C.c_float)))
+    pre = prefix or []
+    O.oracle_self_play_from(cb, C.byref(p), game_id, (C.c_int * max(len(pre), 1))(*pre), len(pre), C.byref(out),
+                            cv.ctypes.data_as(C.POINTER(C.c_int32)), rn.ctypes.data_as(C.POINTER(C.c_int32)),
+                            rw.ctypes.data_as(C.POINTER(C.c_float)))
     return out, cv, rn, rw
 
 
-def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves):
+def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=1.0,
+                  prefixes=None):
     for g in range(n_games):
-        out, ocv, orn, orw = run_oracle(first_id + g, callback_name, evaluator, num_simulation, epsilon, seed, max_moves)
+        pre = prefixes[g] if prefixes else []
+        out, ocv, orn, orw = run_oracle(first_id + g, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=c_puct,
+                                        prefix=pre)
         r = rec[g]
         where = f"game {first_id + g}"
         assert r.game_id == first_id + g
@@ -76,11 +103,11 @@ def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, 
                                  f"visit rows equal before: {np.array_equal(cv[g][:first], ocv[:first])}")
         assert r.winner == out.winner, where
         assert r.finished == out.finished, where
-        n = r.n_moves
+        n, n0 = r.n_moves, len(pre)  # no search happens before the stones of a given opening
         # the engine records a trace row for every next() call, including a final call that returns None
-        assert np.array_equal(cv[g][:n], ocv[:n]), f"{where}: root child visit counts differ"
-        assert np.array_equal(rn[g][:n], orn[:n]), f"{where}: root visits differ"
-        a, b = rw[g][:n], orw[:n]
+        assert np.array_equal(cv[g][n0:n], ocv[n0:n]), f"{where}: root child visit counts differ"
+        assert np.array_equal(rn[g][n0:n], orn[n0:n]), f"{where}: root visits differ"
+        a, b = rw[g][n0:n], orw[n0:n]
         assert np.all(np.abs(a - b) <= REL_TOL * np.maximum(np.abs(b), 1e-30)), f"{where}: root q_sum beyond 1e-5 rel"
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{where}: root q_sum not bit-identical"
 
@@ -222,6 +249,25 @@ def test_selfplay_device_path(evaluator, cbname, sims, eps, n_games, max_moves):
     rec, cv, rn, rw, st = run_engine(n_games, None, first_id=77, num_simulation=sims, epsilon=eps, seed=seed,
                                      evaluator=evaluator, max_moves=max_moves)
     compare_games(n_games, rec, cv, rn, rw, 77, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, max_moves)
+
+
+@pytest.mark.parametrize("evaluator,cbname,sims,c_puct,n_stones", [
+    # Nearly full boards searched with a low c_puct: every simulation runs many stones deep, so the rare rules of
+    # expand_leaf decide the result (co-parents through an earlier path stone, expanded nodes orphaned by the
+    # collector; oracle/pool_model.cpp counts how often they fire in positions like these), full-board leaves
+    # and single-child nodes occur, and the games end with policy() returning None on a full board.
+    (EVAL_NEG, "neg_eval_callback", 300, 0.2, 214),
+    (EVAL_DET, "det_eval_callback", 120, 0.3, 205),
+    (EVAL_NEG, "neg_eval_callback", 64, 1.0, 190),
+    (EVAL_CALLBACK, "neg_eval_callback", 150, 0.2, 212),   # the same through the split descend / expand kernels
+])
+def test_selfplay_deep_trees_late_game(evaluator, cbname, sims, c_puct, n_stones):
+    seed, n_games = 0xC6, 3
+    prefixes = [make_prefix(n_stones + g, 1000 * n_stones + g) for g in range(n_games)]
+    rec, cv, rn, rw, st = run_engine(n_games, cbname if evaluator == EVAL_CALLBACK else None, first_id=300, prefixes=prefixes,
+                                     num_simulation=sims, epsilon=0.0, c_puct=c_puct, seed=seed, evaluator=evaluator)
+    compare_games(n_games, rec, cv, rn, rw, 300, cbname, 0, sims, 0.0, seed, 0, c_puct=c_puct, prefixes=prefixes)
+    assert st.sum_depth > 2 * st.sims  # the trees really are deep
 
 
 def test_selfplay_800_sims_reference_default():
