@@ -58,20 +58,6 @@ __device__ __forceinline__ Slot load_slot(const Slot* p) {  // L2-coherent (slot
     s.epoch = v.w;
     return s;
 }
-__device__ __forceinline__ Slot cas_slot(Slot* p, const Slot& expect, const Slot& desired) {
-    unsigned long long e0 = expect.key, e1 = ((unsigned long long)expect.epoch << 32) | expect.idx;
-    unsigned long long d0 = desired.key, d1 = ((unsigned long long)desired.epoch << 32) | desired.idx;
-    unsigned long long o0, o1;
-    asm volatile(
-        "{\n\t.reg .b128 e, d, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
-        "atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
-        : "=l"(o0), "=l"(o1)
-        : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(p)
-        : "memory");
-    Slot o;
-    o.key = o0, o.idx = (uint32_t)o1, o.epoch = (uint32_t)(o1 >> 32);
-    return o;
-}
 __device__ __forceinline__ Rec load_rec(const Rec* p) {
     uint4 v = *reinterpret_cast<const uint4*>(p);
     Rec r;
@@ -98,51 +84,6 @@ __device__ __forceinline__ void xh_insert(Slot* idx, uint32_t Imask, uint32_t ep
     uint32_t pos = hash_slot(key) & Imask;
     while (__ldcg(&idx[pos].epoch) == epoch) pos = (pos + 1) & Imask;
     __stcg(reinterpret_cast<uint4*>(&idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), val, epoch));
-}
-
-// insert (key -> idx) for the current epoch; keys inserted concurrently by the lanes of the warp are
-// distinct and not yet present.  `pos`/`seen` = first non-current slot found by a preceding lookup.
-__device__ __forceinline__ void index_insert(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val,
-                                             uint32_t pos, Slot seen) {
-    Slot want;
-    want.key = key, want.idx = val, want.epoch = epoch;
-    for (;;) {
-        Slot old = cas_slot(&idx[pos], seen, want);
-        if (old.key == seen.key && old.idx == seen.idx && old.epoch == seen.epoch) return;
-        seen = old;  // what is really there
-        while (seen.epoch == epoch) {  // taken by another key of this epoch: keep probing
-            pos = (pos + 1) & Imask;
-            seen = load_slot(&idx[pos]);
-        }
-    }
-}
-// continuation of an insert whose first CAS found the slot `pos` taken by another key of this epoch
-__device__ __noinline__ void index_insert_after_conflict(Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t val,
-                                                         uint32_t pos) {
-    Slot want;
-    want.key = key, want.idx = val, want.epoch = epoch;
-    for (;;) {
-        Slot seen;
-        do {
-            pos = (pos + 1) & Imask;
-            seen = load_slot(&idx[pos]);
-        } while (seen.epoch == epoch);
-        Slot old = cas_slot(&idx[pos], seen, want);
-        if (old.epoch != epoch) return;  // a stale slot only ever changes by being claimed, so old == seen
-    }
-}
-// lookup; returns true and idx if present, else false with (pos, seen) = the free slot reached
-__device__ __forceinline__ bool index_find(const Slot* idx, uint32_t Imask, uint32_t epoch, uint64_t key, uint32_t& pos,
-                                           Slot& seen, uint32_t& val) {
-    for (;;) {
-        if (seen.epoch != epoch) return false;
-        if (seen.key == key) {
-            val = seen.idx;
-            return true;
-        }
-        pos = (pos + 1) & Imask;
-        seen = load_slot(&idx[pos]);
-    }
 }
 
 struct Leaf {

@@ -145,6 +145,21 @@ def test_lean_cost_model_equals_reference_cost_model():
     assert np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
 
 
+def test_pool_model():
+    """oracle/pool_model.cpp: the device node pool's way of sharing transposed children (sibling link runs,
+    key table of expanded nodes, orphan flags — DESIGN.md §3) played side by side with the map-based
+    restatement: every move, root statistic and child visit count identical, rare rules exercised."""
+    import subprocess
+    exe = os.path.join(c6lib.ORACLE_DIR, "_build", "pool_model")
+    if not os.path.exists(exe):
+        c6lib.build_oracle()
+    r = subprocess.run([exe, "2", "quick"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all cases identical to the oracle" in r.stdout
+    late = [l for l in r.stdout.splitlines() if l.startswith("neg_late")][0].split()
+    assert int(late[late.index("S1") + 4]) > 0 and int(late[late.index("S2") + 4]) > 0  # S1 hits, S2 hits
+
+
 def test_b1_hand_trace(oracle):
     """derived by hand from the reference source, independent of any code here."""
     b1 = load("b1_hand_trace.json")
