@@ -54,21 +54,25 @@ __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const C
 // per-warp shared-memory stage
 // ------------------------------------------------------------------------------------------------
 // NOISE: 0 = epsilon == 0 (the draw is multiplied by 0: skipped), 1 = Dirichlet alpha < 1, 2 = alpha >= 1
-// One stage per warp.  Both memory phases fill it with cp.async from ROLLED loops (every request of a lane is
-// in flight before the first is waited for), so neither the addresses nor the results occupy registers and
-// the code of a phase exists once.
+// One stage per warp, indexed by child RANK (position in the node's link run = row-major order of its empty
+// cells): slot [k >> 5][k & 31] belongs to child k and is handled by lane k & 31 in round k >> 5, so a node with
+// C children costs ceil(C/32) rounds of every per-child loop — not one round per board word — and the link run
+// is read with fully coalesced requests.  Both memory phases fill the stage with cp.async from ROLLED loops
+// (every request of a lane is in flight before the first is waited for), so neither the addresses nor the
+// results occupy registers and the code of a phase exists once.
 template <int NOISE>
 struct WarpStage {
-    uint4 child[8][32];  // select: {N, W, P, link} of this lane's child in board word j; expand reads the siblings here
+    uint4 child[8][32];  // select: {N, W, P, link} of child k; expand reads the leaf's siblings here
     union {
-        uint32_t ci[8][32];  // select: record index of that child
-        float prior[8][32];  // expand: priors of the new children
+        uint32_t ci[8][32];  // select: record index of child k
+        float prior[8][32];  // expand: prior of new child k
     };
     union {
-        double gamma[NOISE ? 8 : 4][32];  // select: Gamma draws of one step
-        uint32_t pos[8][32];              // expand: record index of the child
+        double gamma[NOISE ? 8 : 4][32];  // select: Gamma draw of child k
+        uint32_t pos[8][32];              // expand: record index of child k
     };
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
+    uint8_t cell[256];  // expand: bit position of the empty cell of rank k; select: ranks whose draw needs the slow path
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -111,30 +115,40 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #define C6_UNROLL(n) C6_PRAGMA_(unroll n)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Memory phase of a select step: for the node whose empty-cell masks are in st.empty and whose link run starts
-// at `link`, this lane's child of every board word — record indices into st.ci, then records into st.child,
-// eight requests of each kind in flight per lane.
+// Memory phase of a select step: for the node with C children whose link run starts at `link`, record indices
+// into st.ci, then records into st.child; ceil(C/32) requests of each kind in flight per lane.
 template <int NOISE>
-__device__ __forceinline__ void stage_children(const Warp& w, WarpStage<NOISE>& st, uint32_t link, int lane, uint32_t Rm, uint32_t Lm) {
-    const uint32_t lt = (1u << lane) - 1u;
-    int pre = 0;
+__device__ __forceinline__ void stage_children(const Warp& w, WarpStage<NOISE>& st, uint32_t link, int C, int lane, uint32_t Rm,
+                                               uint32_t Lm) {
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t e = st.empty[j];
-        if ((e >> lane) & 1u) cp_async4(&st.ci[j][lane], &w.lnk[(link + (uint32_t)(pre + __popc(e & lt))) & Lm]);
-        pre += __popc(e);
+    for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(link + (uint32_t)k) & Lm]);
+    cp_async_wait_all();
+#pragma unroll 1
+    for (int k = lane; k < C; k += 32) {
+#if C6_CHILD_CG
+        cp_async16_cg(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+#else
+        cp_async16(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+#endif
     }
     cp_async_wait_all();
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j)
-        if ((st.empty[j] >> lane) & 1u) {
-#if C6_CHILD_CG
-            cp_async16_cg(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
-#else
-            cp_async16(&st.child[j][lane], &w.rec[st.ci[j][lane] & Rm]);
-#endif
+}
+
+// Bit position of the empty cell of rank k (warp-uniform k) from the empty masks in st.empty.
+template <int NOISE>
+__device__ __forceinline__ uint32_t kth_empty(const WarpStage<NOISE>& st, uint32_t k, uint32_t lt, int lane) {
+    uint32_t bit = 0, pre = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = st.empty[j];
+        const uint32_t c = (uint32_t)__popc(e);
+        if (k - pre < c) {  // warp-uniform; k - pre wraps to a huge value once pre > k
+            const bool hit = ((e >> lane) & 1u) && (uint32_t)__popc(e & lt) == k - pre;
+            bit = 32u * j + (uint32_t)(__ffs((int)__ballot_sync(FULL, hit)) - 1);
         }
-    cp_async_wait_all();
+        pre += c;
+    }
+    return bit;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,60 +184,54 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             }
             child = w.lnk[r.link & Lm];
         } else {
-            // memory phase: this lane's child of every board word — links, then records, eight requests of
-            // each kind in flight per lane
+            // memory phase: the link run, then the child records, ceil(C/32) requests of each kind in flight per lane
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
-            __syncwarp();
-            int pre = 0;
-            stage_children(w, st, r.link, lane, Rm, Lm);
+            stage_children(w, st, r.link, C, lane, Rm, Lm);
             // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
             // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
-            // sampler for every child; the ~1-3% of draws that need the other branch or another trial are
-            // finished together in pass B (one diverged excursion per step instead of one per board word);
-            // pass C sums in a fixed order: lane-partials in word order, then a butterfly.
+            // sampler for every child; the ~3% of draws that need the other branch or another trial are listed
+            // and finished together, one per lane, in pass B (one diverged excursion per step); pass C sums in a
+            // fixed order: per lane the draws k = lane, lane + 32, ..., then a butterfly.
             int s_local = 0;
             double part = 0.0;
             if (NOISE) {
                 const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
                 unsigned pend = 0;
-                pre = 0;
 C6_UNROLL(C6_NOISE_UNROLL)
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t e = st.empty[j];
-                    if ((e >> lane) & 1u) {
-                        const uint32_t k = (uint32_t)(pre + __popc(e & lt));
-                        double gj;
-                        if (NOISE == 1) {
-                            if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, k, nk0, cs.game_id, gj)) pend |= 1u << j;
-                        } else {
-                            gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, k, nk0, cs.game_id);
-                        }
-                        st.gamma[j][lane] = gj;
+                for (int k = lane; k < C; k += 32) {
+                    double gj;
+                    if (NOISE == 1) {
+                        if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
+                    } else {
+                        gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
                     }
-                    pre += __popc(e);
+                    st.gamma[0][k] = gj;
                 }
-                if (NOISE == 1) {
-                    while (__any_sync(FULL, pend != 0)) {
-                        if (pend) {
-                            const int j = __ffs((int)pend) - 1;
-                            pend &= pend - 1;
-                            int before = 0;
-                            for (int jj = 0; jj < j; ++jj) before += __popc(st.empty[jj]);
-                            const uint32_t k = (uint32_t)(before + __popc(st.empty[j] & lt));
-                            st.gamma[j][lane] = gamma_small(mt, D.gp.shape, D.gp.inv_shape, D.gp.b, cs.sim_index, (uint32_t)depth, k,
-                                                            nk0, cs.game_id);
-                        }
+                if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
+                    int np = 0;
+#pragma unroll 1
+                    for (int i = 0; 32 * i < C; ++i) {
+                        const bool p = (pend >> i) & 1u;
+                        const unsigned bal = __ballot_sync(FULL, p);
+                        if (p) st.cell[np + __popc(bal & lt)] = (uint8_t)(32 * i + lane);
+                        np += __popc(bal);
                     }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int i = lane; i < np; i += 32) {
+                        const uint32_t k = st.cell[i];
+                        st.gamma[0][k] = gamma_small(mt, D.gp.shape, D.gp.inv_shape, D.gp.b, cs.sim_index, (uint32_t)depth, k, nk0,
+                                                     cs.game_id);
+                    }
+                    __syncwarp();
                 }
             }
 #pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                if ((st.empty[j] >> lane) & 1u) {
-                    s_local += (int)st.child[j][lane].x;
-                    if (NOISE) part = part + st.gamma[j][lane];
-                }
+            for (int k = lane; k < C; k += 32) {
+                s_local += (int)st.child[0][k].x;
+                if (NOISE) part = part + st.gamma[0][k];
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
@@ -240,22 +248,20 @@ C6_UNROLL(C6_NOISE_UNROLL)
             float bs = 0.f;
             uint32_t bb = NIL;
 #pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                if ((st.empty[j] >> lane) & 1u) {
-                    const uint4 ch = st.child[j][lane];
-                    const int cn = (int)ch.x;
-                    const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
-                    float nz = 0.f;
-                    if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[j][lane] * inv);
-                    const float visit = (float)cn;
-                    const float q = cn > 0 ? cw / visit : 0.f;                        // q_value (:77-79)
-                    const float prob = eps * nz + one_m_eps * cp;                     // :269
-                    const float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
-                    const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
-                    if (bb == NIL || sc > bs) bs = sc, bb = 32u * j + lane;
-                }
+            for (int k = lane; k < C; k += 32) {
+                const uint4 ch = st.child[0][k];
+                const int cn = (int)ch.x;
+                const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
+                float nz = 0.f;
+                if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[0][k] * inv);
+                const float visit = (float)cn;
+                const float q = cn > 0 ? cw / visit : 0.f;                        // q_value (:77-79)
+                const float prob = eps * nz + one_m_eps * cp;                     // :269
+                const float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
+                const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
+                if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k;
             }
-            // maximum; exact ties -> lowest row-major index (the reference picks uniformly, :291-295)
+            // maximum; exact ties -> lowest row-major index = lowest rank (the reference picks uniformly, :291-295)
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
                 const float os = __shfl_xor_sync(FULL, bs, off);
@@ -263,9 +269,9 @@ C6_UNROLL(C6_NOISE_UNROLL)
                 const bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
                 if (take) bs = os, bb = ob;
             }
-            chosen_bit = bb;
-            __syncwarp();  // cp.async results of the other lanes
-            child = st.ci[bb >> 5][bb & 31];
+            __syncwarp();  // cp.async results and st.empty of the other lanes
+            child = st.ci[0][bb];
+            chosen_bit = kth_empty(st, bb, lt, lane);
             __syncwarp();  // the stage is rewritten by the next step
         }
         // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
@@ -316,7 +322,7 @@ __device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, const Leaf&
 }
 
 // ------------------------------------------------------------------------------------------------
-// leaf evaluators: value() for the warp, prior(j) for this lane's cell of word j (already masked:
+// leaf evaluators: value() for the warp, prior(bit) for the cell at bit position `bit` (already masked:
 // only asked for empty cells).  Twins of the oracle's evaluators.
 // ------------------------------------------------------------------------------------------------
 // RandomEvaluator (:137-169) on Philox, fused with get_from (:218-234) and recover_way8
@@ -346,9 +352,9 @@ struct EvPhilox {
         }
         return sum / 8.f;
     }
-    __device__ __forceinline__ float prior(int j) const {
+    __device__ __forceinline__ float prior(uint32_t bit) const {
         float t[4];
-        pairs((uint32_t)cell_of_bit(32u * j + lane), t);
+        pairs((uint32_t)cell_of_bit(bit), t);
         float total = 0.f;
         total = total + t[0], total = total + t[1], total = total + t[2], total = total + t[3];
         return total / 8.f;
@@ -385,8 +391,7 @@ struct EvHash {
         for (int s = 0; s < 8; ++s) sum = sum + ((float)(uint32_t)(h[s] >> 40) * (1.0f / 8388608.0f) - 1.0f);
         return sum / 8.f;
     }
-    __device__ __forceinline__ float prior(int j) const {
-        uint32_t bit = 32u * j + lane;
+    __device__ __forceinline__ float prior(uint32_t bit) const {
         int r = (int)(bit >> 4), c = (int)(bit & 15);
         float pv[8];
 #pragma unroll
@@ -415,8 +420,7 @@ struct EvBatch {
         for (int s = 0; s < 8; ++s) sum = sum + __shfl_sync(FULL, myv, s);  // iter().sum::<f32>() order (:224)
         return sum / 8.f;
     }
-    __device__ __forceinline__ float prior(int j) const {
-        uint32_t bit = 32u * j + lane;
+    __device__ __forceinline__ float prior(uint32_t bit) const {
         int r = (int)(bit >> 4), c = (int)(bit & 15);
         float pv[8];
 #pragma unroll
@@ -450,12 +454,14 @@ struct EvBatch {
 // the next expanding parent, :371), so a fresh record is equivalent.
 //
 // S1 + S2, out of line: rare (late-game deep paths), kept out of the hot instruction stream.  `cm0/cm1` = the
-// leaf's stones of colour m, `skip` = bit of a_d when rule F covers it (else NIL).  Returns the updated mask
-// of resolved board words; record indices go to pos[j*32 + lane].
+// leaf's stones of colour m, `skip` = bit of a_d when rule F covers it (else NIL), `cell[k]` = bit position of the
+// leaf's empty cell of rank k.  `mine` / `res`: bit i = this lane's child k = 32 i + lane exists / already has a
+// record.  Returns the updated `res`; record indices go to pos[k].
 __device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint32_t epoch, const uint32_t* lnk, uint32_t Lm,
                                               const Rec* rec, uint32_t Rm, const uint64_t* Z, const GameState* gs, uint32_t* pos,
-                                              const uint32_t* empty, uint4 cm0, uint4 cm1, uint64_t key, int stones, uint32_t zoff,
-                                              uint32_t skip, unsigned mine, unsigned res, int lane, int depth) {
+                                              const uint32_t* empty, const uint8_t* cell, uint4 cm0, uint4 cm1, uint64_t key,
+                                              int stones, uint32_t zoff, uint32_t skip, unsigned mine, unsigned res, int lane,
+                                              int depth) {
     const uint32_t cm[8] = {cm0.x, cm0.y, cm0.z, cm0.w, cm1.x, cm1.y, cm1.z, cm1.w};
     if (depth >= 3) {
         const uint32_t* rootcol = zoff ? gs->W : gs->B;
@@ -469,14 +475,14 @@ __device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint
                 const uint32_t sp = 32u * j + (uint32_t)b;
                 const uint32_t rsp = (uint32_t)(before + __popc(empty[j] & ((1u << b) - 1u)));
                 const uint64_t ks = key ^ Z[zoff + sp];
-                for (int jj = 0; jj < 8; ++jj)
-                    if (((mine & ~res) >> jj) & 1u) {
-                        const uint32_t cbit = 32u * jj + (uint32_t)lane;
+                for (int i = 0; i < 8; ++i)
+                    if (((mine & ~res) >> i) & 1u) {
+                        const uint32_t cbit = cell[32 * i + lane];
                         const uint32_t e = xh_find(idx, Im, epoch, ks ^ Z[zoff + cbit]);
                         if (e != NIL) {
                             const uint32_t link = rec[e & Rm].link;
-                            pos[jj * 32 + lane] = lnk[(link + rsp - (cbit < sp ? 1u : 0u)) & Lm];
-                            res |= 1u << jj;
+                            pos[i * 32 + lane] = lnk[(link + rsp - (cbit < sp ? 1u : 0u)) & Lm];
+                            res |= 1u << i;
                         }
                     }
             }
@@ -485,10 +491,10 @@ __device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint
     }
     const uint32_t s1 = (uint32_t)stones + 1u;
     if ((gs->orph[s1 >> 5] >> (s1 & 31)) & 1u) {
-        for (int jj = 0; jj < 8; ++jj)
-            if (((mine & ~res) >> jj) & 1u) {
-                const uint32_t x = xh_find(idx, Im, epoch, key ^ Z[zoff + 32u * jj + (uint32_t)lane]);
-                if (x != NIL) pos[jj * 32 + lane] = x, res |= 1u << jj;
+        for (int i = 0; i < 8; ++i)
+            if (((mine & ~res) >> i) & 1u) {
+                const uint32_t x = xh_find(idx, Im, epoch, key ^ Z[zoff + cell[32 * i + lane]]);
+                if (x != NIL) pos[i * 32 + lane] = x, res |= 1u << i;
             }
     }
     return res;
@@ -524,13 +530,9 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     // rule F applies when the last path stone has the colour of the stone the children add
     const bool sib = L.depth >= 1 && turn_of(L.stones - 1) == turn;
     const uint32_t lj = L.last_bit >> 5, lm = 1u << (L.last_bit & 31);
-    if (!STAGED && sib) {  // the parent's children: its empties are the leaf's plus the last stone
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lane == j) st.empty[j] = (~(L.B[j] | L.W[j]) & valid_mask(j)) | (j == (int)lj ? lm : 0u);
-        __syncwarp();
+    if (!STAGED && sib) {  // the parent's children (its empties are the leaf's plus the last stone)
         const uint32_t prec = w.path(D)[L.depth - 1];
-        stage_children(w, st, w.rec[prec].link, lane, Rm, Lm);
+        stage_children(w, st, w.rec[prec].link, C + 1, lane, Rm, Lm);
         __syncwarp();
     }
 #pragma unroll
@@ -538,39 +540,47 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
     __syncwarp();
     const uint64_t key = L.key;
-    unsigned mine = 0;  // bit j: this lane has a child in board word j
-    uint32_t r0 = 0;    // rank of the last path stone among the empties of a sibling that lacks it (before the c < a_d correction)
+    // bit position of every child by rank, and r0 = rank of the last path stone among the empties of a sibling that
+    // lacks it (before the c < a_d correction)
+    uint32_t r0 = 0;
+    {
+        int pre = 0;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t e = st.empty[j];
-        mine |= ((e >> lane) & 1u) << j;
-        r0 += j < (int)lj ? __popc(e) : (j == (int)lj ? __popc(e & (lm - 1u)) : 0);
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t e = st.empty[j];
+            if ((e >> lane) & 1u) st.cell[pre + __popc(e & lt)] = (uint8_t)(32 * j + lane);
+            r0 += j < (int)lj ? __popc(e) : (j == (int)lj ? __popc(e & (lm - 1u)) : 0);
+            pre += __popc(e);
+        }
     }
-    // A: rule F — the link of every shared child in flight; priors computed under the latency
-    unsigned res = 0;  // bit j: the child of word j already has a record, index in st.pos
+    __syncwarp();
+    unsigned mine = 0;  // bit i: this lane has child k = 32 i + lane
+#pragma unroll 1
+    for (int k = lane; k < C; k += 32) mine |= 1u << (k >> 5);
+    // A: rule F — the link of every shared child in flight; priors computed under the latency.  The sibling P + c
+    // of the leaf under its parent P has rank k + [c > a_d] there.
+    unsigned res = 0;  // bit i: child k already has a record, index in st.pos
     if (sib) {
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j)
-            if ((mine >> j) & 1u) {
-                const uint4 sv = st.child[j][lane];  // the sibling P + c
-                if ((int)sv.x >= 1) {
-                    const uint32_t cbit = 32u * j + (uint32_t)lane;
-                    cp_async4(&st.pos[j][lane], &w.lnk[(sv.w + r0 - (cbit < L.last_bit ? 1u : 0u)) & Lm]);
-                    res |= 1u << j;
-                }
+        for (int k = lane; k < C; k += 32) {
+            const uint32_t cbit = st.cell[k];
+            const uint4 sv = st.child[0][k + (cbit > L.last_bit ? 1 : 0)];
+            if ((int)sv.x >= 1) {
+                cp_async4(&st.pos[0][k], &w.lnk[(sv.w + r0 - (cbit < L.last_bit ? 1u : 0u)) & Lm]);
+                res |= 1u << (k >> 5);
             }
+        }
     }
 C6_UNROLL(C6_PRIOR_UNROLL)
-    for (int j = 0; j < 8; ++j)
-        if ((mine >> j) & 1u) st.prior[j][lane] = ev.prior(j);
+    for (int k = lane; k < C; k += 32) st.prior[0][k] = ev.prior((uint32_t)st.cell[k]);
     // rules S1 / S2 (warp-uniform test)
     {
         const uint32_t s1 = (uint32_t)L.stones + 1u;
         if (L.depth >= 3 || ((w.gs->orph[s1 >> 5] >> (s1 & 31)) & 1u)) {
             const uint4 cm0 = turn < 0 ? make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]) : make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]);
             const uint4 cm1 = turn < 0 ? make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]) : make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]);
-            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, cm0, cm1, key, L.stones,
-                               zoff, sib ? L.last_bit : NIL, mine, res, lane, L.depth);
+            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, cm0, cm1, key,
+                               L.stones, zoff, sib ? L.last_bit : NIL, mine, res, lane, L.depth);
         }
     }
     cp_async_wait_all();
@@ -578,30 +588,25 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     const unsigned isnew = mine & ~res;
     uint32_t base = cs.rec_head;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const bool nw = (isnew >> j) & 1u;
+    for (int i = 0; 32 * i < C; ++i) {
+        const bool nw = (isnew >> i) & 1u;
         const unsigned bal = __ballot_sync(FULL, nw);
-        if (nw) st.pos[j][lane] = base + __popc(bal & lt);
+        if (nw) st.pos[i][lane] = base + __popc(bal & lt);
         base += __popc(bal);
     }
     // C: records, priors, link run
-    int pre = 0;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t e = st.empty[j];
-        if ((mine >> j) & 1u) {
-            const uint32_t child = st.pos[j][lane] & Rm;
-            const float pr = st.prior[j][lane];
-            if ((isnew >> j) & 1u) {
-                Rec nr;
-                nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
-                store_rec(&w.rec[child], nr);
-            } else {
-                w.rec[child].p = pr;  // n_prob is overwritten by the last expanding parent (:371)
-            }
-            w.lnk[(link_base + (uint32_t)(pre + __popc(e & lt))) & Lm] = child;
+    for (int k = lane; k < C; k += 32) {
+        const uint32_t child = st.pos[0][k] & Rm;
+        const float pr = st.prior[0][k];
+        if ((isnew >> (k >> 5)) & 1u) {
+            Rec nr;
+            nr.n = 0, nr.w = 0.f, nr.p = pr, nr.link = NIL;
+            store_rec(&w.rec[child], nr);
+        } else {
+            w.rec[child].p = pr;  // n_prob is overwritten by the last expanding parent (:371)
         }
-        pre += __popc(e);
+        w.lnk[(link_base + (uint32_t)k) & Lm] = child;
     }
     __syncwarp();
     // the leaf itself: visit += 1, children attached (:353-357,374-377), findable by key from now on

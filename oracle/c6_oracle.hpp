@@ -475,7 +475,8 @@ struct AlphaZero {
     }
 
     // Dirichlet(alpha; n) twin of the engine's sampler: Gamma draws keyed (sim, depth, child),
-    // summed in the engine's lane order (bit position 16*row+col: lane = bit & 31), then scaled.
+    // summed in the engine's lane order (child k of the row-major child list belongs to lane k & 31: per-lane
+    // partial sums in k order, then a butterfly), then scaled.
     std::vector<double> dirichlet(const Simulate& sim, int depth, const std::vector<const Node*>& child,
                                   const Board& parent) {
         size_t n = child.size();
@@ -485,14 +486,12 @@ struct AlphaZero {
         for (size_t k = 0; k < n; ++k) {
             g[k] = gamma_sample(param.dirichlet_alpha, ctx.sim_index, (uint32_t)depth, (uint32_t)k, ctx.seed ^ DOMAIN_NOISE,
                                 ctx.game_id);
-            Pos p = *diff_board(child[k]->board, parent);
-            int bit = 16 * p.first + p.second;
-            partial[bit & 31] = partial[bit & 31] + g[k];
+            partial[k & 31] = partial[k & 31] + g[k];
         }
         for (int off = 16; off >= 1; off >>= 1)
             for (int l = 0; l < off; ++l) partial[l] = partial[l] + partial[l + off];
         double sum = partial[0];
-        (void)sim;
+        (void)sim, (void)parent;
         if (!(sum > 0.0)) {
             for (auto& x : g) x = 1.0 / (double)n;
         } else {

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "c6_oracle.hpp"
+#include "c6_default_policy.hpp"
 
 using namespace c6o;
 
@@ -309,6 +310,59 @@ void oracle_play_with(Callback cb, const OracleParams* p, uint32_t game_id, cons
     const SearchStats& st = black.az.stats;
     out->sims = st.sims, out->sum_ck = st.sum_ck, out->sum_cleaf = st.sum_cleaf, out->sum_depth = st.sum_depth, out->evals = st.evals,
     out->max_nodes = st.max_nodes;
+}
+
+// ---- DefaultPolicy (pure MCTS with random rollouts, default_policy/mod.rs) under Agent::play ----------------
+struct OracleDpOut {
+    int winner, n_moves;
+    int moves[BOARD_CAPACITY];
+    int32_t root_visit[BOARD_CAPACITY], root_black_win[BOARD_CAPACITY];  // root node after the searches of move m
+    uint64_t searches, rollouts, rollout_stones, select_steps, children_scanned, replaced, nodes;
+};
+static void dp_play_one(int num_iter, uint32_t seed, uint32_t game_id, int max_moves, OracleDpOut* out) {
+    DefaultPolicy pol(num_iter, seed, game_id);
+    Game game;
+    std::memset(out, 0, sizeof *out);
+    for (;;) {
+        if (max_moves > 0 && out->n_moves >= max_moves) break;
+        auto pos = pol.next(game);
+        if (!pos) break;
+        const DpNode& root = pol.map.at(DefaultPolicy::hash(game.board));
+        out->root_visit[out->n_moves] = root.visit, out->root_black_win[out->n_moves] = root.black_win;
+        out->moves[out->n_moves++] = pos->first * BOARD_SIZE + pos->second;
+        if (!game.set(*pos).empty()) std::abort();
+        Player e = game.is_game_end();
+        if (e != Player::None) {
+            out->winner = (int)e;
+            break;
+        }
+    }
+    const DpStats& s = pol.stats;
+    out->searches = s.searches, out->rollouts = s.rollouts, out->rollout_stones = s.rollout_stones;
+    out->select_steps = s.select_steps, out->children_scanned = s.children_scanned, out->replaced = s.replaced;
+    out->nodes = pol.map.size();
+}
+void oracle_default_policy_play(int num_iter, uint32_t seed, uint32_t game_id, int max_moves, OracleDpOut* out) {
+    dp_play_one(num_iter, seed, game_id, max_moves, out);
+}
+// n_games on n_threads OS threads (one game per task like AsyncAgent::run); returns wall seconds
+double oracle_default_policy_many(int num_iter, uint32_t seed, uint32_t first_game_id, int n_games, int max_moves, int n_threads,
+                                  OracleDpOut* outs) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    std::atomic<int> nextg{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&]() {
+            for (;;) {
+                int g = nextg.fetch_add(1);
+                if (g >= n_games) break;
+                dp_play_one(num_iter, seed, first_game_id + (uint32_t)g, max_moves, &outs[g]);
+            }
+        });
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 int oracle_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "c6_oracle.hpp"
+#include "c6_default_policy.hpp"
 
 using namespace c6o;
 
@@ -427,6 +428,94 @@ static void test_rng() {
     CHECK(std::fabs(q3 / NS - 0.7 * 1.7) < 0.03);
 }
 
+
+// libconnect6/src/policy/default_policy/tests.rs:6-31 (test_select), :34-63 (test_expand), :66-112 (test_update),
+// :115-131 (test_next), :134-150 (test_self_play)
+static bool in_possible(const Simulate& sim, Pos p) {
+    return std::find(sim.possible.begin(), sim.possible.end(), p) != sim.possible.end();
+}
+static void test_default_policy() {
+    {  // test_select: expand + update until some child has a non-zero win ratio, then select returns a legal move
+        Game game;
+        Simulate sim = Simulate::from_game(game);
+        DefaultPolicy policy(50, 0xC6, 0);
+        policy.init(sim);
+        for (int guard = 0; guard < 1000; ++guard) {
+            if (auto pos = policy.select(sim)) {
+                CHECK(in_possible(sim, *pos));
+                CHECK(sim.validate(pos->first, pos->second));
+                break;
+            }
+            CHECK(!policy.select(sim));
+            policy.cur_i = (uint32_t)guard;
+            Pos p = policy.expand(sim);
+            Simulate expanded = sim;
+            expanded.simulate_in(p.first, p.second);
+            policy.update(expanded, {p});
+        }
+    }
+    {  // test_expand
+        Game game;
+        Simulate sim = Simulate::from_game(game);
+        DefaultPolicy policy(50, 0xC6, 1);
+        policy.init(sim);
+        while (auto pos = policy.select(sim)) sim.simulate_in(pos->first, pos->second);
+        Pos p = policy.expand(sim);
+        CHECK(in_possible(sim, p));
+        CHECK(sim.validate(p.first, p.second));
+        CHECK(policy.map.size() == 2);
+        auto it = policy.map.find(DefaultPolicy::hash(empty_board()));
+        CHECK(it != policy.map.end());
+        CHECK(it->second.next_node.size() == 1);
+        CHECK(policy.map.count(it->second.next_node[0]) == 1);
+    }
+    {  // test_update
+        Game game;
+        Simulate sim = Simulate::from_game(game);
+        DefaultPolicy policy(50, 0xC6, 2);
+        policy.init(sim);
+        std::vector<Pos> path;
+        while (auto pos = policy.select(sim)) {
+            sim.simulate_in(pos->first, pos->second);
+            path.push_back(*pos);
+        }
+        Pos p = policy.expand(sim);
+        Simulate expanded = sim;
+        expanded.simulate_in(p.first, p.second);
+        path.push_back(p);
+        policy.update(expanded, path);
+        CHECK(policy.map.size() == 2);
+        const DpNode& parent = policy.map.at(DefaultPolicy::hash(empty_board()));
+        CHECK(parent.next_node.size() == 1);
+        CHECK(parent.visit == 1);  // a random rollout from one stone always ends with a winner in practice
+        const DpNode& child = policy.map.at(parent.next_node[0]);
+        CHECK(child.next_node.empty());
+        CHECK(child.visit == 1);
+        CHECK(child.black_win == parent.black_win);
+        int num = 0;
+        for (auto& row : child.board)
+            for (auto c : row) num += c != N;
+        CHECK(num == 1);
+    }
+    {  // test_next
+        Game game;
+        Simulate sim = Simulate::from_game(game);
+        DefaultPolicy policy(50, 0xC6, 3);
+        policy.init(sim);
+        auto pos = policy.policy(sim);
+        CHECK(pos.has_value());
+        CHECK(sim.validate(pos->first, pos->second));
+        CHECK(in_possible(sim, *pos));
+    }
+    for (uint32_t game_id = 0; game_id < 4; ++game_id) {  // test_self_play (with_num_iter(10)) + the doc test (2)
+        DefaultPolicy policy(game_id == 3 ? 2 : 10, 0xC6, game_id);
+        PlayResult result = agent_play(policy);
+        CHECK(result.error.empty());
+        if (!result.path.empty() && result.winner != N) CHECK(result.path.back().turn == result.winner);
+        CHECK(policy.stats.searches >= (uint64_t)policy.num_iter * result.path.size());
+    }
+}
+
 int main() {
     test_player();
     test_base_search();
@@ -443,6 +532,7 @@ int main() {
     test_hand_trace(true);
     test_hand_trace(false);
     test_lean_equals_faithful();
+    test_default_policy();
     std::printf("%d checks, %d failures\n", g_checks, g_fail);
     return g_fail ? 1 : 0;
 }
