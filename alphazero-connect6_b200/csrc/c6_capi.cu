@@ -516,6 +516,19 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
            cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db))
 }
 
+int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
+                           c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats) {
+    static_assert(sizeof(c6_record) == sizeof(GameRecord), "record layout");
+    C6_TRY(unsigned long long st[8]; if (n_games > 0 && !out) throw std::runtime_error("c6_default_policy_play: out is NULL");
+           const float ms = default_policy_play(num_iter, seed, first_game_id, (long long)n_games, max_moves, device,
+                                                reinterpret_cast<GameRecord*>(out), root_visit, root_black_win, st);
+           if (stats) {
+               stats->searches = st[0], stats->rollouts = st[1], stats->rollout_stones = st[2], stats->select_steps = st[3];
+               stats->children_scanned = st[4], stats->replaced = st[5], stats->nodes = st[6], stats->errors = st[7];
+               stats->kernel_ms = ms;
+           })
+}
+
 // Host<->device copy bandwidth of this box with pinned buffers (GB/s): H2D alone, D2H alone, and both at
 // once on two streams (per direction).  This is the ceiling of the host-callback evaluator path.
 int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs) {

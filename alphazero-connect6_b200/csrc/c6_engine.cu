@@ -364,6 +364,8 @@ static void make_zobrist(uint64_t* Zb) {  // same sequence as the test oracle's 
         }
 }
 
+void make_zobrist_table(uint64_t* Zb) { make_zobrist(Zb); }  // c6_default_policy.cu
+
 size_t Engine::bytes_per_game() const {
     size_t R = (size_t)1 << cfg_.log2_records;
     return R * sizeof(Rec) + 2 * R * sizeof(uint32_t) + d_->dev.I * sizeof(Slot) + d_->dev.E * (64 + 4 + 8) + 232 * 4 +

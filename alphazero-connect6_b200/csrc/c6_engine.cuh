@@ -199,6 +199,9 @@ class Engine {
 
 // Stand-alone kernels of the path (config 3 microbenches), host launchers.
 // boards: n x 16 u32 (8 words black, 8 words white); winners: n x i8.
+// DefaultPolicy (pure MCTS with random rollouts) self-play, one thread per game (c6_default_policy.cu); returns kernel ms
+float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, long long n_games, int max_moves, int device,
+                          GameRecord* out, int32_t* root_visit, int32_t* root_bw, unsigned long long* stats);
 void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s);
 void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStream_t s);
 // playouts: winner i8, stones u8 (and final boards if d_boards != nullptr)

@@ -92,13 +92,30 @@ __device__ __forceinline__ void load_math_tab(MathTab& T) {
     if (threadIdx.x < 32) T.expt[threadIdx.x] = EXP_TAB_C[threadIdx.x];
 }
 
+// Coefficients whose low word is not zero cannot be DFMA immediates; as literals the compiler rebuilds each of
+// them with two moves per use (r01g capture: ~30 of the 168 instructions of a draw), from the constant bank they
+// are operands.  Same bits either way.
+#ifndef C6_CBANK_COEF
+#define C6_CBANK_COEF 1
+#endif
+static __device__ __constant__ double MATH_K[13] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, 1.0 / 3.0, 0.6931471803691238,
+                                                    1.9082149292705877e-10, 46.16624130844683, 5.9631716539705866e-12,
+                                                    0.02166084938653512, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+#if C6_CBANK_COEF
+#define C6_K(i, v) MATH_K[i]
+#else
+#define C6_K(i, v) (v)
+#endif
+
 // natural log of a positive finite double, division-free: x = 2^e m, m in [1,2) falls in one of 64
 // intervals with centre c_i; r = m/c_i - 1 (|r| < 2^-7) by one fma with the tabulated reciprocal;
 // ln x = e ln2 + ln c_i + log1p(r), log1p as a degree-8 alternating series.  Absolute error ~1e-16.
+// NORMAL: the caller guarantees a normal (not subnormal) argument, which skips the rescaling test; same value.
+template <bool NORMAL = false>
 __device__ __forceinline__ double det_log(const MathTab& T, double x) {
     int e = 0;
     uint64_t b = double_to_bits(x);
-    if ((b >> 52) == 0) {
+    if (!NORMAL && (b >> 52) == 0) {
         x = x * 18014398509481984.0;
         b = double_to_bits(x);
         e = -54;
@@ -108,28 +125,30 @@ __device__ __forceinline__ double det_log(const MathTab& T, double x) {
     const double2 t = T.logt[(uint32_t)(b >> 46) & 63u];
     const double r = det_fma(m, t.x, -1.0);
     double p = -1.0 / 8.0;
-    p = det_fma(p, r, 1.0 / 7.0);
-    p = det_fma(p, r, -1.0 / 6.0);
-    p = det_fma(p, r, 1.0 / 5.0);
+    p = det_fma(p, r, C6_K(0, 1.0 / 7.0));
+    p = det_fma(p, r, C6_K(1, -1.0 / 6.0));
+    p = det_fma(p, r, C6_K(2, 1.0 / 5.0));
     p = det_fma(p, r, -1.0 / 4.0);
-    p = det_fma(p, r, 1.0 / 3.0);
+    p = det_fma(p, r, C6_K(3, 1.0 / 3.0));
     p = det_fma(p, r, -0.5);
     p = det_fma(p, r * r, r);  // r + r^2 (-1/2 + r/3 - ...)
     const double ed = (double)e;
-    return det_fma(ed, 0.6931471803691238, t.y + det_fma(ed, 1.9082149292705877e-10, p));
+    return det_fma(ed, C6_K(4, 0.6931471803691238), t.y + det_fma(ed, C6_K(5, 1.9082149292705877e-10), p));
 }
 
 // e^x: x = (32 q + j) ln2/32 + r, |r| <= ln2/64; e^x = 2^q 2^(j/32) (1 + expm1(r)), expm1 to r^6;
 // scaled by 2^q in two exact steps (subnormal results round once).
+// NONPOS: the caller guarantees x <= 0, which skips the overflow clamp; same value.
+template <bool NONPOS = false>
 __device__ __forceinline__ double det_exp(const MathTab& T, double x) {
     if (x < -745.2) return 0.0;
-    if (x > 709.0) x = 709.0;
-    const double kd = (double)__double2ll_rd(det_fma(x, 46.16624130844683, 0.5));  // floor(x 32/ln2 + 1/2)
-    const double r = det_fma(-kd, 5.9631716539705866e-12, det_fma(-kd, 0.02166084938653512, x));
-    double p = 1.0 / 720.0;
-    p = det_fma(p, r, 1.0 / 120.0);
-    p = det_fma(p, r, 1.0 / 24.0);
-    p = det_fma(p, r, 1.0 / 6.0);
+    if (!NONPOS && x > 709.0) x = 709.0;
+    const double kd = (double)__double2ll_rd(det_fma(x, C6_K(6, 46.16624130844683), 0.5));  // floor(x 32/ln2 + 1/2)
+    const double r = det_fma(-kd, C6_K(7, 5.9631716539705866e-12), det_fma(-kd, C6_K(8, 0.02166084938653512), x));
+    double p = C6_K(9, 1.0 / 720.0);
+    p = det_fma(p, r, C6_K(10, 1.0 / 120.0));
+    p = det_fma(p, r, C6_K(11, 1.0 / 24.0));
+    p = det_fma(p, r, C6_K(12, 1.0 / 6.0));
     p = det_fma(p, r, 0.5);
     p = det_fma(p, r, 1.0);
     p = p * r;  // expm1(r)
@@ -175,7 +194,8 @@ __device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaPa
     const double p = gp.b * u;
     x = 0.0;
     if (p > 1.0) return false;
-    x = det_exp(T, det_log(T, p) * gp.inv_shape);
+    // p = b u with u >= 2^-53: normal; ln p <= 0
+    x = det_exp<true>(T, det_log<true>(T, p) * gp.inv_shape);
     return v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0);
 }
 static __device__ __noinline__ double gamma_small(const MathTab& T, double shape, double inv_shape, double bb, uint32_t a, uint32_t b,

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #endif
 }
 #ifndef C6_CHILD_CG
-#define C6_CHILD_CG 0
+#define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
 #endif
 #ifndef C6_NOISE_UNROLL
 #define C6_NOISE_UNROLL 1
@@ -168,8 +168,8 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     uint32_t cur = g.root;
     int depth = 0;
     const float eps = D.eps, one_m_eps = 1.f - D.eps, cpuct = D.cpuct;
+    Rec r = load_rec(&w.rec[cur]);
     for (;;) {
-        const Rec r = load_rec(&w.rec[cur]);
         if (r.n == 0) break;  // no children: leaf (:251-253)
         if (lane == 0) w.path(D)[depth] = cur;
         const int C = CELLS - L.stones;
@@ -183,6 +183,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 if (e) chosen_bit = 32 * j + (__ffs((int)e) - 1);
             }
             child = w.lnk[r.link & Lm];
+            r = load_rec(&w.rec[child & Rm]);
         } else {
             // memory phase: the link run, then the child records, ceil(C/32) requests of each kind in flight per lane
 #pragma unroll
@@ -210,13 +211,20 @@ C6_UNROLL(C6_NOISE_UNROLL)
                     st.gamma[0][k] = gj;
                 }
                 if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
-                    int np = 0;
-#pragma unroll 1
-                    for (int i = 0; 32 * i < C; ++i) {
-                        const bool p = (pend >> i) & 1u;
-                        const unsigned bal = __ballot_sync(FULL, p);
-                        if (p) st.cell[np + __popc(bal & lt)] = (uint8_t)(32 * i + lane);
-                        np += __popc(bal);
+                    // list the pending ranks (any order): exclusive prefix sum of the per-lane counts
+                    const int mycnt = __popc(pend);
+                    int incl = mycnt;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(FULL, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    const int np = __shfl_sync(FULL, incl, 31);
+                    int at = incl - mycnt;
+                    while (pend) {
+                        const int i = __ffs((int)pend) - 1;
+                        pend &= pend - 1;
+                        st.cell[at++] = (uint8_t)(32 * i + lane);
                     }
                     __syncwarp();
 #pragma unroll 1
@@ -255,7 +263,8 @@ C6_UNROLL(C6_NOISE_UNROLL)
                 float nz = 0.f;
                 if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[0][k] * inv);
                 const float visit = (float)cn;
-                const float q = cn > 0 ? cw / visit : 0.f;                        // q_value (:77-79)
+                // q_value (:77-79); the denominator is kept non-zero so the IEEE division never leaves its fast path
+                const float q = cn > 0 ? cw / (cn > 0 ? visit : 1.f) : 0.f;
                 const float prob = eps * nz + one_m_eps * cp;                     // :269
                 const float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
                 const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
@@ -271,6 +280,10 @@ C6_UNROLL(C6_NOISE_UNROLL)
             }
             __syncwarp();  // cp.async results and st.empty of the other lanes
             child = st.ci[0][bb];
+            {  // the chosen child's record is already staged: no second trip to memory for the next step
+                const uint4 ch = st.child[0][bb];
+                r.n = (int32_t)ch.x, r.w = __uint_as_float(ch.y), r.p = __uint_as_float(ch.z), r.link = ch.w;
+            }
             chosen_bit = kth_empty(st, bb, lt, lane);
             __syncwarp();  // the stage is rewritten by the next step
         }

@@ -171,6 +171,7 @@ def run():
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-steady", action="store_true", help="skip the whole-game steady-state window (games/s)")
     ap.add_argument("--log2-records", type=int, default=18)
     ap.add_argument("--epsilon", type=float, default=None, help="override epsilon (0 disables Dirichlet noise)")
     args = ap.parse_args()
@@ -245,6 +246,32 @@ def run():
                 "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
                 "avg_depth": d["sum_depth"] / max(d["sims"], 1), "avg_sum_ck": d["sum_ck"] / max(d["sims"], 1),
                 "avg_cleaf": d["sum_cleaf"] / max(d["evals"], 1)}
+    # steady state: keep stepping until every slot has finished at least one game (slots refill from the queue, so
+    # the resident games are then spread over all phases of a game), then time a window: simulations/s over whole
+    # games and finished games/s (the second half of BASELINE.json's metric)
+    steady = None
+    if not args.no_steady:
+        run_in, window = 240, 60
+        assert L.c6_engine_timed_steps(e, run_in, C.byref(ms)) == 0, L.c6_last_error()
+        sa, sb = c6lib.Stats(), c6lib.Stats()
+        L.c6_engine_stats(e, C.byref(sa))
+        if dist is not None:
+            dist.barrier()
+        assert L.c6_engine_timed_steps(e, window, C.byref(ms)) == 0, L.c6_last_error()
+        L.c6_engine_stats(e, C.byref(sb))
+        w_ms, w_sims, w_games = float(ms.value), float(sb.sims - sa.sims), float(sb.games_done - sa.games_done)
+        if dist is not None:
+            import torch
+            t = torch.tensor([w_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            w_ms = float(t.item())
+            s = torch.tensor([w_sims, w_games], device="cuda", dtype=torch.float64)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            w_sims, w_games = float(s[0].item()), float(s[1].item())
+        steady = {"simulations_per_sec": w_sims / (w_ms * 1e-3), "games_per_sec": w_games / (w_ms * 1e-3),
+                  "stones_per_game": (w_sims / SIMS) / max(w_games, 1.0), "ms_per_step": w_ms / window,
+                  "window": f"{window} steps after {args.warmup + args.steps + run_in} (every slot refilled at least once); "
+                            f"{int(w_games)} games finished in the window"}
     L.c6_engine_destroy(e)
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -252,6 +279,8 @@ def run():
            "dtype": "f32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
            "gpu_launches": total_launches, "clocks": clk.summary(),
            "peak_records_per_game": int(st1.peak_rec), "bytes_per_game": int(st1.bytes_per_game)}
+    if steady is not None:
+        out["steady_state"] = steady
 
     # end to end through the reference-facing evaluator contract: host callback, host buffers
     if not args.no_e2e:

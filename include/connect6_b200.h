@@ -195,6 +195,18 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
                       int8_t* winners_out, uint8_t* stones_out, uint32_t* boards_out, int64_t n_out,
                       uint64_t* total_stones);
 
+/* DefaultPolicy — the reference's pure MCTS with random rollouts (policy/default_policy/mod.rs:94-271) — under
+ * Agent::play (agent/agent_impl/mod.rs:121-178) for n_games games on the GPU, `num_iter` searches per stone
+ * (DefaultPolicy::new() uses 50, mod.rs:104).  One policy instance per game plays both colours, as
+ * `Agent::new(&mut policy).play()` does.  Random choices: Philox streams keyed (seed, game id).
+ * root_visit / root_black_win (may be NULL): n_games x 225 i32, the root node's counters when stone m was chosen. */
+typedef struct c6_dp_stats {
+    uint64_t searches, rollouts, rollout_stones, select_steps, children_scanned, replaced, nodes, errors;
+    float kernel_ms;
+} c6_dp_stats;
+int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
+                           c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats);
+
 /* parity probes of the Dirichlet-noise sampler (tests): Gamma(shape) draw i of stream (i, 7, 9) keyed
  * (k0, k1); the engine's deterministic f64 log / exp on xs (log only where xs > 0) */
 int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device);

@@ -11,5 +11,5 @@ timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 
 tail -2 $OUT/smoke.log
 timeout 900 python bench.py $BENCH_ARGS > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err
 cat $OUT/bench.json
-timeout 600 python bench.py --epsilon 0 --no-e2e --no-cpu-baseline > $OUT/bench_eps0.json 2> $OUT/bench_eps0.err
+timeout 600 python bench.py --epsilon 0 --no-e2e --no-cpu-baseline --no-steady > $OUT/bench_eps0.json 2> $OUT/bench_eps0.err
 cat $OUT/bench_eps0.json

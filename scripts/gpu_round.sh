@@ -12,14 +12,14 @@ tail -5 $OUT/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/smoke.log
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" >> $OUT/bench.err
 cat $OUT/bench.json
-timeout 600 python bench.py --epsilon 0 --no-e2e --no-cpu-baseline > $OUT/bench_eps0.json 2> $OUT/bench_eps0.err
+timeout 600 python bench.py --epsilon 0 --no-e2e --no-cpu-baseline --no-steady > $OUT/bench_eps0.json 2> $OUT/bench_eps0.err
 cat $OUT/bench_eps0.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
 cat $OUT/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-steady > $OUT/bench_under_ncu.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sims_device -s 3 -c 1 -o $OUT/prof_sims \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" >> $OUT/ncu_full.log
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-steady > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" >> $OUT/ncu_full.log
 tail -3 $OUT/ncu_full.log
 timeout 300 python scripts/micro.py > $OUT/micro.jsonl 2> $OUT/micro.err; cat $OUT/micro.jsonl
 kill $SMI

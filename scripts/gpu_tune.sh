@@ -5,7 +5,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu-baseline $EXTRA > $OUT/$name.json 2> $OUT/$name.err
+  env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu-baseline --no-steady $EXTRA > $OUT/$name.json 2> $OUT/$name.err
   python - "$OUT/$name.json" "$name" <<'PY'
 import json,sys
 try:
