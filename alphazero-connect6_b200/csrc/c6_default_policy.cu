@@ -266,7 +266,8 @@ void make_zobrist_table(uint64_t* Zb);  // c6_engine.cu
 // Returns the milliseconds spent inside the kernel (CUDA events).
 float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, long long n_games, int max_moves, int device,
                           GameRecord* out, int32_t* root_visit, int32_t* root_bw, unsigned long long* stats) {
-    if (num_iter < 0 || n_games < 0) throw std::runtime_error("default_policy_play: bad arguments");
+    // num_iter == 0 panics in the reference (policy() looks the root up in a map nobody filled, mod.rs:131)
+    if (num_iter < 1 || n_games < 0) throw std::runtime_error("default_policy_play: num_iter must be >= 1 and n_games >= 0");
     DP_CK(cudaSetDevice(device));
     for (int i = 0; i < 8; ++i) stats[i] = 0;
     if (n_games == 0) return 0.f;

@@ -187,9 +187,8 @@ inline GammaParams gamma_params(double shape) {
 //   P <= 1 : X = P^(1/shape),           accept iff V <= e^-X   (squeeze: e^-X >= 1 - X + X^2/2 - X^3/6)
 //   P >  1 : X = -ln((b - P)/shape),    accept iff V <= X^(shape-1)
 // gamma_small_fast tries trial 0 on the hot branch only and reports failure; gamma_small is the full loop.
-__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, uint32_t a, uint32_t b, uint32_t c,
-                                                 uint32_t k0, uint32_t k1, double& x) {
-    const Philox4 r = philox4x32_10(a, b, c, 0u, k0, k1);
+// (split in two so that a caller can have the Philox block of its next draw in flight under the f64 chain of this one)
+__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, const Philox4& r, double& x) {
     const double u = u64_to_open01(r.x, r.y), v = u64_to_open01(r.z, r.w);
     const double p = gp.b * u;
     x = 0.0;
@@ -197,6 +196,10 @@ __device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaPa
     // p = b u with u >= 2^-53: normal; ln p <= 0
     x = det_exp<true>(T, det_log<true>(T, p) * gp.inv_shape);
     return v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0);
+}
+__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, uint32_t a, uint32_t b, uint32_t c,
+                                                 uint32_t k0, uint32_t k1, double& x) {
+    return gamma_small_fast(T, gp, philox4x32_10(a, b, c, 0u, k0, k1), x);
 }
 static __device__ __noinline__ double gamma_small(const MathTab& T, double shape, double inv_shape, double bb, uint32_t a, uint32_t b,
                                            uint32_t c, uint32_t k0, uint32_t k1) {

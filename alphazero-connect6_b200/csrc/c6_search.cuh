@@ -200,15 +200,17 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             if (NOISE) {
                 const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
                 unsigned pend = 0;
+                {
 C6_UNROLL(C6_NOISE_UNROLL)
-                for (int k = lane; k < C; k += 32) {
-                    double gj;
-                    if (NOISE == 1) {
-                        if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
-                    } else {
-                        gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
+                    for (int k = lane; k < C; k += 32) {
+                        double gj;
+                        if (NOISE == 1) {
+                            if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
+                        } else {
+                            gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
+                        }
+                        st.gamma[0][k] = gj;
                     }
-                    st.gamma[0][k] = gj;
                 }
                 if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
                     // list the pending ranks (any order): exclusive prefix sum of the per-lane counts

@@ -53,6 +53,11 @@ class Stats(C.Structure):
                [("peak_rec", C.c_uint32), ("peak_lnk", C.c_uint32), ("kernel_launches", C.c_uint64), ("bytes_per_game", C.c_uint64)]
 
 
+class DpStats(C.Structure):  # c6_dp_stats
+    _fields_ = [(n, C.c_uint64) for n in ("searches", "rollouts", "rollout_stones", "select_steps", "children_scanned",
+                                          "replaced", "nodes", "errors")] + [("kernel_ms", C.c_float)]
+
+
 EVAL_CALLBACK, EVAL_PHILOX, EVAL_DET, EVAL_NEG, EVAL_DEVICE_CALLBACK = 0, 1, 2, 3, 4
 DEVICE_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 
@@ -124,6 +129,8 @@ def product():
         L.c6_bench_win_check.argtypes = [C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_int8), C.c_int64]
         L.c6_bench_playouts.argtypes = [C.c_int64, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int8),
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
+        L.c6_default_policy_play.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int, C.c_int, C.POINTER(Record),
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(DpStats)]
         L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_int, C.c_int]
         L.c6_probe_math.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]
         L.c6_probe_pcie.argtypes = [C.c_int64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3

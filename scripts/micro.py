@@ -24,3 +24,24 @@ assert L.c6_bench_playouts(0, n, 0xC6, 3, 0, C.byref(ms), None, None, None, 0, C
 print(json.dumps({"bench": "random_playouts", "playouts": n, "ms": ms.value, "playouts_per_s": n / (ms.value * 1e-3),
                   "stones_per_s": tot.value / (ms.value * 1e-3), "avg_stones": tot.value / n,
                   "written_GBps": n * 72 / (ms.value * 1e-3) / 1e9}))
+
+# DefaultPolicy (pure MCTS, 50 searches per stone = DefaultPolicy::new()) self-play: whole games on the GPU, one thread per
+# game, against the oracle restatement on all host cores (one OS thread per game like AsyncAgent) on a bounded sample.
+for n_games in (65536, 262144):
+    rec = (c6lib.Record * n_games)()
+    st = c6lib.DpStats()
+    assert L.c6_default_policy_play(50, 0xC6, 0, n_games, 0, 0, rec, None, None, C.byref(st)) == 0, L.c6_last_error()
+    stones = sum(rec[g].n_moves for g in range(0, n_games, 64)) * 64
+    secs = st.kernel_ms * 1e-3
+    print(json.dumps({"bench": "default_policy_self_play", "games": n_games, "num_iter": 50, "kernel_ms": st.kernel_ms,
+                      "games_per_s": n_games / secs, "searches_per_s": st.searches / secs,
+                      "rollout_stones_per_s": st.rollout_stones / secs, "avg_stones_per_game": stones / n_games,
+                      "avg_rollout_stones": st.rollout_stones / max(st.rollouts, 1)}))
+if "--no-cpu" not in sys.argv:
+    O = c6lib.oracle()
+    cores = O.oracle_hardware_concurrency()
+    outs = (c6lib.OracleDpOut * (2 * cores))()
+    secs = O.oracle_default_policy_many(50, 0xC6, 0, 2 * cores, 0, cores, outs)
+    print(json.dumps({"bench": "default_policy_self_play_cpu_oracle", "games": 2 * cores, "cores": cores, "seconds": secs,
+                      "games_per_s": 2 * cores / secs, "searches_per_s": sum(o.searches for o in outs) / secs,
+                      "rollout_stones_per_s": sum(o.rollout_stones for o in outs) / secs}))

@@ -29,6 +29,12 @@ class OracleGameOut(C.Structure):
                 ("turns", C.c_int32 * 225)] + [(n, C.c_uint64) for n in ("sims", "sum_ck", "sum_cleaf", "sum_depth", "evals", "max_nodes")]
 
 
+class OracleDpOut(C.Structure):
+    _fields_ = [("winner", C.c_int), ("n_moves", C.c_int), ("moves", C.c_int * 225), ("root_visit", C.c_int32 * 225),
+                ("root_black_win", C.c_int32 * 225)] + \
+               [(n, C.c_uint64) for n in ("searches", "rollouts", "rollout_stones", "select_steps", "children_scanned", "replaced", "nodes")]
+
+
 _oracle = None
 
 
@@ -69,6 +75,9 @@ def oracle():
         L.oracle_self_play_many.restype = C.c_double
         L.oracle_self_play_many.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.c_int, C.c_int, C.POINTER(OracleGameOut)]
         L.oracle_play_with.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(C.c_int), C.c_int, C.POINTER(OracleGameOut)]
+        L.oracle_default_policy_play.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(OracleDpOut)]
+        L.oracle_default_policy_many.restype = C.c_double
+        L.oracle_default_policy_many.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(OracleDpOut)]
         L.oracle_search_batch.argtypes = [C.POINTER(C.c_int8), C.c_int64, C.POINTER(C.c_int8), C.c_int]
         _oracle = L
     return _oracle
