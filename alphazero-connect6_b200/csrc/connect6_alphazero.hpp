@@ -144,4 +144,39 @@ class AlphaZero : public Policy {
     bool started_ = false;
 };
 
+// DefaultPolicy — pure MCTS with random rollouts (LC/policy/default_policy/mod.rs:94-271: `new()` = 50 searches
+// per stone, `with_num_iter(n)`).  The GPU plays whole games (one thread per game, c6_default_policy.cu), so the
+// mirror is of `Agent::new(&mut DefaultPolicy::new()).play()` repeated n times — what AsyncAgent::run does with a
+// policy generator (LC/agent/async_agent/mod.rs:100-137) — not of a single `next()`.
+class DefaultPolicy {
+   public:
+    DefaultPolicy() {}                                                       // DefaultPolicy::new
+    static DefaultPolicy with_num_iter(int num_iter) {                       // DefaultPolicy::with_num_iter
+        DefaultPolicy p;
+        p.num_iter_ = num_iter;
+        return p;
+    }
+    // n games, results in game-id order (game g uses the Philox streams of (seed, first_game_id + g))
+    std::vector<PlayResult> play(int n_games, uint32_t seed = 0xC6, uint32_t first_game_id = 0, int device = 0) const {
+        std::vector<c6::GameRecord> rec((size_t)std::max(n_games, 0));
+        unsigned long long stats[8];
+        c6::default_policy_play(num_iter_, seed, first_game_id, n_games, 0, device, rec.data(), nullptr, nullptr, stats);
+        std::vector<PlayResult> out(rec.size());
+        for (size_t g = 0; g < rec.size(); ++g) {
+            Game game;
+            out[g].winner = player_from(rec[g].winner);
+            for (int m = 0; m < rec[g].n_moves; ++m) {
+                const Pos pos((size_t)(rec[g].moves[m] / 15), (size_t)(rec[g].moves[m] % 15));
+                out[g].path.push_back(Path{game.get_turn(), game.get_board(), pos});
+                if (!game.set(pos).empty()) throw std::runtime_error("DefaultPolicy::play: illegal stone in a record");
+            }
+        }
+        return out;
+    }
+    int num_iter() const { return num_iter_; }
+
+   private:
+    int num_iter_ = 50;
+};
+
 }  // namespace connect6

@@ -104,6 +104,24 @@ def self_play(obj, num_simulation, epsilon, dirichlet_alpha, c_puct, debug, num_
     return results[0] if n == 1 else tuple(results)
 
 
+def default_policy_play(num_iter=50, num_game=1, seed=None, first_game_id=0, device=None):
+    """`Agent::new(&mut DefaultPolicy::with_num_iter(num_iter)).play()` for num_game games on the GPU (pure MCTS with
+    random rollouts, libconnect6/src/policy/default_policy/mod.rs:94-271; not exported by the reference's pybind).
+    Returns a tuple of (winner, path) in the format of self_play."""
+    L = _capi.product()
+    n = int(num_game)
+    if n <= 0:
+        return ()
+    if seed is None:
+        seed = int(os.environ.get("C6_SEED", "0"), 0) if os.environ.get("C6_SEED") else int.from_bytes(os.urandom(4), "little")
+    if device is None:
+        device = int(os.environ.get("C6_DEVICE", "0"))
+    rec = (_capi.Record * n)()
+    if L.c6_default_policy_play(int(num_iter), int(seed), int(first_game_id), n, 0, int(device), rec, None, None, None) != 0:
+        raise RuntimeError(L.c6_last_error().decode())
+    return tuple(_expand(rec[i]) for i in range(n))
+
+
 def _print_game(path, winner):
     """Agent::debug transcript (agent_impl/mod.rs:127-129,147-161; game_impl/mod.rs:217-237)."""
     def show(board):

@@ -88,3 +88,18 @@ def test_default_policy_gpu_at_scale_properties():
     assert L.c6_default_policy_play(it, 0xC6, 4000, 64, 0, 0, sub, None, None, None) == 0
     for i in range(64):
         assert bytes(sub[i].moves) == bytes(rec[4000 + i].moves) and sub[i].winner == rec[4000 + i].winner
+
+
+@pytest.mark.gpu
+def test_pyconnect6_default_policy_play():
+    """Python surface: records expanded to the reference's (winner, [(turn, board, (row, col))]) shape."""
+    from pyconnect6 import pyconnect6 as native
+    games = native.default_policy_play(num_iter=10, num_game=3, seed=0xC6, first_game_id=1000)
+    want = oracle_games(10, 0xC6, 1000, 3)
+    assert len(games) == 3
+    for (winner, path), w in zip(games, want):
+        assert winner == w.winner and [r * 15 + c for _, _, (r, c) in path] == list(w.moves[:w.n_moves])
+        board = [0] * 225
+        for turn, b, (r, c) in path:  # Path.board is the board BEFORE the stone (agent_impl/mod.rs:139-143)
+            assert b == board and b[r * 15 + c] == 0
+            board[r * 15 + c] = turn
