@@ -16,9 +16,10 @@ ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--waves", type=int, default=96)
 ap.add_argument("--warm", type=int, default=16)
 ap.add_argument("--sims", type=int, default=800)
+ap.add_argument("--device", type=int, default=0)
 a = ap.parse_args()
 L = c6lib.product()
-cfg = c6lib.make_config(num_simulation=a.sims, epsilon=0.25, dirichlet_alpha=0.03, c_puct=1.0, seed=0xC6, device=0, slots=a.games,
+cfg = c6lib.make_config(num_simulation=a.sims, epsilon=0.25, dirichlet_alpha=0.03, c_puct=1.0, seed=0xC6, device=a.device, slots=a.games,
                         log2_records=18, evaluator=c6lib.EVAL_CALLBACK)
 e = L.c6_engine_create(C.byref(cfg))
 assert e, L.c6_last_error()
