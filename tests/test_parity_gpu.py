@@ -270,6 +270,24 @@ def test_selfplay_deep_trees_late_game(evaluator, cbname, sims, c_puct, n_stones
     assert st.sum_depth > 2 * st.sims  # the trees really are deep
 
 
+@pytest.mark.parametrize("evaluator,cbname,sims,c_puct,n_stones", [
+    # Dirichlet noise ON near the end of the game: nodes with 2..40 children, so the rank-indexed per-child loops run
+    # one or two partly filled rounds, the slow-path draws of a step fit one partly filled pass, and single-child /
+    # full-board shortcuts sit next to noisy steps.
+    (EVAL_PHILOX, None, 200, 1.0, 186),
+    (EVAL_PHILOX, None, 120, 0.3, 205),
+    (EVAL_NEG, "neg_eval_callback", 90, 0.5, 216),
+    (EVAL_CALLBACK, "det_eval_callback", 60, 1.0, 196),
+])
+def test_selfplay_late_game_with_noise(evaluator, cbname, sims, c_puct, n_stones):
+    seed, n_games, eps = 0xC6, 3, 0.25
+    prefixes = [make_prefix(n_stones + g, 7000 * n_stones + g) for g in range(n_games)]
+    rec, cv, rn, rw, st = run_engine(n_games, cbname if evaluator == EVAL_CALLBACK else None, first_id=700, prefixes=prefixes,
+                                     num_simulation=sims, epsilon=eps, c_puct=c_puct, seed=seed, evaluator=evaluator)
+    compare_games(n_games, rec, cv, rn, rw, 700, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, 0, c_puct=c_puct,
+                  prefixes=prefixes)
+
+
 def test_selfplay_800_sims_reference_default():
     """Reference default budget (800 simulations, eps .25, alpha .03) for the first stones of two games."""
     seed, sims, eps, mm = 0xC6, 800, 0.25, 6
