@@ -3,13 +3,14 @@
 //   expand / get_from       LC/policy/alphazero_policy/mod.rs:218-234,331-381, augment.rs:60-92
 //   update                  LC/policy/alphazero_policy/mod.rs:386-408
 //
-// Shaped by two rounds of ncu evidence (profiles/r01a_*): the first fused kernel was 105 KB of SASS with
+// Shaped by the ncu evidence under profiles/: the first fused kernel (r01a) was 105 KB of SASS with
 // `stall_no_instruction` as its top stall (instruction-cache thrash: 20 warps at unrelated places of an
 // unrolled body), spent two thirds of its instructions in the f64 Gamma sampler and pushed 100+ GB per
-// launch through local memory.  Hence:
-//   (1) memory phases stay unrolled (eight independent loads in flight per lane), arithmetic phases
-//       are ROLLED loops over the eight board words that read their operands from a per-warp
-//       shared-memory stage filled by cp.async — one copy of the PUCT, Gamma and Philox code each;
+// launch through local memory; up to r01e every per-child loop ran one round per board WORD (8 rounds, 216 of
+// 256 lanes busy in the opening, far fewer later).  Hence:
+//   (1) every per-child phase is a ROLLED loop over child RANKS (k = lane, lane + 32, ... < C: ceil(C/32) rounds)
+//       that reads its operands from a per-warp shared-memory stage filled by cp.async, all requests of a
+//       phase in flight before the first is waited for — one copy of the PUCT, Gamma and Philox code each;
 //   (2) everything a move needs from the game state lives in registers (`Cursor`);
 //   (3) an expansion does not hash its children: a child shared with another parent ("transposition",
 //       `entry(hash).or_insert`, :367-370) is found by following the link run of the expanded sibling
@@ -200,17 +201,15 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             if (NOISE) {
                 const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
                 unsigned pend = 0;
-                {
 C6_UNROLL(C6_NOISE_UNROLL)
-                    for (int k = lane; k < C; k += 32) {
-                        double gj;
-                        if (NOISE == 1) {
-                            if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
-                        } else {
-                            gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
-                        }
-                        st.gamma[0][k] = gj;
+                for (int k = lane; k < C; k += 32) {
+                    double gj;
+                    if (NOISE == 1) {
+                        if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
+                    } else {
+                        gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
                     }
+                    st.gamma[0][k] = gj;
                 }
                 if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
                     // list the pending ranks (any order): exclusive prefix sum of the per-lane counts

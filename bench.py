@@ -134,7 +134,7 @@ def workload_config(n_gpus):
     return {"workload": "4096 concurrent self-play games per GPU, AlphaZero policy + RandomEvaluator, 800 simulations/stone "
                         "(BASELINE.json configs[1]); reference default hyper-parameters epsilon=0.25 alpha=0.03 c_puct=1",
             "games_per_gpu": GAMES_PER_GPU, "num_simulation": SIMS, "epsilon": EPS, "dirichlet_alpha": ALPHA,
-            "step": "one stone for every resident game (4096 x 800 simulations + move choice + node collection)",
+            "step": "one stone for every resident game (4096 x 800 simulations + move choice + node collection), one kernel launch",
             "sharding": f"game id -> rank, {n_gpus} rank(s), no data-path collective",
             "l2": "working set >> L2 (node pool of 4096 games is tens of GB); no flush needed"}
 
@@ -240,7 +240,7 @@ def run():
     traffic, traffic_src = ncu_traffic(d["sims"] / k_launches)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
-                "kernel": "k_sims_device<philox,noise> (1 launch/step)", "kernel_ms_per_launch": k_ms,
+                "kernel": "k_sims_device<philox,noise> (1 launch/step: 800 searches per game, then the stone and node collection)", "kernel_ms_per_launch": k_ms,
                 "kernel_share_of_step": k_ms * k_launches / float(ms.value),
                 "algorithmic_bytes_per_launch": bytes_alg / k_launches, "peak_source": peak_src,
                 "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
