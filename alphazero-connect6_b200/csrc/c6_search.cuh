@@ -264,10 +264,17 @@ C6_UNROLL(C6_NOISE_UNROLL)
                 float nz = 0.f;
                 if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[0][k] * inv);
                 const float visit = (float)cn;
-                // q_value (:77-79); the denominator is kept non-zero so the IEEE division never leaves its fast path
-                const float q = cn > 0 ? cw / (cn > 0 ? visit : 1.f) : 0.f;
+                // q_value (:77-79) and u (:270).  The IEEE division's fast path is left for a subroutine whenever an
+                // operand is zero — and an unvisited child has W = 0, a freshly expanded node has visit_sum = 0 — so both
+                // divisions are fed stand-in operands in those lanes and the exact result (0, or the zero numerator
+                // itself) is selected afterwards: same values, no calls (r01k capture: 5 % of all instructions)
+                const bool seen = cn > 0 && cw != 0.f;
+                const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
+                const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
                 const float prob = eps * nz + one_m_eps * cp;                     // :269
-                const float u = prob * sqrtf(visit_sum - visit) / (1.f + visit);  // :270
+                const float un = prob * sqrtf(visit_sum - visit);
+                const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
+                const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
                 const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
                 if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k;
             }
