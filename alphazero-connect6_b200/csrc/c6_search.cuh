@@ -272,7 +272,8 @@ C6_UNROLL(C6_NOISE_UNROLL)
                 const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
                 const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
                 const float prob = eps * nz + one_m_eps * cp;                     // :269
-                const float un = prob * sqrtf(visit_sum - visit);
+                const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
+                const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
                 const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
                 const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
                 const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
