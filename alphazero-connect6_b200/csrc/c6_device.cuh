@@ -93,6 +93,7 @@ struct Leaf {
     uint32_t rec;
     int depth;
     uint32_t last_bit;  // bit position of the last stone on the path (valid when depth >= 1)
+    float leaf_w, leaf_p;  // W and P of the leaf's record as the descent read them (its N is 0)
 };
 
 struct Warp {  // per-warp view of one game slot: hot bases as pointers, the rest derived from the slot number on use

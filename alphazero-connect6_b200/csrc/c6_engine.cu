@@ -77,11 +77,13 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
         if (w.gs->status != ST_ACTIVE) continue;
         Cursor cs;
         load_cursor(*w.gs, cs);
+        if (lane == 0) st.rootrec = bits_of(load_rec(&w.rec[w.gs->root]));
+        __syncwarp();
         for (int s = 0; s < D.num_sim && !cs.err; ++s) {
             Leaf L;
-            descend<NOISE>(D, w, cs, L, st, mt);
+            descend<NOISE, true>(D, w, cs, L, st, mt);
             if (L.stones == CELLS) {
-                terminal_leaf(D, w, L);
+                terminal_leaf<true>(D, w, st, L);
             } else if (EVAL == EVAL_PHILOX) {
                 EvPhilox ev;
                 ev.init(D, cs, lane);
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
         descend<NOISE>(D, w, cs, L, st, mt);
         int need = 1;
         if (L.stones == CELLS) {
-            terminal_leaf(D, w, L);
+            terminal_leaf<false>(D, w, st, L);
             need = 0;
         }
 #pragma unroll

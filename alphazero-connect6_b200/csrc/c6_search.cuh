@@ -25,6 +25,7 @@ namespace c6 {
 // Per-move copy of the mutable game bookkeeping, identical in every lane of the warp.
 struct Cursor {
     uint32_t rec_head, lnk_head, exp_count, sim_index;
+    uint32_t orph_win, stones0;  // GameState::orph bits of stone counts stones0 .. stones0 + 31 (stones0 = the root's)
     uint32_t rec_tail, lnk_tail, epoch, game_id;
     uint32_t sum_ck, sum_cleaf, sum_depth, evals, sims;
     uint32_t peak_rec, peak_lnk;
@@ -37,6 +38,14 @@ __device__ __forceinline__ void load_cursor(const GameState& g, Cursor& c) {
     c.sum_ck = 0, c.sum_cleaf = 0, c.sum_depth = 0, c.evals = 0, c.sims = 0;
     c.peak_rec = g.peak_rec, c.peak_lnk = g.peak_lnk;
     c.err = 0;
+    c.stones0 = (uint32_t)g.stones;
+    const uint32_t wi = c.stones0 >> 5;
+    c.orph_win = __funnelshift_r(g.orph[wi], wi + 1 < 8 ? g.orph[wi + 1] : 0u, c.stones0 & 31);
+}
+// is some expanded node with `s1` stones flagged as having lost its expanded parents (GameState::orph)?
+__device__ __forceinline__ bool orphan_flag(const GameState& g, const Cursor& c, uint32_t s1) {
+    const uint32_t j = s1 - c.stones0;
+    return j < 32 ? ((c.orph_win >> j) & 1u) != 0 : ((g.orph[s1 >> 5] >> (s1 & 31)) & 1u) != 0;
 }
 __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const Cursor& c, int lane) {
     if (lane == 0) {
@@ -54,6 +63,7 @@ __device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const C
 // ------------------------------------------------------------------------------------------------
 // per-warp shared-memory stage
 // ------------------------------------------------------------------------------------------------
+constexpr int PATH_CACHE = 12;  // path records kept in shared memory (deeper ones are re-read by backup)
 // NOISE: 0 = epsilon == 0 (the draw is multiplied by 0: skipped), 1 = Dirichlet alpha < 1, 2 = alpha >= 1
 // One stage per warp, indexed by child RANK (position in the node's link run = row-major order of its empty
 // cells): slot [k >> 5][k & 31] belongs to child k and is handled by lane k & 31 in round k >> 5, so a node with
@@ -74,6 +84,11 @@ struct WarpStage {
     };
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
     uint8_t cell[256];  // expand: bit position of the empty cell of rank k; select: ranks whose draw needs the slow path
+    // fused kernel only: what this simulation's descent has already read of the records on its path, so that backup
+    // stores without loading (the game's warp is the only writer of its pool), and the root's record across simulations
+    uint4 prec[PATH_CACHE];
+    uint32_t pidx[PATH_CACHE];
+    uint4 rootrec;
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -155,7 +170,15 @@ __device__ __forceinline__ uint32_t kth_empty(const WarpStage<NOISE>& st, uint32
 // ------------------------------------------------------------------------------------------------
 // select
 // ------------------------------------------------------------------------------------------------
-template <int NOISE>
+__device__ __forceinline__ Rec rec_of(const uint4& v) {
+    Rec r;
+    r.n = (int32_t)v.x, r.w = __uint_as_float(v.y), r.p = __uint_as_float(v.z), r.link = v.w;
+    return r;
+}
+__device__ __forceinline__ uint4 bits_of(const Rec& r) { return make_uint4((uint32_t)r.n, __float_as_uint(r.w), __float_as_uint(r.p), r.link); }
+
+// FUSED: called from k_sims_device, where the same warp runs descent, expansion and backup of a simulation back to back.
+template <int NOISE, bool FUSED = false>
 __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf& L, WarpStage<NOISE>& st, const MathTab& mt) {
     const GameState& g = *w.gs;
     const int lane = w.lane;
@@ -169,10 +192,13 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     uint32_t cur = g.root;
     int depth = 0;
     const float eps = D.eps, one_m_eps = 1.f - D.eps, cpuct = D.cpuct;
-    Rec r = load_rec(&w.rec[cur]);
+    Rec r = FUSED ? rec_of(st.rootrec) : load_rec(&w.rec[cur]);
     for (;;) {
         if (r.n == 0) break;  // no children: leaf (:251-253)
-        if (lane == 0) w.path(D)[depth] = cur;
+        if (lane == 0) {
+            if (FUSED && depth < PATH_CACHE) st.pidx[depth] = cur, st.prec[depth] = bits_of(r);
+            if (!FUSED || depth >= PATH_CACHE) w.path(D)[depth] = cur;
+        }
         const int C = CELLS - L.stones;
         const int turn = turn_of(L.stones);
         cs.sum_ck += (uint32_t)C;
@@ -311,20 +337,28 @@ C6_UNROLL(C6_NOISE_UNROLL)
     }
     L.rec = cur;
     L.depth = depth;
+    L.leaf_w = r.w, L.leaf_p = r.p;
     cs.sum_depth += (uint32_t)depth;
     cs.sims += 1;
     __syncwarp();
 }
 
 // update(): only the leaf's parent takes the value, every ancestor (leaf excluded) gets visit += 1.
-__device__ __forceinline__ void backup(const Dev& D, Warp& w, int depth, float v) {
+template <bool FUSED, int NOISE>
+__device__ __forceinline__ void backup(const Dev& D, Warp& w, WarpStage<NOISE>& st, int depth, float v) {
     __syncwarp();
     for (int i = w.lane; i < depth; i += 32) {
-        uint32_t a = w.path(D)[i];
-        Rec r = load_rec(&w.rec[a]);
+        uint32_t a;
+        Rec r;
+        if (FUSED && i < PATH_CACHE) {  // as read by this simulation's descent; nothing has written them since
+            a = st.pidx[i], r = rec_of(st.prec[i]);
+        } else {
+            a = w.path(D)[i], r = load_rec(&w.rec[a]);
+        }
         r.n += 1;
         if (i == depth - 1) r.w = r.w + v;
         store_rec(&w.rec[a], r);
+        if (FUSED && i == 0) st.rootrec = bits_of(r);
     }
     __syncwarp();
 }
@@ -337,10 +371,11 @@ __device__ __noinline__ float terminal_value(uint4 b0, uint4 b1, uint4 w0, uint4
     const uint32_t W[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
     return (float)win_check(B, W);
 }
-__device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, const Leaf& L) {
+template <bool FUSED, int NOISE>
+__device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, WarpStage<NOISE>& st, const Leaf& L) {
     const float v = terminal_value(make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]), make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]),
                                    make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]), make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]));
-    backup(D, w, L.depth, v);
+    backup<FUSED>(D, w, st, L.depth, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -598,7 +633,7 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     // rules S1 / S2 (warp-uniform test)
     {
         const uint32_t s1 = (uint32_t)L.stones + 1u;
-        if (L.depth >= 3 || ((w.gs->orph[s1 >> 5] >> (s1 & 31)) & 1u)) {
+        if (L.depth >= 3 || orphan_flag(*w.gs, cs, s1)) {
             const uint4 cm0 = turn < 0 ? make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]) : make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]);
             const uint4 cm1 = turn < 0 ? make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]) : make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]);
             res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, cm0, cm1, key,
@@ -633,10 +668,16 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     __syncwarp();
     // the leaf itself: visit += 1, children attached (:353-357,374-377), findable by key from now on
     if (lane == 0) {
-        Rec lr = load_rec(&w.rec[L.rec]);
+        Rec lr;
+        if (STAGED) {  // the descent of this very simulation read the leaf's record: N = 0, W and P as in L
+            lr.n = 0, lr.w = L.leaf_w, lr.p = L.leaf_p;
+        } else {
+            lr = load_rec(&w.rec[L.rec]);
+        }
         lr.n += 1;
         lr.link = link_base & Lm;
         store_rec(&w.rec[L.rec], lr);
+        if (STAGED && L.depth == 0) st.rootrec = bits_of(lr);  // the root itself was the leaf
         w.exp_rec(D)[ec] = L.rec;
         w.exp_key(D)[ec] = key;
         xh_insert(w.idx, Im, cs.epoch, key, L.rec);
@@ -648,7 +689,7 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     cs.evals += 1;
     cs.peak_rec = max(cs.peak_rec, base - cs.rec_tail);
     cs.peak_lnk = max(cs.peak_lnk, cs.lnk_head - cs.lnk_tail);
-    backup(D, w, L.depth, v);
+    backup<STAGED>(D, w, st, L.depth, v);
 }
 
 }  // namespace c6
