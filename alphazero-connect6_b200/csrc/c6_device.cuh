@@ -172,18 +172,30 @@ __device__ inline void collect(const Dev& D, Warp& w) {
     uint32_t wcur = 0;
     unsigned long long copied = 0;
     bool overflow = false;
-    for (uint32_t ei = 0; ei < n_exp; ++ei) {
+    // Most expanded nodes lack the stone just played and are dropped: the containment test runs for 32 entries at a
+    // time, one per lane; only the survivors are then handled by the whole warp, in list order.
+    for (uint32_t base = 0; base < n_exp && !overflow; base += 32) {
+      bool keep = false;
+      if (base + (uint32_t)lane < n_exp) {
+          const uint4* q = reinterpret_cast<const uint4*>(w.expB(D) + (size_t)(base + (uint32_t)lane) * 16);
+          const uint4 b0 = q[0], b1 = q[1], w0 = q[2], w1 = q[3];
+          const uint32_t xb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w}, xw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          keep = true;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) keep = keep && ((xb[j] & rootB[j]) == rootB[j]) && ((xw[j] & rootW[j]) == rootW[j]);
+      }
+      unsigned todo = __ballot_sync(FULL, keep);
+      while (todo) {
+        const uint32_t ei = base + (uint32_t)(__ffs((int)todo) - 1);
+        todo &= todo - 1;
         uint32_t eb[8], ew[8];
-        bool sup = true;
         int est = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             eb[j] = w.expB(D)[(size_t)ei * 16 + j];
             ew[j] = w.expB(D)[(size_t)ei * 16 + 8 + j];
-            sup = sup && ((eb[j] & rootB[j]) == rootB[j]) && ((ew[j] & rootW[j]) == rootW[j]);
             est += __popc(eb[j]) + __popc(ew[j]);
         }
-        if (!sup) continue;
         const uint32_t erec = w.exp_rec(D)[ei];
         const uint64_t ekey = w.exp_key(D)[ei];
         const int C = CELLS - est;
@@ -262,6 +274,7 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         if (lane == 0) w.exp_rec(D)[wcur] = new_e, w.exp_key(D)[wcur] = ekey;
         wcur += 1;
         __syncwarp();
+      }
     }
     if (overflow) return set_error(w, D, ERR_REC_FULL);
     // the root itself (unexpanded roots are not on the expanded list)

@@ -574,6 +574,9 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     if (cs.rec_head - cs.rec_tail + (uint32_t)C > D.R) cs.err = ERR_REC_FULL;
     if (ec + 1 > D.E) cs.err = ERR_EXP_FULL;
     if (cs.err) return;
+    // the key-table slot the leaf will be inserted at when the expansion is done: its first probe is in flight from here
+    const uint32_t slot0 = hash_slot(L.key) & Im;
+    const uint32_t slot0_epoch = __ldcg(&w.idx[slot0].epoch);
     // remember the board for the collector, then only the empties are needed
     if (lane < 16) {
         uint32_t word = 0;
@@ -680,7 +683,12 @@ C6_UNROLL(C6_PRIOR_UNROLL)
         if (STAGED && L.depth == 0) st.rootrec = bits_of(lr);  // the root itself was the leaf
         w.exp_rec(D)[ec] = L.rec;
         w.exp_key(D)[ec] = key;
-        xh_insert(w.idx, Im, cs.epoch, key, L.rec);
+        uint32_t pos = slot0;  // xh_insert with the first probe already answered (nothing else inserts in between)
+        if (slot0_epoch == cs.epoch) {
+            pos = (pos + 1) & Im;
+            while (__ldcg(&w.idx[pos].epoch) == cs.epoch) pos = (pos + 1) & Im;
+        }
+        __stcg(reinterpret_cast<uint4*>(&w.idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), L.rec, cs.epoch));
     }
     cs.exp_count = ec + 1;
     cs.lnk_head = link_base + (uint32_t)C;
