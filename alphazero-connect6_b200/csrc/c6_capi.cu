@@ -29,6 +29,18 @@ static_assert(sizeof(c6_record) == sizeof(GameRecord), "record layout");
 
 static thread_local std::string g_err;
 
+// Every c6_* entry point: exceptions stop at the C boundary, the message is kept for c6_last_error().
+template <class F>
+static int guarded(F&& body) {
+    try {
+        body();
+        return 0;
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        return 1;
+    }
+}
+
 [[noreturn]] static void die(const char* where, const char* what) {
     // the reference unwraps and aborts across the FFI (lib.rs:40,107,168)
     std::fprintf(stderr, "libcppconnect6 (B200 engine): %s: %s\n", where, what);
@@ -326,15 +338,6 @@ struct c6_engine {
     int64_t total = 0;
 };
 
-#define C6_TRY(...)                      \
-    try {                                \
-        __VA_ARGS__;                     \
-        return 0;                        \
-    } catch (const std::exception& ex) { \
-        g_err = ex.what();               \
-        return 1;                        \
-    }
-
 void c6_default_config(c6_config* cfg) {
     Config d;
     cfg->num_simulation = d.num_simulation, cfg->epsilon = d.epsilon, cfg->dirichlet_alpha = d.dirichlet_alpha;
@@ -365,34 +368,56 @@ c6_engine* c6_engine_create(const c6_config* cfg) {
     }
 }
 void c6_engine_destroy(c6_engine* e) { delete e; }
-int c6_engine_start(c6_engine* e, uint32_t first, int64_t total) { C6_TRY(e->total = total; e->eng->start(first, total)) }
-int c6_engine_step_device(c6_engine* e) { C6_TRY(e->eng->step_device()) }
-int c6_engine_wave_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->wave_callback(cb)) }
-int c6_engine_waves_device_callback(c6_engine* e, c6_device_callback cb, void* user, int waves) {
-    C6_TRY(e->eng->waves_device_callback(cb, user, waves))
+int c6_engine_start(c6_engine* e, uint32_t first, int64_t total) {
+    return guarded([&] {
+        e->total = total;
+        e->eng->start(first, total);
+    });
 }
-int c6_engine_run_device_callback(c6_engine* e, c6_device_callback cb, void* user) { C6_TRY(e->eng->run_device_callback_to_end(cb, user)) }
-int c6_engine_run_device(c6_engine* e) { C6_TRY(e->eng->run_device_to_end()) }
-int c6_engine_run_callback(c6_engine* e, c6_callback cb) { C6_TRY(e->eng->run_callback_to_end(cb, false)) }
-int c6_engine_sync(c6_engine* e) { C6_TRY(e->eng->sync()) }
+int c6_engine_step_device(c6_engine* e) { return guarded([&] { e->eng->step_device(); }); }
+int c6_engine_wave_callback(c6_engine* e, c6_callback cb) { return guarded([&] { e->eng->wave_callback(cb); }); }
+int c6_engine_waves_device_callback(c6_engine* e, c6_device_callback cb, void* user, int waves) {
+    return guarded([&] {
+        e->eng->waves_device_callback(cb, user, waves);
+    });
+}
+int c6_engine_run_device_callback(c6_engine* e, c6_device_callback cb, void* user) {
+    return guarded([&] {
+        e->eng->run_device_callback_to_end(cb, user);
+    });
+}
+int c6_engine_run_device(c6_engine* e) { return guarded([&] { e->eng->run_device_to_end(); }); }
+int c6_engine_run_callback(c6_engine* e, c6_callback cb) { return guarded([&] { e->eng->run_callback_to_end(cb, false); }); }
+int c6_engine_sync(c6_engine* e) { return guarded([&] { e->eng->sync(); }); }
 void c6_engine_cancel(c6_engine* e) { e->eng->cancel(); }
-int c6_engine_external_move(c6_engine* e, int slot, int row, int col) { C6_TRY(e->eng->external_move(slot, row, col)) }
-int c6_engine_waves_callback(c6_engine* e, c6_callback cb, int waves) { C6_TRY(e->eng->waves_callback(cb, waves)) }
-int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { C6_TRY(*ms = e->eng->timed_steps_device(steps)) }
+int c6_engine_external_move(c6_engine* e, int slot, int row, int col) { return guarded([&] { e->eng->external_move(slot, row, col); }); }
+int c6_engine_waves_callback(c6_engine* e, c6_callback cb, int waves) { return guarded([&] { e->eng->waves_callback(cb, waves); }); }
+int c6_engine_timed_steps(c6_engine* e, int steps, float* ms) { return guarded([&] { *ms = e->eng->timed_steps_device(steps); }); }
 int c6_engine_timed_waves(c6_engine* e, c6_callback cb, int waves, float* ms, double* h2d, double* d2h) {
-    C6_TRY(*ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h))
+    return guarded([&] {
+        *ms = e->eng->timed_waves_callback(cb, waves, h2d, d2h);
+    });
 }
 int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_seconds) {
-    C6_TRY(*wait_seconds = e->eng->host_wait_seconds(); *callback_seconds = e->eng->host_callback_seconds())
+    return guarded([&] {
+        *wait_seconds = e->eng->host_wait_seconds();
+        *callback_seconds = e->eng->host_callback_seconds();
+    });
 }
 int c6_engine_kernel_times(c6_engine* e, double* sims_kernel_ms, long long* sims_kernel_launches) {
-    C6_TRY(*sims_kernel_ms = e->eng->sims_kernel_ms(); *sims_kernel_launches = e->eng->sims_kernel_launches())
+    return guarded([&] {
+        *sims_kernel_ms = e->eng->sims_kernel_ms();
+        *sims_kernel_launches = e->eng->sims_kernel_launches();
+    });
 }
 int c6_engine_stats(c6_engine* e, c6_stats* out) {
-    C6_TRY(Stats s = e->eng->stats(); out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf,
-           out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,
-           out->peak_rec = s.peak_rec, out->peak_lnk = s.peak_lnk, out->kernel_launches = (uint64_t)e->eng->kernel_launches(),
-           out->bytes_per_game = e->eng->bytes_per_game())
+    return guarded([&] {
+        Stats s = e->eng->stats();
+        out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf,
+        out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,
+        out->peak_rec = s.peak_rec, out->peak_lnk = s.peak_lnk, out->kernel_launches = (uint64_t)e->eng->kernel_launches(),
+        out->bytes_per_game = e->eng->bytes_per_game();
+    });
 }
 int64_t c6_engine_games_done(c6_engine* e) {
     try {
@@ -403,13 +428,21 @@ int64_t c6_engine_games_done(c6_engine* e) {
     }
 }
 int c6_engine_records(c6_engine* e, c6_record* out, int64_t n) {
-    C6_TRY(auto r = e->eng->records(); if ((int64_t)r.size() < n) n = (int64_t)r.size();
-           std::memcpy(out, r.data(), (size_t)n * sizeof(GameRecord)))
+    return guarded([&] {
+        auto r = e->eng->records();
+        if ((int64_t)r.size() < n) n = (int64_t)r.size();
+        std::memcpy(out, r.data(), (size_t)n * sizeof(GameRecord));
+    });
 }
 int c6_engine_trace(c6_engine* e, int32_t* cv, int32_t* rn, float* rw) {
-    C6_TRY(std::vector<int32_t> a, b; std::vector<float> c; e->eng->trace(a, b, c);
-           std::memcpy(cv, a.data(), a.size() * 4); std::memcpy(rn, b.data(), b.size() * 4);
-           std::memcpy(rw, c.data(), c.size() * 4))
+    return guarded([&] {
+        std::vector<int32_t> a, b;
+        std::vector<float> c;
+        e->eng->trace(a, b, c);
+        std::memcpy(cv, a.data(), a.size() * 4);
+        std::memcpy(rn, b.data(), b.size() * 4);
+        std::memcpy(rw, c.data(), c.size() * 4);
+    });
 }
 long long c6_engine_validate(c6_engine* e, unsigned long long* detail) {
     try {
@@ -441,25 +474,32 @@ int c6_self_play_device(const c6_config* cfg, uint32_t first, int64_t n_games, c
 // n_games of self-play with a device evaluator, sharded by game id over `devices` (one host thread + engine per GPU)
 int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_devices, uint32_t first, int64_t n_games,
                                 c6_record* out, c6_stats* stats) {
-    C6_TRY(std::vector<int> devs(devices, devices + std::max(n_devices, 0)); if (devs.empty()) devs.push_back(cfg->device);
-           std::vector<GameRecord> rec((size_t)std::max<int64_t>(n_games, 0)); std::mutex m; c6_stats tot; std::memset(&tot, 0, sizeof tot);
-           run_sharded(devs, first, n_games, rec.data(), [&](int device, uint32_t f, int64_t cnt, GameRecord* dst) {
-               Config c = to_config(cfg);
-               c.device = device;
-               c.slots = (int)std::min<int64_t>(std::max<int64_t>(cnt, 1), cfg->slots > 0 ? cfg->slots : cnt);
-               Engine eng(c);
-               eng.start(f, cnt);
-               eng.run_device_to_end();
-               std::vector<GameRecord> r = eng.records();
-               std::copy(r.begin(), r.end(), dst);
-               Stats s = eng.stats();
-               std::lock_guard<std::mutex> l(m);
-               tot.sims += s.sims, tot.sum_ck += s.sum_ck, tot.sum_cleaf += s.sum_cleaf, tot.sum_depth += s.sum_depth, tot.evals += s.evals;
-               tot.gc_copied += s.gc_copied, tot.games_done += s.games_done, tot.kernel_launches += (uint64_t)eng.kernel_launches();
-               tot.peak_rec = std::max(tot.peak_rec, s.peak_rec), tot.peak_lnk = std::max(tot.peak_lnk, s.peak_lnk);
-               tot.bytes_per_game = eng.bytes_per_game();
-           });
-           if (out && n_games > 0) std::memcpy(out, rec.data(), (size_t)n_games * sizeof(GameRecord)); if (stats) *stats = tot)
+    return guarded([&] {
+        std::vector<int> devs(devices, devices + std::max(n_devices, 0));
+        if (devs.empty()) devs.push_back(cfg->device);
+        std::vector<GameRecord> rec((size_t)std::max<int64_t>(n_games, 0));
+        std::mutex m;
+        c6_stats tot;
+        std::memset(&tot, 0, sizeof tot);
+        run_sharded(devs, first, n_games, rec.data(), [&](int device, uint32_t f, int64_t cnt, GameRecord* dst) {
+        Config c = to_config(cfg);
+        c.device = device;
+        c.slots = (int)std::min<int64_t>(std::max<int64_t>(cnt, 1), cfg->slots > 0 ? cfg->slots : cnt);
+        Engine eng(c);
+        eng.start(f, cnt);
+        eng.run_device_to_end();
+        std::vector<GameRecord> r = eng.records();
+        std::copy(r.begin(), r.end(), dst);
+        Stats s = eng.stats();
+        std::lock_guard<std::mutex> l(m);
+        tot.sims += s.sims, tot.sum_ck += s.sum_ck, tot.sum_cleaf += s.sum_cleaf, tot.sum_depth += s.sum_depth, tot.evals += s.evals;
+        tot.gc_copied += s.gc_copied, tot.games_done += s.games_done, tot.kernel_launches += (uint64_t)eng.kernel_launches();
+        tot.peak_rec = std::max(tot.peak_rec, s.peak_rec), tot.peak_lnk = std::max(tot.peak_lnk, s.peak_lnk);
+        tot.bytes_per_game = eng.bytes_per_game();
+        });
+        if (out && n_games > 0) std::memcpy(out, rec.data(), (size_t)n_games * sizeof(GameRecord));
+        if (stats) *stats = tot;
+    });
 }
 
 #define CK(call)                                                                  \
@@ -469,7 +509,11 @@ int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_
     } while (0)
 
 int c6_win_check_host(const uint32_t* boards, int8_t* winners, int64_t n, int device) {
-    C6_TRY(CK(cudaSetDevice(device)); uint32_t* db = nullptr; int8_t* dw = nullptr; if (n > 0) {
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        uint32_t* db = nullptr;
+        int8_t* dw = nullptr;
+        if (n > 0) {
         CK(cudaMalloc(&db, (size_t)n * 64));
         CK(cudaMalloc(&dw, (size_t)n));
         CK(cudaMemcpy(db, boards, (size_t)n * 64, cudaMemcpyHostToDevice));
@@ -477,98 +521,165 @@ int c6_win_check_host(const uint32_t* boards, int8_t* winners, int64_t n, int de
         CK(cudaGetLastError());
         CK(cudaMemcpy(winners, dw, (size_t)n, cudaMemcpyDeviceToHost));
         cudaFree(db), cudaFree(dw);
-    })
+        }
+    });
 }
 
 int c6_bench_win_check(int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter, uint32_t* boards_out,
                        int8_t* winners_out, int64_t n_out) {
-    C6_TRY(CK(cudaSetDevice(device)); uint32_t* db = nullptr; int8_t* dw = nullptr; CK(cudaMalloc(&db, (size_t)n * 64));
-           CK(cudaMalloc(&dw, (size_t)n)); cudaStream_t s; CK(cudaStreamCreate(&s)); launch_random_boards(db, n, seed, s);
-           launch_win_check(db, dw, n, s);  // warm-up
-           CK(cudaStreamSynchronize(s)); cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-           CK(cudaEventRecord(a, s)); for (int i = 0; i < iters; ++i) launch_win_check(db, dw, n, s);
-           CK(cudaEventRecord(b, s)); CK(cudaEventSynchronize(b)); float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
-           *ms_per_iter = iters > 0 ? ms / iters : 0.f; if (n_out > n) n_out = n; if (boards_out && n_out > 0)
-               CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
-           if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
-           cudaEventDestroy(a), cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(db), cudaFree(dw))
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        uint32_t* db = nullptr;
+        int8_t* dw = nullptr;
+        CK(cudaMalloc(&db, (size_t)n * 64));
+        CK(cudaMalloc(&dw, (size_t)n));
+        cudaStream_t s;
+        CK(cudaStreamCreate(&s));
+        launch_random_boards(db, n, seed, s);
+        launch_win_check(db, dw, n, s);
+        // warm-up
+        CK(cudaStreamSynchronize(s));
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, s));
+        for (int i = 0; i < iters; ++i) launch_win_check(db, dw, n, s);
+        CK(cudaEventRecord(b, s));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        *ms_per_iter = iters > 0 ? ms / iters : 0.f;
+        if (n_out > n) n_out = n;
+        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
+        cudaEventDestroy(a), cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(db), cudaFree(dw);
+    });
 }
 
 int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int device, float* ms_per_iter, int8_t* winners_out,
                       uint8_t* stones_out, uint32_t* boards_out, int64_t n_out, uint64_t* total_stones) {
-    C6_TRY(CK(cudaSetDevice(device)); int8_t* dw = nullptr; uint8_t* ds = nullptr; uint32_t* db = nullptr;
-           CK(cudaMalloc(&dw, (size_t)n)); CK(cudaMalloc(&ds, (size_t)n)); CK(cudaMalloc(&db, (size_t)n * 64)); cudaStream_t s;
-           CK(cudaStreamCreate(&s)); launch_playouts(first, n, seed, dw, ds, db, s); CK(cudaStreamSynchronize(s));
-           cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventRecord(a, s));
-           for (int i = 0; i < iters; ++i) launch_playouts(first, n, seed, dw, ds, db, s); CK(cudaEventRecord(b, s));
-           CK(cudaEventSynchronize(b)); float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
-           *ms_per_iter = iters > 0 ? ms / iters : 0.f; if (n_out > n) n_out = n;
-           if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
-           if (stones_out && n_out > 0) CK(cudaMemcpy(stones_out, ds, (size_t)n_out, cudaMemcpyDeviceToHost));
-           if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
-           if (total_stones) {
-               std::vector<uint8_t> hs((size_t)n);
-               CK(cudaMemcpy(hs.data(), ds, (size_t)n, cudaMemcpyDeviceToHost));
-               uint64_t t = 0;
-               for (uint8_t x : hs) t += x;
-               *total_stones = t;
-           } cudaEventDestroy(a),
-           cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db))
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        int8_t* dw = nullptr;
+        uint8_t* ds = nullptr;
+        uint32_t* db = nullptr;
+        CK(cudaMalloc(&dw, (size_t)n));
+        CK(cudaMalloc(&ds, (size_t)n));
+        CK(cudaMalloc(&db, (size_t)n * 64));
+        cudaStream_t s;
+        CK(cudaStreamCreate(&s));
+        launch_playouts(first, n, seed, dw, ds, db, s);
+        CK(cudaStreamSynchronize(s));
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, s));
+        for (int i = 0; i < iters; ++i) launch_playouts(first, n, seed, dw, ds, db, s);
+        CK(cudaEventRecord(b, s));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        *ms_per_iter = iters > 0 ? ms / iters : 0.f;
+        if (n_out > n) n_out = n;
+        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
+        if (stones_out && n_out > 0) CK(cudaMemcpy(stones_out, ds, (size_t)n_out, cudaMemcpyDeviceToHost));
+        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+        if (total_stones) {
+        std::vector<uint8_t> hs((size_t)n);
+        CK(cudaMemcpy(hs.data(), ds, (size_t)n, cudaMemcpyDeviceToHost));
+        uint64_t t = 0;
+        for (uint8_t x : hs) t += x;
+        *total_stones = t;
+        } cudaEventDestroy(a),
+        cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db);
+    });
 }
 
 int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
                            c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats) {
     static_assert(sizeof(c6_record) == sizeof(GameRecord), "record layout");
-    C6_TRY(unsigned long long st[8]; if (n_games > 0 && !out) throw std::runtime_error("c6_default_policy_play: out is NULL");
-           const float ms = default_policy_play(num_iter, seed, first_game_id, (long long)n_games, max_moves, device,
-                                                reinterpret_cast<GameRecord*>(out), root_visit, root_black_win, st);
-           if (stats) {
-               stats->searches = st[0], stats->rollouts = st[1], stats->rollout_stones = st[2], stats->select_steps = st[3];
-               stats->children_scanned = st[4], stats->replaced = st[5], stats->nodes = st[6], stats->errors = st[7];
-               stats->kernel_ms = ms;
-           })
+    return guarded([&] {
+        unsigned long long st[8];
+        if (n_games > 0 && !out) throw std::runtime_error("c6_default_policy_play: out is NULL");
+        const float ms = default_policy_play(num_iter, seed, first_game_id, (long long)n_games, max_moves, device,
+        reinterpret_cast<GameRecord*>(out), root_visit, root_black_win, st);
+        if (stats) {
+        stats->searches = st[0], stats->rollouts = st[1], stats->rollout_stones = st[2], stats->select_steps = st[3];
+        stats->children_scanned = st[4], stats->replaced = st[5], stats->nodes = st[6], stats->errors = st[7];
+        stats->kernel_ms = ms;
+        }
+    });
 }
 
 // Host<->device copy bandwidth of this box with pinned buffers (GB/s): H2D alone, D2H alone, and both at
 // once on two streams (per direction).  This is the ceiling of the host-callback evaluator path.
 int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs) {
-    C6_TRY(CK(cudaSetDevice(device)); void *h1 = nullptr, *h2 = nullptr, *d1 = nullptr, *d2 = nullptr;
-           CK(cudaMallocHost(&h1, (size_t)bytes)); CK(cudaMallocHost(&h2, (size_t)bytes)); CK(cudaMalloc(&d1, (size_t)bytes));
-           CK(cudaMalloc(&d2, (size_t)bytes)); std::memset(h1, 1, (size_t)bytes); std::memset(h2, 2, (size_t)bytes);
-           cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2)); cudaEvent_t a, b, c;
-           CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventCreate(&c));
-           auto timed = [&](int mode) {
-               float ms = 0;
-               for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
-                   CK(cudaDeviceSynchronize());
-                   CK(cudaEventRecord(a, s1));
-                   CK(cudaStreamWaitEvent(s2, a, 0));
-                   for (int i = 0; i < iters; ++i) {
-                       if (mode != 1) CK(cudaMemcpyAsync(d1, h1, (size_t)bytes, cudaMemcpyHostToDevice, s1));
-                       if (mode != 0) CK(cudaMemcpyAsync(h2, d2, (size_t)bytes, cudaMemcpyDeviceToHost, s2));
-                   }
-                   CK(cudaEventRecord(c, s2));
-                   CK(cudaStreamWaitEvent(s1, c, 0));
-                   CK(cudaEventRecord(b, s1));
-                   CK(cudaEventSynchronize(b));
-                   CK(cudaEventElapsedTime(&ms, a, b));
-               }
-               return (double)bytes * iters / (ms * 1e-3) / 1e9;
-           };
-           *h2d_gbs = timed(0); *d2h_gbs = timed(1); *both_gbs = timed(2);
-           cudaEventDestroy(a), cudaEventDestroy(b), cudaEventDestroy(c), cudaStreamDestroy(s1), cudaStreamDestroy(s2);
-           cudaFreeHost(h1), cudaFreeHost(h2), cudaFree(d1), cudaFree(d2))
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        void *h1 = nullptr, *h2 = nullptr, *d1 = nullptr, *d2 = nullptr;
+        CK(cudaMallocHost(&h1, (size_t)bytes));
+        CK(cudaMallocHost(&h2, (size_t)bytes));
+        CK(cudaMalloc(&d1, (size_t)bytes));
+        CK(cudaMalloc(&d2, (size_t)bytes));
+        std::memset(h1, 1, (size_t)bytes);
+        std::memset(h2, 2, (size_t)bytes);
+        cudaStream_t s1, s2;
+        CK(cudaStreamCreate(&s1));
+        CK(cudaStreamCreate(&s2));
+        cudaEvent_t a, b, c;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        CK(cudaEventCreate(&c));
+        auto timed = [&](int mode) {
+        float ms = 0;
+        for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(a, s1));
+        CK(cudaStreamWaitEvent(s2, a, 0));
+        for (int i = 0; i < iters; ++i) {
+        if (mode != 1) CK(cudaMemcpyAsync(d1, h1, (size_t)bytes, cudaMemcpyHostToDevice, s1));
+        if (mode != 0) CK(cudaMemcpyAsync(h2, d2, (size_t)bytes, cudaMemcpyDeviceToHost, s2));
+        }
+        CK(cudaEventRecord(c, s2));
+        CK(cudaStreamWaitEvent(s1, c, 0));
+        CK(cudaEventRecord(b, s1));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&ms, a, b));
+        }
+        return (double)bytes * iters / (ms * 1e-3) / 1e9;
+        };
+        *h2d_gbs = timed(0);
+        *d2h_gbs = timed(1);
+        *both_gbs = timed(2);
+        cudaEventDestroy(a), cudaEventDestroy(b), cudaEventDestroy(c), cudaStreamDestroy(s1), cudaStreamDestroy(s2);
+        cudaFreeHost(h1), cudaFreeHost(h2), cudaFree(d1), cudaFree(d2);
+    });
 }
 int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device) {
-    C6_TRY(CK(cudaSetDevice(device)); double* d = nullptr; CK(cudaMalloc(&d, (size_t)n * 8)); launch_probe_gamma(shape, k0, k1, d, n, 0);
-           CK(cudaGetLastError()); CK(cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost)); cudaFree(d))
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        double* d = nullptr;
+        CK(cudaMalloc(&d, (size_t)n * 8));
+        launch_probe_gamma(shape, k0, k1, d, n, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+    });
 }
 int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device) {
-    C6_TRY(CK(cudaSetDevice(device)); double *dx = nullptr, *dl = nullptr, *de = nullptr; CK(cudaMalloc(&dx, (size_t)n * 8));
-           CK(cudaMalloc(&dl, (size_t)n * 8)); CK(cudaMalloc(&de, (size_t)n * 8));
-           CK(cudaMemcpy(dx, xs, (size_t)n * 8, cudaMemcpyHostToDevice)); launch_probe_math(dx, dl, de, n, 0); CK(cudaGetLastError());
-           CK(cudaMemcpy(logs, dl, (size_t)n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(exps, de, (size_t)n * 8, cudaMemcpyDeviceToHost));
-           cudaFree(dx), cudaFree(dl), cudaFree(de))
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        double *dx = nullptr, *dl = nullptr, *de = nullptr;
+        CK(cudaMalloc(&dx, (size_t)n * 8));
+        CK(cudaMalloc(&dl, (size_t)n * 8));
+        CK(cudaMalloc(&de, (size_t)n * 8));
+        CK(cudaMemcpy(dx, xs, (size_t)n * 8, cudaMemcpyHostToDevice));
+        launch_probe_math(dx, dl, de, n, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(logs, dl, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(exps, de, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dx), cudaFree(dl), cudaFree(de);
+    });
 }
 
 }  // extern "C"
