@@ -260,6 +260,8 @@ def test_selfplay_device_path(evaluator, cbname, sims, eps, n_games, max_moves):
     (EVAL_DET, "det_eval_callback", 120, 0.3, 205),
     (EVAL_NEG, "neg_eval_callback", 64, 1.0, 190),
     (EVAL_CALLBACK, "neg_eval_callback", 150, 0.2, 212),   # the same through the split descend / expand kernels
+    (EVAL_NEG, "neg_eval_callback", 500, 0.0, 203),        # c_puct = 0: average path of 16-19 stones, far past the fused
+                                                           # kernel's 12-deep shared-memory path cache
 ])
 def test_selfplay_deep_trees_late_game(evaluator, cbname, sims, c_puct, n_stones):
     seed, n_games = 0xC6, 3
