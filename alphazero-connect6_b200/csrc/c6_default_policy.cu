@@ -82,7 +82,10 @@ __device__ __forceinline__ bool dp_select(const DpTree& t, uint32_t node, int tu
         if (next != NIL) en_next = t.ents[next];
         const uint32_t c = en.x & 0xFFFFFFu;
         const int4 cn = t.nodes[c];
-        float p = (float)cn.y / (1.f + (float)cn.x);
+        // black_win / (1 + visit); a zero numerator would send the IEEE division into its subroutine, and most
+        // children have no black win yet: stand-in operand, exact result (+0) selected afterwards
+        float p = (cn.y != 0 ? (float)cn.y : 1.f) / (1.f + (float)cn.x);
+        if (cn.y == 0) p = 0.f;
         if (turn > 0) p = -p;
         if (!any || !(p < bp)) any = true, bp = p, child = c, bit = en.x >> 24;
         e = next, en = en_next;
