@@ -237,7 +237,8 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
     out->sims = s.sims, out->sum_ck = s.sum_ck, out->sum_cleaf = s.sum_cleaf, out->sum_depth = s.sum_depth,
     out->evals = s.evals, out->max_nodes = s.max_nodes;
     if (child_visits) {
-        for (size_t m = 0; m < pol.child_visits.size(); ++m) {  // row = stones on the board when next() was called
+        // row = stones on the board when next() was called; the call on a full board (225 stones, returns None) has no row
+        for (size_t m = 0; m < pol.child_visits.size() && m + n_prefix < (size_t)BOARD_CAPACITY; ++m) {
             std::memcpy(child_visits + (m + n_prefix) * BOARD_CAPACITY, pol.child_visits[m].data(), BOARD_CAPACITY * 4);
             root_visit[m + n_prefix] = pol.root_visit[m];
             root_qsum[m + n_prefix] = pol.root_qsum[m];
