@@ -145,6 +145,44 @@ static void print_game_debug(const GameRecord& r) {
     std::fflush(stdout);
 }
 
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(_e));  \
+    } while (0)
+
+// Owning handles: CK() throws, and the C boundary must not leak device / pinned memory, streams or events on the way out.
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    explicit DevBuf(size_t n) { CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); }
+    ~DevBuf() { cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+struct PinnedBuf {
+    void* p = nullptr;
+    explicit PinnedBuf(size_t n) { CK(cudaMallocHost(&p, n)); }
+    ~PinnedBuf() { cudaFreeHost(p); }
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
+struct StreamH {
+    cudaStream_t s = nullptr;
+    StreamH() { CK(cudaStreamCreate(&s)); }
+    ~StreamH() { cudaStreamDestroy(s); }
+    StreamH(const StreamH&) = delete;
+    StreamH& operator=(const StreamH&) = delete;
+};
+struct EventH {
+    cudaEvent_t e = nullptr;
+    EventH() { CK(cudaEventCreate(&e)); }
+    ~EventH() { cudaEventDestroy(e); }
+    EventH(const EventH&) = delete;
+    EventH& operator=(const EventH&) = delete;
+};
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------
@@ -164,6 +202,7 @@ c6_vec cpp_self_play(c6_callback callback, c6_alloc_path alloc_path, c6_alloc_re
         base.seed = env_seed();
         base.log2_records = env_int("C6_LOG2_RECORDS", 18);
         base.evaluator = EVAL_CALLBACK;
+        base.tie_break = env_int("C6_TIE_BREAK", 1);
         const int max_conc = env_int("C6_MAX_CONCURRENT", 8192);
         std::vector<GameRecord> rec((size_t)n);
         auto t0 = std::chrono::steady_clock::now();
@@ -342,7 +381,7 @@ void c6_default_config(c6_config* cfg) {
     Config d;
     cfg->num_simulation = d.num_simulation, cfg->epsilon = d.epsilon, cfg->dirichlet_alpha = d.dirichlet_alpha;
     cfg->c_puct = d.c_puct, cfg->seed = d.seed, cfg->device = 0, cfg->slots = 1, cfg->log2_records = d.log2_records;
-    cfg->evaluator = C6_EVAL_CALLBACK, cfg->trace = 0, cfg->max_moves = 0;
+    cfg->evaluator = C6_EVAL_CALLBACK, cfg->trace = 0, cfg->max_moves = 0, cfg->tie_break = d.tie_break;
 }
 const char* c6_last_error(void) { return g_err.c_str(); }
 int c6_device_count(void) {
@@ -355,6 +394,7 @@ static Config to_config(const c6_config* c) {
     cfg.num_simulation = c->num_simulation, cfg.epsilon = c->epsilon, cfg.dirichlet_alpha = c->dirichlet_alpha;
     cfg.c_puct = c->c_puct, cfg.seed = c->seed, cfg.device = c->device, cfg.slots = c->slots;
     cfg.log2_records = c->log2_records, cfg.evaluator = c->evaluator, cfg.trace = c->trace, cfg.max_moves = c->max_moves;
+    cfg.tie_break = c->tie_break;
     return cfg;
 }
 c6_engine* c6_engine_create(const c6_config* cfg) {
@@ -502,26 +542,16 @@ int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_
     });
 }
 
-#define CK(call)                                                                  \
-    do {                                                                          \
-        cudaError_t _e = (call);                                                  \
-        if (_e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(_e));  \
-    } while (0)
-
 int c6_win_check_host(const uint32_t* boards, int8_t* winners, int64_t n, int device) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        uint32_t* db = nullptr;
-        int8_t* dw = nullptr;
-        if (n > 0) {
-        CK(cudaMalloc(&db, (size_t)n * 64));
-        CK(cudaMalloc(&dw, (size_t)n));
-        CK(cudaMemcpy(db, boards, (size_t)n * 64, cudaMemcpyHostToDevice));
-        launch_win_check(db, dw, n, 0);
+        if (n <= 0) return;
+        DevBuf<uint32_t> db((size_t)n * 16);
+        DevBuf<int8_t> dw((size_t)n);
+        CK(cudaMemcpy(db.p, boards, (size_t)n * 64, cudaMemcpyHostToDevice));
+        launch_win_check(db.p, dw.p, n, 0);
         CK(cudaGetLastError());
-        CK(cudaMemcpy(winners, dw, (size_t)n, cudaMemcpyDeviceToHost));
-        cudaFree(db), cudaFree(dw);
-        }
+        CK(cudaMemcpy(winners, dw.p, (size_t)n, cudaMemcpyDeviceToHost));
     });
 }
 
@@ -529,30 +559,23 @@ int c6_bench_win_check(int64_t n, uint32_t seed, int iters, int device, float* m
                        int8_t* winners_out, int64_t n_out) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        uint32_t* db = nullptr;
-        int8_t* dw = nullptr;
-        CK(cudaMalloc(&db, (size_t)n * 64));
-        CK(cudaMalloc(&dw, (size_t)n));
-        cudaStream_t s;
-        CK(cudaStreamCreate(&s));
-        launch_random_boards(db, n, seed, s);
-        launch_win_check(db, dw, n, s);
-        // warm-up
-        CK(cudaStreamSynchronize(s));
-        cudaEvent_t a, b;
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
-        CK(cudaEventRecord(a, s));
-        for (int i = 0; i < iters; ++i) launch_win_check(db, dw, n, s);
-        CK(cudaEventRecord(b, s));
-        CK(cudaEventSynchronize(b));
+        DevBuf<uint32_t> db((size_t)n * 16);
+        DevBuf<int8_t> dw((size_t)n);
+        StreamH st;
+        EventH a, b;
+        launch_random_boards(db.p, n, seed, st.s);
+        launch_win_check(db.p, dw.p, n, st.s);  // warm-up
+        CK(cudaStreamSynchronize(st.s));
+        CK(cudaEventRecord(a.e, st.s));
+        for (int i = 0; i < iters; ++i) launch_win_check(db.p, dw.p, n, st.s);
+        CK(cudaEventRecord(b.e, st.s));
+        CK(cudaEventSynchronize(b.e));
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, a, b));
+        CK(cudaEventElapsedTime(&ms, a.e, b.e));
         *ms_per_iter = iters > 0 ? ms / iters : 0.f;
         if (n_out > n) n_out = n;
-        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
-        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
-        cudaEventDestroy(a), cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(db), cudaFree(dw);
+        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db.p, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw.p, (size_t)n_out, cudaMemcpyDeviceToHost));
     });
 }
 
@@ -560,38 +583,31 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
                       uint8_t* stones_out, uint32_t* boards_out, int64_t n_out, uint64_t* total_stones) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        int8_t* dw = nullptr;
-        uint8_t* ds = nullptr;
-        uint32_t* db = nullptr;
-        CK(cudaMalloc(&dw, (size_t)n));
-        CK(cudaMalloc(&ds, (size_t)n));
-        CK(cudaMalloc(&db, (size_t)n * 64));
-        cudaStream_t s;
-        CK(cudaStreamCreate(&s));
-        launch_playouts(first, n, seed, dw, ds, db, s);
-        CK(cudaStreamSynchronize(s));
-        cudaEvent_t a, b;
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
-        CK(cudaEventRecord(a, s));
-        for (int i = 0; i < iters; ++i) launch_playouts(first, n, seed, dw, ds, db, s);
-        CK(cudaEventRecord(b, s));
-        CK(cudaEventSynchronize(b));
+        DevBuf<int8_t> dw((size_t)n);
+        DevBuf<uint8_t> ds((size_t)n);
+        DevBuf<uint32_t> db((size_t)n * 16);
+        StreamH st;
+        EventH a, b;
+        launch_playouts(first, n, seed, dw.p, ds.p, db.p, st.s);
+        CK(cudaStreamSynchronize(st.s));
+        CK(cudaEventRecord(a.e, st.s));
+        for (int i = 0; i < iters; ++i) launch_playouts(first, n, seed, dw.p, ds.p, db.p, st.s);
+        CK(cudaEventRecord(b.e, st.s));
+        CK(cudaEventSynchronize(b.e));
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, a, b));
+        CK(cudaEventElapsedTime(&ms, a.e, b.e));
         *ms_per_iter = iters > 0 ? ms / iters : 0.f;
         if (n_out > n) n_out = n;
-        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw, (size_t)n_out, cudaMemcpyDeviceToHost));
-        if (stones_out && n_out > 0) CK(cudaMemcpy(stones_out, ds, (size_t)n_out, cudaMemcpyDeviceToHost));
-        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
+        if (winners_out && n_out > 0) CK(cudaMemcpy(winners_out, dw.p, (size_t)n_out, cudaMemcpyDeviceToHost));
+        if (stones_out && n_out > 0) CK(cudaMemcpy(stones_out, ds.p, (size_t)n_out, cudaMemcpyDeviceToHost));
+        if (boards_out && n_out > 0) CK(cudaMemcpy(boards_out, db.p, (size_t)n_out * 64, cudaMemcpyDeviceToHost));
         if (total_stones) {
-        std::vector<uint8_t> hs((size_t)n);
-        CK(cudaMemcpy(hs.data(), ds, (size_t)n, cudaMemcpyDeviceToHost));
-        uint64_t t = 0;
-        for (uint8_t x : hs) t += x;
-        *total_stones = t;
-        } cudaEventDestroy(a),
-        cudaEventDestroy(b), cudaStreamDestroy(s), cudaFree(dw), cudaFree(ds), cudaFree(db);
+            std::vector<uint8_t> hs((size_t)n);
+            CK(cudaMemcpy(hs.data(), ds.p, (size_t)n, cudaMemcpyDeviceToHost));
+            uint64_t t = 0;
+            for (uint8_t x : hs) t += x;
+            *total_stones = t;
+        }
     });
 }
 
@@ -616,69 +632,73 @@ int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, 
 int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        void *h1 = nullptr, *h2 = nullptr, *d1 = nullptr, *d2 = nullptr;
-        CK(cudaMallocHost(&h1, (size_t)bytes));
-        CK(cudaMallocHost(&h2, (size_t)bytes));
-        CK(cudaMalloc(&d1, (size_t)bytes));
-        CK(cudaMalloc(&d2, (size_t)bytes));
-        std::memset(h1, 1, (size_t)bytes);
-        std::memset(h2, 2, (size_t)bytes);
-        cudaStream_t s1, s2;
-        CK(cudaStreamCreate(&s1));
-        CK(cudaStreamCreate(&s2));
-        cudaEvent_t a, b, c;
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&b));
-        CK(cudaEventCreate(&c));
+        PinnedBuf h1((size_t)bytes), h2((size_t)bytes);
+        DevBuf<char> d1((size_t)bytes), d2((size_t)bytes);
+        std::memset(h1.p, 1, (size_t)bytes);
+        std::memset(h2.p, 2, (size_t)bytes);
+        StreamH s1, s2;
+        EventH a, b, c;
         auto timed = [&](int mode) {
-        float ms = 0;
-        for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
-        CK(cudaDeviceSynchronize());
-        CK(cudaEventRecord(a, s1));
-        CK(cudaStreamWaitEvent(s2, a, 0));
-        for (int i = 0; i < iters; ++i) {
-        if (mode != 1) CK(cudaMemcpyAsync(d1, h1, (size_t)bytes, cudaMemcpyHostToDevice, s1));
-        if (mode != 0) CK(cudaMemcpyAsync(h2, d2, (size_t)bytes, cudaMemcpyDeviceToHost, s2));
-        }
-        CK(cudaEventRecord(c, s2));
-        CK(cudaStreamWaitEvent(s1, c, 0));
-        CK(cudaEventRecord(b, s1));
-        CK(cudaEventSynchronize(b));
-        CK(cudaEventElapsedTime(&ms, a, b));
-        }
-        return (double)bytes * iters / (ms * 1e-3) / 1e9;
+            float ms = 0;
+            for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+                CK(cudaDeviceSynchronize());
+                CK(cudaEventRecord(a.e, s1.s));
+                CK(cudaStreamWaitEvent(s2.s, a.e, 0));
+                for (int i = 0; i < iters; ++i) {
+                    if (mode != 1) CK(cudaMemcpyAsync(d1.p, h1.p, (size_t)bytes, cudaMemcpyHostToDevice, s1.s));
+                    if (mode != 0) CK(cudaMemcpyAsync(h2.p, d2.p, (size_t)bytes, cudaMemcpyDeviceToHost, s2.s));
+                }
+                CK(cudaEventRecord(c.e, s2.s));
+                CK(cudaStreamWaitEvent(s1.s, c.e, 0));
+                CK(cudaEventRecord(b.e, s1.s));
+                CK(cudaEventSynchronize(b.e));
+                CK(cudaEventElapsedTime(&ms, a.e, b.e));
+            }
+            return (double)bytes * iters / (ms * 1e-3) / 1e9;
         };
         *h2d_gbs = timed(0);
         *d2h_gbs = timed(1);
         *both_gbs = timed(2);
-        cudaEventDestroy(a), cudaEventDestroy(b), cudaEventDestroy(c), cudaStreamDestroy(s1), cudaStreamDestroy(s2);
-        cudaFreeHost(h1), cudaFreeHost(h2), cudaFree(d1), cudaFree(d2);
     });
 }
-int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device) {
+int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, float* out, int n, int device) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        double* d = nullptr;
-        CK(cudaMalloc(&d, (size_t)n * 8));
-        launch_probe_gamma(shape, k0, k1, d, n, 0);
+        DevBuf<float> d((size_t)n);
+        launch_probe_gamma(shape, k0, k1, d.p, n, 0);
         CK(cudaGetLastError());
-        CK(cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost));
-        cudaFree(d);
+        CK(cudaMemcpy(out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+int c6_probe_math32(const float* xs, float* lg2s, float* ex2s, int n, int device) {
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        DevBuf<float> dx((size_t)n), dl((size_t)n), de((size_t)n);
+        CK(cudaMemcpy(dx.p, xs, (size_t)n * 4, cudaMemcpyHostToDevice));
+        launch_probe_math32(dx.p, dl.p, de.p, n, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(lg2s, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ex2s, de.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+int c6_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* out, int n, int device) {
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        DevBuf<uint32_t> d((size_t)n);
+        launch_probe_tie(seed, game, count, d.p, n, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     });
 }
 int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device) {
     return guarded([&] {
         CK(cudaSetDevice(device));
-        double *dx = nullptr, *dl = nullptr, *de = nullptr;
-        CK(cudaMalloc(&dx, (size_t)n * 8));
-        CK(cudaMalloc(&dl, (size_t)n * 8));
-        CK(cudaMalloc(&de, (size_t)n * 8));
-        CK(cudaMemcpy(dx, xs, (size_t)n * 8, cudaMemcpyHostToDevice));
-        launch_probe_math(dx, dl, de, n, 0);
+        DevBuf<double> dx((size_t)n), dl((size_t)n), de((size_t)n);
+        CK(cudaMemcpy(dx.p, xs, (size_t)n * 8, cudaMemcpyHostToDevice));
+        launch_probe_math(dx.p, dl.p, de.p, n, 0);
         CK(cudaGetLastError());
-        CK(cudaMemcpy(logs, dl, (size_t)n * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(exps, de, (size_t)n * 8, cudaMemcpyDeviceToHost));
-        cudaFree(dx), cudaFree(dl), cudaFree(de);
+        CK(cudaMemcpy(logs, dl.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(exps, de.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -44,6 +44,7 @@ struct Dev {
     uint32_t seed;
     int trace;
     int max_moves;
+    int tie_break;  // 0: exact PUCT ties go to the lowest rank, 1: uniformly among the tied (Philox keyed (sim, depth))
 };
 
 #ifdef __CUDACC__

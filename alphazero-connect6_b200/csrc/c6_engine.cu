@@ -406,7 +406,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.E = 4096;
     D.I = 8192;  // key table of expanded nodes: power of two >= 2 * E
     D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
-    D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves;
+    D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves, D.tie_break = cfg_.tie_break;
     const size_t G = (size_t)D.G;
     d_->rec_bytes = G * D.R * sizeof(Rec);
     d_->lnk_bytes = G * D.L * sizeof(uint32_t);

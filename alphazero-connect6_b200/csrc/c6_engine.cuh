@@ -99,6 +99,8 @@ struct Config {
     int32_t evaluator = EVAL_CALLBACK;
     int32_t trace = 0;            // record root child visits per move (tests)
     int32_t max_moves = 0;        // stop games after this many stones (<=0: play to the end)
+    int32_t tie_break = 1;        // exact PUCT ties: 1 = uniform among the tied children like the reference (mod.rs:291-295),
+                                  // drawn from Philox (seed, game; sim, depth); 0 = lowest row-major index (hand-checkable traces)
 };
 
 struct Stats {
@@ -208,8 +210,10 @@ void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStre
 void launch_playouts(int64_t first, int64_t n, uint32_t seed, int8_t* d_winner, uint8_t* d_stones,
                      uint32_t* d_boards, cudaStream_t s);
 
-void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* d_out, int n, cudaStream_t s);
+void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, float* d_out, int n, cudaStream_t s);
 void launch_probe_math(const double* d_xs, double* d_logs, double* d_exps, int n, cudaStream_t s);
+void launch_probe_math32(const float* d_xs, float* d_lg, float* d_ex, int n, cudaStream_t s);
+void launch_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* d_out, int n, cudaStream_t s);
 
 const char* last_error();
 

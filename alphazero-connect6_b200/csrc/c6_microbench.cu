@@ -122,39 +122,56 @@ __global__ void __launch_bounds__(128) k_playouts(long long first, long long n, 
     }
 }
 
-// Parity probes for the noise sampler (tests only): draw i of stream (i, 7, 9) keyed (k0, k1), and the
-// deterministic log / exp on given inputs, so that every bit can be compared with the oracle.
-__global__ void k_probe_gamma(double shape, double inv_shape, double bb, uint32_t k0, uint32_t k1, double* out, int n) {
+// Parity probes for the noise sampler (tests only): log2 of Gamma draw (7, 9, k = i) of the stream keyed (k0, k1) exactly as
+// a select step computes it (hot branch of trial 0 first, then the full loop), the f32 log2 / exp2 and the f64 log / exp on
+// given inputs, so that every bit can be compared with the oracle.
+__global__ void k_probe_gamma(GammaParams gp, uint32_t k0, uint32_t k1, float* out, int n) {
     __shared__ MathTab mt;
     load_math_tab(mt);
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    GammaParams gp;
-    gp.shape = shape, gp.inv_shape = inv_shape, gp.b = bb;
-    double x;
-    if (shape < 1.0) {
-        if (!gamma_small_fast(mt, gp, (uint32_t)i, 7u, 9u, k0, k1, x)) x = gamma_small(mt, shape, inv_shape, bb, (uint32_t)i, 7u, 9u, k0, k1);
+    const uint32_t k = (uint32_t)i;
+    float l;
+    if (gp.shape < 1.0) {
+        uint32_t u, v;
+        gamma_words(7u, 9u, k, 0u, k0, k1, u, v);
+        if (!gamma_log2_fast(mt, gp, u, v, l)) l = gamma_log2_full(mt, gp.b, gp.inv_a, gp.c1, gp.am1, 7u, 9u, k, k0, k1);
     } else {
-        x = gamma_large(mt, shape, (uint32_t)i, 7u, 9u, k0, k1);
+        l = gamma_large_log2(gp.shape, 7u, 9u, k, k0, k1);
     }
-    out[i] = x;
+    out[i] = l;
 }
 __global__ void k_probe_math(const double* xs, double* logs, double* exps, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    logs[i] = xs[i] > 0.0 ? det_log(xs[i]) : 0.0;
+    exps[i] = det_exp(xs[i]);
+}
+__global__ void k_probe_math32(const float* xs, float* lg, float* ex, int n) {
     __shared__ MathTab mt;
     load_math_tab(mt);
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    logs[i] = xs[i] > 0.0 ? det_log(mt, xs[i]) : 0.0;
-    exps[i] = det_exp(mt, xs[i]);
+    lg[i] = xs[i] > 0.f ? lg2_det(mt, xs[i]) : 0.f;
+    ex[i] = ex2_det(xs[i]);
 }
-void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* d_out, int n, cudaStream_t s) {
-    GammaParams gp = gamma_params(shape);
-    k_probe_gamma<<<(n + 127) / 128, 128, 0, s>>>(gp.shape, gp.inv_shape, gp.b, k0, k1, d_out, n);
+__global__ void k_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tie_pick((uint32_t)i, (uint32_t)(i % 7), seed, game, count);
+}
+void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, float* d_out, int n, cudaStream_t s) {
+    k_probe_gamma<<<(n + 127) / 128, 128, 0, s>>>(gamma_params(shape), k0, k1, d_out, n);
 }
 void launch_probe_math(const double* d_xs, double* d_logs, double* d_exps, int n, cudaStream_t s) {
     k_probe_math<<<(n + 127) / 128, 128, 0, s>>>(d_xs, d_logs, d_exps, n);
+}
+void launch_probe_math32(const float* d_xs, float* d_lg, float* d_ex, int n, cudaStream_t s) {
+    k_probe_math32<<<(n + 127) / 128, 128, 0, s>>>(d_xs, d_lg, d_ex, n);
+}
+void launch_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* d_out, int n, cudaStream_t s) {
+    k_probe_tie<<<(n + 127) / 128, 128, 0, s>>>(seed, game, count, d_out, n);
 }
 
 void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s) {

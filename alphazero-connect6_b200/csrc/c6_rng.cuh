@@ -5,14 +5,16 @@
 //   RandomEvaluator                        LC/policy/alphazero_policy/mod.rs:137-169
 // with Philox4x32-10 streams keyed by (seed, game) and counted by (simulation, depth, child), so a
 // game's search is a pure function of its id.  Dirichlet(alpha; C) = C independent Gamma(alpha, 1)
-// draws normalised by their sum in f64, as rand 0.6 builds it.  The Gamma draws use exact rejection
-// samplers chosen for the GPU: Ahrens–Dieter GS for alpha < 1 (the default 0.03; ~175 instructions a
-// draw against ~700 for Marsaglia–Tsang + boost — the first ncu profile had the sampler at two thirds
-// of all instructions), Marsaglia–Tsang on polar normals for alpha >= 1.  log/exp are fixed
-// polynomials over IEEE + - * / fma only, and this translation unit is compiled with -fmad=false, so
-// every value is reproducible bit for bit on a CPU (tests/ compare against the oracle's independent
-// restatement).  rand's own stream is unseedable (thread_rng) and unpinned by any reference test, so
-// only the distribution is contractual.
+// draws normalised by their sum, as rand 0.6 builds it.  The Gamma draws use exact rejection samplers
+// chosen for the GPU: Ahrens–Dieter GS for alpha < 1 (the default 0.03), kept in log2 space and in f32
+// since round 2 (the r01 captures had the f64 sampler at half of all instructions: Philox 18 %, f64
+// log / exp 22 %, diverged slow path 12 %; a draw is now one half of a Philox block, a 14-instruction
+// log2 and an integer-built bound), Marsaglia–Tsang on polar normals in f64 for alpha >= 1.  log2 /
+// exp2 (and the f64 log / exp) are tables + fixed polynomials over IEEE + - * fma only, and this
+// translation unit is compiled with -fmad=false, so every value is reproducible bit for bit on a CPU
+// (tests/ compare against the oracle's independent restatement).  rand's own stream is unseedable
+// (thread_rng) and unpinned by any reference test, so only the distribution is contractual
+// (tests/test_oracle.py: Kolmogorov–Smirnov against the Gamma CDF, moments).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -78,82 +80,93 @@ __host__ __device__ __forceinline__ double u64_to_open01(uint32_t lo, uint32_t h
 
 #ifdef __CUDACC__
 // IEEE fused multiply-add, explicit (the translation unit is compiled with -fmad=false, so nothing else
-// contracts): one rounding, identical on sm_100a and x86-64 FMA3 (the oracle uses __builtin_fma).
+// contracts): one rounding, identical on sm_100a and x86-64 FMA3 (the oracle uses __builtin_fma / __builtin_fmaf).
 __device__ __forceinline__ double det_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float det_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-// Tables of the log / exp below, staged in shared memory by every kernel that samples noise (per-lane
-// indices would serialise in the constant cache).
+// Table of the f32 log2 below, staged in shared memory by every kernel that samples noise (per-lane indices
+// would serialise in the constant cache).  The f64 log / exp of the alpha >= 1 sampler (not the default, out of
+// line) read their tables from the constant bank.
 struct MathTab {
-    double2 logt[64];  // {1/c_i, ln c_i}, c_i = 1 + (2i+1)/128
-    double expt[32];   // 2^(j/32)
+    float2 lg2t[33];  // {r_i, -log2 r_i}, r_i = f32(1/c_i), c_i = bits 0x3F340000 + i 2^18
 };
 __device__ __forceinline__ void load_math_tab(MathTab& T) {
-    if (threadIdx.x < 64) T.logt[threadIdx.x] = LOG_TAB_C[threadIdx.x];  // blocks have at least 64 threads
-    if (threadIdx.x < 32) T.expt[threadIdx.x] = EXP_TAB_C[threadIdx.x];
+    if (threadIdx.x < 33) T.lg2t[threadIdx.x] = LG2F_TAB_C[threadIdx.x];  // blocks have at least 64 threads
 }
 
-// Coefficients whose low word is not zero cannot be DFMA immediates; as literals the compiler rebuilds each of
-// them with two moves per use (r01g capture: ~30 of the 168 instructions of a draw), from the constant bank they
-// are operands.  Same bits either way.
-#ifndef C6_CBANK_COEF
-#define C6_CBANK_COEF 1
-#endif
-static __device__ __constant__ double MATH_K[13] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, 1.0 / 3.0, 0.6931471803691238,
-                                                    1.9082149292705877e-10, 46.16624130844683, 5.9631716539705866e-12,
-                                                    0.02166084938653512, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
-#if C6_CBANK_COEF
-#define C6_K(i, v) MATH_K[i]
-#else
-#define C6_K(i, v) (v)
-#endif
+// ------------------------------------------------------------------------------------------------
+// f32 log2 / exp2: table + polynomial over explicit fmaf, bit-identical to oracle/c6_rng.hpp.
+// ------------------------------------------------------------------------------------------------
+// log2 of a positive normal f32.  x = 2^e m, m in [sqrt(1/2), sqrt(2)); the interval centre c nearest to m (33
+// centres, one of them exactly 1) gives r = m / c - 1 through the tabulated reciprocal, |r| <= 2^-6;
+// log2 x = e - log2(1/c) + log2(1 + r), log2(1 + r) to r^4.  Absolute error ~2^-25 + 2^-24 |log2 x|.
+__device__ __forceinline__ float lg2_det(const MathTab& T, float x) {
+    const uint32_t bits = __float_as_uint(x);
+    const int e = (int)(bits - 0x3F3504F3u) >> 23;
+    const uint32_t mb = bits - ((uint32_t)e << 23);
+    const float2 t = T.lg2t[(mb + 0x20000u - 0x3F340000u) >> 18];
+    const float r = det_fmaf(__uint_as_float(mb), t.x, -1.0f);
+    float p = det_fmaf(r, LG2F_POLY_C[3], LG2F_POLY_C[2]);
+    p = det_fmaf(r, p, LG2F_POLY_C[1]);
+    p = det_fmaf(r, p, LG2F_POLY_C[0]);
+    return (float)e + det_fmaf(r, p, t.y);
+}
+// 2^t for t < 127; 0 below -125.  t = n + f, n = rint(t), 2^f by a degree-6 polynomial (relative error ~1.3 ulp),
+// scaled through the exponent field.
+__device__ __forceinline__ float ex2_det(float t) {
+    const float n = rintf(t);
+    const float f = t - n;
+    float p = EX2F_POLY_C[6];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) p = det_fmaf(p, f, EX2F_POLY_C[i]);
+    const float y = __uint_as_float(__float_as_uint(p) + ((uint32_t)(int)n << 23));
+    return t < -125.0f ? 0.0f : y;
+}
 
 // natural log of a positive finite double, division-free: x = 2^e m, m in [1,2) falls in one of 64
 // intervals with centre c_i; r = m/c_i - 1 (|r| < 2^-7) by one fma with the tabulated reciprocal;
 // ln x = e ln2 + ln c_i + log1p(r), log1p as a degree-8 alternating series.  Absolute error ~1e-16.
-// NORMAL: the caller guarantees a normal (not subnormal) argument, which skips the rescaling test; same value.
-template <bool NORMAL = false>
-__device__ __forceinline__ double det_log(const MathTab& T, double x) {
+// (alpha >= 1 sampler and the parity probes only.)
+static __device__ __noinline__ double det_log(double x) {
     int e = 0;
     uint64_t b = double_to_bits(x);
-    if (!NORMAL && (b >> 52) == 0) {
+    if ((b >> 52) == 0) {
         x = x * 18014398509481984.0;
         b = double_to_bits(x);
         e = -54;
     }
     e += (int)((b >> 52) & 0x7FF) - 1023;
     const double m = bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-    const double2 t = T.logt[(uint32_t)(b >> 46) & 63u];
+    const double2 t = LOG_TAB_C[(uint32_t)(b >> 46) & 63u];
     const double r = det_fma(m, t.x, -1.0);
     double p = -1.0 / 8.0;
-    p = det_fma(p, r, C6_K(0, 1.0 / 7.0));
-    p = det_fma(p, r, C6_K(1, -1.0 / 6.0));
-    p = det_fma(p, r, C6_K(2, 1.0 / 5.0));
+    p = det_fma(p, r, 1.0 / 7.0);
+    p = det_fma(p, r, -1.0 / 6.0);
+    p = det_fma(p, r, 1.0 / 5.0);
     p = det_fma(p, r, -1.0 / 4.0);
-    p = det_fma(p, r, C6_K(3, 1.0 / 3.0));
+    p = det_fma(p, r, 1.0 / 3.0);
     p = det_fma(p, r, -0.5);
     p = det_fma(p, r * r, r);  // r + r^2 (-1/2 + r/3 - ...)
     const double ed = (double)e;
-    return det_fma(ed, C6_K(4, 0.6931471803691238), t.y + det_fma(ed, C6_K(5, 1.9082149292705877e-10), p));
+    return det_fma(ed, 0.6931471803691238, t.y + det_fma(ed, 1.9082149292705877e-10, p));
 }
 
 // e^x: x = (32 q + j) ln2/32 + r, |r| <= ln2/64; e^x = 2^q 2^(j/32) (1 + expm1(r)), expm1 to r^6;
-// scaled by 2^q in two exact steps (subnormal results round once).
-// NONPOS: the caller guarantees x <= 0, which skips the overflow clamp; same value.
-template <bool NONPOS = false>
-__device__ __forceinline__ double det_exp(const MathTab& T, double x) {
+// scaled by 2^q in two exact steps (subnormal results round once).  (Parity probes only.)
+static __device__ __noinline__ double det_exp(double x) {
     if (x < -745.2) return 0.0;
-    if (!NONPOS && x > 709.0) x = 709.0;
-    const double kd = (double)__double2ll_rd(det_fma(x, C6_K(6, 46.16624130844683), 0.5));  // floor(x 32/ln2 + 1/2)
-    const double r = det_fma(-kd, C6_K(7, 5.9631716539705866e-12), det_fma(-kd, C6_K(8, 0.02166084938653512), x));
-    double p = C6_K(9, 1.0 / 720.0);
-    p = det_fma(p, r, C6_K(10, 1.0 / 120.0));
-    p = det_fma(p, r, C6_K(11, 1.0 / 24.0));
-    p = det_fma(p, r, C6_K(12, 1.0 / 6.0));
+    if (x > 709.0) x = 709.0;
+    const double kd = (double)__double2ll_rd(det_fma(x, 46.16624130844683, 0.5));  // floor(x 32/ln2 + 1/2)
+    const double r = det_fma(-kd, 5.9631716539705866e-12, det_fma(-kd, 0.02166084938653512, x));
+    double p = 1.0 / 720.0;
+    p = det_fma(p, r, 1.0 / 120.0);
+    p = det_fma(p, r, 1.0 / 24.0);
+    p = det_fma(p, r, 1.0 / 6.0);
     p = det_fma(p, r, 0.5);
     p = det_fma(p, r, 1.0);
     p = p * r;  // expm1(r)
     const int k = (int)kd;
-    const double tj = T.expt[k & 31];
+    const double tj = EXP_TAB_C[k & 31];
     const double y = det_fma(tj, p, tj);
     const int q = k >> 5;
     const int q1 = q / 2, q2 = q - q1;
@@ -163,67 +176,79 @@ __device__ __forceinline__ double det_exp(const MathTab& T, double x) {
 }
 
 __device__ __forceinline__ double det_sqrt(double x) { return __dsqrt_rn(x); }
+#endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------------
-// Gamma(shape, 1) draw number (a, b, c) of the stream keyed (k0, k1): Philox block `trial` of counter
-// (a, b, c, trial) feeds trial number `trial` of a rejection sampler, so a draw is a pure function of
-// its coordinates and costs one Philox call per trial.
+// log2 of a Gamma(shape, 1) draw, f32 (twin: oracle/c6_rng.hpp "The sampler the search uses").  The noise of a
+// select step is normalised like a softmax, noise_k = 2^(L_k - Lmax) / sum_j 2^(L_j - Lmax), so a draw never
+// has to exist as a number (with alpha = 0.03 almost all of them underflow even f64).
 // ------------------------------------------------------------------------------------------------
-#endif  // __CUDACC__
 struct GammaParams {  // per-run constants, computed once on the host (IEEE ops only)
-    double shape, inv_shape, b;  // b = (e + shape) / e
+    double shape;
+    float b, inv_a, c1, am1;  // shape < 1: (e + a)/e, 1/a, b/a, a - 1, each rounded to f32 once
 };
 inline GammaParams gamma_params(double shape) {
     GammaParams g;
     g.shape = shape;
-    g.inv_shape = 1.0 / shape;
-    g.b = (2.718281828459045 + shape) / 2.718281828459045;
+    const double b = (2.718281828459045 + shape) / 2.718281828459045;
+    g.b = (float)b, g.inv_a = (float)(1.0 / shape), g.c1 = (float)(b / shape), g.am1 = (float)(shape - 1.0);
     return g;
 }
+constexpr uint32_t DOMAIN_TIE = 0x54494542u;
 #ifdef __CUDACC__
+__device__ __forceinline__ float unit_of(uint32_t w) { return det_fmaf((float)w, 0x1p-32f, 0x1p-33f); }  // (w + 1/2) 2^-32
 
-// shape < 1 (the reference default is 0.03): Ahrens–Dieter GS rejection sampler — exact for every
-// 0 < shape < 1, acceptance > 98% at 0.03.  With P = b U:
-//   P <= 1 : X = P^(1/shape),           accept iff V <= e^-X   (squeeze: e^-X >= 1 - X + X^2/2 - X^3/6)
-//   P >  1 : X = -ln((b - P)/shape),    accept iff V <= X^(shape-1)
-// gamma_small_fast tries trial 0 on the hot branch only and reports failure; gamma_small is the full loop.
-// (split in two so that a caller can have the Philox block of its next draw in flight under the f64 chain of this one)
-__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, const Philox4& r, double& x) {
-    const double u = u64_to_open01(r.x, r.y), v = u64_to_open01(r.z, r.w);
-    const double p = gp.b * u;
-    x = 0.0;
-    if (p > 1.0) return false;
-    // p = b u with u >= 2^-53: normal; ln p <= 0
-    x = det_exp<true>(T, det_log<true>(T, p) * gp.inv_shape);
-    return v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0);
+// shape < 1 (the reference default is 0.03): Ahrens–Dieter GS rejection sampler — exact for every 0 < shape < 1,
+// acceptance > 98% at 0.03.  With P = b U:
+//   P <= 1 : X = P^(1/shape),          accept iff V <= e^-X      (1 - V >= 1 - e^-X)
+//   P >  1 : X = -ln((b - P)/shape),   accept iff V <= X^(shape-1)
+// gamma_log2_fast tries trial 0 on the hot branch with a sufficient test (1 - V >= 2^floor(L) (1 + frac L) >= X)
+// and reports failure (~5% of the draws); gamma_log2_full is the whole loop.
+__device__ __forceinline__ bool gamma_log2_fast(const MathTab& T, const GammaParams& gp, uint32_t u, uint32_t v, float& L) {
+    const float P = gp.b * unit_of(u);
+    L = lg2_det(T, fminf(P, 1.0f)) * gp.inv_a;
+    const float Lc = fmaxf(L, -64.0f);
+    const float kf = floorf(Lc);
+    const float xub = __uint_as_float(__float_as_uint(1.0f + (Lc - kf)) + ((uint32_t)(int)kf << 23));
+    return P <= 1.0f && unit_of(~v) >= xub;
 }
-__device__ __forceinline__ bool gamma_small_fast(const MathTab& T, const GammaParams& gp, uint32_t a, uint32_t b, uint32_t c,
-                                                 uint32_t k0, uint32_t k1, double& x) {
-    return gamma_small_fast(T, gp, philox4x32_10(a, b, c, 0u, k0, k1), x);
+// words of trial `trial` of draw k: trial 0 shares a Philox block between draws k and k ^ 32
+__device__ __forceinline__ void gamma_words(uint32_t a, uint32_t b, uint32_t k, uint32_t trial, uint32_t k0, uint32_t k1, uint32_t& u,
+                                            uint32_t& v) {
+    const bool first = trial == 0;
+    const Philox4 r = philox4x32_10(a, b, first ? (((k >> 6) << 5) | (k & 31u)) : k, trial, k0, k1);
+    const bool hi = first && ((k >> 5) & 1u);
+    u = hi ? r.z : r.x, v = hi ? r.w : r.y;
 }
-static __device__ __noinline__ double gamma_small(const MathTab& T, double shape, double inv_shape, double bb, uint32_t a, uint32_t b,
-                                           uint32_t c, uint32_t k0, uint32_t k1) {
-    double x = 0.0;
+static __device__ __noinline__ float gamma_log2_full(const MathTab& T, float gb, float inv_a, float c1, float am1, uint32_t a,
+                                                      uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
+    float L = 0.0f;
     for (uint32_t trial = 0; trial < 64u; ++trial) {
-        const Philox4 r = philox4x32_10(a, b, c, trial, k0, k1);
-        const double u = u64_to_open01(r.x, r.y), v = u64_to_open01(r.z, r.w);
-        const double p = bb * u;
-        if (p <= 1.0) {
-            x = det_exp(T, det_log(T, p) * inv_shape);
-            if (v <= det_fma(x, det_fma(x, det_fma(x, -1.0 / 6.0, 0.5), -1.0), 1.0)) break;
-            if (v <= det_exp(T, -x)) break;
+        uint32_t u, v;
+        gamma_words(a, b, k, trial, k0, k1, u, v);
+        const float P = gb * unit_of(u);
+        if (P <= 1.0f) {
+            L = lg2_det(T, P) * inv_a;
+            if (L < -40.0f) break;  // 1 - e^-X < 2^-40 < the smallest 1 - V
+            const float X = ex2_det(L);
+            float d;
+            if (X < 0x1p-6f)
+                d = X * det_fmaf(X, det_fmaf(X, det_fmaf(X, -1.0f / 24.0f, 1.0f / 6.0f), -0.5f), 1.0f);
+            else
+                d = 1.0f - ex2_det(X * -1.44269504f);
+            if (unit_of(~v) >= d) break;
         } else {
-            x = -det_log(T, (bb - p) * inv_shape);
-            if (v <= det_exp(T, (shape - 1.0) * det_log(T, x))) break;
+            const float X = lg2_det(T, c1 * unit_of(~u)) * -0.693147182f;
+            L = lg2_det(T, fmaxf(X, 0x1p-100f));
+            if (lg2_det(T, unit_of(v)) <= am1 * L) break;
         }
     }
-    return x;
+    return L;
 }
 
-// shape >= 1: Marsaglia–Tsang (2000) on normals from the Marsaglia polar method; trial t reads blocks
-// 2t (polar pair) and 2t+1 (acceptance uniform).  Not on the default path; kept out of line.
-static __device__ __noinline__ double gamma_large(const MathTab& T, double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0,
-                                           uint32_t k1) {
+// shape >= 1: Marsaglia–Tsang (2000) on normals from the Marsaglia polar method, in f64; trial t reads blocks
+// 2t (polar pair) and 2t+1 (acceptance uniform).  Not on the default path; kept out of line.  Returns the draw.
+static __device__ __noinline__ double gamma_large(double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1) {
     const double d = shape - 1.0 / 3.0;
     const double cc = 1.0 / det_sqrt(9.0 * d);
     double out = d;
@@ -232,7 +257,7 @@ static __device__ __noinline__ double gamma_large(const MathTab& T, double shape
         const double p = 2.0 * u64_to_open01(r.x, r.y) - 1.0, q = 2.0 * u64_to_open01(r.z, r.w) - 1.0;
         const double s = p * p + q * q;
         if (s >= 1.0 || s == 0.0) continue;
-        const double x = p * det_sqrt(-2.0 * det_log(T, s) / s);
+        const double x = p * det_sqrt(-2.0 * det_log(s) / s);
         const double vc = 1.0 + cc * x;
         if (vc <= 0.0) continue;
         const double v = vc * vc * vc;
@@ -241,9 +266,17 @@ static __device__ __noinline__ double gamma_large(const MathTab& T, double shape
         const double x2 = x * x;
         out = d * v;
         if (u < 1.0 - 0.0331 * x2 * x2) break;
-        if (det_log(T, u) < 0.5 * x2 + d * (1.0 - v + det_log(T, v))) break;
+        if (det_log(u) < 0.5 * x2 + d * (1.0 - v + det_log(v))) break;
     }
     return out;
+}
+__device__ __forceinline__ float gamma_large_log2(double shape, uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1) {
+    return (float)(det_log(gamma_large(shape, a, b, c, k0, k1)) * 1.4426950408889634);
+}
+
+// uniform pick among n exactly tied children (alphazero_policy/mod.rs:291-295): floor(u n / 2^32)
+__device__ __forceinline__ uint32_t tie_pick(uint32_t sim, uint32_t depth, uint32_t seed, uint32_t game, uint32_t n) {
+    return __umulhi(philox4x32_10(sim, depth, 0u, 0u, seed ^ DOMAIN_TIE, game).x, n);
 }
 #endif  // __CUDACC__
 

@@ -79,8 +79,8 @@ struct WarpStage {
         float prior[8][32];  // expand: prior of new child k
     };
     union {
-        double gamma[NOISE ? 8 : 4][32];  // select: Gamma draw of child k
-        uint32_t pos[8][32];              // expand: record index of child k
+        float lw[8][32];      // select: log2 Gamma draw of child k, then its softmax weight, then its PUCT score
+        uint32_t pos[8][32];  // expand: record index of child k
     };
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
     uint8_t cell[256];  // expand: bit position of the empty cell of rank k; select: ranks whose draw needs the slow path
@@ -180,6 +180,7 @@ __device__ __forceinline__ uint4 bits_of(const Rec& r) { return make_uint4((uint
 // FUSED: called from k_sims_device, where the same warp runs descent, expansion and backup of a simulation back to back.
 template <int NOISE, bool FUSED = false>
 __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf& L, WarpStage<NOISE>& st, const MathTab& mt) {
+    const bool tie_philox = D.tie_break != 0;
     const GameState& g = *w.gs;
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1;
@@ -217,101 +218,149 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             for (int j = 0; j < 8; ++j)
                 if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
             stage_children(w, st, r.link, C, lane, Rm, Lm);
-            // arithmetic phase 1: visit sum (:265) and the Dirichlet(alpha; C) draw made at every node with
-            // C >= 2 (:262,283): Gamma draws keyed (sim, depth, child k).  Pass A tries the hot branch of the
-            // sampler for every child; the ~3% of draws that need the other branch or another trial are listed
-            // and finished together, one per lane, in pass B (one diverged excursion per step); pass C sums in a
-            // fixed order: per lane the draws k = lane, lane + 32, ..., then a butterfly.
+            // visit sum (:265)
             int s_local = 0;
-            double part = 0.0;
-            if (NOISE) {
-                const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
-                unsigned pend = 0;
-C6_UNROLL(C6_NOISE_UNROLL)
-                for (int k = lane; k < C; k += 32) {
-                    double gj;
-                    if (NOISE == 1) {
-                        if (!gamma_small_fast(mt, D.gp, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id, gj)) pend |= 1u << (k >> 5);
-                    } else {
-                        gj = gamma_large(mt, D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
-                    }
-                    st.gamma[0][k] = gj;
-                }
-                if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
-                    // list the pending ranks (any order): exclusive prefix sum of the per-lane counts
-                    const int mycnt = __popc(pend);
-                    int incl = mycnt;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int o = __shfl_up_sync(FULL, incl, off);
-                        if (lane >= off) incl += o;
-                    }
-                    const int np = __shfl_sync(FULL, incl, 31);
-                    int at = incl - mycnt;
-                    while (pend) {
-                        const int i = __ffs((int)pend) - 1;
-                        pend &= pend - 1;
-                        st.cell[at++] = (uint8_t)(32 * i + lane);
-                    }
-                    __syncwarp();
 #pragma unroll 1
-                    for (int i = lane; i < np; i += 32) {
-                        const uint32_t k = st.cell[i];
-                        st.gamma[0][k] = gamma_small(mt, D.gp.shape, D.gp.inv_shape, D.gp.b, cs.sim_index, (uint32_t)depth, k, nk0,
-                                                     cs.game_id);
-                    }
-                    __syncwarp();
-                }
-            }
-#pragma unroll 1
-            for (int k = lane; k < C; k += 32) {
-                s_local += (int)st.child[0][k].x;
-                if (NOISE) part = part + st.gamma[0][k];
-            }
+            for (int k = lane; k < C; k += 32) s_local += (int)st.child[0][k].x;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
-            const float visit_sum = (float)s_local;  // :265
-            double inv = 0.0;
-            bool flat = false;
-            if (NOISE) {
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(FULL, part, off);
-                flat = !(part > 0.0);
-                inv = flat ? 0.0 : 1.0 / part;
-            }
-            // arithmetic phase 2: PUCT (:266-280)
-            float bs = 0.f;
+            const float visit_sum = (float)s_local;
             uint32_t bb = NIL;
+            if (s_local == 0) {
+                // No child has been visited: q = 0 and u = prob * sqrt(0 - 0) / 1 = +-0 for every child, a
+                // C-way exact tie whatever the priors and the noise are — the reference draws its Dirichlet sample here
+                // too and then picks uniformly (:291-295).  One tie draw instead of C Gamma draws and the PUCT pass.
+                bb = tie_philox ? tie_pick(cs.sim_index, (uint32_t)depth, D.seed, cs.game_id, (uint32_t)C) : 0u;
+            } else {
+                // arithmetic phase 1: the Dirichlet(alpha; C) draw made at every node with C >= 2 (:262,283): log2 Gamma
+                // draws keyed (sim, depth, child k), two per Philox block (children k and k + 32 of a lane).  Pass A tries
+                // the hot branch of the sampler for every child; the ~5% of draws that need the other branch or another
+                // trial are listed and finished together, one per lane, in pass B (one diverged excursion per step);
+                // pass C turns the draws into softmax weights 2^(L - Lmax) and sums them in a fixed order: per lane the
+                // children k = lane, lane + 32, ..., then a butterfly.
+                float inv = 0.f;
+                if (NOISE) {
+                    const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
+                    float lmax = -3.0e38f;
+                    unsigned pend = 0;
+                    if (NOISE == 1) {
 #pragma unroll 1
-            for (int k = lane; k < C; k += 32) {
-                const uint4 ch = st.child[0][k];
-                const int cn = (int)ch.x;
-                const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
-                float nz = 0.f;
-                if (NOISE) nz = flat ? (float)(1.0 / (double)C) : (float)(st.gamma[0][k] * inv);
-                const float visit = (float)cn;
-                // q_value (:77-79) and u (:270).  The IEEE division's fast path is left for a subroutine whenever an
-                // operand is zero — and an unvisited child has W = 0, a freshly expanded node has visit_sum = 0 — so both
-                // divisions are fed stand-in operands in those lanes and the exact result (0, or the zero numerator
-                // itself) is selected afterwards: same values, no calls (r01k capture: 5 % of all instructions)
-                const bool seen = cn > 0 && cw != 0.f;
-                const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
-                const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
-                const float prob = eps * nz + one_m_eps * cp;                     // :269
-                const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
-                const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
-                const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
-                const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
-                const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
-                if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k;
-            }
-            // maximum; exact ties -> lowest row-major index = lowest rank (the reference picks uniformly, :291-295)
+                        for (int k = lane; k < C; k += 64) {
+                            const Philox4 r = philox4x32_10(cs.sim_index, (uint32_t)depth, (uint32_t)(((k >> 6) << 5) | lane), 0u, nk0, cs.game_id);
+                            float l0, l1;
+                            const bool ok0 = gamma_log2_fast(mt, D.gp, r.x, r.y, l0);
+                            const bool ok1 = gamma_log2_fast(mt, D.gp, r.z, r.w, l1);
+                            st.lw[0][k] = l0;
+                            if (ok0) lmax = fmaxf(lmax, l0); else pend |= 1u << (k >> 5);
+                            if (k + 32 < C) {
+                                st.lw[0][k + 32] = l1;
+                                if (ok1) lmax = fmaxf(lmax, l1); else pend |= 2u << (k >> 5);
+                            }
+                        }
+                        if (__any_sync(FULL, pend != 0)) {
+                            // list the pending ranks (any order): exclusive prefix sum of the per-lane counts
+                            const int mycnt = __popc(pend);
+                            int incl = mycnt;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const float os = __shfl_xor_sync(FULL, bs, off);
-                const uint32_t ob = __shfl_xor_sync(FULL, bb, off);
-                const bool take = ob != NIL && (bb == NIL || os > bs || (os == bs && ob < bb));
-                if (take) bs = os, bb = ob;
+                            for (int off = 1; off < 32; off <<= 1) {
+                                const int o = __shfl_up_sync(FULL, incl, off);
+                                if (lane >= off) incl += o;
+                            }
+                            const int np = __shfl_sync(FULL, incl, 31);
+                            int at = incl - mycnt;
+                            while (pend) {
+                                const int i = __ffs((int)pend) - 1;
+                                pend &= pend - 1;
+                                st.cell[at++] = (uint8_t)(32 * i + lane);
+                            }
+                            __syncwarp();
+#pragma unroll 1
+                            for (int i = lane; i < np; i += 32) {
+                                const uint32_t k = st.cell[i];
+                                const float l = gamma_log2_full(mt, D.gp.b, D.gp.inv_a, D.gp.c1, D.gp.am1, cs.sim_index, (uint32_t)depth, k, nk0,
+                                                                cs.game_id);
+                                st.lw[0][k] = l;
+                                lmax = fmaxf(lmax, l);
+                            }
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int k = lane; k < C; k += 32) {
+                            const float l = gamma_large_log2(D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
+                            st.lw[0][k] = l;
+                            lmax = fmaxf(lmax, l);
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(FULL, lmax, off));
+                    __syncwarp();  // pass B wrote other lanes' slots
+                    float part = 0.f;
+#pragma unroll 1
+                    for (int k = lane; k < C; k += 32) {
+                        const float wk = ex2_det(st.lw[0][k] - lmax);
+                        st.lw[0][k] = wk;
+                        part = part + wk;
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) part = part + __shfl_xor_sync(FULL, part, off);
+                    inv = 1.0f / part;  // the largest draw weighs exactly 1: part >= 1
+                }
+                // arithmetic phase 2: PUCT (:266-280); per lane the best score, its lowest rank and how many of the lane's
+                // children share it
+                float bs = 0.f;
+                uint32_t cnt = 0;
+#pragma unroll 1
+                for (int k = lane; k < C; k += 32) {
+                    const uint4 ch = st.child[0][k];
+                    const int cn = (int)ch.x;
+                    const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
+                    float nz = 0.f;
+                    if (NOISE) nz = st.lw[0][k] * inv;
+                    const float visit = (float)cn;
+                    // q_value (:77-79) and u (:270).  The IEEE division's fast path is left for a subroutine whenever an
+                    // operand is zero — and an unvisited child has W = 0 — so both divisions are fed stand-in operands in
+                    // those lanes and the exact result (0, or the zero numerator itself) is selected afterwards: same
+                    // values, no calls (r01k capture: 5 % of all instructions)
+                    const bool seen = cn > 0 && cw != 0.f;
+                    const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
+                    const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
+                    const float prob = eps * nz + one_m_eps * cp;                     // :269
+                    const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
+                    const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
+                    const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
+                    const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
+                    const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
+                    st.lw[0][k] = sc;
+                    if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k, cnt = 1;
+                    else if (sc == bs) cnt += 1;
+                }
+                // maximum over the warp: score, lowest rank holding it, number of children holding it
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float os = __shfl_xor_sync(FULL, bs, off);
+                    const uint32_t ob = __shfl_xor_sync(FULL, bb, off);
+                    const uint32_t oc = __shfl_xor_sync(FULL, cnt, off);
+                    if (ob != NIL) {
+                        if (bb == NIL || os > bs) bs = os, bb = ob, cnt = oc;
+                        else if (os == bs) cnt += oc, bb = min(bb, ob);
+                    }
+                }
+                // exact ties: uniformly among the tied children (:291-295) or, for hand-checkable traces, the lowest rank
+                if (tie_philox && cnt > 1) {
+                    uint32_t j = tie_pick(cs.sim_index, (uint32_t)depth, D.seed, cs.game_id, cnt);
+                    __syncwarp();
+#pragma unroll 1
+                    for (int i = 0; 32 * i < C; ++i) {
+                        const int k = 32 * i + lane;
+                        const unsigned bal = __ballot_sync(FULL, k < C && st.lw[0][k] == bs);
+                        const uint32_t c = (uint32_t)__popc(bal);
+                        if (j < c) {
+                            bb = 32u * i + __fns(bal, 0, (int)j + 1);
+                            break;
+                        }
+                        j -= c;
+                    }
+                }
             }
             __syncwarp();  // cp.async results and st.empty of the other lanes
             child = st.ci[0][bb];

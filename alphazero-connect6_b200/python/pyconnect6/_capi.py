@@ -40,7 +40,7 @@ ALLOC_PATH = ALLOC_RESULT = ALLOC_INT = ALLOC_FLOAT = C.CFUNCTYPE(C.c_void_p, C.
 class Config(C.Structure):
     _fields_ = [("num_simulation", C.c_int32), ("epsilon", C.c_float), ("dirichlet_alpha", C.c_double),
                 ("c_puct", C.c_float), ("seed", C.c_uint32), ("device", C.c_int32), ("slots", C.c_int32),
-                ("log2_records", C.c_int32), ("evaluator", C.c_int32), ("trace", C.c_int32), ("max_moves", C.c_int32)]
+                ("log2_records", C.c_int32), ("evaluator", C.c_int32), ("trace", C.c_int32), ("max_moves", C.c_int32), ("tie_break", C.c_int32)]
 
 
 class Record(C.Structure):
@@ -131,7 +131,9 @@ def product():
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
         L.c6_default_policy_play.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int, C.c_int, C.POINTER(Record),
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(DpStats)]
-        L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int, C.c_int]
+        L.c6_probe_math32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int]
+        L.c6_probe_tie.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int, C.c_int]
         L.c6_probe_math.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]
         L.c6_probe_pcie.argtypes = [C.c_int64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3
         _product = L

@@ -115,6 +115,8 @@ typedef struct c6_config {
     int32_t evaluator;       /* C6_EVAL_* */
     int32_t trace;           /* keep root child visits per move */
     int32_t max_moves;       /* stop each game after this many stones (0 = play out) */
+    int32_t tie_break;       /* exact PUCT ties: 1 = uniform among the tied children as alphazero_policy/mod.rs:291-295 does
+                                (Philox keyed (seed, game), counted by (simulation, depth)); 0 = lowest row-major index */
 } c6_config;
 
 /* 240 B per finished game */
@@ -207,10 +209,13 @@ typedef struct c6_dp_stats {
 int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
                            c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats);
 
-/* parity probes of the Dirichlet-noise sampler (tests): Gamma(shape) draw i of stream (i, 7, 9) keyed
- * (k0, k1); the engine's deterministic f64 log / exp on xs (log only where xs > 0) */
-int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, double* out, int n, int device);
+/* parity probes of the Dirichlet-noise sampler (tests): log2 of Gamma(shape) draw (7, 9, k = i) of the stream keyed
+ * (k0, k1) exactly as a select step computes it; the engine's deterministic f32 log2 / exp2 and f64 log / exp on xs
+ * (logs only where xs > 0); the uniform tie-break pick (sim = i, depth = i % 7) among `count` tied children */
+int c6_probe_gamma(double shape, uint32_t k0, uint32_t k1, float* out, int n, int device);
+int c6_probe_math32(const float* xs, float* lg2s, float* ex2s, int n, int device);
 int c6_probe_math(const double* xs, double* logs, double* exps, int n, int device);
+int c6_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* out, int n, int device);
 
 /* pinned host<->device copy bandwidth in GB/s: H2D alone, D2H alone, both at once (per direction) */
 int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs);

@@ -14,7 +14,9 @@
 // reference's own known-answer tests (oracle_tests.cpp) — see DESIGN.md "Oracle".
 //
 // Two seams replace the reference's `thread_rng()` uses, as SURVEY.md §0.3/§8c define parity:
-//   TieBreak::LowestIndex  instead of a uniform pick among exactly equal PUCT scores (mod.rs:291-295)
+//   TieBreak::Philox       the reference's uniform pick among exactly equal PUCT scores (mod.rs:291-295) drawn from a
+//                          Philox stream keyed (seed, game) and counted by (simulation, depth) — the engine's default;
+//   TieBreak::LowestIndex  the first of the tied children in row-major order (kept selectable: hand-derived traces)
 //   NoiseMode::Philox      instead of rand's Dirichlet (mod.rs:262,283); NoiseMode::None only
 //                          valid when epsilon == 0 (the draw is multiplied by 0: mod.rs:269).
 // Two cost models, identical results:
@@ -429,7 +431,7 @@ struct PhiloxRandomEvaluator : Evaluator {
               std::vector<FBoard>& policies) override;
 };
 
-enum class TieBreak { LowestIndex, Random };
+enum class TieBreak { LowestIndex, Random, Philox };
 enum class NoiseMode { None, Philox };
 
 struct SearchStats {  // device-counter twins for the roofline's algorithmic-bytes formula
@@ -474,30 +476,28 @@ struct AlphaZero {
         return true;
     }
 
-    // Dirichlet(alpha; n) twin of the engine's sampler: Gamma draws keyed (sim, depth, child),
-    // summed in the engine's lane order (child k of the row-major child list belongs to lane k & 31: per-lane
-    // partial sums in k order, then a butterfly), then scaled.
-    std::vector<double> dirichlet(const Simulate& sim, int depth, const std::vector<const Node*>& child,
-                                  const Board& parent) {
-        size_t n = child.size();
-        std::vector<double> g(n);
-        double partial[32];
-        for (auto& p : partial) p = 0.0;
+    // Dirichlet(alpha; n) twin of the engine's sampler (c6_rng.hpp: log2-space Gamma draws keyed (sim, depth, child)),
+    // normalised like a softmax: w_k = 2^(L_k - Lmax), noise_k = w_k / sum w.  The sum is taken in the engine's lane
+    // order (child k of the row-major child list belongs to lane k & 31: per-lane partial sums in k order, then a
+    // butterfly).  f32 throughout: the reference casts its f64 draw to f32 right here (mod.rs:267).
+    std::vector<float> dirichlet(int depth, size_t n) {
+        std::vector<float> g(n);
+        float lmax = 0.f;
         for (size_t k = 0; k < n; ++k) {
-            g[k] = gamma_sample(param.dirichlet_alpha, ctx.sim_index, (uint32_t)depth, (uint32_t)k, ctx.seed ^ DOMAIN_NOISE,
-                                ctx.game_id);
+            g[k] = gamma_log2_sample(param.dirichlet_alpha, ctx.sim_index, (uint32_t)depth, (uint32_t)k, ctx.seed ^ DOMAIN_NOISE,
+                                     ctx.game_id);
+            if (k == 0 || g[k] > lmax) lmax = g[k];
+        }
+        float partial[32];
+        for (auto& p : partial) p = 0.f;
+        for (size_t k = 0; k < n; ++k) {
+            g[k] = ex2_det(g[k] - lmax);
             partial[k & 31] = partial[k & 31] + g[k];
         }
         for (int off = 16; off >= 1; off >>= 1)
             for (int l = 0; l < off; ++l) partial[l] = partial[l] + partial[l + off];
-        double sum = partial[0];
-        (void)sim, (void)parent;
-        if (!(sum > 0.0)) {
-            for (auto& x : g) x = 1.0 / (double)n;
-        } else {
-            double inv = 1.0 / sum;
-            for (auto& x : g) x = x * inv;
-        }
+        const float inv = 1.0f / partial[0];  // the largest draw contributes exactly 1: the sum is >= 1
+        for (auto& x : g) x = x * inv;
         return g;
     }
 
@@ -514,18 +514,17 @@ struct AlphaZero {
         float epsilon = param.epsilon;
         double alpha = param.dirichlet_alpha;
         (void)alpha;
-        std::vector<double> noise_v;
+        std::vector<float> noise_v;
         if (noise == NoiseMode::Philox)
-            noise_v = dirichlet(sim, depth, child_nodes, tree_node.board);
+            noise_v = dirichlet(depth, child_nodes.size());
         else
-            noise_v.assign(child_nodes.size(), 0.0);
+            noise_v.assign(child_nodes.size(), 0.f);
 
         float c_puct = param.c_puct;
         int32_t vs = 0;
         for (auto* n : child_nodes) vs += n->visit;
         float visit_sum = (float)vs;
-        auto puct = [&](const Node& node, double noise_d) {
-            float noise_f = (float)noise_d;
+        auto puct = [&](const Node& node, float noise_f) {
             float visit = (float)node.visit;
             float prob = epsilon * noise_f + (1.f - epsilon) * node.n_prob;
             return prob * std::sqrt(visit_sum - visit) / (1.f + visit);
@@ -548,6 +547,8 @@ struct AlphaZero {
         if (tie == TieBreak::Random) {
             tie_rng = splitmix64(tie_rng);
             pick = ties[tie_rng % ties.size()];
+        } else if (tie == TieBreak::Philox && ties.size() > 1) {
+            pick = ties[tie_pick(ctx.sim_index, (uint32_t)depth, ctx.seed, ctx.game_id, (uint32_t)ties.size())];
         }
         return hash(child_nodes[pick]->board);
     }

@@ -206,4 +206,132 @@ inline double gamma_sample(double shape, uint32_t a, uint32_t b, uint32_t c, uin
     return shape < 1.0 ? gamma_small_shape(shape, a, b, c, k0, k1) : gamma_large_shape(shape, a, b, c, k0, k1);
 }
 
+// ----------------------------------------------------------------------------------------------
+// The sampler the search uses since round 2: log2 of a Gamma(shape, 1) draw, in f32.
+//
+// The reference normalises the Gamma draws by their sum in f64 and casts the result to f32
+// (alphazero_policy/mod.rs:262-267).  With alpha = 0.03 almost every draw is astronomically small
+// (X = P^(1/alpha)), so the engine keeps L = log2 X instead of X — no underflow for any alpha — and
+// normalises like a softmax: noise_k = 2^(L_k - Lmax) / sum_j 2^(L_j - Lmax).  Same distribution
+// (Ahrens–Dieter GS is still the exact rejection sampler; only the arithmetic is f32 where the
+// reference's is f64 rounded to f32 at the end), one third of the instructions on the GPU.
+//   * uniforms: 32-bit Philox words, U = (u + 1/2) 2^-32, complement 1 - U from ~u (both exact
+//     before the conversion to f32);
+//   * draw k of a select step takes trial 0 from words (2h, 2h+1) of block (a, b, kb, 0),
+//     kb = (k >> 6) << 5 | (k & 31), h = (k >> 5) & 1 (two draws per Philox call); trial t >= 1
+//     from words (0, 1) of block (a, b, k, t);
+//   * trial 0 is first tried on the hot branch with a sufficient acceptance test (2^L <= 2^floor(L)
+//     (1 + frac L)); only if that fails the full rejection loop runs (from trial 0 again).
+// lg2_det / ex2_det: table + polynomial, explicit fmaf only — bit-identical on x86-64 and the GPU.
+// ----------------------------------------------------------------------------------------------
+inline float u2f(uint32_t b) {
+    float f;
+    std::memcpy(&f, &b, 4);
+    return f;
+}
+inline uint32_t f2u(float f) {
+    uint32_t b;
+    std::memcpy(&b, &f, 4);
+    return b;
+}
+inline float fmaf1(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+
+// log2 of a positive normal f32.  x = 2^e m with m in [sqrt(1/2), sqrt(2)); the interval centre c nearest to m
+// (33 centres, one of them exactly 1) gives r = m / c - 1 through the tabulated f32 reciprocal, |r| <= 2^-6;
+// log2 x = e - log2(1/c) + log2(1 + r).
+inline float lg2_det(float x) {
+    const uint32_t bits = f2u(x);
+    const int32_t e = (int32_t)(bits - 0x3F3504F3u) >> 23;
+    const uint32_t mb = bits - ((uint32_t)e << 23);
+    const float* row = LG2F_TABLE[(mb + 0x20000u - 0x3F340000u) >> 18];
+    const float r = fmaf1(u2f(mb), row[0], -1.0f);
+    float p = fmaf1(r, LG2F_POLY[3], LG2F_POLY[2]);
+    p = fmaf1(r, p, LG2F_POLY[1]);
+    p = fmaf1(r, p, LG2F_POLY[0]);
+    return (float)e + fmaf1(r, p, row[1]);
+}
+// 2^t for t < 127; 0 below -125.  t = n + f, n = rint(t), 2^f by a degree-6 polynomial, scaled through the exponent.
+inline float ex2_det(float t) {
+    if (t < -125.0f) return 0.0f;
+    const float n = __builtin_rintf(t);  // round-half-even (default rounding mode), as CUDA's rintf
+    const float f = t - n;
+    float p = EX2F_POLY[6];
+    for (int i = 5; i >= 0; --i) p = fmaf1(p, f, EX2F_POLY[i]);
+    return u2f(f2u(p) + ((uint32_t)(int32_t)n << 23));
+}
+
+struct GammaF {  // per-run constants of the shape < 1 sampler, rounded to f32 once on the host
+    float b, inv_a, c1, am1;  // (e + a)/e, 1/a, b/a, a - 1
+};
+inline GammaF gamma_f(double shape) {
+    const double b = (2.718281828459045 + shape) / 2.718281828459045;
+    return GammaF{(float)b, (float)(1.0 / shape), (float)(b / shape), (float)(shape - 1.0)};
+}
+inline float unit_of(uint32_t w) { return fmaf1((float)w, 0x1p-32f, 0x1p-33f); }  // (w + 1/2) 2^-32, rounded once
+
+// hot branch of trial 0; false = undecided (the full loop decides)
+inline bool gamma_log2_fast(const GammaF& g, uint32_t u, uint32_t v, float& L) {
+    const float P = g.b * unit_of(u);
+    L = 0.0f;
+    if (P > 1.0f) return false;
+    L = lg2_det(P) * g.inv_a;
+    const float Lc = L < -64.0f ? -64.0f : L;
+    const float kf = __builtin_floorf(Lc);
+    const float xub = u2f(f2u(1.0f + (Lc - kf)) + ((uint32_t)(int32_t)kf << 23));  // 2^k (1 + f) >= 2^(k + f)
+    return unit_of(~v) >= xub;  // 1 - V >= X >= 1 - e^-X
+}
+inline void gamma_words(uint32_t a, uint32_t b, uint32_t k, uint32_t trial, uint32_t k0, uint32_t k1, uint32_t& u, uint32_t& v) {
+    if (trial == 0) {
+        const Philox4 r = philox4x32_10(a, b, ((k >> 6) << 5) | (k & 31u), 0u, k0, k1);
+        const uint32_t h = (k >> 5) & 1u;
+        u = r.v[2 * h], v = r.v[2 * h + 1];
+    } else {
+        const Philox4 r = philox4x32_10(a, b, k, trial, k0, k1);
+        u = r.v[0], v = r.v[1];
+    }
+}
+inline float gamma_log2_full(const GammaF& g, uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
+    float L = 0.0f;
+    for (uint32_t t = 0; t < 64; ++t) {
+        uint32_t u, v;
+        gamma_words(a, b, k, t, k0, k1, u, v);
+        const float P = g.b * unit_of(u);
+        if (P <= 1.0f) {  // X = P^(1/a); accept iff V <= e^-X, i.e. 1 - V >= 1 - e^-X
+            L = lg2_det(P) * g.inv_a;
+            if (L < -40.0f) return L;  // 1 - e^-X < 2^-40 < the smallest 1 - V
+            const float X = ex2_det(L);
+            float d;
+            if (X < 0x1p-6f)
+                d = X * fmaf1(X, fmaf1(X, fmaf1(X, -1.0f / 24.0f, 1.0f / 6.0f), -0.5f), 1.0f);  // X - X^2/2 + X^3/6 - X^4/24
+            else
+                d = 1.0f - ex2_det(X * -1.44269504f);
+            if (unit_of(~v) >= d) return L;
+        } else {  // X = -ln((b - P)/a) = -ln((b/a)(1 - U)); accept iff V <= X^(a-1)
+            const float X = lg2_det(g.c1 * unit_of(~u)) * -0.693147182f;
+            L = lg2_det(X > 0x1p-100f ? X : 0x1p-100f);
+            if (lg2_det(unit_of(v)) <= g.am1 * L) return L;
+        }
+    }
+    return L;
+}
+// log2 of draw (a, b, k) of the stream keyed (k0, k1)
+inline float gamma_log2_sample(double shape, uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
+    if (shape >= 1.0) return (float)(det_log(gamma_large_shape(shape, a, b, k, k0, k1)) * 1.4426950408889634);
+    const GammaF g = gamma_f(shape);
+    uint32_t u, v;
+    gamma_words(a, b, k, 0, k0, k1, u, v);
+    float L;
+    if (gamma_log2_fast(g, u, v, L)) return L;
+    return gamma_log2_full(g, a, b, k, k0, k1);
+}
+
+// Exact ties of the PUCT maximum are broken uniformly (alphazero_policy/mod.rs:291-295): tie number
+// floor(u n / 2^32) of the n tied children in row-major order, u = word 0 of Philox block (sim, depth, 0, 0)
+// keyed (seed ^ TIE, game).
+constexpr uint32_t DOMAIN_TIE = 0x54494542u;  // "TIEB"
+inline uint32_t tie_pick(uint32_t sim, uint32_t depth, uint32_t seed, uint32_t game, uint32_t n) {
+    const Philox4 r = philox4x32_10(sim, depth, 0u, 0u, seed ^ DOMAIN_TIE, game);
+    return (uint32_t)(((uint64_t)r.v[0] * (uint64_t)n) >> 32);
+}
+
 }  // namespace c6o

@@ -105,6 +105,19 @@ double oracle_det_exp(double x) { return det_exp(x); }
 double oracle_gamma(uint32_t a, uint32_t b, uint32_t c, uint32_t k0, uint32_t k1, double shape) {
     return gamma_sample(shape, a, b, c, k0, k1);
 }
+// the search's sampler: log2 of Gamma draw (a, b, k) in f32; f32 log2 / exp2
+float oracle_gamma_log2(uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1, double shape) {
+    return gamma_log2_sample(shape, a, b, k, k0, k1);
+}
+void oracle_gamma_log2_many(uint32_t a, uint32_t b, uint32_t k_first, int n, uint32_t k0, uint32_t k1, double shape, float* out) {
+    for (int i = 0; i < n; ++i) out[i] = gamma_log2_sample(shape, a, b, k_first + (uint32_t)i, k0, k1);
+}
+float oracle_lg2(float x) { return lg2_det(x); }
+float oracle_ex2(float x) { return ex2_det(x); }
+void oracle_math32_many(const float* xs, int n, float* lg, float* ex) {
+    for (int i = 0; i < n; ++i) lg[i] = xs[i] > 0.f ? lg2_det(xs[i]) : 0.f, ex[i] = ex2_det(xs[i]);
+}
+uint32_t oracle_tie_pick(uint32_t sim, uint32_t depth, uint32_t seed, uint32_t game, uint32_t n) { return tie_pick(sim, depth, seed, game, n); }
 
 // Random playout (default_policy/mod.rs:186-203 rollout loop) from the empty board with the
 // engine's Philox stream: stone n of playout p picks index (u32 * remaining) >> 32 of the
@@ -172,7 +185,7 @@ struct OracleParams {
     float c_puct;
     uint32_t seed;
     int32_t noise_mode;  // 0 none (epsilon must be 0), 1 philox
-    int32_t tie_mode;    // 0 lowest index, 1 random
+    int32_t tie_mode;    // 0 lowest index, 1 random (splitmix), 2 Philox keyed (sim, depth): the engine default
     int32_t faithful;    // 0 lean, 1 reference cost model
     int32_t evaluator;   // 0 callback, 1 philox random evaluator
     int32_t max_moves;   // stop after this many stones (<=0: play to the end)
@@ -198,7 +211,7 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
     else
         ev.reset(new CppEval(cb));
     AlphaZeroPolicy pol(ev.get(), hp);
-    pol.az.tie = p.tie_mode ? TieBreak::Random : TieBreak::LowestIndex;
+    pol.az.tie = p.tie_mode == 2 ? TieBreak::Philox : (p.tie_mode ? TieBreak::Random : TieBreak::LowestIndex);
     pol.az.noise = p.noise_mode ? NoiseMode::Philox : NoiseMode::None;
     pol.az.faithful = p.faithful != 0;
     pol.az.ctx.seed = p.seed;
@@ -292,7 +305,7 @@ void oracle_play_with(Callback cb, const OracleParams* p, uint32_t game_id, cons
     else
         ev.reset(new CppEval(cb));
     AlphaZeroPolicy black(ev.get(), hp);
-    black.az.tie = TieBreak::LowestIndex;
+    black.az.tie = p->tie_mode == 2 ? TieBreak::Philox : TieBreak::LowestIndex;
     black.az.noise = p->noise_mode ? NoiseMode::Philox : NoiseMode::None;
     black.az.faithful = p->faithful != 0;
     black.az.ctx.seed = p->seed, black.az.ctx.game_id = game_id;

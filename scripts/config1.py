@@ -42,7 +42,7 @@ for sims in (2, 800):
                       "stones": rec[0].n_moves, "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
 
     mm = 0 if sims == 2 else 12  # the 800-simulation oracle game is timed on its first 12 stones and scaled by simulations
-    p = c6lib.OracleParams(sims, 0.25, 0.03, 1.0, 0xC6, 1, 0, 1, 1, mm)
+    p = c6lib.OracleParams(sims, 0.25, 0.03, 1.0, 0xC6, 1, 2, 1, 1, mm)
     out = c6lib.OracleGameOut()
     t0 = time.perf_counter()
     O.oracle_self_play(None, C.byref(p), 0, C.byref(out), None, None, None)

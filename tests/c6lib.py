@@ -18,6 +18,10 @@ ORACLE_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 ORACLE_TESTS = os.path.join(ORACLE_DIR, "_build", "oracle_tests")
 
 
+TIE_LOWEST, TIE_PHILOX = 0, 1          # c6_config.tie_break
+ORACLE_TIE = {0: 0, 1: 2}               # -> OracleParams.tie_mode (1 is the oracle's non-reproducible splitmix pick)
+
+
 class OracleParams(C.Structure):
     _fields_ = [("num_simulation", C.c_int32), ("epsilon", C.c_float), ("dirichlet_alpha", C.c_double),
                 ("c_puct", C.c_float), ("seed", C.c_uint32), ("noise_mode", C.c_int32), ("tie_mode", C.c_int32),
@@ -66,6 +70,12 @@ def oracle():
         L.oracle_det_exp.argtypes = [C.c_double]
         L.oracle_gamma.restype = C.c_double
         L.oracle_gamma.argtypes = [C.c_uint32] * 5 + [C.c_double]
+        L.oracle_gamma_log2.restype = C.c_float
+        L.oracle_gamma_log2.argtypes = [C.c_uint32] * 5 + [C.c_double]
+        L.oracle_gamma_log2_many.argtypes = [C.c_uint32] * 3 + [C.c_int] + [C.c_uint32] * 2 + [C.c_double, C.POINTER(C.c_float)]
+        L.oracle_math32_many.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.oracle_tie_pick.restype = C.c_uint32
+        L.oracle_tie_pick.argtypes = [C.c_uint32] * 5
         L.oracle_playout.argtypes = [C.c_uint32, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int8)]
         L.oracle_script_game.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
         L.oracle_self_play.argtypes = [C.c_void_p, C.POINTER(OracleParams), C.c_uint32, C.POINTER(OracleGameOut),

@@ -102,7 +102,8 @@ def test_scripted_game_known_answer(oracle):
 def run_oracle_case(case, g, faithful=0):
     O = c6lib.oracle()
     p = c6lib.OracleParams(case["num_simulation"], case["epsilon"], case["dirichlet_alpha"], case["c_puct"], case["seed"],
-                           1 if case["epsilon"] != 0 else 0, 0, faithful, case["evaluator"], case["max_moves"])
+                           1 if case["epsilon"] != 0 else 0, c6lib.ORACLE_TIE[case.get("tie_break", 0)], faithful, case["evaluator"],
+                           case["max_moves"])
     out = c6lib.OracleGameOut()
     cv = np.zeros((225, 225), dtype=np.int32)
     rn = np.zeros(225, dtype=np.int32)
@@ -192,11 +193,69 @@ def test_deterministic_log_exp(oracle):
 
 
 def test_gamma_sampler_distribution(oracle):
-    """Gamma(alpha=0.03) twin of rand 0.6's Dirichlet building block: mean/variance = alpha."""
-    n = 40000
-    xs = np.array([oracle.oracle_gamma(i, 0, 0, 123, 7, 0.03) for i in range(n)])
-    assert np.all(xs >= 0)
-    assert abs(xs.mean() - 0.03) < 0.006
-    assert abs(xs.var() - 0.03) < 0.02
-    xs1 = np.array([oracle.oracle_gamma(i, 1, 2, 123, 7, 1.5) for i in range(n)])
-    assert abs(xs1.mean() - 1.5) < 0.03 and abs(xs1.var() - 1.5) < 0.1
+    """The search's sampler (log2 of a Gamma(alpha) draw, f32): the distribution is what is contractual (rand 0.6's own
+    stream is unseedable).  Kolmogorov-Smirnov against the Gamma CDF in log space, mean = variance = alpha, and
+    E[ln X] = digamma(alpha), for the default alpha = 0.03, two other shapes below 1 and the alpha >= 1 path."""
+    from scipy import special, stats
+    n = 400000
+    FP = C.POINTER(C.c_float)
+    for shape in (0.03, 0.3, 0.7, 1.0, 2.5):
+        lg = np.zeros(n, dtype=np.float32)
+        oracle.oracle_gamma_log2_many(3, 1, 0, n, 123, 7, shape, lg.ctypes.data_as(FP))
+        x = np.exp2(lg.astype(np.float64))
+        ks = stats.kstest(special.gammainc(shape, x), "uniform")
+        assert ks.statistic < 0.004, (shape, ks)          # 1.36 / sqrt(n) = 0.0021 is the 5 % critical value
+        assert abs(x.mean() - shape) < 6 * np.sqrt(shape / n) + 1e-4, (shape, x.mean())
+        assert abs(x.var() - shape) < 0.05 * shape + 0.01, (shape, x.var())
+        sd = np.sqrt(special.polygamma(1, shape) / n)
+        assert abs(lg.astype(np.float64).mean() * np.log(2) - special.digamma(shape)) < 6 * sd, shape
+    # two draws share a Philox block (k and k ^ 32): they must still be uncorrelated
+    lg = np.zeros(1 << 16, dtype=np.float32)
+    oracle.oracle_gamma_log2_many(3, 1, 0, len(lg), 123, 7, 0.03, lg.ctypes.data_as(FP))
+    a = lg.reshape(-1, 2, 32)
+    assert abs(np.corrcoef(a[:, 0, :].ravel(), a[:, 1, :].ravel())[0, 1]) < 0.02
+
+
+def test_f32_log2_exp2_accuracy(oracle):
+    """lg2_det / ex2_det (tables + fixed polynomials over fmaf, so that CPU and GPU agree bit for bit) against libm."""
+    FP = C.POINTER(C.c_float)
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.exp(rng.uniform(-87, 88, 100000)), 1.0 - np.arange(1, 5000) * 2.0 ** -24, 1.0 + np.arange(5000) * 2.0 ** -23]).astype(np.float32)
+    lg, ex = np.zeros_like(xs), np.zeros_like(xs)
+    oracle.oracle_math32_many(xs.ctypes.data_as(FP), len(xs), lg.ctypes.data_as(FP), ex.ctypes.data_as(FP))
+    ref = np.log2(xs.astype(np.float64))
+    assert np.all(np.abs(lg - ref) <= 2.0 ** -25 + 2.0 ** -23 * np.abs(ref))
+    near = np.abs(xs - 1) < 0.01
+    assert np.all(np.abs(lg[near] - ref[near]) <= 1.5e-7 * np.abs(ref[near]) + 1e-38)   # relative accuracy where the largest draws live
+    ts = rng.uniform(-125, 0, 100000).astype(np.float32)
+    oracle.oracle_math32_many(ts.ctypes.data_as(FP), len(ts), lg[:len(ts)].ctypes.data_as(FP), ex[:len(ts)].ctypes.data_as(FP))
+    r = np.exp2(ts.astype(np.float64))
+    assert np.all(np.abs(ex[:len(ts)] - r) <= 1.2e-7 * r)
+    one = np.array([0.0, -126.0, -1.0], dtype=np.float32)
+    oracle.oracle_math32_many(one.ctypes.data_as(FP), 3, lg[:3].ctypes.data_as(FP), ex[:3].ctypes.data_as(FP))
+    assert ex[:3].tolist() == [1.0, 0.0, 0.5]
+
+
+def test_tie_break_is_uniform(oracle):
+    """TieBreak::Philox: floor(u n / 2^32) over the tied children, one draw per (simulation, depth)."""
+    for n in (2, 7, 225):
+        picks = np.array([oracle.oracle_tie_pick(s, s % 5, 0xC6, 3, n) for s in range(20000)])
+        assert picks.min() == 0 and picks.max() == n - 1
+        cnt = np.bincount(picks, minlength=n)
+        assert np.all(np.abs(cnt - 20000 / n) < 6 * np.sqrt(20000 / n) + 1)
+
+
+def test_first_level_visits_are_not_biased_to_the_top_left(oracle):
+    """With the uniform tie-break the second visit of every fresh node goes to a uniformly chosen child, not to the first
+    empty cell: over many games the root's first visited child is spread over the board."""
+    first_children = []
+    for g in range(300):
+        p = c6lib.OracleParams(2, 0.25, 0.03, 1.0, 0xC6, 1, c6lib.ORACLE_TIE[1], 0, 1, 1)
+        out = c6lib.OracleGameOut()
+        oracle.oracle_self_play(None, C.byref(p), g, C.byref(out), None, None, None)
+        first_children.append(out.moves[0])
+    assert len(set(first_children)) > 150 and min(first_children) < 40 and max(first_children) > 180
+    p = c6lib.OracleParams(2, 0.25, 0.03, 1.0, 0xC6, 1, c6lib.ORACLE_TIE[0], 0, 1, 1)
+    out = c6lib.OracleGameOut()
+    oracle.oracle_self_play(None, C.byref(p), 0, C.byref(out), None, None, None)
+    assert out.moves[0] == 0  # lowest-index mode: 2 simulations always end on cell (0, 0)

@@ -42,6 +42,7 @@ def run_engine(n_games, callback_name=None, first_id=0, prefixes=None, **cfg_kw)
     cfg_kw.setdefault("slots", n_games)
     cfg_kw.setdefault("trace", 1)
     cfg_kw.setdefault("log2_records", 18)
+    cfg_kw.setdefault("tie_break", 1)  # the product default: exact PUCT ties are broken uniformly (Philox), as the reference does
     cfg = c6lib.make_config(**cfg_kw)
     e = L.c6_engine_create(C.byref(cfg))
     assert e, L.c6_last_error()
@@ -70,9 +71,9 @@ def run_engine(n_games, callback_name=None, first_id=0, prefixes=None, **cfg_kw)
         L.c6_engine_destroy(e)
 
 
-def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0, prefix=None):
+def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0, prefix=None, tie=1):
     O = c6lib.oracle()
-    p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, 0, 0, evaluator, max_moves)
+    p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, c6lib.ORACLE_TIE[tie], 0, evaluator, max_moves)
     out = c6lib.OracleGameOut()
     cv = np.zeros((225, 225), dtype=np.int32)
     rn = np.zeros(225, dtype=np.int32)
@@ -86,11 +87,11 @@ def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed,
 
 
 def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=1.0,
-                  prefixes=None):
+                  prefixes=None, tie=1):
     for g in range(n_games):
         pre = prefixes[g] if prefixes else []
         out, ocv, orn, orw = run_oracle(first_id + g, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=c_puct,
-                                        prefix=pre)
+                                        prefix=pre, tie=tie)
         r = rec[g]
         where = f"game {first_id + g}"
         assert r.game_id == first_id + g
@@ -219,36 +220,54 @@ def test_playouts_match_oracle():
 # ---------------------------------------------------------------------------------------------
 # self-play: callback path (C-ABI evaluator contract) and device evaluators
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cbname,sims,eps,n_games,max_moves", [
-    ("const_eval_callback", 4, 0.0, 1, 12),     # SURVEY B.1 hand trace
-    ("det_eval_callback", 2, 0.0, 6, 0),        # reference sample budget, full games
-    ("neg_eval_callback", 2, 0.25, 6, 0),       # light_weight() defaults incl. noise
-    ("det_eval_callback", 48, 0.0, 4, 30),
-    ("neg_eval_callback", 48, 0.0, 4, 30),
-    ("neg_eval_callback", 32, 0.25, 4, 24),
+@pytest.mark.parametrize("cbname,sims,eps,n_games,max_moves,tie", [
+    ("const_eval_callback", 4, 0.0, 1, 12, 0),     # SURVEY B.1 hand trace (derived for the lowest-index tie-break)
+    ("const_eval_callback", 24, 0.0, 3, 12, 1),    # constant priors: every select step is a many-way exact tie
+    ("det_eval_callback", 2, 0.0, 6, 0, 1),        # reference sample budget, full games
+    ("neg_eval_callback", 2, 0.25, 6, 0, 1),       # light_weight() defaults incl. noise
+    ("det_eval_callback", 48, 0.0, 4, 30, 1),
+    ("neg_eval_callback", 48, 0.0, 4, 30, 0),
+    ("neg_eval_callback", 32, 0.25, 4, 24, 1),
+    ("neg_eval_callback", 32, 0.25, 4, 24, 0),
 ])
-def test_selfplay_callback_path(cbname, sims, eps, n_games, max_moves):
+def test_selfplay_callback_path(cbname, sims, eps, n_games, max_moves, tie):
     seed = 0xC6
     rec, cv, rn, rw, st = run_engine(n_games, cbname, first_id=10, num_simulation=sims, epsilon=eps, seed=seed,
-                                     evaluator=EVAL_CALLBACK, max_moves=max_moves)
-    compare_games(n_games, rec, cv, rn, rw, 10, cbname, 0, sims, eps, seed, max_moves)
-    if cbname == "const_eval_callback":
+                                     evaluator=EVAL_CALLBACK, max_moves=max_moves, tie_break=tie)
+    compare_games(n_games, rec, cv, rn, rw, 10, cbname, 0, sims, eps, seed, max_moves, tie=tie)
+    if cbname == "const_eval_callback" and tie == 0:
         assert [rec[0].moves[i] for i in range(7)] == [2, 4, 5, 6, 7, 8, 9]  # (0,2),(0,4),(0,5),... as derived by hand
 
 
-@pytest.mark.parametrize("evaluator,cbname,sims,eps,n_games,max_moves", [
-    (EVAL_PHILOX, None, 2, 0.0, 8, 0),
-    (EVAL_PHILOX, None, 2, 0.25, 8, 0),
-    (EVAL_PHILOX, None, 64, 0.0, 4, 24),
-    (EVAL_PHILOX, None, 64, 0.25, 4, 24),
-    (EVAL_DET, "det_eval_callback", 40, 0.0, 4, 24),
-    (EVAL_NEG, "neg_eval_callback", 40, 0.25, 4, 24),
+@pytest.mark.parametrize("evaluator,cbname,sims,eps,n_games,max_moves,tie", [
+    (EVAL_PHILOX, None, 2, 0.0, 8, 0, 1),
+    (EVAL_PHILOX, None, 2, 0.25, 8, 0, 1),
+    (EVAL_PHILOX, None, 64, 0.0, 4, 24, 1),
+    (EVAL_PHILOX, None, 64, 0.25, 4, 24, 1),
+    (EVAL_PHILOX, None, 64, 0.25, 4, 24, 0),
+    (EVAL_DET, "det_eval_callback", 40, 0.0, 4, 24, 1),
+    (EVAL_DET, "det_eval_callback", 40, 0.0, 4, 24, 0),
+    (EVAL_NEG, "neg_eval_callback", 40, 0.25, 4, 24, 1),
 ])
-def test_selfplay_device_path(evaluator, cbname, sims, eps, n_games, max_moves):
+def test_selfplay_device_path(evaluator, cbname, sims, eps, n_games, max_moves, tie):
     seed = 0xC6
     rec, cv, rn, rw, st = run_engine(n_games, None, first_id=77, num_simulation=sims, epsilon=eps, seed=seed,
-                                     evaluator=evaluator, max_moves=max_moves)
-    compare_games(n_games, rec, cv, rn, rw, 77, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, max_moves)
+                                     evaluator=evaluator, max_moves=max_moves, tie_break=tie)
+    compare_games(n_games, rec, cv, rn, rw, 77, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, max_moves, tie=tie)
+
+
+@pytest.mark.parametrize("alpha", [0.3, 1.0, 2.5])
+def test_selfplay_other_dirichlet_alphas(alpha):
+    """Noise with another shape: alpha < 1 runs the same f32 log-space sampler, alpha >= 1 the f64 Marsaglia-Tsang one."""
+    L = c6lib.product()
+    seed, sims, eps, n, mm = 0xC6, 24, 0.25, 3, 10
+    cfg = c6lib.make_config(num_simulation=sims, epsilon=eps, dirichlet_alpha=alpha, seed=seed, evaluator=EVAL_PHILOX, slots=n, max_moves=mm,
+                            log2_records=16)
+    rec = (c6lib.Record * n)()
+    assert L.c6_self_play_device(C.byref(cfg), 900, n, rec, None) == 0, L.c6_last_error()
+    for g in range(n):
+        out, *_ = run_oracle(900 + g, None, 1, sims, eps, seed, mm, alpha=alpha)
+        assert [rec[g].moves[i] for i in range(rec[g].n_moves)] == [out.moves[i] for i in range(out.n_moves)], (alpha, g)
 
 
 @pytest.mark.parametrize("evaluator,cbname,sims,c_puct,n_stones", [
@@ -366,7 +385,8 @@ _TRACES = json.load(open(os.path.join(_GOLDEN, "selfplay_traces.json")))
 def test_engine_reproduces_golden_traces(case):
     n = len(case["games"])
     first = case["first_id"]
-    kw = dict(num_simulation=case["num_simulation"], epsilon=case["epsilon"], seed=case["seed"], max_moves=case["max_moves"])
+    kw = dict(num_simulation=case["num_simulation"], epsilon=case["epsilon"], seed=case["seed"], max_moves=case["max_moves"],
+              tie_break=case["tie_break"])
     if case["evaluator"] == 1:
         rec, cv, rn, rw, st = run_engine(n, None, first_id=first, evaluator=EVAL_PHILOX, **kw)
     else:
@@ -487,16 +507,30 @@ def test_reference_catch2_suite_full():
 
 
 def test_noise_sampler_bitwise_vs_oracle():
-    """Every Gamma draw, log and exp of the engine's Dirichlet-noise sampler equals the oracle's
-    independent restatement bit for bit (alpha = 0.03 default, 0.7, and the alpha >= 1 path)."""
+    """Every log2-Gamma draw of the engine's Dirichlet-noise sampler (alpha = 0.03 default, 0.003, 0.7, and the f64 alpha >= 1
+    path), its f32 log2 / exp2, its f64 log / exp and its tie-break picks equal the oracle's independent restatement bit for bit."""
     L, O = c6lib.product(), c6lib.oracle()
-    n = 1 << 15
-    for shape in (0.03, 0.7, 1.0, 2.5):
-        out = np.zeros(n, dtype=np.float64)
-        assert L.c6_probe_gamma(shape, 0xABCDEF01, 77, out.ctypes.data_as(C.POINTER(C.c_double)), n, 0) == 0, L.c6_last_error()
-        want = np.array([O.oracle_gamma(i, 7, 9, 0xABCDEF01, 77, shape) for i in range(n)])
-        assert np.array_equal(out.view(np.uint64), want.view(np.uint64)), shape
+    n = 1 << 17
+    FP = C.POINTER(C.c_float)
+    for shape in (0.03, 0.003, 0.7, 1.0, 2.5):
+        out = np.zeros(n, dtype=np.float32)
+        assert L.c6_probe_gamma(shape, 0xABCDEF01, 77, out.ctypes.data_as(FP), n, 0) == 0, L.c6_last_error()
+        want = np.zeros(n, dtype=np.float32)
+        O.oracle_gamma_log2_many(7, 9, 0, n, 0xABCDEF01, 77, shape, want.ctypes.data_as(FP))
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), shape
     rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-130, 127, 50000), rng.uniform(-1, 1, 50000), np.exp(rng.uniform(-87, 88, 50000)),
+                         1.0 - np.arange(1, 3000) * 2.0 ** -24, 1.0 + np.arange(0, 3000) * 2.0 ** -23,
+                         [1.1754944e-38, 1.0, 2.0, 0.5, 0.70710677, 0.70710683, 1.4142135, 1.4142137, -125.0, -125.00001, -126.0, 3.4e38]]).astype(np.float32)
+    lg, ex, wl, we = (np.zeros_like(xs) for _ in range(4))
+    assert L.c6_probe_math32(xs.ctypes.data_as(FP), lg.ctypes.data_as(FP), ex.ctypes.data_as(FP), len(xs), 0) == 0
+    O.oracle_math32_many(xs.ctypes.data_as(FP), len(xs), wl.ctypes.data_as(FP), we.ctypes.data_as(FP))
+    ok = xs < 127.0  # ex2_det is defined for t < 127
+    assert np.array_equal(lg.view(np.uint32), wl.view(np.uint32))
+    assert np.array_equal(ex[ok].view(np.uint32), we[ok].view(np.uint32))
+    pos = xs > 0
+    ref = np.log2(xs[pos].astype(np.float64))
+    assert np.all(np.abs(lg[pos] - ref) <= 2.0 ** -23 * np.maximum(1.0, np.abs(ref)))
     xs = np.concatenate([rng.uniform(-745, 709, 20000), rng.uniform(-1, 1, 20000), np.exp(rng.uniform(-700, 700, 20000)),
                          [5e-324, 1e-310, 1.0, 1.0 - 2 ** -53, 1.0 + 2 ** -52, 2.0, 0.5, -800.0, 800.0, 1e308]])
     logs, exps = np.zeros_like(xs), np.zeros_like(xs)
@@ -506,8 +540,11 @@ def test_noise_sampler_bitwise_vs_oracle():
     we = np.array([O.oracle_det_exp(x) for x in xs])
     assert np.array_equal(logs.view(np.uint64), wl.view(np.uint64))
     assert np.array_equal(exps.view(np.uint64), we.view(np.uint64))
-    pos = xs > 0
-    assert np.all(np.abs(logs[pos] - np.log(xs[pos])) <= 4e-16 * np.maximum(1.0, np.abs(np.log(xs[pos]))))
+    for count in (2, 3, 224, 225):
+        got = np.zeros(4096, dtype=np.uint32)
+        assert L.c6_probe_tie(0xC6, 5, count, got.ctypes.data_as(C.POINTER(C.c_uint32)), len(got), 0) == 0
+        assert got.tolist() == [O.oracle_tie_pick(i, i % 7, 0xC6, 5, count) for i in range(len(got))]
+        assert got.max() < count and len(set(got.tolist())) == min(count, 225)
 
 
 @pytest.mark.parametrize("pipeline", ["1", "3", "7"])
@@ -531,7 +568,7 @@ def test_cpp_play_with_matches_oracle():
     white = [(2, 4), (9, 10), (14, 6), (13, 10), (13, 0), (1, 1), (4, 5), (2, 0), (8, 6), (12, 14)]  # collides with no Black stone (checked below)
     sims, eps, seed = 24, 0.25, 4242
     O = c6lib.oracle()
-    p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1, 0, 0, 0, 0)
+    p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1, c6lib.ORACLE_TIE[1], 0, 0, 0)
     out = c6lib.OracleGameOut()
     wm = (C.c_int * (2 * len(white)))(*[x for m in white for x in m])
     O.oracle_play_with(c6lib.oracle_callback("neg_eval_callback"), C.byref(p), 0, wm, len(white), C.byref(out))
