@@ -484,6 +484,9 @@ int c6_engine_trace(c6_engine* e, int32_t* cv, int32_t* rn, float* rw) {
         std::memcpy(rw, c.data(), c.size() * 4);
     });
 }
+int c6_engine_trace_game(c6_engine* e, int64_t game, int32_t* cv, int32_t* rn, float* rw) {
+    return guarded([&] { e->eng->trace_game(game, cv, rn, rw); });
+}
 long long c6_engine_validate(c6_engine* e, unsigned long long* detail) {
     try {
         return e->eng->validate(detail);

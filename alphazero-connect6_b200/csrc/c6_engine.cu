@@ -967,4 +967,14 @@ void Engine::trace(std::vector<int32_t>& cv, std::vector<int32_t>& rn, std::vect
     C6_CUDA(cudaMemcpy(rw.data(), d_->dev.tr_w, rw.size() * 4, cudaMemcpyDeviceToHost));
 }
 
+void Engine::trace_game(int64_t game, int32_t* cv, int32_t* rn, float* rw) {
+    sync();
+    if (!cfg_.trace) throw std::runtime_error("c6: trace not enabled");
+    if (game < 0 || game >= total_games_) throw std::runtime_error("c6: trace_game: game index out of range");
+    const size_t row = (size_t)game * CELLS;
+    C6_CUDA(cudaMemcpy(cv, d_->dev.tr_visits + row * CELLS, (size_t)CELLS * CELLS * 4, cudaMemcpyDeviceToHost));
+    C6_CUDA(cudaMemcpy(rn, d_->dev.tr_n + row, CELLS * 4, cudaMemcpyDeviceToHost));
+    C6_CUDA(cudaMemcpy(rw, d_->dev.tr_w + row, CELLS * 4, cudaMemcpyDeviceToHost));
+}
+
 }  // namespace c6

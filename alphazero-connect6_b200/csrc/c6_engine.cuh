@@ -156,6 +156,8 @@ class Engine {
     std::vector<GameRecord> records();   // synchronises; index = game id - first_id
     // trace (cfg.trace): root child visits [game][move][225], root N and W per move
     void trace(std::vector<int32_t>& child_visits, std::vector<int32_t>& root_n, std::vector<float>& root_w);
+    // the same for one game (index = game id - first_id): 225 x 225 child visits, 225 root N, 225 root W
+    void trace_game(int64_t game, int32_t* child_visits, int32_t* root_n, float* root_w);
     const Config& config() const { return cfg_; }
     cudaStream_t stream() const { return stream_; }
     size_t bytes_per_game() const;

@@ -121,6 +121,7 @@ def product():
         L.c6_engine_games_done.argtypes = [C.c_void_p]
         L.c6_engine_records.argtypes = [C.c_void_p, C.POINTER(Record), C.c_int64]
         L.c6_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        L.c6_engine_trace_game.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.c6_engine_validate.restype = C.c_longlong
         L.c6_engine_validate.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.c6_self_play_device.argtypes = [C.POINTER(Config), C.c_uint32, C.c_int64, C.POINTER(Record), C.POINTER(Stats)]

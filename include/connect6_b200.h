@@ -172,6 +172,8 @@ int64_t c6_engine_games_done(c6_engine* e);
 int c6_engine_records(c6_engine* e, c6_record* out, int64_t n); /* n = total_games */
 /* child_visits: total_games x 225 x 225 (i32, -1 = occupied / no entry), root_n / root_w: total_games x 225 */
 int c6_engine_trace(c6_engine* e, int32_t* child_visits, int32_t* root_n, float* root_w);
+/* the same for one game (index = game id - first_game_id): child_visits 225 x 225, root_n / root_w 225 */
+int c6_engine_trace_game(c6_engine* e, int64_t game, int32_t* child_visits, int32_t* root_n, float* root_w);
 /* node-pool invariant check of every resident game; returns the number of violations (-1 on error);
  * detail (may be NULL): 16 x {game<<32|code, a, b, c} */
 long long c6_engine_validate(c6_engine* e, unsigned long long* detail);

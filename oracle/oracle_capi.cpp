@@ -379,6 +379,52 @@ double oracle_default_policy_many(int num_iter, uint32_t seed, uint32_t first_ga
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Batch forms for the BASELINE configs[2] sizes (16M boards, 1M playouts): bit-packed boards in the engine's layout
+// (n x 16 u32: words 0-7 black, 8-15 white, bit 16*row+col), unpacked here and fed to the same search() / rollout.
+static Board board_from_packed(const uint32_t* w) {
+    Board b = empty_board();
+    for (int r = 0; r < BOARD_SIZE; ++r)
+        for (int c = 0; c < BOARD_SIZE; ++c) {
+            const int bit = 16 * r + c;
+            if ((w[bit >> 5] >> (bit & 31)) & 1u) b[r][c] = Player::Black;
+            if ((w[8 + (bit >> 5)] >> (bit & 31)) & 1u) b[r][c] = Player::White;
+        }
+    return b;
+}
+void oracle_search_batch_packed(const uint32_t* boards, int64_t n, int8_t* winners, int n_threads) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([=]() {
+            for (int64_t i = t; i < n; i += n_threads) winners[i] = (int8_t)search(board_from_packed(boards + i * 16));
+        });
+    for (auto& x : th) x.join();
+}
+void oracle_playout(uint32_t seed, uint64_t playout, int* winner, int* stones, int8_t* final_board);
+void oracle_playout_batch(uint32_t seed, uint64_t first, int64_t n, int8_t* winners, uint8_t* stones, uint32_t* boards, int n_threads) {
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([=]() {
+            for (int64_t i = t; i < n; i += n_threads) {
+                int w, s;
+                int8_t fb[BOARD_CAPACITY];
+                oracle_playout(seed, first + (uint64_t)i, &w, &s, fb);
+                winners[i] = (int8_t)w, stones[i] = (uint8_t)s;
+                if (boards) {
+                    uint32_t* o = boards + i * 16;
+                    for (int j = 0; j < 16; ++j) o[j] = 0;
+                    for (int c = 0; c < BOARD_CAPACITY; ++c) {
+                        const int bit = 16 * (c / BOARD_SIZE) + c % BOARD_SIZE;
+                        if (fb[c] < 0) o[bit >> 5] |= 1u << (bit & 31);
+                        if (fb[c] > 0) o[8 + (bit >> 5)] |= 1u << (bit & 31);
+                    }
+                }
+            }
+        });
+    for (auto& x : th) x.join();
+}
+
 int oracle_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 // 16M-board style batch win check (config 3a): boards as int8 [n][225]

@@ -89,6 +89,8 @@ def oracle():
         L.oracle_default_policy_many.restype = C.c_double
         L.oracle_default_policy_many.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(OracleDpOut)]
         L.oracle_search_batch.argtypes = [C.POINTER(C.c_int8), C.c_int64, C.POINTER(C.c_int8), C.c_int]
+        L.oracle_search_batch_packed.argtypes = [C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_int8), C.c_int]
+        L.oracle_playout_batch.argtypes = [C.c_uint32, C.c_uint64, C.c_int64, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int]
         _oracle = L
     return _oracle
 

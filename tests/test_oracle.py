@@ -125,8 +125,6 @@ def check_against_trace(g, winner, finished, moves, cv, rn, rw):
 
 @pytest.mark.parametrize("case", load("selfplay_traces.json"), ids=lambda c: c["name"])
 def test_oracle_reproduces_committed_traces(case):
-    if case["num_simulation"] >= 800:
-        pytest.skip("800-simulation trace is replayed by the GPU suite; too slow for the CPU suite budget")
     for g in case["games"]:
         out, cv, rn, rw = run_oracle_case(case, g)
         check_against_trace(g, out.winner, out.finished, [out.moves[i] for i in range(out.n_moves)], cv, rn, rw)

@@ -117,21 +117,27 @@ def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, 
 # win detection / playouts (BASELINE configs[2])
 # ---------------------------------------------------------------------------------------------
 def test_win_check_random_boards():
+    """BASELINE configs[2] / SURVEY 8d (3a) at its full size: 16,777,216 random boards (cells iid over {Black, None, White}),
+    every winner compared with the oracle's search() (threaded batch call on the bit-packed boards)."""
     L, O = c6lib.product(), c6lib.oracle()
-    n = 1 << 17
+    n = 1 << 24
     ms = C.c_float()
     boards = np.zeros((n, 16), dtype=np.uint32)
     winners = np.zeros(n, dtype=np.int8)
     assert L.c6_bench_win_check(n, 0xC6, 1, 0, C.byref(ms), boards.ctypes.data_as(C.POINTER(C.c_uint32)),
                                 winners.ctypes.data_as(C.POINTER(C.c_int8)), n) == 0, L.c6_last_error()
-    cells = c6lib.unpack_boards(boards)
+    cells = c6lib.unpack_boards(boards[:1 << 16])
     # generator sanity: three symbols, roughly uniform
     frac = [(cells == v).mean() for v in (-1, 0, 1)]
     assert all(abs(f - 1 / 3) < 0.01 for f in frac), frac
     ow = np.zeros(n, dtype=np.int8)
-    O.oracle_search_batch(cells.ctypes.data_as(C.POINTER(C.c_int8)), n, ow.ctypes.data_as(C.POINTER(C.c_int8)), 0)
-    assert np.array_equal(winners, ow)
-    assert len(set(ow.tolist())) == 3  # all three outcomes occur
+    O.oracle_search_batch_packed(boards.ctypes.data_as(C.POINTER(C.c_uint32)), n, ow.ctypes.data_as(C.POINTER(C.c_int8)), 0)
+    assert np.array_equal(winners, ow), f"{int((winners != ow).sum())} of {n} winners differ, first at {int(np.argmax(winners != ow))}"
+    assert len(set(ow[:1 << 16].tolist())) == 3  # all three outcomes occur
+    # the unpacked entry point of the oracle (the restatement proper) agrees with the packed one on a slice
+    ow2 = np.zeros(1 << 16, dtype=np.int8)
+    O.oracle_search_batch(cells.ctypes.data_as(C.POINTER(C.c_int8)), 1 << 16, ow2.ctypes.data_as(C.POINTER(C.c_int8)), 0)
+    assert np.array_equal(ow2, ow[:1 << 16])
 
 
 def test_win_check_reference_vectors():
@@ -192,8 +198,10 @@ def test_win_check_empty_batch():
 
 
 def test_playouts_match_oracle():
+    """1,048,576 random playouts compared end to end (winner, stone count, final board) with the oracle's
+    rollout on the same Philox stream."""
     L, O = c6lib.product(), c6lib.oracle()
-    n, first = 4096, 123456789012
+    n, first = 1 << 20, 123456789012
     ms = C.c_float()
     w = np.zeros(n, dtype=np.int8)
     s = np.zeros(n, dtype=np.uint8)
@@ -202,19 +210,22 @@ def test_playouts_match_oracle():
     assert L.c6_bench_playouts(first, n, 0xC6, 1, 0, C.byref(ms), w.ctypes.data_as(C.POINTER(C.c_int8)),
                                s.ctypes.data_as(C.POINTER(C.c_uint8)), b.ctypes.data_as(C.POINTER(C.c_uint32)), n, C.byref(tot)) == 0, L.c6_last_error()
     assert tot.value == int(s.astype(np.int64).sum())
-    cells = c6lib.unpack_boards(b)
-    for i in range(0, n, 8):
-        ow, os_ = C.c_int(), C.c_int()
-        ob = np.zeros(225, dtype=np.int8)
-        O.oracle_playout(0xC6, first + i, C.byref(ow), C.byref(os_), ob.ctypes.data_as(C.POINTER(C.c_int8)))
-        assert (w[i], s[i]) == (ow.value, os_.value), i
-        assert np.array_equal(cells[i], ob), i
-    # property at scale: the winner is the colour of the last stone, stone counts follow the turn rule
-    for i in range(n):
-        if w[i] != 0:
-            last = s[i] - 1
-            turn = -1 if last == 0 else (1 if ((last - 1) // 2) % 2 == 0 else -1)
-            assert w[i] == turn
+    ow, os_, ob = np.zeros(n, dtype=np.int8), np.zeros(n, dtype=np.uint8), np.zeros((n, 16), dtype=np.uint32)
+    O.oracle_playout_batch(0xC6, first, n, ow.ctypes.data_as(C.POINTER(C.c_int8)), os_.ctypes.data_as(C.POINTER(C.c_uint8)),
+                           ob.ctypes.data_as(C.POINTER(C.c_uint32)), 0)
+    assert np.array_equal(w, ow) and np.array_equal(s, os_)
+    assert np.array_equal(b, ob)
+    # the single-playout entry point (unpacked board) agrees on a few
+    cells = c6lib.unpack_boards(b[:64])
+    for i in range(0, 64, 8):
+        w1, s1 = C.c_int(), C.c_int()
+        b1 = np.zeros(225, dtype=np.int8)
+        O.oracle_playout(0xC6, first + i, C.byref(w1), C.byref(s1), b1.ctypes.data_as(C.POINTER(C.c_int8)))
+        assert (w[i], s[i]) == (w1.value, s1.value) and np.array_equal(cells[i], b1)
+    # property: the winner is the colour of the last stone, stone counts follow the turn rule
+    last = s.astype(np.int64) - 1
+    turn = np.where(last == 0, -1, np.where(((last - 1) // 2) % 2 == 0, 1, -1))
+    assert np.all((w == 0) | (w == turn))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -406,6 +417,72 @@ def test_engine_reproduces_golden_traces(case):
     assert (st.sims, st.sum_ck, st.sum_cleaf, st.sum_depth) == (tot["sims"], tot["sum_ck"], tot["sum_cleaf"], tot["sum_depth"])
 
 
+_HEADLINE = json.load(open(os.path.join(_GOLDEN, "selfplay_headline.json")))
+
+
+@pytest.mark.parametrize("case", _HEADLINE, ids=lambda c: c["name"])
+def test_headline_whole_games_in_full_engine(case):
+    """Whole games at the headline configuration (800 simulations per stone, eps .25, RandomEvaluator) and 64 whole games at 50
+    simulations, played INSIDE a 4,096-slot engine with slot refill: the golden game ids are scattered among filler games
+    (some start in a refilled slot), and every stone, root visit count, root value sum (bits) and child-visit checksum must
+    equal the committed oracle trace (tests/golden/make_headline.py)."""
+    L = c6lib.product()
+    total, slots = case["total_games"], case["slots"]
+    cfg = c6lib.make_config(num_simulation=case["num_simulation"], epsilon=case["epsilon"], dirichlet_alpha=case["dirichlet_alpha"],
+                            c_puct=case["c_puct"], seed=case["seed"], evaluator=EVAL_PHILOX, slots=slots, trace=1, log2_records=18,
+                            tie_break=case["tie_break"])
+    e = L.c6_engine_create(C.byref(cfg))
+    assert e, L.c6_last_error()
+    try:
+        assert L.c6_engine_start(e, 0, total) == 0, L.c6_last_error()
+        assert L.c6_engine_run_device(e) == 0, L.c6_last_error()
+        rec = (c6lib.Record * total)()
+        assert L.c6_engine_records(e, rec, total) == 0, L.c6_last_error()
+        st = c6lib.Stats()
+        assert L.c6_engine_stats(e, C.byref(st)) == 0
+        assert st.games_done == total
+        assert st.peak_rec <= (1 << 18)
+        cv = np.zeros((225, 225), dtype=np.int32)
+        rn = np.zeros(225, dtype=np.int32)
+        rw = np.zeros(225, dtype=np.float32)
+        for want in case["games"]:
+            g = want["game_id"]
+            r = rec[g]
+            m = r.n_moves
+            got = [r.moves[i] for i in range(m)]
+            if got != want["moves"]:
+                first = next((i for i in range(min(m, len(want["moves"]))) if got[i] != want["moves"][i]), min(m, len(want["moves"])))
+                raise AssertionError(f"{case['name']} game {g}: stones diverge at {first}: engine {got[first:first + 3]} oracle {want['moves'][first:first + 3]}")
+            assert (r.winner, r.finished, r.game_id) == (want["winner"], 1, g)
+            assert L.c6_engine_trace_game(e, g, cv.ctypes.data_as(C.POINTER(C.c_int32)), rn.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          rw.ctypes.data_as(C.POINTER(C.c_float))) == 0, L.c6_last_error()
+            assert rn[:m].tolist() == want["root_visit"], g
+            assert rw[:m].view(np.uint32).tolist() == want["root_qsum_bits"], g
+            assert [int((cv[i].astype(np.int64) * np.arange(1, 226)).sum()) for i in range(m)] == want["child_visit_checksum"], g
+        # every filler game is a legal finished game too
+        for g in range(total):
+            r = rec[g]
+            assert r.finished == 1 and r.game_id == g and len({r.moves[i] for i in range(r.n_moves)}) == r.n_moves
+    finally:
+        L.c6_engine_destroy(e)
+
+
+def test_first_level_visits_spread_over_the_board():
+    """with the uniform tie-break the first stone of 10,000 two-simulation games (= the child the second
+    simulation picked among 225 exactly tied ones) is spread over the whole board; in lowest-index mode it is always cell 0."""
+    L = c6lib.product()
+    n = 10000
+    rec = (c6lib.Record * n)()
+    cfg = c6lib.make_config(num_simulation=2, epsilon=0.25, seed=9, evaluator=EVAL_PHILOX, slots=2048, max_moves=1, log2_records=10)
+    assert L.c6_self_play_device(C.byref(cfg), 0, n, rec, None) == 0, L.c6_last_error()
+    cnt = np.bincount([rec[g].moves[0] for g in range(n)], minlength=225)
+    assert cnt.min() > 0 and cnt.max() < 4 * n / 225, (cnt.min(), cnt.max())
+    assert abs(cnt[0] - n / 225) < 6 * np.sqrt(n / 225)
+    cfg.tie_break = 0
+    assert L.c6_self_play_device(C.byref(cfg), 0, 64, rec, None) == 0, L.c6_last_error()
+    assert all(rec[g].moves[0] == 0 for g in range(64))
+
+
 def test_sharded_equals_unsharded():
     """Records are a pure function of (seed, game id): two half-shards == one run."""
     from pyconnect6 import sharded
@@ -499,8 +576,7 @@ def test_reference_catch2_suite_full():
     against this library."""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "test_cppbind")
-    if not os.path.exists(exe):
-        pytest.skip("tests/_build/test_cppbind not prebuilt (reference tree was not mounted at build time)")
+    assert os.path.exists(exe), "tests/_build/test_cppbind is missing: __graft_entry__.build() makes it where /root/reference is mounted, and it travels with the snapshot"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "All tests passed" in r.stdout
@@ -614,8 +690,7 @@ def test_reference_cpp_sample_runs():
     2 simulations, debug transcript), prebuilt by build() against the reference's header."""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "sample_cpp")
-    if not os.path.exists(exe):
-        pytest.skip("tests/_build/sample_cpp not prebuilt (reference tree was not mounted at build time)")
+    assert os.path.exists(exe), "tests/_build/sample_cpp is missing: __graft_entry__.build() makes it where /root/reference is mounted, and it travels with the snapshot"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Winner : " in r.stdout and "0 A B C D E F G H I J K L M N O" in r.stdout
