@@ -444,6 +444,7 @@ int c6_engine_host_times(c6_engine* e, double* wait_seconds, double* callback_se
         *callback_seconds = e->eng->host_callback_seconds();
     });
 }
+long long c6_engine_host_blocked_waits(c6_engine* e) { return e->eng->host_blocked_waits(); }
 int c6_engine_kernel_times(c6_engine* e, double* sims_kernel_ms, long long* sims_kernel_launches) {
     return guarded([&] {
         *sims_kernel_ms = e->eng->sims_kernel_ms();
@@ -719,12 +720,12 @@ int c6_probe_math(const double* xs, double* logs, double* exps, int n, int devic
 #include <thread>
 
 namespace {
-// Minimal persistent fork-join pool for the sample evaluator (a user evaluator would bring its own).
-// Workers spin briefly on the generation counter before sleeping: the engine calls the evaluator every
-// few tens of microseconds in steady state, and a futex wake-up per call would cost more than the fill.
+// Minimal persistent fork-join pool for the sample evaluators (a user evaluator would bring its own).  Workers poll the
+// generation counter for the host's polling budget (c6::host_spin_budget_us(): 200 us with cores to spare, 5 us when
+// several ranks share the box) and then sleep on a condition variable.
 class ForkJoin {
    public:
-    explicit ForkJoin(int n) : n_(n), spin_limit_(env_int("C6_SAMPLE_SPIN", 20000)) {
+    explicit ForkJoin(int n) : n_(n), spin_us_(env_int("C6_SAMPLE_SPIN_US", c6::host_spin_budget_us())) {
         for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
     }
     ~ForkJoin() {
@@ -746,7 +747,10 @@ class ForkJoin {
         }
         if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         f(0);
-        while (left_.load(std::memory_order_acquire) != 0) cpu_relax();
+        const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
+        while (left_.load(std::memory_order_acquire) != 0) {
+            if (std::chrono::steady_clock::now() < until) cpu_relax(); else std::this_thread::yield();
+        }
     }
 
    private:
@@ -758,9 +762,9 @@ class ForkJoin {
     void loop(int t) {
         unsigned long seen = 0;
         for (;;) {
-            int spins = 0;
+            const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
             while (gen_.load(std::memory_order_acquire) == seen) {
-                if (++spins < spin_limit_) {
+                if (std::chrono::steady_clock::now() < until) {
                     cpu_relax();
                 } else {
                     std::unique_lock<std::mutex> l(m_);
@@ -775,7 +779,7 @@ class ForkJoin {
             left_.fetch_sub(1, std::memory_order_release);
         }
     }
-    int n_, spin_limit_;
+    int n_, spin_us_;
     std::vector<std::thread> th_;
     std::mutex m_;
     std::condition_variable cv_;
@@ -784,6 +788,17 @@ class ForkJoin {
     std::atomic<int> left_{0}, sleepers_{0};
     bool stop_ = false;
 };
+
+// the pool shared by the sample evaluators: at most 4 threads (more compete with the engine's host thread and the CUDA
+// driver's own on a 16-vCPU box, profiles/e2e4, e2e5), and never more than this rank's share of the host cores
+ForkJoin& sample_pool() {
+    static ForkJoin pool(env_int("C6_SAMPLE_THREADS", std::max(1, std::min(c6::host_cores_per_rank(), 4))));
+    return pool;
+}
+std::mutex& sample_pool_mutex() {  // the pool is shared: callers from several engines take turns
+    static std::mutex m;
+    return m;
+}
 }  // namespace
 
 // U[-1,1) values and policies from a counter hash of the flat element index (two 32-bit multiplies per float,
@@ -794,10 +809,13 @@ static inline uint32_t sample_mix(uint32_t x) {
     return x;
 }
 static inline float sample_unit(uint32_t x) { return (float)(int)(x >> 8) * (1.0f / 8388608.0f) - 1.0f; }
+static void sample_fill_scalar(uint32_t base, float* out, size_t lo, size_t hi) {
+    for (size_t e = lo; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+}
 #if defined(__GNUC__) && defined(__x86_64__)
 #include <immintrin.h>
 __attribute__((target("avx2")))
-static void sample_fill_flat(uint32_t base, float* out, size_t lo, size_t hi) {
+static void sample_fill_avx2(uint32_t base, float* out, size_t lo, size_t hi) {
     size_t e = lo;
     for (; e < hi && ((uintptr_t)(out + e) & 31u); ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
     const __m256i step = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
@@ -815,14 +833,43 @@ static void sample_fill_flat(uint32_t base, float* out, size_t lo, size_t hi) {
     for (; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
     _mm_sfence();
 }
-#else
-static void sample_fill_flat(uint32_t base, float* out, size_t lo, size_t hi) {
-    for (size_t e = lo; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+// policy = f(board): reads every board cell and overwrites it in place (cached read-modify-write: the evaluator of a
+// real network reads its input).  p = 1/2 - board/4 + cell pattern/1024 — cheap on purpose: the leg measures the path.
+__attribute__((target("avx2")))
+static void reading_fill_avx2(float* pol, size_t lo, size_t hi, float* acc_out) {
+    size_t e = lo;
+    float acc = 0.f;
+    for (; e < hi && ((uintptr_t)(pol + e) & 31u); ++e) acc += pol[e], pol[e] = 0.5f - 0.25f * pol[e] + (float)(e & 1023u) * (1.0f / 1048576.0f);
+    __m256 vacc = _mm256_setzero_ps();
+    const __m256 half = _mm256_set1_ps(0.5f), q = _mm256_set1_ps(-0.25f), sc = _mm256_set1_ps(1.0f / 1048576.0f);
+    const __m256i step = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7), mask = _mm256_set1_epi32(1023);
+    for (; e + 8 <= hi; e += 8) {
+        const __m256 b = _mm256_load_ps(pol + e);
+        vacc = _mm256_add_ps(vacc, b);
+        const __m256 pat = _mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_and_si256(_mm256_add_epi32(_mm256_set1_epi32((int)(uint32_t)e), step), mask)), sc);
+        _mm256_store_ps(pol + e, _mm256_add_ps(_mm256_add_ps(half, _mm256_mul_ps(q, b)), pat));
+    }
+    float tmp[8];
+    _mm256_storeu_ps(tmp, vacc);
+    for (float t : tmp) acc += t;
+    for (; e < hi; ++e) acc += pol[e], pol[e] = 0.5f - 0.25f * pol[e] + (float)(e & 1023u) * (1.0f / 1048576.0f);
+    *acc_out = acc;
 }
+static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+#else
+static const bool g_have_avx2 = false;
+static void sample_fill_avx2(uint32_t, float*, size_t, size_t) {}
+static void reading_fill_avx2(float*, size_t, size_t, float*) {}
 #endif
+static void reading_fill_scalar(float* pol, size_t lo, size_t hi, float* acc_out) {
+    float acc = 0.f;
+    for (size_t e = lo; e < hi; ++e) acc += pol[e], pol[e] = 0.5f - 0.25f * pol[e] + (float)(e & 1023u) * (1.0f / 1048576.0f);
+    *acc_out = acc;
+}
 static void sample_fill(uint32_t base, float* values, float* policies, int lo, int hi) {
     for (int n = lo; n < hi; ++n) values[n] = sample_unit(sample_mix((base ^ 0x5bd1e995u) + (uint32_t)n));
-    sample_fill_flat(base * 0x9E3779B1u, policies, (size_t)lo * 225, (size_t)hi * 225);
+    // runtime dispatch: the AVX2 body must not run on an x86-64 host without AVX2
+    (g_have_avx2 ? sample_fill_avx2 : sample_fill_scalar)(base * 0x9E3779B1u, policies, (size_t)lo * 225, (size_t)hi * 225);
 }
 
 extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
@@ -830,11 +877,61 @@ extern "C" void c6_sample_random_callback(int player, float* values, float* poli
     const uint32_t base = (call_no.fetch_add(1) * 0x9E3779B9u) ^ ((uint32_t)(player + 2) << 28);
     static const int pool_min = env_int("C6_SAMPLE_POOL_MIN", 512);
     if (len < pool_min) return sample_fill(base, values, policies, 0, len);
-    // a few workers: more compete with the engine's two host threads and the CUDA driver's own on the 16-vCPU
-    // B200 box (profiles/e2e4, e2e5)
-    static ForkJoin pool(env_int("C6_SAMPLE_THREADS", (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 4u))));
-    static std::mutex one_at_a_time;  // the pool is shared: callers from several engines take turns
-    std::lock_guard<std::mutex> l(one_at_a_time);
+    ForkJoin& pool = sample_pool();
+    std::lock_guard<std::mutex> l(sample_pool_mutex());
     const int nt = pool.size();
     pool.run([&](int t) { sample_fill(base, values, policies, (int)((long long)len * t / nt), (int)((long long)len * (t + 1) / nt)); });
 }
+
+// The second sample evaluator: every board is read (value = mean stone colour of the board as seen by `player`, priors a
+// function of the cell) and overwritten in place.
+extern "C" void c6_sample_reading_callback(int player, float* values, float* policies, int len) {
+    auto fill = [&](int lo, int hi) {
+        for (int n = lo; n < hi; ++n) {
+            float acc = 0.f;
+            (g_have_avx2 ? reading_fill_avx2 : reading_fill_scalar)(policies, (size_t)n * 225, (size_t)(n + 1) * 225, &acc);
+            values[n] = (float)player * acc * (1.0f / 225.0f);
+        }
+    };
+    static const int pool_min = env_int("C6_SAMPLE_POOL_MIN", 512);
+    if (len < pool_min) return fill(0, len);
+    ForkJoin& pool = sample_pool();
+    std::lock_guard<std::mutex> l(sample_pool_mutex());
+    const int nt = pool.size();
+    pool.run([&](int t) { fill((int)((long long)len * t / nt), (int)((long long)len * (t + 1) / nt)); });
+}
+
+// Pin the calling thread (and the threads it creates afterwards: the sample pool, the engine's launcher) to the CPUs of the
+// NUMA node the GPU hangs off, so that pinned evaluator buffers are first-touched next to it.  Returns the node, or -1 when
+// the topology is not exposed (single node, containers without /sys PCI NUMA data): then nothing is changed.
+#include <sched.h>
+#include <fstream>
+extern "C" int c6_bind_host_to_device_numa(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    int node = -1;
+    {
+        std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+        if (!(f >> node) || node < 0) return -1;
+    }
+    std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    std::string list;
+    if (!(f >> list) || list.empty()) return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_cpus = 0;
+    for (size_t i = 0; i < list.size();) {
+        char* end = nullptr;
+        long a = std::strtol(list.c_str() + i, &end, 10), b = a;
+        if (end == list.c_str() + i) break;
+        if (*end == '-') b = std::strtol(end + 1, &end, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET((int)c, &set), ++n_cpus;
+        i = (size_t)(end - list.c_str()) + (*end == ',' ? 1 : 0);
+        if (*end != ',') break;
+    }
+    if (n_cpus == 0 || sched_setaffinity(0, sizeof set, &set) != 0) return -1;
+    return node;
+}
+extern "C" int c6_host_cores_per_rank(void) { return c6::host_cores_per_rank(); }
+extern "C" int c6_host_spin_budget_us(void) { return c6::host_spin_budget_us(); }

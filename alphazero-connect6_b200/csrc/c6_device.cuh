@@ -87,8 +87,7 @@ __device__ __forceinline__ void xh_insert(Slot* idx, uint32_t Imask, uint32_t ep
     __stcg(reinterpret_cast<uint4*>(&idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), val, epoch));
 }
 
-struct Leaf {
-    uint32_t B[8], W[8];
+struct Leaf {  // the board itself is in the warp's stage (WarpStage::B / W)
     uint64_t key;
     int stones;
     uint32_t rec;

@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
                 expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             } else if (EVAL == EVAL_DET) {
                 EvHash<false> ev;
-                ev.init(L, Zs, lane);
+                ev.init(L, st.B, st.W, Zs, lane);
                 expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             } else {
                 EvHash<true> ev;
-                ev.init(L, Zs, lane);
+                ev.init(L, st.B, st.W, Zs, lane);
                 expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
             load_cursor(gs, cs);
             if (gs.need_eval) {
                 Leaf L;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) L.B[j] = gs.leafB[j], L.W[j] = gs.leafW[j];
+                if (lane < 8) st.B[lane] = gs.leafB[lane], st.W[lane] = gs.leafW[lane];
+                __syncwarp();
                 L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth, L.last_bit = gs.leaf_last;
                 const float* region = D.batch + (size_t)g0 * 8 * (CELLS + 1);
                 EvBatch ev;
@@ -188,9 +188,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
             terminal_leaf<false>(D, w, st, L);
             need = 0;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lane == j) gs.leafB[j] = L.B[j], gs.leafW[j] = L.W[j];
+        if (lane < 8) gs.leafB[lane] = st.B[lane], gs.leafW[lane] = st.W[lane];
         if (lane == 0) {
             gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key, gs.leaf_last = L.last_bit;
             gs.need_eval = need;
@@ -467,8 +465,11 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         } else {
             C6_CUDA(cudaStreamCreateWithFlags(&gr.s, cudaStreamNonBlocking));
         }
-        C6_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming));
+        // blocking-sync event: a thread that waits on it sleeps in the driver instead of spinning (callback path:
+        // the calling thread waits for a group's leaf batch; eight ranks on one host must not burn eight cores on it)
+        C6_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming | cudaEventBlockingSync));
     }
+    spin_us_ = host_spin_budget_us();
     C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
     if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
         const size_t nb = G * 8 * (CELLS + 1) * sizeof(float);
@@ -591,6 +592,30 @@ static inline void cpu_relax() {
 }
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Host cores this process may keep busy: hardware threads divided by the number of ranks sharing the box
+// (LOCAL_WORLD_SIZE under torchrun; C6_LOCAL_RANKS overrides).
+int host_cores_per_rank() {
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int ranks = 1;
+    for (const char* name : {"C6_LOCAL_RANKS", "LOCAL_WORLD_SIZE"})
+        if (const char* v = std::getenv(name)) {
+            if (*v && std::atoi(v) > 0) {
+                ranks = std::atoi(v);
+                break;
+            }
+        }
+    return std::max(1, hw / ranks);
+}
+// How long a host thread may poll before it blocks (C6_SPIN_US overrides): with cores to spare polling is the
+// fastest hand-over; with 4 cores per rank (8 ranks on a 32-CPU box) every polling thread takes a core from the
+// evaluator, so it blocks almost at once.
+int host_spin_budget_us() {
+    if (const char* v = std::getenv("C6_SPIN_US"))
+        if (*v) return std::max(0, std::atoi(v));
+    return host_cores_per_rank() >= 8 ? 200 : 5;
+}
+
 // Enqueue for group p: [H2D of `len` evaluated boards] -> k_step(do_back, do_front) [-> k_gather].
 void Engine::group_issue(int p, size_t len, bool do_back, bool do_front) {
     Dev& D = d_->dev;
@@ -622,6 +647,7 @@ void Engine::group_issue(int p, size_t len, bool do_back, bool do_front) {
             k_publish<<<1, 1, 0, gr.s>>>(D, p, gr.seq);
             launches_ += 1;
         }
+        C6_CUDA(cudaEventRecord(gr.ev, gr.s));
     }
     C6_CUDA(cudaGetLastError());
 }
@@ -636,13 +662,16 @@ size_t Engine::group_eval(int p, Callback cb) {
     const double t0 = now_s();
     volatile int* hs = d_->h_sync + 4 * p;
     const int want = gr.seq;
-    for (unsigned spins = 1; hs[2] != want; ++spins) {
+    // bounded poll of the sequence number the gather kernel publishes, then a blocking wait on the event recorded
+    // behind it (the thread sleeps in the driver; a failed kernel surfaces as the event's error)
+    const double spin_until = t0 + 1e-6 * spin_us_;
+    while (hs[2] != want) {
         cpu_relax();
-        if ((spins & 0xFFFFu) == 0) {  // a failed kernel never publishes: look at the stream now and then
+        if (now_s() >= spin_until) {
             if (abort_.load(std::memory_order_relaxed)) throw std::runtime_error("c6: wave aborted");
-            cudaError_t q = cudaStreamQuery(gr.s);
-            if (q != cudaSuccess && q != cudaErrorNotReady) C6_CUDA(q);
-            if (q == cudaSuccess && hs[2] != want) throw std::runtime_error("c6: leaf batch was never published");
+            C6_CUDA(cudaEventSynchronize(gr.ev));
+            if (hs[2] != want) throw std::runtime_error("c6: leaf batch was never published");
+            host_blocked_waits_ += 1;
         }
     }
     const double t1 = now_s();
@@ -686,9 +715,10 @@ void Engine::waves_callback_threaded(Callback cb, int waves) {
     abort_.store(false);
     std::exception_ptr launcher_error;
     auto wait_for = [&](std::atomic<int>& a, int want) {
-        for (int spins = 0; a.load(std::memory_order_acquire) < want; ++spins) {
+        const double until = now_s() + 1e-6 * spin_us_;
+        while (a.load(std::memory_order_acquire) < want) {
             if (abort_.load(std::memory_order_relaxed)) return false;
-            if (spins < 4096) cpu_relax(); else std::this_thread::yield();
+            if (now_s() < until) cpu_relax(); else std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         return true;
     };

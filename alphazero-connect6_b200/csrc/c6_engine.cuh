@@ -164,6 +164,8 @@ class Engine {
     long long kernel_launches() const { return launches_; }
     double host_wait_seconds() const { return host_wait_s_; }
     double host_callback_seconds() const { return host_callback_s_; }
+    long long host_blocked_waits() const { return host_blocked_waits_; }
+    int host_spin_us() const { return spin_us_; }
     // timed_steps_device() brackets every launch of the fused search kernel with its own pair of CUDA events on
     // the engine stream: cumulative milliseconds and launch count (bench.py's roofline denominator)
     double sims_kernel_ms() const { return sims_kernel_ms_; }
@@ -198,6 +200,8 @@ class Engine {
     std::vector<cudaEvent_t> kev_;  // event pairs of the timed region in flight
     bool time_kernels_ = false;
     double host_wait_s_ = 0, host_callback_s_ = 0;  // callback path: time blocked on the GPU / inside the user Callback
+    long long host_blocked_waits_ = 0;              // waits that outlasted the polling budget and slept in the driver
+    int spin_us_ = 200;                             // polling budget of a host-side wait (host_spin_budget_us())
     std::atomic<bool> cancel_{false};
 };
 
@@ -218,5 +222,8 @@ void launch_probe_math32(const float* d_xs, float* d_lg, float* d_ex, int n, cud
 void launch_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* d_out, int n, cudaStream_t s);
 
 const char* last_error();
+// host cores this process may keep busy (hardware threads / ranks sharing the box) and the polling budget derived from it
+int host_cores_per_rank();
+int host_spin_budget_us();
 
 }  // namespace c6

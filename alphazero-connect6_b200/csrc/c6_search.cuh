@@ -82,6 +82,7 @@ struct WarpStage {
         float lw[8][32];      // select: log2 Gamma draw of child k, then its softmax weight, then its PUCT score
         uint32_t pos[8][32];  // expand: record index of child k
     };
+    uint32_t B[8], W[8];  // bit boards of the node the descent stands on / of the leaf being expanded (warp-uniform data)
     uint32_t empty[8];  // empty-cell mask of the current node, one board word each
     uint8_t cell[256];  // expand: bit position of the empty cell of rank k; select: ranks whose draw needs the slow path
     // fused kernel only: what this simulation's descent has already read of the records on its path, so that backup
@@ -120,6 +121,12 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 }
 #ifndef C6_CHILD_CG
 #define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
+#endif
+#ifndef C6_EV_UNROLL
+#define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
+#endif
+#ifndef C6_EV_UNROLL
+#define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
 #endif
 #ifndef C6_NOISE_UNROLL
 #define C6_NOISE_UNROLL 1
@@ -177,7 +184,39 @@ __device__ __forceinline__ Rec rec_of(const uint4& v) {
 }
 __device__ __forceinline__ uint4 bits_of(const Rec& r) { return make_uint4((uint32_t)r.n, __float_as_uint(r.w), __float_as_uint(r.p), r.link); }
 
+// One round pair of the noise draw of a select step: children k and k + 32 of this lane share a Philox block.
+template <int NOISE>
+__device__ __forceinline__ void noise_rounds(const Dev& D, const Cursor& cs, WarpStage<NOISE>& st, const MathTab& mt, int depth, int C,
+                                             int lane, int& k, int kend, float& lmax, unsigned& pend) {
+    const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
+    if (NOISE == 1) {
+#pragma unroll 1
+        for (; k < kend; k += 64) {
+            const Philox4 r = philox4x32_10(cs.sim_index, (uint32_t)depth, (uint32_t)(((k >> 6) << 5) | lane), 0u, nk0, cs.game_id);
+            float l0, l1;
+            const bool ok0 = gamma_log2_fast(mt, D.gp, r.x, r.y, l0);
+            const bool ok1 = gamma_log2_fast(mt, D.gp, r.z, r.w, l1);
+            st.lw[0][k] = l0;
+            if (ok0) lmax = fmaxf(lmax, l0); else pend |= 1u << (k >> 5);
+            if (k + 32 < C) {
+                st.lw[0][k + 32] = l1;
+                if (ok1) lmax = fmaxf(lmax, l1); else pend |= 2u << (k >> 5);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (; k < kend; k += 64)
+            for (int kk = k; kk < C && kk <= k + 32; kk += 32) {
+                const float l = gamma_large_log2(D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)kk, nk0, cs.game_id);
+                st.lw[0][kk] = l;
+                lmax = fmaxf(lmax, l);
+            }
+    }
+}
+
 // FUSED: called from k_sims_device, where the same warp runs descent, expansion and backup of a simulation back to back.
+// The board of the node the descent stands on lives in the warp's stage (st.B / st.W, warp-uniform data: one copy per warp
+// instead of sixteen registers per lane).
 template <int NOISE, bool FUSED = false>
 __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf& L, WarpStage<NOISE>& st, const MathTab& mt) {
     const bool tie_philox = D.tie_break != 0;
@@ -185,8 +224,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1;
     const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) L.B[j] = g.B[j], L.W[j] = g.W[j];
+    if (lane < 8) st.B[lane] = g.B[lane], st.W[lane] = g.W[lane];
     L.key = g.key;
     L.stones = g.stones;
     L.last_bit = 0;
@@ -204,26 +242,53 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
         const int turn = turn_of(L.stones);
         cs.sum_ck += (uint32_t)C;
         uint32_t chosen_bit = 0, child = 0;
+        __syncwarp();  // st.B / st.W of this node are in place
+        if (lane < 8) st.empty[lane] = ~(st.B[lane] | st.W[lane]) & (lane < 7 ? 0x7FFF7FFFu : 0x00007FFFu);
         if (C == 1) {  // single child: taken without scoring (:254-257)
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                uint32_t e = ~(L.B[j] | L.W[j]) & valid_mask(j);
+                const uint32_t e = st.empty[j];
                 if (e) chosen_bit = 32 * j + (__ffs((int)e) - 1);
             }
             child = w.lnk[r.link & Lm];
             r = load_rec(&w.rec[child & Rm]);
         } else {
-            // memory phase: the link run, then the child records, ceil(C/32) requests of each kind in flight per lane
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
-            stage_children(w, st, r.link, C, lane, Rm, Lm);
-            // visit sum (:265)
+            // Memory phases and noise phase interleaved.  The link run, then the child records, are two dependent trips
+            // (ceil(C/32) requests of each kind in flight per lane, cp.async straight into the stage).  The Dirichlet(alpha; C)
+            // draw made at every node with C >= 2 (:262,283) depends on nothing but C: log2 Gamma draws keyed (sim, depth,
+            // child k), two per Philox block.  A node that has been descended through before (N >= 2) has a visited child,
+            // so its noise is certainly needed: the draws run under the two trips.  A node with N == 1 has usually no
+            // visited child (see below) and waits for the records first.
+            const bool early = NOISE != 0 && r.n >= 2;
+            float lmax = -3.0e38f;
+            unsigned pend = 0;
             int s_local = 0;
+            int kn = lane;  // next rank this lane draws
 #pragma unroll 1
-            for (int k = lane; k < C; k += 32) s_local += (int)st.child[0][k].x;
+            for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
+#pragma unroll 1
+            for (int part = 0; part < 3; ++part) {
+                if (NOISE && (part < 2 ? early : (!early && s_local != 0))) noise_rounds(D, cs, st, mt, depth, C, lane, kn, part == 0 ? min(C, 64) : C, lmax, pend);
+                if (part == 2) break;
+                cp_async_wait_all();
+                if (part == 0) {
+#pragma unroll 1
+                    for (int k = lane; k < C; k += 32) {
+#if C6_CHILD_CG
+                        cp_async16_cg(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+#else
+                        cp_async16(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+#endif
+                    }
+                } else {
+                    // visit sum (:265)
+#pragma unroll 1
+                    for (int k = lane; k < C; k += 32) s_local += (int)st.child[0][k].x;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
+                    for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
+                }
+            }
             const float visit_sum = (float)s_local;
             uint32_t bb = NIL;
             if (s_local == 0) {
@@ -232,61 +297,33 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 // too and then picks uniformly (:291-295).  One tie draw instead of C Gamma draws and the PUCT pass.
                 bb = tie_philox ? tie_pick(cs.sim_index, (uint32_t)depth, D.seed, cs.game_id, (uint32_t)C) : 0u;
             } else {
-                // arithmetic phase 1: the Dirichlet(alpha; C) draw made at every node with C >= 2 (:262,283): log2 Gamma
-                // draws keyed (sim, depth, child k), two per Philox block (children k and k + 32 of a lane).  Pass A tries
-                // the hot branch of the sampler for every child; the ~5% of draws that need the other branch or another
-                // trial are listed and finished together, one per lane, in pass B (one diverged excursion per step);
-                // pass C turns the draws into softmax weights 2^(L - Lmax) and sums them in a fixed order: per lane the
-                // children k = lane, lane + 32, ..., then a butterfly.
+                // Pass B: the ~5% of draws that need the sampler's other branch or another trial are listed and finished
+                // together, one per lane (one diverged excursion per step); pass C turns the draws into softmax weights
+                // 2^(L - Lmax) and sums them in a fixed order: per lane the children k = lane, lane + 32, ..., then a butterfly.
                 float inv = 0.f;
                 if (NOISE) {
-                    const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
-                    float lmax = -3.0e38f;
-                    unsigned pend = 0;
-                    if (NOISE == 1) {
-#pragma unroll 1
-                        for (int k = lane; k < C; k += 64) {
-                            const Philox4 r = philox4x32_10(cs.sim_index, (uint32_t)depth, (uint32_t)(((k >> 6) << 5) | lane), 0u, nk0, cs.game_id);
-                            float l0, l1;
-                            const bool ok0 = gamma_log2_fast(mt, D.gp, r.x, r.y, l0);
-                            const bool ok1 = gamma_log2_fast(mt, D.gp, r.z, r.w, l1);
-                            st.lw[0][k] = l0;
-                            if (ok0) lmax = fmaxf(lmax, l0); else pend |= 1u << (k >> 5);
-                            if (k + 32 < C) {
-                                st.lw[0][k + 32] = l1;
-                                if (ok1) lmax = fmaxf(lmax, l1); else pend |= 2u << (k >> 5);
-                            }
-                        }
-                        if (__any_sync(FULL, pend != 0)) {
-                            // list the pending ranks (any order): exclusive prefix sum of the per-lane counts
-                            const int mycnt = __popc(pend);
-                            int incl = mycnt;
+                    if (NOISE == 1 && __any_sync(FULL, pend != 0)) {
+                        // list the pending ranks (any order): exclusive prefix sum of the per-lane counts
+                        const int mycnt = __popc(pend);
+                        int incl = mycnt;
 #pragma unroll
-                            for (int off = 1; off < 32; off <<= 1) {
-                                const int o = __shfl_up_sync(FULL, incl, off);
-                                if (lane >= off) incl += o;
-                            }
-                            const int np = __shfl_sync(FULL, incl, 31);
-                            int at = incl - mycnt;
-                            while (pend) {
-                                const int i = __ffs((int)pend) - 1;
-                                pend &= pend - 1;
-                                st.cell[at++] = (uint8_t)(32 * i + lane);
-                            }
-                            __syncwarp();
-#pragma unroll 1
-                            for (int i = lane; i < np; i += 32) {
-                                const uint32_t k = st.cell[i];
-                                const float l = gamma_log2_full(mt, D.gp.b, D.gp.inv_a, D.gp.c1, D.gp.am1, cs.sim_index, (uint32_t)depth, k, nk0,
-                                                                cs.game_id);
-                                st.lw[0][k] = l;
-                                lmax = fmaxf(lmax, l);
-                            }
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const int o = __shfl_up_sync(FULL, incl, off);
+                            if (lane >= off) incl += o;
                         }
-                    } else {
+                        const int np = __shfl_sync(FULL, incl, 31);
+                        int at = incl - mycnt;
+                        while (pend) {
+                            const int i = __ffs((int)pend) - 1;
+                            pend &= pend - 1;
+                            st.cell[at++] = (uint8_t)(32 * i + lane);
+                        }
+                        __syncwarp();
 #pragma unroll 1
-                        for (int k = lane; k < C; k += 32) {
-                            const float l = gamma_large_log2(D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)k, nk0, cs.game_id);
+                        for (int i = lane; i < np; i += 32) {
+                            const uint32_t k = st.cell[i];
+                            const float l = gamma_log2_full(mt, D.gp.b, D.gp.inv_a, D.gp.c1, D.gp.am1, cs.sim_index, (uint32_t)depth, k,
+                                                            D.seed ^ DOMAIN_NOISE, cs.game_id);
                             st.lw[0][k] = l;
                             lmax = fmaxf(lmax, l);
                         }
@@ -309,30 +346,42 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 // children share it
                 float bs = 0.f;
                 uint32_t cnt = 0;
+                const float sqrt_s = sqrtf(visit_sum);  // visit_sum >= 1 here
 #pragma unroll 1
-                for (int k = lane; k < C; k += 32) {
-                    const uint4 ch = st.child[0][k];
-                    const int cn = (int)ch.x;
-                    const float cw = __uint_as_float(ch.y), cp = __uint_as_float(ch.z);
+                for (int k = lane; k - lane < C; k += 32) {  // every lane runs every round (warp vote inside)
+                    const bool in = k < C;
+                    const uint4 ch = st.child[0][in ? k : 0];
+                    const int cn = in ? (int)ch.x : 0;
+                    const float cp = __uint_as_float(ch.z);
                     float nz = 0.f;
-                    if (NOISE) nz = st.lw[0][k] * inv;
-                    const float visit = (float)cn;
-                    // q_value (:77-79) and u (:270).  The IEEE division's fast path is left for a subroutine whenever an
-                    // operand is zero — and an unvisited child has W = 0 — so both divisions are fed stand-in operands in
-                    // those lanes and the exact result (0, or the zero numerator itself) is selected afterwards: same
-                    // values, no calls (r01k capture: 5 % of all instructions)
-                    const bool seen = cn > 0 && cw != 0.f;
-                    const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
-                    const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
-                    const float prob = eps * nz + one_m_eps * cp;                     // :269
-                    const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
-                    const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
-                    const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
-                    const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
-                    const float sc = (turn < 0 ? -q : q) + cpuct * u;                 // :272-280
-                    st.lw[0][k] = sc;
-                    if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k, cnt = 1;
-                    else if (sc == bs) cnt += 1;
+                    if (NOISE) nz = st.lw[0][in ? k : 0] * inv;
+                    const float prob = eps * nz + one_m_eps * cp;  // :269
+                    float sc;
+                    if (__all_sync(FULL, cn == 0)) {
+                        // a round of unvisited children (the rule below the root): q = 0 (:77-79), sqrt(S - 0) = sqrt(S) for all of
+                        // them and the division by 1 + 0 is the identity — the same bits without the two divisions and the root
+                        sc = (turn < 0 ? -0.f : 0.f) + cpuct * (prob * sqrt_s);
+                    } else {
+                        const float cw = __uint_as_float(ch.y);
+                        const float visit = (float)cn;
+                        // q_value (:77-79) and u (:270).  The IEEE division's fast path is left for a subroutine whenever an
+                        // operand is zero — and an unvisited child has W = 0 — so both divisions are fed stand-in operands in
+                        // those lanes and the exact result (0, or the zero numerator itself) is selected afterwards: same
+                        // values, no calls (r01k capture: 5 % of all instructions)
+                        const bool seen = cn > 0 && cw != 0.f;
+                        const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
+                        const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
+                        const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
+                        const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
+                        const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
+                        const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
+                        sc = (turn < 0 ? -q : q) + cpuct * u;  // :272-280
+                    }
+                    if (in) {
+                        st.lw[0][k] = sc;
+                        if (bb == NIL || sc > bs) bs = sc, bb = (uint32_t)k, cnt = 1;
+                        else if (sc == bs) cnt += 1;
+                    }
                 }
                 // maximum over the warp: score, lowest rank holding it, number of children holding it
 #pragma unroll
@@ -369,14 +418,12 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 r.n = (int32_t)ch.x, r.w = __uint_as_float(ch.y), r.p = __uint_as_float(ch.z), r.link = ch.w;
             }
             chosen_bit = kth_empty(st, bb, lt, lane);
-            __syncwarp();  // the stage is rewritten by the next step
         }
         // Simulate::simulate_in (LC/policy/simulate/mod.rs:262-274)
-        const uint32_t wj = chosen_bit >> 5, m = 1u << (chosen_bit & 31);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t mm = (j == (int)wj) ? m : 0u;
-            if (turn < 0) L.B[j] |= mm; else L.W[j] |= mm;
+        __syncwarp();  // every lane is done with the stage of this step
+        if (lane == 0) {
+            uint32_t* col = turn < 0 ? st.B : st.W;
+            col[chosen_bit >> 5] |= 1u << (chosen_bit & 31);
         }
         L.key ^= ldz(&w.Z[(turn > 0 ? 256 : 0) + chosen_bit]);
         L.stones += 1;
@@ -413,17 +460,17 @@ __device__ __forceinline__ void backup(const Dev& D, Warp& w, WarpStage<NOISE>& 
 }
 
 // full-board leaf (:338-348): no evaluator call, no visit increment, value = winner.  Reached a handful
-// of times per game at most: the win check is kept out of line (arguments by value, so nothing of the
-// caller is forced onto the stack) and out of the hot instruction stream.
-__device__ __noinline__ float terminal_value(uint4 b0, uint4 b1, uint4 w0, uint4 w1) {
-    const uint32_t B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const uint32_t W[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+// of times per game at most: the win check is kept out of line and out of the hot instruction stream.
+__device__ __noinline__ float terminal_value(const uint32_t* sb, const uint32_t* sw) {
+    uint32_t B[8], W[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) B[j] = sb[j], W[j] = sw[j];
     return (float)win_check(B, W);
 }
 template <bool FUSED, int NOISE>
 __device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, WarpStage<NOISE>& st, const Leaf& L) {
-    const float v = terminal_value(make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]), make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]),
-                                   make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]), make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]));
+    __syncwarp();
+    const float v = terminal_value(st.B, st.W);
     backup<FUSED>(D, w, st, L.depth, v);
 }
 
@@ -442,12 +489,19 @@ struct EvPhilox {
     }
     // eight U[-1,1) draws of `cell` folded pairwise in plane order: {d0+d1, d2+d3, d4+d5, d6+d7}
     __device__ __forceinline__ void pairs(uint32_t cell, float (&t)[4]) const {
+#if C6_EV_UNROLL
+        // both Philox blocks in flight together: four independent multiply chains instead of two
+        const Philox4 a = philox4x32_10(sim, cell, 0u, 0, k0, k1), b = philox4x32_10(sim, cell, 1u, 0, k0, k1);
+        t[0] = u32_to_pm1(a.x) + u32_to_pm1(a.y), t[1] = u32_to_pm1(a.z) + u32_to_pm1(a.w);
+        t[2] = u32_to_pm1(b.x) + u32_to_pm1(b.y), t[3] = u32_to_pm1(b.z) + u32_to_pm1(b.w);
+#else
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
             Philox4 a = philox4x32_10(sim, cell, half, 0, k0, k1);
             const float lo = u32_to_pm1(a.x) + u32_to_pm1(a.y), hi = u32_to_pm1(a.z) + u32_to_pm1(a.w);
             if (half == 0) t[0] = lo, t[1] = hi; else t[2] = lo, t[3] = hi;
         }
+#endif
     }
     __device__ __forceinline__ float value() const {  // ((((((((0+v0)+v1)+..)+v7)/8 (:224)
         float sum = 0.f;
@@ -472,7 +526,7 @@ template <bool NEG>
 struct EvHash {
     uint64_t h[8];
     int lane;
-    __device__ __forceinline__ void init(const Leaf& L, const uint64_t* Z, int lane_) {
+    __device__ __forceinline__ void init(const Leaf& L, const uint32_t* sB, const uint32_t* sW, const uint64_t* Z, int lane_) {
         lane = lane_;
         const int turn = turn_of(L.stones);
 #pragma unroll
@@ -483,8 +537,8 @@ struct EvHash {
                 uint32_t bit = 32u * j + lane;
                 int r = (int)(bit >> 4), c = (int)(bit & 15), rr, cc;
                 sym_fwd(s, r, c, rr, cc);
-                if ((L.B[j] >> lane) & 1u) k ^= Z[rr * 16 + cc];
-                if ((L.W[j] >> lane) & 1u) k ^= Z[256 + rr * 16 + cc];
+                if ((sB[j] >> lane) & 1u) k ^= Z[rr * 16 + cc];
+                if ((sW[j] >> lane) & 1u) k ^= Z[256 + rr * 16 + cc];
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) k ^= __shfl_xor_sync(FULL, k, off);
@@ -559,16 +613,15 @@ struct EvBatch {
 // An unexpanded node that nothing links any more carries no state (N = 0, W = 0, its prior is overwritten by
 // the next expanding parent, :371), so a fresh record is equivalent.
 //
-// S1 + S2, out of line: rare (late-game deep paths), kept out of the hot instruction stream.  `cm0/cm1` = the
-// leaf's stones of colour m, `skip` = bit of a_d when rule F covers it (else NIL), `cell[k]` = bit position of the
+// S1 + S2, out of line: rare (late-game deep paths), kept out of the hot instruction stream.  `cm` = the
+// leaf's stones of colour m (a board in the warp's stage), `skip` = bit of a_d when rule F covers it (else NIL), `cell[k]` = bit position of the
 // leaf's empty cell of rank k.  `mine` / `res`: bit i = this lane's child k = 32 i + lane exists / already has a
 // record.  Returns the updated `res`; record indices go to pos[k].
 __device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint32_t epoch, const uint32_t* lnk, uint32_t Lm,
                                               const Rec* rec, uint32_t Rm, const uint64_t* Z, const GameState* gs, uint32_t* pos,
-                                              const uint32_t* empty, const uint8_t* cell, uint4 cm0, uint4 cm1, uint64_t key,
+                                              const uint32_t* empty, const uint8_t* cell, const uint32_t* cm, uint64_t key,
                                               int stones, uint32_t zoff, uint32_t skip, unsigned mine, unsigned res, int lane,
                                               int depth) {
-    const uint32_t cm[8] = {cm0.x, cm0.y, cm0.z, cm0.w, cm1.x, cm1.y, cm1.z, cm1.w};
     if (depth >= 3) {
         const uint32_t* rootcol = zoff ? gs->W : gs->B;
         int before = 0;  // empty cells of the leaf in the words below j
@@ -626,16 +679,9 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     // the key-table slot the leaf will be inserted at when the expansion is done: its first probe is in flight from here
     const uint32_t slot0 = hash_slot(L.key) & Im;
     const uint32_t slot0_epoch = __ldcg(&w.idx[slot0].epoch);
-    // remember the board for the collector, then only the empties are needed
-    if (lane < 16) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (lane == j) word = L.B[j];
-            if (lane == j + 8) word = L.W[j];
-        }
-        w.expB(D)[(size_t)ec * 16 + lane] = word;
-    }
+    // remember the board (st.B / st.W, contiguous) for the collector
+    __syncwarp();
+    if (lane < 16) w.expB(D)[(size_t)ec * 16 + lane] = lane < 8 ? st.B[lane] : st.W[lane - 8];
     // rule F applies when the last path stone has the colour of the stone the children add
     const bool sib = L.depth >= 1 && turn_of(L.stones - 1) == turn;
     const uint32_t lj = L.last_bit >> 5, lm = 1u << (L.last_bit & 31);
@@ -644,9 +690,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
         stage_children(w, st, w.rec[prec].link, C + 1, lane, Rm, Lm);
         __syncwarp();
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        if (lane == j) st.empty[j] = ~(L.B[j] | L.W[j]) & valid_mask(j);
+    if (lane < 8) st.empty[lane] = ~(st.B[lane] | st.W[lane]) & (lane < 7 ? 0x7FFF7FFFu : 0x00007FFFu);
     __syncwarp();
     const uint64_t key = L.key;
     // bit position of every child by rank, and r0 = rank of the last path stone among the empties of a sibling that
@@ -686,9 +730,7 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     {
         const uint32_t s1 = (uint32_t)L.stones + 1u;
         if (L.depth >= 3 || orphan_flag(*w.gs, cs, s1)) {
-            const uint4 cm0 = turn < 0 ? make_uint4(L.B[0], L.B[1], L.B[2], L.B[3]) : make_uint4(L.W[0], L.W[1], L.W[2], L.W[3]);
-            const uint4 cm1 = turn < 0 ? make_uint4(L.B[4], L.B[5], L.B[6], L.B[7]) : make_uint4(L.W[4], L.W[5], L.W[6], L.W[7]);
-            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, cm0, cm1, key,
+            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, turn < 0 ? st.B : st.W, key,
                                L.stones, zoff, sib ? L.last_bit : NIL, mine, res, lane, L.depth);
         }
     }

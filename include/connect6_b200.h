@@ -222,8 +222,19 @@ int c6_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* out, in
 /* pinned host<->device copy bandwidth in GB/s: H2D alone, D2H alone, both at once (per direction) */
 int c6_probe_pcie(int64_t bytes, int iters, int device, double* h2d_gbs, double* d2h_gbs, double* both_gbs);
 
-/* sample host evaluator (random values/policies), the twin of Connect6/sample/cpp/main.cpp:6-28 */
+/* sample host evaluator (random values/policies), the twin of Connect6/sample/cpp/main.cpp:6-28 (write-only, like it) */
 void c6_sample_random_callback(int player, float* values, float* policies, int len);
+/* a second sample evaluator that READS every board before overwriting it (value = mean stone colour, priors f(cell)) */
+void c6_sample_reading_callback(int player, float* values, float* policies, int len);
+/* pin the calling thread (and threads it creates later) to the CPUs of the GPU's NUMA node; returns the node or -1
+ * (topology not exposed: nothing changed) */
+int c6_bind_host_to_device_numa(int device);
+/* host cores this process may keep busy (hardware threads / LOCAL_WORLD_SIZE) and the polling budget (microseconds) a
+ * host-side wait gets before it blocks (C6_SPIN_US overrides) */
+int c6_host_cores_per_rank(void);
+int c6_host_spin_budget_us(void);
+/* callback path, cumulative: waits of the calling thread that outlasted the polling budget and slept in the driver */
+long long c6_engine_host_blocked_waits(c6_engine* e);
 
 #ifdef __cplusplus
 }

@@ -299,7 +299,7 @@ def test_selfplay_deep_trees_late_game(evaluator, cbname, sims, c_puct, n_stones
     rec, cv, rn, rw, st = run_engine(n_games, cbname if evaluator == EVAL_CALLBACK else None, first_id=300, prefixes=prefixes,
                                      num_simulation=sims, epsilon=0.0, c_puct=c_puct, seed=seed, evaluator=evaluator)
     compare_games(n_games, rec, cv, rn, rw, 300, cbname, 0, sims, 0.0, seed, 0, c_puct=c_puct, prefixes=prefixes)
-    assert st.sum_depth > 2 * st.sims  # the trees really are deep
+    assert st.sum_depth > 1.9 * st.sims  # the trees really are deep
 
 
 @pytest.mark.parametrize("evaluator,cbname,sims,c_puct,n_stones", [
