@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
         Warp w = make_warp(D, g, Zs, lane);
         if (w.gs->status != ST_ACTIVE) continue;
         Cursor cs;
-        load_cursor(*w.gs, cs);
+        load_cursor(*w.gs, cs, st, lane);
         if (lane == 0) st.rootrec = bits_of(load_rec(&w.rec[w.gs->root]));
         __syncwarp();
         for (int s = 0; s < D.num_sim && !cs.err; ++s) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
             }
             cs.sim_index += 1;
         }
-        store_cursor(D, *w.gs, cs, lane);
+        store_cursor(D, *w.gs, cs, st, lane);
 #if C6_FUSE_MOVE_END
         // the stone itself, in the same launch: this warp's collection overlaps the other warps' searches instead of
         // running as a latency-bound kernel of its own
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
     if (do_back && gs.status == ST_ACTIVE) {
         if (D.num_sim > 0) {
             Cursor cs;
-            load_cursor(gs, cs);
+            load_cursor(gs, cs, st, lane);
             if (gs.need_eval) {
                 Leaf L;
                 if (lane < 8) st.B[lane] = gs.leafB[lane], st.W[lane] = gs.leafW[lane];
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
                 expand_leaf<false>(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
-            store_cursor(D, gs, cs, lane);
+            store_cursor(D, gs, cs, st, lane);
             if (gs.status == ST_ACTIVE && lane == 0) {
                 gs.sims_this_move += 1;
                 gs.need_eval = 0;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
     int flag = 0;
     if (gs.status == ST_ACTIVE && D.num_sim > 0) {
         Cursor cs;
-        load_cursor(gs, cs);
+        load_cursor(gs, cs, st, lane);
         Leaf L;
         descend<NOISE>(D, w, cs, L, st, mt);
         int need = 1;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
             gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key, gs.leaf_last = L.last_bit;
             gs.need_eval = need;
         }
-        store_cursor(D, gs, cs, lane);
+        store_cursor(D, gs, cs, st, lane);
         flag = need ? (turn_of(L.stones) < 0 ? 1 : 2) : 0;
     } else if (lane == 0) {
         gs.need_eval = 0;

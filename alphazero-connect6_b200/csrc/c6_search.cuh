@@ -22,36 +22,51 @@
 
 namespace c6 {
 
-// Per-move copy of the mutable game bookkeeping, identical in every lane of the warp.
+// Per-move copy of the mutable game bookkeeping, identical in every lane of the warp: what the inner loops need in
+// registers; the rest — bounds that do not change during a move and the statistics counters — sits in the warp's stage
+// (WarpStage::meta, lane 0 updates the counters).  The r02a capture had these spilled: 219 M local loads / stores per
+// launch whose 128-byte lines competed with the node pool for L1 and L2 (22 % of the L2 sectors), and long-scoreboard
+// stalls on lines as trivial as `sum_ck += C`.
 struct Cursor {
-    uint32_t rec_head, lnk_head, exp_count, sim_index;
-    uint32_t orph_win, stones0;  // GameState::orph bits of stone counts stones0 .. stones0 + 31 (stones0 = the root's)
-    uint32_t rec_tail, lnk_tail, epoch, game_id;
-    uint32_t sum_ck, sum_cleaf, sum_depth, evals, sims;
-    uint32_t peak_rec, peak_lnk;
+    uint32_t rec_head, lnk_head, exp_count, sim_index, game_id;
     int err;
 };
+struct WarpMeta {
+    uint32_t rec_tail, lnk_tail, epoch;
+    uint32_t orph_win, stones0;  // GameState::orph bits of stone counts stones0 .. stones0 + 31 (stones0 = the root's)
+    uint32_t sum_ck, sum_cleaf, sum_depth, evals, sims, peak_rec, peak_lnk;
+};
 
-__device__ __forceinline__ void load_cursor(const GameState& g, Cursor& c) {
+template <class Stage>
+__device__ __forceinline__ void load_cursor(const GameState& g, Cursor& c, Stage& st, int lane) {
     c.rec_head = g.rec_head, c.lnk_head = g.lnk_head, c.exp_count = g.exp_count, c.sim_index = g.sim_index;
-    c.rec_tail = g.rec_tail, c.lnk_tail = g.lnk_tail, c.epoch = g.epoch, c.game_id = g.game_id;
-    c.sum_ck = 0, c.sum_cleaf = 0, c.sum_depth = 0, c.evals = 0, c.sims = 0;
-    c.peak_rec = g.peak_rec, c.peak_lnk = g.peak_lnk;
+    c.game_id = g.game_id;
     c.err = 0;
-    c.stones0 = (uint32_t)g.stones;
-    const uint32_t wi = c.stones0 >> 5;
-    c.orph_win = __funnelshift_r(g.orph[wi], wi + 1 < 8 ? g.orph[wi + 1] : 0u, c.stones0 & 31);
+    __syncwarp();
+    if (lane == 0) {
+        WarpMeta& m = st.meta;
+        m.rec_tail = g.rec_tail, m.lnk_tail = g.lnk_tail, m.epoch = g.epoch;
+        m.sum_ck = 0, m.sum_cleaf = 0, m.sum_depth = 0, m.evals = 0, m.sims = 0;
+        m.peak_rec = g.peak_rec, m.peak_lnk = g.peak_lnk;
+        m.stones0 = (uint32_t)g.stones;
+        const uint32_t wi = m.stones0 >> 5;
+        m.orph_win = __funnelshift_r(g.orph[wi], wi + 1 < 8 ? g.orph[wi + 1] : 0u, m.stones0 & 31);
+    }
+    __syncwarp();
 }
 // is some expanded node with `s1` stones flagged as having lost its expanded parents (GameState::orph)?
-__device__ __forceinline__ bool orphan_flag(const GameState& g, const Cursor& c, uint32_t s1) {
-    const uint32_t j = s1 - c.stones0;
-    return j < 32 ? ((c.orph_win >> j) & 1u) != 0 : ((g.orph[s1 >> 5] >> (s1 & 31)) & 1u) != 0;
+__device__ __forceinline__ bool orphan_flag(const GameState& g, const WarpMeta& m, uint32_t s1) {
+    const uint32_t j = s1 - m.stones0;
+    return j < 32 ? ((m.orph_win >> j) & 1u) != 0 : ((g.orph[s1 >> 5] >> (s1 & 31)) & 1u) != 0;
 }
-__device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const Cursor& c, int lane) {
+template <class Stage>
+__device__ __forceinline__ void store_cursor(const Dev& D, GameState& g, const Cursor& c, Stage& st, int lane) {
+    __syncwarp();
     if (lane == 0) {
+        const WarpMeta& m = st.meta;
         g.rec_head = c.rec_head, g.lnk_head = c.lnk_head, g.exp_count = c.exp_count, g.sim_index = c.sim_index;
-        g.sum_ck += c.sum_ck, g.sum_cleaf += c.sum_cleaf, g.sum_depth += c.sum_depth, g.evals += c.evals, g.sims += c.sims;
-        g.peak_rec = c.peak_rec, g.peak_lnk = c.peak_lnk;
+        g.sum_ck += m.sum_ck, g.sum_cleaf += m.sum_cleaf, g.sum_depth += m.sum_depth, g.evals += m.evals, g.sims += m.sims;
+        g.peak_rec = m.peak_rec, g.peak_lnk = m.peak_lnk;
         if (c.err) {
             g.status = ST_ERROR, g.err = c.err;
             atomicAdd(D.gcount + 2, 1ull);
@@ -90,6 +105,7 @@ struct WarpStage {
     uint4 prec[PATH_CACHE];
     uint32_t pidx[PATH_CACHE];
     uint4 rootrec;
+    WarpMeta meta;  // per-move bounds and statistics counters of the game (see Cursor)
 };
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -240,7 +256,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
         }
         const int C = CELLS - L.stones;
         const int turn = turn_of(L.stones);
-        cs.sum_ck += (uint32_t)C;
+        if (lane == 0) st.meta.sum_ck += (uint32_t)C;
         uint32_t chosen_bit = 0, child = 0;
         __syncwarp();  // st.B / st.W of this node are in place
         if (lane < 8) st.empty[lane] = ~(st.B[lane] | st.W[lane]) & (lane < 7 ? 0x7FFF7FFFu : 0x00007FFFu);
@@ -434,8 +450,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
     L.rec = cur;
     L.depth = depth;
     L.leaf_w = r.w, L.leaf_p = r.p;
-    cs.sum_depth += (uint32_t)depth;
-    cs.sims += 1;
+    if (lane == 0) st.meta.sum_depth += (uint32_t)depth, st.meta.sims += 1;
     __syncwarp();
 }
 
@@ -672,8 +687,9 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     const uint32_t zoff = turn > 0 ? 256u : 0u;
     const uint32_t link_base = cs.lnk_head;
     const uint32_t ec = cs.exp_count;
-    if (cs.lnk_head - cs.lnk_tail + (uint32_t)C > D.L) cs.err = ERR_LNK_FULL;
-    if (cs.rec_head - cs.rec_tail + (uint32_t)C > D.R) cs.err = ERR_REC_FULL;
+    const uint32_t rec_tail = st.meta.rec_tail, lnk_tail = st.meta.lnk_tail, epoch = st.meta.epoch;
+    if (cs.lnk_head - lnk_tail + (uint32_t)C > D.L) cs.err = ERR_LNK_FULL;
+    if (cs.rec_head - rec_tail + (uint32_t)C > D.R) cs.err = ERR_REC_FULL;
     if (ec + 1 > D.E) cs.err = ERR_EXP_FULL;
     if (cs.err) return;
     // the key-table slot the leaf will be inserted at when the expansion is done: its first probe is in flight from here
@@ -729,8 +745,8 @@ C6_UNROLL(C6_PRIOR_UNROLL)
     // rules S1 / S2 (warp-uniform test)
     {
         const uint32_t s1 = (uint32_t)L.stones + 1u;
-        if (L.depth >= 3 || orphan_flag(*w.gs, cs, s1)) {
-            res = resolve_rare(w.idx, Im, cs.epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, turn < 0 ? st.B : st.W, key,
+        if (L.depth >= 3 || orphan_flag(*w.gs, st.meta, s1)) {
+            res = resolve_rare(w.idx, Im, epoch, w.lnk, Lm, w.rec, Rm, D.Z, w.gs, &st.pos[0][0], st.empty, st.cell, turn < 0 ? st.B : st.W, key,
                                L.stones, zoff, sib ? L.last_bit : NIL, mine, res, lane, L.depth);
         }
     }
@@ -775,19 +791,21 @@ C6_UNROLL(C6_PRIOR_UNROLL)
         w.exp_rec(D)[ec] = L.rec;
         w.exp_key(D)[ec] = key;
         uint32_t pos = slot0;  // xh_insert with the first probe already answered (nothing else inserts in between)
-        if (slot0_epoch == cs.epoch) {
+        if (slot0_epoch == epoch) {
             pos = (pos + 1) & Im;
-            while (__ldcg(&w.idx[pos].epoch) == cs.epoch) pos = (pos + 1) & Im;
+            while (__ldcg(&w.idx[pos].epoch) == epoch) pos = (pos + 1) & Im;
         }
-        __stcg(reinterpret_cast<uint4*>(&w.idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), L.rec, cs.epoch));
+        __stcg(reinterpret_cast<uint4*>(&w.idx[pos]), make_uint4((uint32_t)key, (uint32_t)(key >> 32), L.rec, epoch));
     }
     cs.exp_count = ec + 1;
     cs.lnk_head = link_base + (uint32_t)C;
     cs.rec_head = base;
-    cs.sum_cleaf += (uint32_t)C;
-    cs.evals += 1;
-    cs.peak_rec = max(cs.peak_rec, base - cs.rec_tail);
-    cs.peak_lnk = max(cs.peak_lnk, cs.lnk_head - cs.lnk_tail);
+    if (lane == 0) {
+        WarpMeta& m = st.meta;
+        m.sum_cleaf += (uint32_t)C, m.evals += 1;
+        m.peak_rec = max(m.peak_rec, base - rec_tail);
+        m.peak_lnk = max(m.peak_lnk, cs.lnk_head - lnk_tail);
+    }
     backup<STAGED>(D, w, st, L.depth, v);
 }
 

@@ -641,14 +641,18 @@ def test_cpp_play_with_matches_oracle():
     the oracle's MultiPolicy(AlphaZero, scripted White) with the same evaluator, seed and tie-break."""
     import subprocess
     import sys
-    white = [(2, 4), (9, 10), (14, 6), (13, 10), (13, 0), (1, 1), (4, 5), (2, 0), (8, 6), (12, 14)]  # collides with no Black stone (checked below)
     sims, eps, seed = 24, 0.25, 4242
     O = c6lib.oracle()
     p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1, c6lib.ORACLE_TIE[1], 0, 0, 0)
-    out = c6lib.OracleGameOut()
-    wm = (C.c_int * (2 * len(white)))(*[x for m in white for x in m])
-    O.oracle_play_with(c6lib.oracle_callback("neg_eval_callback"), C.byref(p), 0, wm, len(white), C.byref(out))
-    assert out.finished == 1  # the script does not collide with Black's stones
+    for attempt in range(50):  # a White script that does not collide with the stones Black turns out to play
+        rng = np.random.default_rng(attempt)
+        white = [(int(c) // 15, int(c) % 15) for c in rng.choice(225, size=10, replace=False)]
+        out = c6lib.OracleGameOut()
+        wm = (C.c_int * (2 * len(white)))(*[x for m in white for x in m])
+        O.oracle_play_with(c6lib.oracle_callback("neg_eval_callback"), C.byref(p), 0, wm, len(white), C.byref(out))
+        if out.finished == 1 and out.n_moves >= 12:
+            break
+    assert out.finished == 1
     want = [out.moves[i] for i in range(out.n_moves)]
     code = (
         "import ctypes as C, c6lib\n"
