@@ -68,6 +68,7 @@ typedef c6_play_result* (*c6_alloc_result)(int size);
 typedef int* (*c6_alloc_int)(int size);
 typedef float* (*c6_alloc_float)(int size);
 
+#ifndef C6_OMIT_REFERENCE_ABI /* define it when the reference's own connect6.hpp (which declares these) is included too */
 /* connect6.hpp:44-48 / lib.rs:19-58 — games driven by a user policy callback (host game loop). */
 c6_vec cpp_play(c6_policy_callback callback, c6_alloc_path alloc_path, c6_alloc_result alloc_result, bool debug,
                 int num_game_thread);
@@ -89,6 +90,7 @@ c6_vec_int test_with_raw_vec(c6_alloc_int allocator);
 c6_vec_int test_echo_raw_vec(int* ptr, int len, c6_alloc_int allocator);
 c6_vec_float test_echo_cppeval(int turn, int* boards, int len, c6_callback callback, c6_alloc_float allocator);
 c6_vec_int test_cpp_policy(float* board, c6_policy_callback callback, c6_alloc_int allocator);
+#endif /* C6_OMIT_REFERENCE_ABI */
 
 /* ------------------------------------------------------------------------------------------ */
 /* Part 2 — engine interface                                                                   */

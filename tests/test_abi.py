@@ -280,3 +280,72 @@ def build_reference_sample():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6/sample/cpp"), reason="reference tree not mounted")
 def test_reference_cpp_sample_links_against_our_library():
     assert os.path.exists(build_reference_sample())
+
+
+# ---------------------------------------------------------------------------------------------
+# More of the reference's own acceptance material, built IN PLACE where /root/reference is mounted (nothing is copied into
+# the repo); outputs go to tests/_build/ (git-ignored, travels to the GPU box with the snapshot) and the GPU suite runs them.
+# ---------------------------------------------------------------------------------------------
+BUILD_DIR = os.path.join(ROOT, "tests", "_build")
+REF_PY = {"ref_test_pybind.pyc": "/root/reference/Connect6/pybind/test_pybind/test_pybind.py",
+          "ref_random_policy.pyc": "/root/reference/Connect6/sample/python/random_policy.py"}
+
+
+def build_reference_python():
+    """The reference's Python acceptance test and sample, byte-compiled from where they lie (PB/test_pybind/test_pybind.py:16-49,
+    Connect6/sample/python/random_policy.py:28-37): the .pyc files are what the GPU box executes against our pyconnect6."""
+    import py_compile
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    out = []
+    for name, src in REF_PY.items():
+        out.append(py_compile.compile(src, cfile=os.path.join(BUILD_DIR, name), doraise=True))
+    return out
+
+
+DEVICE_OVERLOAD_EXE = os.path.join(BUILD_DIR, "device_overload")
+HOST_MIRROR_EXE = os.path.join(BUILD_DIR, "host_mirror")
+
+
+def _stale(exe, *srcs):
+    return not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(s) for s in (c6lib.LIB_PATH, *srcs))
+
+
+def build_device_overload():
+    """tests/cpp/device_overload.cu: the reference's own connect6.hpp (in place) + include/connect6_device.hpp, the opt-in
+    device-pointer Connect6::self_play overload, with a CUDA-kernel evaluator."""
+    src = os.path.join(ROOT, "tests", "cpp", "device_overload.cu")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if _stale(DEVICE_OVERLOAD_EXE, src, os.path.join(ROOT, "include", "connect6_device.hpp")):
+        cmd = ["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I", "/root/reference/Connect6/cppbind/headers",
+               "-I", os.path.join(ROOT, "include"), src, "-o", DEVICE_OVERLOAD_EXE, "-L", os.path.dirname(c6lib.LIB_PATH), "-lcppconnect6",
+               "-Xlinker", "-rpath=$ORIGIN/../../alphazero-connect6_b200/lib"]
+        subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
+    return DEVICE_OVERLOAD_EXE
+
+
+def build_host_mirror():
+    """tests/cpp/host_mirror.cpp: RandomEvaluator, AsyncAgent (generic and batched) and AlphaZero of the host-side mirror."""
+    src = os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    csrc = os.path.join(c6lib.PKG, "csrc")
+    if _stale(HOST_MIRROR_EXE, src, os.path.join(csrc, "connect6_alphazero.hpp"), os.path.join(csrc, "connect6_host.hpp")):
+        cmd = ["g++", "-std=c++17", "-O1", "-I", csrc, "-I", "/usr/local/cuda/include", src, "-o", HOST_MIRROR_EXE,
+               "-L", os.path.dirname(c6lib.LIB_PATH), "-lcppconnect6", "-Wl,-rpath,$ORIGIN/../../alphazero-connect6_b200/lib", "-pthread", "-ldl"]
+        subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=600)
+    return HOST_MIRROR_EXE
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6/pybind"), reason="reference tree not mounted")
+def test_reference_pybind_echo_test_runs_in_place():
+    """PB/test_pybind/test_pybind.py::test_echo_pyeval, the reference's own file run where it lies against our pyconnect6
+    (its other test, test_result_length, searches: the GPU suite runs the byte-compiled file)."""
+    env = dict(os.environ, PYTHONPATH=os.path.join(c6lib.PKG, "python"))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "/root/reference/Connect6/pybind/test_pybind/test_pybind.py",
+                        "-k", "test_echo_pyeval"], capture_output=True, text=True, env=env, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6"), reason="reference tree not mounted")
+def test_extra_acceptance_binaries_build():
+    assert all(os.path.exists(p) for p in build_reference_python())
+    assert os.path.exists(build_device_overload()) and os.path.exists(build_host_mirror())

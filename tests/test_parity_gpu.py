@@ -764,3 +764,71 @@ def test_torch_policy_value_net_drives_self_play():
     games = sharded.records_from_bytes(rec)
     assert all(g["n_moves"] == 12 and len(set(g["moves"])) == 12 for g in games)
     assert st.sims == 16 * 8 * 12 and st.evals > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own callers, unchanged: byte-compiled / compiled in place by __graft_entry__.build()
+# ---------------------------------------------------------------------------------------------
+_BUILD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build")
+_PYPKG = os.path.join(c6lib.PKG, "python")
+
+
+def test_reference_pybind_tests_run_unchanged():
+    """PB/test_pybind/test_pybind.py:16-49 (test_result_length: self_play 2 simulations x 2 games; test_echo_pyeval),
+    byte-compiled from the reference tree, imported and run against our pyconnect6."""
+    import subprocess
+    import sys
+    pyc = os.path.join(_BUILD, "ref_test_pybind.pyc")
+    assert os.path.exists(pyc), "tests/_build/ref_test_pybind.pyc is missing: __graft_entry__.build() makes it where /root/reference is mounted"
+    code = ("import importlib.machinery, importlib.util, sys\n"
+            f"loader = importlib.machinery.SourcelessFileLoader('ref_test_pybind', {pyc!r})\n"
+            "spec = importlib.util.spec_from_loader('ref_test_pybind', loader)\n"
+            "m = importlib.util.module_from_spec(spec); loader.exec_module(m)\n"
+            "tests = [n for n in dir(m) if n.startswith('test_')]\n"
+            "assert sorted(tests) == ['test_echo_pyeval', 'test_result_length'], tests\n"
+            "for n in tests: getattr(m, n)()\n"
+            "print('REFERENCE PYTESTS PASSED', len(tests))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=_PYPKG), timeout=600)
+    assert r.returncode == 0 and "REFERENCE PYTESTS PASSED 2" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_reference_python_sample_runs_unchanged():
+    """Connect6/sample/python/random_policy.py:28-37 (BASELINE configs[0] in its Python form: one game, random evaluator, 2
+    simulations, debug transcript), byte-compiled from the reference tree and executed as a script."""
+    import subprocess
+    import sys
+    pyc = os.path.join(_BUILD, "ref_random_policy.pyc")
+    assert os.path.exists(pyc), "tests/_build/ref_random_policy.pyc is missing: __graft_entry__.build() makes it where /root/reference is mounted"
+    r = subprocess.run([sys.executable, pyc], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=_PYPKG), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    last = r.stdout.strip().splitlines()[-1]
+    assert last.startswith("winner ") and ", len " in last, last
+    assert "0 A B C D E F G H I J K L M N O" in r.stdout and "remain" in r.stdout  # debug=True prints the game
+
+
+def test_device_pointer_overload_of_the_reference_cpp_api():
+    """include/connect6_device.hpp on top of the reference's own connect6.hpp: Connect6::self_play(DeviceCallback, ...) with a
+    CUDA-kernel evaluator (constant value .5 / prior .25); every stone must equal the oracle's game with const_eval_callback."""
+    import subprocess
+    exe = os.path.join(_BUILD, "device_overload")
+    assert os.path.exists(exe), "tests/_build/device_overload is missing: __graft_entry__.build() makes it where /root/reference is mounted"
+    games, sims, seed = 5, 12, 0x51
+    r = subprocess.run([exe, str(games), str(sims), str(seed)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("GAME")]
+    assert len(lines) == games
+    for g, l in enumerate(lines):
+        out, *_ = run_oracle(g, "const_eval_callback", 0, sims, 0.25, seed, 0)
+        assert int(l[1]) == out.winner and [int(x) for x in l[2:]] == [out.moves[i] for i in range(out.n_moves)], g
+    tail = r.stdout.strip().splitlines()[-1].split()
+    assert tail[0] == "CALLS" and int(tail[1]) > 0 and int(tail[5]) == 0  # boards on entry, values pre-zeroed
+
+
+def test_host_mirror_random_evaluator_and_async_agent():
+    """RandomEvaluator, AsyncAgent::run (generic thread-per-game form and the batched GPU form) and AlphaZero of the C++ mirror
+    of the reference's Rust API (async_agent/tests.rs:8-47, alphazero_policy/tests.rs:186-204)."""
+    import subprocess
+    exe = os.path.join(_BUILD, "host_mirror")
+    assert os.path.exists(exe), "tests/_build/host_mirror is missing: __graft_entry__.build() makes it"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "host mirror ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
