@@ -615,6 +615,40 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
     });
 }
 
+// Replay feed with DEVICE pointers: records (n_games x 240 B) and the exclusive prefix sum of their stone counts in HBM, the
+// four float32 tensors of the reference trainer's ReplayBuffer::sample layout out (cpp_weighted/ReplayBuffer.hpp:38-65).
+int c6_expand_records_device(const c6_record* d_records, const long long* d_row_offset, int n_games, float* d_winners, float* d_players,
+                             float* d_boards, float* d_positions, void* stream) {
+    return guarded([&] {
+        launch_expand_records(reinterpret_cast<const GameRecord*>(d_records), d_row_offset, n_games, d_winners, d_players, d_boards,
+                              d_positions, static_cast<cudaStream_t>(stream));
+        CK(cudaGetLastError());
+    });
+}
+// The same from host records into host arrays sized for sum(n_moves) samples (tests, small feeds); returns the sample count in *n_rows.
+int c6_expand_records_host(const c6_record* records, int n_games, int device, float* winners, float* players, float* boards,
+                           float* positions, long long* n_rows) {
+    return guarded([&] {
+        CK(cudaSetDevice(device));
+        std::vector<long long> off((size_t)std::max(n_games, 0) + 1, 0);
+        for (int g = 0; g < n_games; ++g) off[g + 1] = off[g] + records[g].n_moves;
+        const long long rows = off[std::max(n_games, 0)];
+        if (n_rows) *n_rows = rows;
+        if (n_games <= 0 || rows == 0) return;
+        DevBuf<c6_record> dr((size_t)n_games);
+        DevBuf<long long> doff((size_t)n_games);
+        DevBuf<float> dw((size_t)rows), dp((size_t)rows), dpos((size_t)rows), db((size_t)rows * 225);
+        CK(cudaMemcpy(dr.p, records, (size_t)n_games * sizeof(c6_record), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(doff.p, off.data(), (size_t)n_games * sizeof(long long), cudaMemcpyHostToDevice));
+        launch_expand_records(reinterpret_cast<const GameRecord*>(dr.p), doff.p, n_games, dw.p, dp.p, db.p, dpos.p, 0);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(winners, dw.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(players, dp.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(positions, dpos.p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(boards, db.p, (size_t)rows * 225 * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
 int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
                            c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats) {
     static_assert(sizeof(c6_record) == sizeof(GameRecord), "record layout");

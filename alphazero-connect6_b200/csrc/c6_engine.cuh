@@ -216,6 +216,9 @@ void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStre
 void launch_playouts(int64_t first, int64_t n, uint32_t seed, int8_t* d_winner, uint8_t* d_stones,
                      uint32_t* d_boards, cudaStream_t s);
 
+// replay feed (c6_replay.cu): packed records -> float32 training tensors in HBM, one warp per game
+void launch_expand_records(const GameRecord* d_rec, const long long* d_row_offset, int n_games, float* d_winners, float* d_players,
+                           float* d_boards, float* d_positions, cudaStream_t s);
 void launch_probe_gamma(double shape, uint32_t k0, uint32_t k1, float* d_out, int n, cudaStream_t s);
 void launch_probe_math(const double* d_xs, double* d_logs, double* d_exps, int n, cudaStream_t s);
 void launch_probe_math32(const float* d_xs, float* d_lg, float* d_ex, int n, cudaStream_t s);

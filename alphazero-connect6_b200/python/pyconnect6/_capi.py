@@ -132,6 +132,9 @@ def product():
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_uint64)]
         L.c6_default_policy_play.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.c_int, C.c_int, C.POINTER(Record),
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(DpStats)]
+        FP = C.POINTER(C.c_float)
+        L.c6_expand_records_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.c6_expand_records_host.argtypes = [C.POINTER(Record), C.c_int, C.c_int, FP, FP, FP, FP, C.POINTER(C.c_longlong)]
         L.c6_probe_gamma.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_int, C.c_int]
         L.c6_probe_math32.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int]
         L.c6_probe_tie.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_int, C.c_int]

@@ -68,3 +68,86 @@ def as_game_results(records):
             board[cell] = int(colours[s])
         out.append((int(winner[g]), path))
     return out
+
+
+class PackedBuffer:
+    """Drop-in for the reference's replay `Buffer` (AlphaZero/py_weighted/buffer.py:4-44: same constructor, `push_game`,
+    `sample`, `clear_half`, `__len__`, same retention rule: the newest `max_size` samples) that keeps samples packed —
+    (game, stone) pairs over 240-byte records — and expands only what `sample` returns.  `push_records` takes the engine's
+    packed records directly; `push_game` still accepts the nested `(winner, [(turn, board, (row, col)), ...])` form."""
+
+    def __init__(self, max_size, board_size, num_sample):
+        self.max_size, self.board_size, self.num_sample = max_size, board_size, num_sample
+        self._games = []                       # (winner, moves uint8[n])
+        self._index = np.zeros((0, 2), np.int64)  # live samples, oldest first: (game slot, stone number)
+
+    def __len__(self):
+        return len(self._index)
+
+    def _append(self, winner, moves):
+        slot = len(self._games)
+        self._games.append((int(winner), np.asarray(moves, dtype=np.uint8)))
+        new = np.stack([np.full(len(moves), slot, np.int64), np.arange(len(moves), dtype=np.int64)], axis=1)
+        self._index = np.concatenate([self._index, new])
+        if len(self._index) > self.max_size:
+            self._index = self._index[-self.max_size:]
+
+    def push_records(self, records):
+        winner, n_moves, moves = _fields(records)
+        for g in range(len(n_moves)):
+            self._append(winner[g], moves[g, :n_moves[g]])
+
+    def push_game(self, game_result):
+        win, path = game_result
+        self._append(win, [row * self.board_size + col for (_, _, (row, col)) in path])
+
+    def _expand(self, slot, stone):
+        winner, moves = self._games[slot]
+        colours = stone_colours(max(len(moves), 1))
+        board = [0] * CELLS
+        for s in range(stone):
+            board[int(moves[s])] = int(colours[s])
+        return winner, int(colours[stone]), board, int(moves[stone])
+
+    def contents(self):
+        """Every live sample, oldest first, in the reference buffer's element format (winner, player, board, position)."""
+        return [self._expand(int(g), int(s)) for g, s in self._index]
+
+    def sample(self):
+        index_set = np.random.choice(len(self._index), self.num_sample, replace=False)
+        wins, players, boards, policies = [], [], [], []
+        for i in index_set:
+            win, player, board, pos = self._expand(int(self._index[i, 0]), int(self._index[i, 1]))
+            wins.append(win), players.append(player), boards.append(board), policies.append(pos)
+        return wins, players, boards, policies
+
+    def clear_half(self):
+        self._index = self._index[len(self._index) // 2:]
+
+
+def training_tuples_device(records, device=0):
+    """The tuples of `training_tuples` as float32 torch tensors in HBM — (winners[N], players[N], boards[N, 225], positions[N]),
+    the layout of the reference trainer's `ReplayBuffer::sample` (cpp_weighted/ReplayBuffer.hpp:38-65) — expanded on the GPU
+    from the packed records (uint8 array / bytes, or a CUDA uint8 tensor that never leaves the device)."""
+    import torch
+    from . import _capi
+    L = _capi.product()
+    dev = torch.device("cuda", device)
+    if isinstance(records, torch.Tensor):
+        rec = records.to(dev).contiguous().view(torch.uint8).reshape(-1, RECORD_BYTES)
+    else:
+        rec = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint8).reshape(-1, RECORD_BYTES).copy()).to(dev)
+    n_games = rec.shape[0]
+    n_moves = rec[:, 1].to(torch.int64)
+    offsets = (torch.cumsum(n_moves, 0) - n_moves).contiguous()
+    rows = int(n_moves.sum().item())
+    winners = torch.empty(rows, dtype=torch.float32, device=dev)
+    players = torch.empty_like(winners)
+    positions = torch.empty_like(winners)
+    boards = torch.empty((rows, CELLS), dtype=torch.float32, device=dev)
+    if n_games and rows:
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if L.c6_expand_records_device(rec.data_ptr(), offsets.data_ptr(), n_games, winners.data_ptr(), players.data_ptr(), boards.data_ptr(),
+                                      positions.data_ptr(), stream) != 0:
+            raise RuntimeError(L.c6_last_error().decode())
+    return winners, players, boards, positions

@@ -213,6 +213,15 @@ typedef struct c6_dp_stats {
 int c6_default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, int64_t n_games, int max_moves, int device,
                            c6_record* out, int32_t* root_visit, int32_t* root_black_win, c6_dp_stats* stats);
 
+/* Replay-buffer feed (AlphaZero/cpp_weighted/ReplayBuffer.hpp:22-65, py_weighted/buffer.py:22-31): one sample per stone =
+ * (winner, player, board BEFORE the stone as 225 floats, position row*15+col), written as the four float32 tensors the
+ * reference trainer's sample() builds.  Device form: every pointer is a device pointer, d_row_offset[g] = number of stones of
+ * the games before g, `stream` a cudaStream_t (0 = default).  Host form: host pointers, arrays sized for sum(n_moves) rows. */
+int c6_expand_records_device(const c6_record* d_records, const long long* d_row_offset, int n_games, float* d_winners, float* d_players,
+                             float* d_boards, float* d_positions, void* stream);
+int c6_expand_records_host(const c6_record* records, int n_games, int device, float* winners, float* players, float* boards,
+                           float* positions, long long* n_rows);
+
 /* parity probes of the Dirichlet-noise sampler (tests): log2 of Gamma(shape) draw (7, 9, k = i) of the stream keyed
  * (k0, k1) exactly as a select step computes it; the engine's deterministic f32 log2 / exp2 and f64 log / exp on xs
  * (logs only where xs > 0); the uniform tie-break pick (sim = i, depth = i % 7) among `count` tied children */
