@@ -203,6 +203,7 @@ c6_vec cpp_self_play(c6_callback callback, c6_alloc_path alloc_path, c6_alloc_re
         base.log2_records = env_int("C6_LOG2_RECORDS", 18);
         base.evaluator = EVAL_CALLBACK;
         base.tie_break = env_int("C6_TIE_BREAK", 1);
+        base.virtual_loss = env_int("C6_VIRTUAL_LOSS", 1);  // opt-in multi-leaf mode (not the reference's sequential search)
         const int max_conc = env_int("C6_MAX_CONCURRENT", 8192);
         std::vector<GameRecord> rec((size_t)n);
         auto t0 = std::chrono::steady_clock::now();
@@ -381,7 +382,7 @@ void c6_default_config(c6_config* cfg) {
     Config d;
     cfg->num_simulation = d.num_simulation, cfg->epsilon = d.epsilon, cfg->dirichlet_alpha = d.dirichlet_alpha;
     cfg->c_puct = d.c_puct, cfg->seed = d.seed, cfg->device = 0, cfg->slots = 1, cfg->log2_records = d.log2_records;
-    cfg->evaluator = C6_EVAL_CALLBACK, cfg->trace = 0, cfg->max_moves = 0, cfg->tie_break = d.tie_break;
+    cfg->evaluator = C6_EVAL_CALLBACK, cfg->trace = 0, cfg->max_moves = 0, cfg->tie_break = d.tie_break, cfg->virtual_loss = 1;
 }
 const char* c6_last_error(void) { return g_err.c_str(); }
 int c6_device_count(void) {
@@ -394,7 +395,7 @@ static Config to_config(const c6_config* c) {
     cfg.num_simulation = c->num_simulation, cfg.epsilon = c->epsilon, cfg.dirichlet_alpha = c->dirichlet_alpha;
     cfg.c_puct = c->c_puct, cfg.seed = c->seed, cfg.device = c->device, cfg.slots = c->slots;
     cfg.log2_records = c->log2_records, cfg.evaluator = c->evaluator, cfg.trace = c->trace, cfg.max_moves = c->max_moves;
-    cfg.tie_break = c->tie_break;
+    cfg.tie_break = c->tie_break, cfg.virtual_loss = c->virtual_loss;
     return cfg;
 }
 c6_engine* c6_engine_create(const c6_config* cfg) {

@@ -16,7 +16,7 @@ struct Dev {
     uint32_t* expB;  // [G][Ecap][16] bitboards of expanded nodes (8 words black, 8 white)
     uint32_t* exp_rec;
     uint64_t* exp_key;
-    uint32_t* path;  // [G][232]
+    uint32_t* path;  // [G][K][232]: one row per leaf a game may have waiting
     GameState* gs;
     GameRecord* records;
     const uint64_t* Z;  // [2][256] Zobrist keys by bit position
@@ -44,6 +44,7 @@ struct Dev {
     uint32_t seed;
     int trace;
     int max_moves;
+    int K;          // Config::virtual_loss: leaves a game may have waiting at once (1 = the reference's schedule)
     int tie_break;  // 0: exact PUCT ties go to the lowest rank, 1: uniformly among the tied (Philox keyed (sim, depth))
 };
 
@@ -102,12 +103,13 @@ struct Warp {  // per-warp view of one game slot: hot bases as pointers, the res
     Slot* idx;
     GameState* gs;
     const uint64_t* Z;  // shared-memory copy
+    uint32_t* pth;      // the path row in use (the waiting leaf being descended to / expanded)
     int lane;
     int g;
     __device__ __forceinline__ uint32_t* expB(const Dev& D) const { return D.expB + (size_t)g * D.E * 16; }
     __device__ __forceinline__ uint32_t* exp_rec(const Dev& D) const { return D.exp_rec + (size_t)g * D.E; }
     __device__ __forceinline__ uint64_t* exp_key(const Dev& D) const { return D.exp_key + (size_t)g * D.E; }
-    __device__ __forceinline__ uint32_t* path(const Dev& D) const { return D.path + (size_t)g * 232; }
+    __device__ __forceinline__ uint32_t* path(const Dev&) const { return pth; }
 };
 
 __device__ __forceinline__ Warp make_warp(const Dev& D, int g, const uint64_t* Zs, int lane) {
@@ -117,6 +119,7 @@ __device__ __forceinline__ Warp make_warp(const Dev& D, int g, const uint64_t* Z
     w.idx = D.idx + (size_t)g * D.I;
     w.gs = D.gs + g;
     w.Z = Zs;
+    w.pth = D.path + (size_t)g * D.K * 232;
     w.lane = lane;
     w.g = g;
     return w;
@@ -143,7 +146,7 @@ __device__ inline void init_game(const Dev& D, Warp& w, uint32_t game_id) {
         g.game_id = game_id;
         g.epoch += 1;
         g.rec_head = 1, g.rec_tail = 0, g.lnk_head = 0, g.lnk_tail = 0, g.exp_count = 0;
-        g.sim_index = 0, g.sims_this_move = 0, g.n_moves = 0, g.need_eval = 0;
+        g.sim_index = 0, g.sims_this_move = 0, g.n_moves = 0, g.n_pend = 0;
         Rec r;
         r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
         store_rec(&w.rec[0], r);

@@ -128,12 +128,61 @@ __global__ void __launch_bounds__(32) k_external_move(Dev D, int slot, int cell)
     if (w.gs->status == ST_ACTIVE) external_move(D, w, bit_of_cell(cell));
 }
 
+// Device-evaluator path in multi-leaf mode (Config::virtual_loss = K > 1, opt-in): the same per-game work as k_sims_device on the
+// wave schedule of c6_search.cuh (wave_descents / wave_expansions; oracle twin AlphaZero::search_wave).
+template <int EVAL, int NOISE>
+__global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device_vl(Dev D) {
+    const uint64_t* Zs = D.Z;
+    __shared__ WarpStage<NOISE> stage[4];
+    __shared__ MathTab mt;
+    if (NOISE) load_math_tab(mt);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(D.cursor, 1);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= D.G) break;
+        Warp w = make_warp(D, g, Zs, lane);
+        if (w.gs->status != ST_ACTIVE) continue;
+        Cursor cs;
+        load_cursor(*w.gs, cs, st, lane);
+        int done = 0;
+        while (done < D.num_sim && !cs.err) {
+            wave_descents<NOISE>(D, w, cs, st, mt, done);
+            if (EVAL == EVAL_PHILOX) {
+                wave_expansions<NOISE>(D, w, cs, st, [&](const PendingLeaf& p, const Leaf&) {
+                    EvPhilox ev;
+                    ev.init(D, cs.game_id, p.sim_index, lane);
+                    return ev;
+                });
+            } else if (EVAL == EVAL_DET) {
+                wave_expansions<NOISE>(D, w, cs, st, [&](const PendingLeaf&, const Leaf& L) {
+                    EvHash<false> ev;
+                    ev.init(L, st.B, st.W, Zs, lane);
+                    return ev;
+                });
+            } else {
+                wave_expansions<NOISE>(D, w, cs, st, [&](const PendingLeaf&, const Leaf& L) {
+                    EvHash<true> ev;
+                    ev.init(L, st.B, st.W, Zs, lane);
+                    return ev;
+                });
+            }
+        }
+        store_cursor(D, *w.gs, cs, st, lane);
+        if (w.gs->status == ST_ACTIVE) finish_move_outofline(D, w);
+    }
+}
+
 // Callback path, kernel 1 — one wave of one pipeline group (slots g0..g1), one warp per game:
-//   back half  (do_back):  recover_way8 + get_from on the evaluator's answer, expansion, backup; after the
-//                          game's num_sim-th simulation of this stone also policy(), Game::set, win check, node
-//                          collection / slot refill (what k_move_end does on the device-evaluator path);
-//   front half (do_front): descend to the next leaf and park it in the game state; leaf_flag[g] = 0 (nothing
-//                          to evaluate), 1 (Black to move at the leaf) or 2 (White).
+//   back half  (do_back):  recover_way8 + get_from on the evaluator's answers, expansion of the waiting leaves, their values;
+//                          once the game's num_sim simulations of this stone are done also policy(), Game::set, win check,
+//                          node collection / slot refill (what k_move_end does on the device-evaluator path);
+//   front half (do_front): the descents of the next wave (one on the reference's schedule, up to K in multi-leaf mode); the
+//                          leaves are parked in the game state; leaf_flag[g * K + i] = 0 (nothing to evaluate), 1 (Black to
+//                          move at leaf i) or 2 (White).
 // Both halves of consecutive waves touch only this game's own state, so they share a launch: a wave of a group
 // is k_step -> k_gather -> (evaluator) -> one H2D copy.
 template <int NOISE>
@@ -150,99 +199,88 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
     Warp w = make_warp(D, g, Zs, lane);
     GameState& gs = *w.gs;
     if (do_back && gs.status == ST_ACTIVE) {
-        if (D.num_sim > 0) {
+        if (D.num_sim > 0 && gs.n_pend > 0) {
             Cursor cs;
             load_cursor(gs, cs, st, lane);
-            if (gs.need_eval) {
-                Leaf L;
-                if (lane < 8) st.B[lane] = gs.leafB[lane], st.W[lane] = gs.leafW[lane];
-                __syncwarp();
-                L.key = gs.leaf_key, L.stones = gs.leaf_stones, L.rec = gs.leaf_rec, L.depth = gs.depth, L.last_bit = gs.leaf_last;
-                const float* region = D.batch + (size_t)g0 * 8 * (CELLS + 1);
+            const size_t nk = (size_t)(g1 - g0) * D.K;
+            const float* region = D.batch + (size_t)g0 * D.K * 8 * (CELLS + 1);
+            wave_expansions<NOISE>(D, w, cs, st, [&](const PendingLeaf& p, const Leaf&) {
                 EvBatch ev;
-                ev.values = region + (size_t)gs.batch_pos * 8;
-                ev.pol = region + (size_t)(g1 - g0) * 8 + (size_t)gs.batch_pos * 8 * CELLS;
+                ev.values = region + (size_t)p.batch_pos * 8;
+                ev.pol = region + nk * 8 + (size_t)p.batch_pos * 8 * CELLS;
                 ev.lane = lane;
-                expand_leaf<false>(D, w, cs, L, ev, ev.value(), st);
-            }
-            cs.sim_index += 1;
+                return ev;
+            });
             store_cursor(D, gs, cs, st, lane);
-            if (gs.status == ST_ACTIVE && lane == 0) {
-                gs.sims_this_move += 1;
-                gs.need_eval = 0;
-            }
-            __syncwarp();
         }
         if (gs.status == ST_ACTIVE && gs.sims_this_move >= D.num_sim) finish_move(D, w);
         __syncwarp();
     }
     if (!do_front) return;
-    int flag = 0;
+    int n_pend = 0;
     if (gs.status == ST_ACTIVE && D.num_sim > 0) {
         Cursor cs;
         load_cursor(gs, cs, st, lane);
-        Leaf L;
-        descend<NOISE>(D, w, cs, L, st, mt);
-        int need = 1;
-        if (L.stones == CELLS) {
-            terminal_leaf<false>(D, w, st, L);
-            need = 0;
-        }
-        if (lane < 8) gs.leafB[lane] = st.B[lane], gs.leafW[lane] = st.W[lane];
-        if (lane == 0) {
-            gs.leaf_rec = L.rec, gs.depth = L.depth, gs.leaf_stones = L.stones, gs.leaf_key = L.key, gs.leaf_last = L.last_bit;
-            gs.need_eval = need;
-        }
+        int stm = gs.sims_this_move;
+        wave_descents<NOISE>(D, w, cs, st, mt, stm);
+        if (lane == 0) gs.sims_this_move = stm;
         store_cursor(D, gs, cs, st, lane);
-        flag = need ? (turn_of(L.stones) < 0 ? 1 : 2) : 0;
+        n_pend = gs.n_pend;
     } else if (lane == 0) {
-        gs.need_eval = 0;
+        gs.n_pend = 0;
     }
-    if (lane == 0) D.leaf_flag[g] = (uint8_t)flag;
+    if (lane < D.K) D.leaf_flag[(size_t)g * D.K + lane] = (uint8_t)(lane < n_pend ? (turn_of(gs.pend[lane].stones) < 0 ? 1 : 2) : 0);
 }
 
-// Callback path, kernel 2: the leaves of the group ordered into a Black-to-move run followed by a
-// White-to-move run (the Callback ABI takes one `player` per call, CB/libcppconnect6/src/cppbind/cppeval/
-// mod.rs:8-13; every warp ranks its own leaf from the group's flag bytes), then augment_way8 + board_to_float
-// for every leaf in the API layout float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73,
-// CB/.../cpp_support.rs:10-18).  The batch region of a group is [values n*8 | boards n*8*225] floats.
+// Callback path, kernel 2: the waiting leaves of the group (slot q = (game - g0) * K + i for leaf i of a game) ordered into a
+// Black-to-move run followed by a White-to-move run (the Callback ABI takes one `player` per call, CB/libcppconnect6/src/
+// cppbind/cppeval/mod.rs:8-13; every warp ranks its own leaf from the group's flag bytes), then augment_way8 + board_to_float
+// for every leaf in the API layout float[len][15][15] (LC/policy/alphazero_policy/augment.rs:60-73, CB/.../cpp_support.rs:10-18),
+// one warp per leaf slot.  The batch region of a group of n games is [values n*K*8 | boards n*K*8*225] floats.  A lane builds
+// four consecutive floats of the batch and stores them as one float4 (7,200 B per leaf = 450 float4: coalesced 512 B per warp).
 // to_host: the boards go straight to the mapped pinned host buffer the user Callback reads (no copy call);
 // the last block to finish publishes {Black leaves, White leaves, seq} to the host, which polls seq.
 __global__ void __launch_bounds__(128) k_gather(Dev D, int g0, int g1, int group, int seq, int to_host, int publish) {
+    __shared__ uint32_t boards[4][16];
     const int lane = threadIdx.x & 31;
-    const int g = g0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int n = g1 - g0;
-    const int myflag = g < g1 ? (int)D.leaf_flag[g] : 0;
+    const int K = D.K;
+    const int nk = (g1 - g0) * K;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint8_t* flags = D.leaf_flag + (size_t)g0 * K;
+    const int myflag = q < nk ? (int)flags[q] : 0;
     int nB = 0, nW = 0, rank = 0;
     if (myflag || threadIdx.x < 32) {  // warp-uniform
-        for (int base = g0; base < g1; base += 32) {
+        for (int base = 0; base < nk; base += 32) {
             const int i = base + lane;
-            const int f = i < g1 ? (int)D.leaf_flag[i] : 0;
+            const int f = i < nk ? (int)flags[i] : 0;
             const unsigned mb = __ballot_sync(FULL, f == 1), mw = __ballot_sync(FULL, f == 2);
             nB += __popc(mb), nW += __popc(mw);
             const unsigned mine = myflag == 1 ? mb : mw;
-            if (base + 32 <= g) rank += __popc(mine);
-            else if (base <= g) rank += __popc(mine & ((1u << (g - base)) - 1u));
+            if (base + 32 <= q) rank += __popc(mine);
+            else if (base <= q) rank += __popc(mine & ((1u << (q - base)) - 1u));
         }
     }
     if (myflag) {
-        GameState& gs = D.gs[g];
+        PendingLeaf& p = D.gs[g0 + q / K].pend[q % K];
         const int slot = myflag == 1 ? rank : nB + rank;
-        if (lane == 0) gs.batch_pos = slot;
-        uint32_t B[8], W[8];
+        if (lane == 0) p.batch_pos = slot;
+        uint32_t* sb = boards[threadIdx.x >> 5];  // words 0-7 black, 8-15 white
+        if (lane < 16) sb[lane] = lane < 8 ? p.B[lane] : p.W[lane - 8];
+        __syncwarp();
+        float* region = (to_host ? D.hbatch : D.batch) + (size_t)g0 * K * 8 * (CELLS + 1);
+        float4* out = reinterpret_cast<float4*>(region + (size_t)nk * 8 + (size_t)slot * 8 * CELLS);  // 7,200 B per leaf: 16-byte aligned
+        for (int v = lane; v < 8 * CELLS / 4; v += 32) {
+            float f[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) B[j] = gs.leafB[j], W[j] = gs.leafW[j];
-        float* region = (to_host ? D.hbatch : D.batch) + (size_t)g0 * 8 * (CELLS + 1);
-        float* out = region + (size_t)n * 8 + (size_t)slot * 8 * CELLS;
-        for (int i = lane; i < 8 * CELLS; i += 32) {
-            int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
-            sym_inv(s, rr, cc, r, c);
-            uint32_t bit = (uint32_t)(r * 16 + c);
-            uint32_t bw = 0, ww = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if ((int)(bit >> 5) == j) bw = B[j], ww = W[j];
-            out[i] = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
+            for (int t = 0; t < 4; ++t) {
+                const int i = 4 * v + t;
+                int s = i / CELLS, o = i - s * CELLS, rr = o / 15, cc = o - rr * 15, r, c;
+                sym_inv(s, rr, cc, r, c);
+                const uint32_t bit = (uint32_t)(r * 16 + c);
+                const uint32_t bw = sb[bit >> 5], ww = sb[8 + (bit >> 5)];
+                f[t] = ((bw >> (bit & 31)) & 1u) ? -1.f : (((ww >> (bit & 31)) & 1u) ? 1.f : 0.f);
+            }
+            out[v] = make_float4(f[0], f[1], f[2], f[3]);
         }
         if (!to_host && lane < 8) region[(size_t)slot * 8 + lane] = 0.f;  // values pre-zeroed (cppeval/mod.rs:34); the host path zeroes its own
     }
@@ -384,6 +422,8 @@ size_t Engine::bytes_per_game() const {
 Engine::Engine(const Config& cfg) : cfg_(cfg) {
     if (cfg_.slots < 1) throw std::runtime_error("c6: slots must be >= 1");
     if (cfg_.log2_records < 10 || cfg_.log2_records > 24) throw std::runtime_error("c6: log2_records out of range [10,24]");
+    if (cfg_.virtual_loss < 1) cfg_.virtual_loss = 1;
+    if (cfg_.virtual_loss > VL_MAX) throw std::runtime_error("c6: virtual_loss out of range [1," + std::to_string(VL_MAX) + "]");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -405,13 +445,14 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.I = 8192;  // key table of expanded nodes: power of two >= 2 * E
     D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
     D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves, D.tie_break = cfg_.tie_break;
+    D.K = cfg_.virtual_loss;
     const size_t G = (size_t)D.G;
     d_->rec_bytes = G * D.R * sizeof(Rec);
     d_->lnk_bytes = G * D.L * sizeof(uint32_t);
     d_->idx_bytes = G * D.I * sizeof(Slot);
     size_t free_b = 0, total_b = 0;
     C6_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t need = d_->rec_bytes + d_->lnk_bytes + d_->idx_bytes + G * D.E * 76 + G * 8 * (CELLS + 1) * 4 + (64u << 20);
+    size_t need = d_->rec_bytes + d_->lnk_bytes + d_->idx_bytes + G * D.E * 76 + G * D.K * 8 * (CELLS + 1) * 4 + (64u << 20);
     if (need > free_b) {
         char buf[256];
         std::snprintf(buf, sizeof buf,
@@ -428,7 +469,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     C6_CUDA(cudaMalloc(&D.expB, G * D.E * 64));
     C6_CUDA(cudaMalloc(&D.exp_rec, G * D.E * 4));
     C6_CUDA(cudaMalloc(&D.exp_key, G * D.E * 8));
-    C6_CUDA(cudaMalloc(&D.path, G * 232 * 4));
+    C6_CUDA(cudaMalloc(&D.path, G * D.K * 232 * 4));
     C6_CUDA(cudaMalloc(&D.gs, G * sizeof(GameState)));
     C6_CUDA(cudaMemsetAsync(D.gs, 0, G * sizeof(GameState), stream_));
     uint64_t hz[512];
@@ -449,8 +490,8 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     }
     C6_CUDA(cudaMalloc(&D.gdone, n_groups * sizeof(int)));
     C6_CUDA(cudaMemsetAsync(D.gdone, 0, n_groups * sizeof(int), stream_));
-    C6_CUDA(cudaMalloc(&D.leaf_flag, G));
-    C6_CUDA(cudaMemsetAsync(D.leaf_flag, 0, G, stream_));
+    C6_CUDA(cudaMalloc(&D.leaf_flag, G * D.K));
+    C6_CUDA(cudaMemsetAsync(D.leaf_flag, 0, G * D.K, stream_));
     C6_CUDA(cudaHostAlloc(&d_->h_sync, 4 * n_groups * sizeof(int), cudaHostAllocMapped));
     std::memset(d_->h_sync, 0, 4 * n_groups * sizeof(int));
     C6_CUDA(cudaHostGetDevicePointer((void**)&D.hsync, d_->h_sync, 0));
@@ -472,7 +513,7 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     spin_us_ = host_spin_budget_us();
     C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
     if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
-        const size_t nb = G * 8 * (CELLS + 1) * sizeof(float);
+        const size_t nb = G * D.K * 8 * (CELLS + 1) * sizeof(float);
         C6_CUDA(cudaMalloc(&D.batch, nb));
         if (cfg_.evaluator == EVAL_CALLBACK) {
             C6_CUDA(cudaHostAlloc(&d_->h_batch, nb, cudaHostAllocMapped));
@@ -535,18 +576,22 @@ static int noise_mode(const Config& c) { return c.epsilon == 0.f ? 0 : (c.dirich
 
 // the one (evaluator, noise) variant of the fused kernel this engine runs
 using SimKernel = void (*)(Dev);
-static SimKernel sim_kernel(int evaluator, int noise) {
+static SimKernel sim_kernel(int evaluator, int noise, bool multi_leaf) {
     static const SimKernel table[3][3] = {
         {k_sims_device<EVAL_PHILOX, 0>, k_sims_device<EVAL_PHILOX, 1>, k_sims_device<EVAL_PHILOX, 2>},
         {k_sims_device<EVAL_DET, 0>, k_sims_device<EVAL_DET, 1>, k_sims_device<EVAL_DET, 2>},
         {k_sims_device<EVAL_NEG, 0>, k_sims_device<EVAL_NEG, 1>, k_sims_device<EVAL_NEG, 2>}};
-    return table[evaluator - EVAL_PHILOX][noise];
+    static const SimKernel table_vl[3][3] = {
+        {k_sims_device_vl<EVAL_PHILOX, 0>, k_sims_device_vl<EVAL_PHILOX, 1>, k_sims_device_vl<EVAL_PHILOX, 2>},
+        {k_sims_device_vl<EVAL_DET, 0>, k_sims_device_vl<EVAL_DET, 1>, k_sims_device_vl<EVAL_DET, 2>},
+        {k_sims_device_vl<EVAL_NEG, 0>, k_sims_device_vl<EVAL_NEG, 1>, k_sims_device_vl<EVAL_NEG, 2>}};
+    return (multi_leaf ? table_vl : table)[evaluator - EVAL_PHILOX][noise];
 }
 
 void Engine::step_device() {
     Dev& D = d_->dev;
     if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) throw std::runtime_error("c6: step_device needs a built-in device evaluator");
-    const SimKernel kern = sim_kernel(cfg_.evaluator, noise_mode(cfg_));
+    const SimKernel kern = sim_kernel(cfg_.evaluator, noise_mode(cfg_), cfg_.virtual_loss > 1);
     if (d_->persistent_blocks == 0) {
         int per_sm = 0;
         C6_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
@@ -621,10 +666,11 @@ void Engine::group_issue(int p, size_t len, bool do_back, bool do_front) {
     Dev& D = d_->dev;
     Group& gr = d_->groups[p];
     const int n = gr.g1 - gr.g0, grid = warps_grid(n);
-    const size_t roff = (size_t)gr.g0 * 8 * (CELLS + 1);
+    const size_t nk = (size_t)n * D.K;  // leaf slots of the group
+    const size_t roff = (size_t)gr.g0 * D.K * 8 * (CELLS + 1);
     const bool host_cb = cfg_.evaluator == EVAL_CALLBACK;
     if (do_back && len && host_cb) {
-        const size_t bytes = ((size_t)n * 8 + len * CELLS) * sizeof(float);  // all values of the region + the evaluated boards
+        const size_t bytes = (nk * 8 + len * CELLS) * sizeof(float);  // all values of the region + the evaluated boards
         C6_CUDA(cudaMemcpyAsync(D.batch + roff, d_->h_batch + roff, bytes, cudaMemcpyHostToDevice, gr.s));
         h2d_bytes_ += (double)bytes;
     }
@@ -639,11 +685,11 @@ void Engine::group_issue(int p, size_t len, bool do_back, bool do_front) {
     if (do_front && cfg_.num_simulation > 0) {
         gr.seq += 1;
         const bool zc = host_cb && zero_copy_;
-        k_gather<<<grid, 128, 0, gr.s>>>(D, gr.g0, gr.g1, p, gr.seq, zc ? 1 : 0, (zc || !host_cb) ? 1 : 0);
+        k_gather<<<warps_grid((int)nk), 128, 0, gr.s>>>(D, gr.g0, gr.g1, p, gr.seq, zc ? 1 : 0, (zc || !host_cb) ? 1 : 0);
         launches_ += 1;
         if (host_cb && !zc) {
-            const size_t boff = roff + (size_t)n * 8;
-            C6_CUDA(cudaMemcpyAsync(d_->h_batch + boff, D.batch + boff, (size_t)n * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
+            const size_t boff = roff + nk * 8;
+            C6_CUDA(cudaMemcpyAsync(d_->h_batch + boff, D.batch + boff, nk * 8 * CELLS * sizeof(float), cudaMemcpyDeviceToHost, gr.s));
             k_publish<<<1, 1, 0, gr.s>>>(D, p, gr.seq);
             launches_ += 1;
         }
@@ -677,24 +723,25 @@ size_t Engine::group_eval(int p, Callback cb) {
     const double t1 = now_s();
     host_wait_s_ += t1 - t0;
     const int nB = hs[0], nW = hs[1];
-    const size_t len = (size_t)(nB + nW) * 8, roff = (size_t)gr.g0 * 8 * (CELLS + 1);
+    const size_t len = (size_t)(nB + nW) * 8, roff = (size_t)gr.g0 * D.K * 8 * (CELLS + 1);
+    const size_t nk = (size_t)n * D.K;
     if (!len) return 0;
     if (cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
         float* dv = D.batch + roff;  // zeroed by k_gather
-        float* db = dv + (size_t)n * 8;
+        float* db = dv + nk * 8;
         if (nB) dcb_(-1, dv, db, nB * 8, (void*)gr.s, dcb_user_);
         if (nW) dcb_(1, dv + (size_t)nB * 8, db + (size_t)nB * 8 * CELLS, nW * 8, (void*)gr.s, dcb_user_);
         host_callback_s_ += now_s() - t1;
         return 0;  // nothing to copy back
     }
     float* hv = d_->h_batch + roff;
-    float* hb = hv + (size_t)n * 8;
+    float* hb = hv + nk * 8;
     std::memset(hv, 0, len * sizeof(float));  // values pre-zeroed (cppeval/mod.rs:34)
     const double t2 = now_s();
     if (nB) cb(-1, hv, hb, nB * 8);
     if (nW) cb(1, hv + (size_t)nB * 8, hb + (size_t)nB * 8 * CELLS, nW * 8);
     host_callback_s_ += now_s() - t2;
-    d2h_bytes_ += (double)(zero_copy_ ? len : (size_t)n * 8) * CELLS * sizeof(float) + 12;
+    d2h_bytes_ += (double)(zero_copy_ ? len : nk * 8) * CELLS * sizeof(float) + 12;
     return len;
 }
 

@@ -39,6 +39,20 @@ struct __align__(16) Slot {
     uint32_t epoch;
 };
 
+constexpr int VL_MAX = 8;  // most leaves one game may have waiting for their evaluation (Config::virtual_loss)
+
+// A leaf waiting for its evaluation: between two launches on the callback paths, within a wave in multi-leaf mode.
+struct PendingLeaf {
+    uint32_t B[8], W[8];  // bit boards of the leaf
+    uint64_t key;
+    uint32_t rec;         // its record
+    int32_t depth;        // length of the path that reached it (the path itself: Dev::path, one row per waiting leaf)
+    int32_t stones;
+    uint32_t last_bit;    // bit position of the last stone on the path (valid when depth >= 1)
+    uint32_t sim_index;   // simulation index of the descent: keys the evaluator / noise streams of this leaf
+    int32_t batch_pos;    // position of the leaf in its group's evaluator batch (callback paths)
+};
+
 enum Status : int32_t { ST_IDLE = 0, ST_ACTIVE = 1, ST_DONE = 2, ST_ERROR = 3 };
 enum ErrCode : int32_t { ERR_NONE = 0, ERR_REC_FULL = 1, ERR_LNK_FULL = 2, ERR_EXP_FULL = 3 };
 enum EvalKind : int32_t { EVAL_CALLBACK = 0, EVAL_PHILOX = 1, EVAL_DET = 2, EVAL_NEG = 3, EVAL_DEVICE_CALLBACK = 4 };
@@ -59,15 +73,10 @@ struct GameState {
     uint32_t sim_index;       // simulations started in this game (Philox counter)
     int32_t sims_this_move;
     int32_t n_moves;
-    // per-simulation scratch shared by the select / expand kernels of the callback path
-    uint32_t leaf_rec;
-    int32_t depth;
-    int32_t leaf_stones;
-    int32_t need_eval;
-    int32_t batch_pos;
-    uint32_t leaf_last;       // bit position of the last stone on the path to the parked leaf
-    uint64_t leaf_key;
-    uint32_t leafB[8], leafW[8];
+    // leaves waiting for their evaluation (one on the reference's sequential schedule, up to virtual_loss in multi-leaf mode)
+    int32_t n_pend;
+    int32_t pad0;
+    PendingLeaf pend[VL_MAX];
     // bit s: some expanded node with s stones kept by the collector has no expanded parent left (its former
     // parent did not contain the new root); expansions that create children with s stones look those up by key
     uint32_t orph[8];
@@ -99,6 +108,10 @@ struct Config {
     int32_t evaluator = EVAL_CALLBACK;
     int32_t trace = 0;            // record root child visits per move (tests)
     int32_t max_moves = 0;        // stop games after this many stones (<=0: play to the end)
+    int32_t virtual_loss = 1;     // 1 = the reference's strictly sequential simulations (mod.rs:468-470).  K > 1 (opt-in, NOT the
+                                  // reference's search): a move is searched in waves of up to K descents — each applies its visits at
+                                  // once (the virtual loss the next descent sees) — whose leaves are evaluated together and expanded
+                                  // afterwards; K leaves per game and evaluator call.  Oracle twin: AlphaZero::search_wave.
     int32_t tie_break = 1;        // exact PUCT ties: 1 = uniform among the tied children like the reference (mod.rs:291-295),
                                   // drawn from Philox (seed, game; sim, depth); 0 = lowest row-major index (hand-checkable traces)
 };

@@ -455,10 +455,13 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
 }
 
 // update(): only the leaf's parent takes the value, every ancestor (leaf excluded) gets visit += 1.
-template <bool FUSED, int NOISE>
+// MODE 0: both halves (the reference's schedule); 1: the visits only, 2: the value only (multi-leaf mode: the visits are
+// applied when the descent ends, the value when the leaf has been evaluated).
+template <bool FUSED, int NOISE, int MODE = 0>
 __device__ __forceinline__ void backup(const Dev& D, Warp& w, WarpStage<NOISE>& st, int depth, float v) {
     __syncwarp();
-    for (int i = w.lane; i < depth; i += 32) {
+    for (int i = MODE == 2 ? depth - 1 + w.lane : w.lane; i < depth; i += 32) {
+        if (i < 0) continue;
         uint32_t a;
         Rec r;
         if (FUSED && i < PATH_CACHE) {  // as read by this simulation's descent; nothing has written them since
@@ -466,8 +469,8 @@ __device__ __forceinline__ void backup(const Dev& D, Warp& w, WarpStage<NOISE>& 
         } else {
             a = w.path(D)[i], r = load_rec(&w.rec[a]);
         }
-        r.n += 1;
-        if (i == depth - 1) r.w = r.w + v;
+        if (MODE != 2) r.n += 1;
+        if (MODE != 1 && i == depth - 1) r.w = r.w + v;
         store_rec(&w.rec[a], r);
         if (FUSED && i == 0) st.rootrec = bits_of(r);
     }
@@ -501,6 +504,9 @@ struct EvPhilox {
     int lane;
     __device__ __forceinline__ void init(const Dev& D, const Cursor& cs, int lane_) {
         k0 = D.seed ^ DOMAIN_EVAL, k1 = cs.game_id, sim = cs.sim_index, lane = lane_;
+    }
+    __device__ __forceinline__ void init(const Dev& D, uint32_t game_id, uint32_t sim_index, int lane_) {
+        k0 = D.seed ^ DOMAIN_EVAL, k1 = game_id, sim = sim_index, lane = lane_;
     }
     // eight U[-1,1) draws of `cell` folded pairwise in plane order: {d0+d1, d2+d3, d4+d5, d6+d7}
     __device__ __forceinline__ void pairs(uint32_t cell, float (&t)[4]) const {
@@ -676,7 +682,8 @@ __device__ __noinline__ unsigned resolve_rare(const Slot* idx, uint32_t Im, uint
 
 // STAGED: st.child still holds the children of the leaf's parent from the last select step (fused kernel);
 // otherwise (the expansion runs in a later launch than the descent) they are staged again here.
-template <bool STAGED, class Ev, int NOISE>
+// VMODE: backup mode once the leaf is expanded (0 = visits and value, 2 = value only: see backup)
+template <bool STAGED, int VMODE = 0, class Ev, int NOISE>
 __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, const Leaf& L, const Ev& ev, float v,
                                             WarpStage<NOISE>& st) {
     const int lane = w.lane;
@@ -806,7 +813,80 @@ C6_UNROLL(C6_PRIOR_UNROLL)
         m.peak_rec = max(m.peak_rec, base - rec_tail);
         m.peak_lnk = max(m.peak_lnk, cs.lnk_head - lnk_tail);
     }
-    backup<STAGED>(D, w, st, L.depth, v);
+    backup<STAGED, NOISE, VMODE>(D, w, st, L.depth, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Waves: the schedule shared by the callback paths (K = 1: the reference's; the leaf waits for the evaluator between two
+// launches) and the opt-in multi-leaf mode (K = Config::virtual_loss > 1; oracle twin: AlphaZero::search_wave).
+//   front half: up to K descents.  Each applies the visits of update() (:400-406) at once — for K > 1 they are the virtual
+//     loss the next descent of the wave sees — and parks its leaf in GameState::pend.  A descent that ends in a leaf already
+//     waiting in this wave is discarded and ends the wave; a full-board leaf has its value at once (:338-348).
+//   back half: the waiting leaves are expanded in descent order, each with the streams of its own simulation index, and each
+//     adds its value to its parent (:394-398).
+// ------------------------------------------------------------------------------------------------
+template <int NOISE>
+__device__ __forceinline__ void wave_descents(const Dev& D, Warp& w, Cursor& cs, WarpStage<NOISE>& st, const MathTab& mt, int& sims_this_move) {
+    GameState& gs = *w.gs;
+    const int lane = w.lane;
+    uint32_t* const path0 = w.pth;
+    int n_pend = 0;
+#pragma unroll 1
+    for (int j = 0; j < D.K && sims_this_move < D.num_sim; ++j) {
+        w.pth = path0 + n_pend * 232;
+        Leaf L;
+        descend<NOISE, false>(D, w, cs, L, st, mt);
+        const uint32_t index = cs.sim_index;
+        cs.sim_index += 1;
+        const bool terminal = L.stones == CELLS;
+        bool dup = false;
+        if (!terminal)
+            for (int i = 0; i < n_pend; ++i) dup = dup || gs.pend[i].rec == L.rec;
+        if (dup) {  // the discarded descent changed nothing; it is not a simulation
+            if (lane == 0) st.meta.sims -= 1;
+            break;
+        }
+        backup<false, NOISE, 1>(D, w, st, L.depth, 0.f);
+        sims_this_move += 1;
+        if (terminal) {
+            const float v = terminal_value(st.B, st.W);
+            backup<false, NOISE, 2>(D, w, st, L.depth, v);
+            continue;
+        }
+        PendingLeaf& p = gs.pend[n_pend];
+        if (lane < 8) p.B[lane] = st.B[lane], p.W[lane] = st.W[lane];
+        if (lane == 0) p.key = L.key, p.rec = L.rec, p.depth = L.depth, p.stones = L.stones, p.last_bit = L.last_bit, p.sim_index = index, p.batch_pos = 0;
+        __syncwarp();
+        n_pend += 1;
+    }
+    w.pth = path0;
+    if (lane == 0) gs.n_pend = n_pend;
+    __syncwarp();
+}
+
+// make_ev(p, L): the evaluator of waiting leaf p (its board is in st.B / st.W when it is called)
+template <int NOISE, class MakeEv>
+__device__ __forceinline__ void wave_expansions(const Dev& D, Warp& w, Cursor& cs, WarpStage<NOISE>& st, MakeEv make_ev) {
+    GameState& gs = *w.gs;
+    const int lane = w.lane;
+    uint32_t* const path0 = w.pth;
+    const int n = gs.n_pend;
+#pragma unroll 1
+    for (int i = 0; i < n && !cs.err; ++i) {
+        const PendingLeaf& p = gs.pend[i];
+        __syncwarp();
+        if (lane < 8) st.B[lane] = p.B[lane], st.W[lane] = p.W[lane];
+        Leaf L;
+        L.key = p.key, L.stones = p.stones, L.rec = p.rec, L.depth = p.depth, L.last_bit = p.last_bit, L.leaf_w = 0.f, L.leaf_p = 0.f;
+        __syncwarp();
+        w.pth = path0 + i * 232;
+        const auto ev = make_ev(p, L);
+        expand_leaf<false, 2>(D, w, cs, L, ev, ev.value(), st);
+    }
+    w.pth = path0;
+    __syncwarp();
+    if (lane == 0) gs.n_pend = 0;
+    __syncwarp();
 }
 
 }  // namespace c6

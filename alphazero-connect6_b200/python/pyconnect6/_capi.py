@@ -40,7 +40,7 @@ ALLOC_PATH = ALLOC_RESULT = ALLOC_INT = ALLOC_FLOAT = C.CFUNCTYPE(C.c_void_p, C.
 class Config(C.Structure):
     _fields_ = [("num_simulation", C.c_int32), ("epsilon", C.c_float), ("dirichlet_alpha", C.c_double),
                 ("c_puct", C.c_float), ("seed", C.c_uint32), ("device", C.c_int32), ("slots", C.c_int32),
-                ("log2_records", C.c_int32), ("evaluator", C.c_int32), ("trace", C.c_int32), ("max_moves", C.c_int32), ("tie_break", C.c_int32)]
+                ("log2_records", C.c_int32), ("evaluator", C.c_int32), ("trace", C.c_int32), ("max_moves", C.c_int32), ("virtual_loss", C.c_int32), ("tie_break", C.c_int32)]
 
 
 class Record(C.Structure):

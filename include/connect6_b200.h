@@ -117,6 +117,9 @@ typedef struct c6_config {
     int32_t evaluator;       /* C6_EVAL_* */
     int32_t trace;           /* keep root child visits per move */
     int32_t max_moves;       /* stop each game after this many stones (0 = play out) */
+    int32_t virtual_loss;    /* 1 = the reference's strictly sequential simulations (default).  K in 2..8, opt-in and NOT the
+                                reference's search: waves of up to K descents per game whose visits are applied at once (virtual
+                                loss) and whose leaves are evaluated in one batch and expanded afterwards */
     int32_t tie_break;       /* exact PUCT ties: 1 = uniform among the tied children as alphazero_policy/mod.rs:291-295 does
                                 (Philox keyed (seed, game), counted by (simulation, depth)); 0 = lowest row-major index */
 } c6_config;

@@ -451,6 +451,9 @@ struct AlphaZero {
     EvalCtx ctx;
     SearchStats stats;
     uint64_t tie_rng = 0x1234567ull;  // only for TieBreak::Random
+    // NOT in the reference (its simulations are strictly sequential, mod.rs:468-470): with virtual_loss = K > 1 a move is searched
+    // in waves of up to K descents whose leaves are expanded afterwards — the engine's opt-in multi-leaf mode (search_wave below)
+    int virtual_loss = 1;
     // trace of the last next(): root child visits (row-major cells, -1 where occupied), root stats
     std::array<int32_t, BOARD_CAPACITY> last_child_visits{};
     int32_t last_root_visit = 0;
@@ -650,6 +653,74 @@ struct AlphaZero {
         ctx.sim_index += 1;
     }
 
+    // Multi-leaf search, the twin of the engine's opt-in virtual-loss mode (Config::virtual_loss = K).  One wave:
+    //   1. up to K descents, one after the other.  A descent applies the VISITS of update() (:400-406: every node on the path
+    //      except the leaf gets visit += 1) at once — they are the virtual loss: the next descent of the wave sees them in
+    //      sqrt(S - n) / (1 + n) and in q = q_sum / visit — and defers the VALUE (:394-398) until the leaf has been evaluated;
+    //   2. a descent that ends in a leaf which is already waiting in this wave is discarded (it changes nothing, does not count as
+    //      a simulation, and ends the wave); a full-board leaf has its value at once (:338-348);
+    //   3. the waiting leaves are expanded in descent order, each with the evaluator / noise streams of its own simulation index,
+    //      and each adds its value to its parent's q_sum.
+    // With K = 1 this is search_once.  Every simulation index is used by one descent only (discarded ones consume theirs).
+    void search_wave(const Simulate& simulate0, int& done) {
+        struct Waiting {
+            Simulate sim;
+            std::vector<Pos> path;
+            uint32_t sim_index;
+            uint64_t hashed;
+        };
+        init(simulate0);
+        std::vector<Waiting> waiting;
+        for (int j = 0; j < virtual_loss && done < param.num_simulation; ++j) {
+            Simulate simulate = simulate0.deep_clone();
+            std::vector<Pos> path;
+            while (auto pos = select(simulate, (int)path.size())) {
+                path.push_back(*pos);
+                simulate.simulate_in(pos->first, pos->second);
+            }
+            const uint64_t leaf = hash(simulate.board);
+            const uint32_t index = ctx.sim_index;
+            ctx.sim_index += 1;
+            stats.sum_depth += path.size();
+            bool dup = false;
+            for (const Waiting& w : waiting) dup = dup || w.hashed == leaf;
+            if (dup) break;
+            {  // the visits of update(), now
+                Simulate s = simulate.deep_clone();
+                for (auto it = path.rbegin(); it != path.rend(); ++it) {
+                    s.rollback_in(it->first, it->second);
+                    Node& node = map.at(hash(s.board));
+                    node.visit += 1;
+                    node.recalc_q();
+                }
+            }
+            done += 1;
+            stats.sims += 1;
+            if (map.at(leaf).num_player == (size_t)BOARD_CAPACITY) {
+                expand(simulate);  // full board: sets the value from search(), no evaluator call
+                add_value(simulate, path);
+                continue;
+            }
+            waiting.push_back(Waiting{simulate, path, index, leaf});
+        }
+        for (const Waiting& w : waiting) {
+            const uint32_t keep = ctx.sim_index;
+            ctx.sim_index = w.sim_index;
+            expand(w.sim);
+            ctx.sim_index = keep;
+            add_value(w.sim, w.path);
+        }
+    }
+    void add_value(const Simulate& sim, const std::vector<Pos>& path) {  // the first half of update() (:394-398)
+        if (path.empty()) return;
+        const float value = map.at(hash(sim.board)).value;
+        Simulate s = sim.deep_clone();
+        s.rollback_in(path.back().first, path.back().second);
+        Node& parent = map.at(hash(s.board));
+        parent.q_sum += value;
+        parent.recalc_q();
+    }
+
     std::optional<Pos> policy(const Simulate& sim) {  // :433-452 — Rust max_by keeps the LAST maximum
         const Node& tree_node = map.at(hash(sim.board));
         std::vector<const Node*> child_node;
@@ -680,7 +751,11 @@ struct AlphaZero {
     std::optional<Pos> next(const Game& game) {  // :464-489
         Simulate simulate = Simulate::from_game(game);
         init(simulate);
-        for (int i = 0; i < param.num_simulation; ++i) search_once(simulate);
+        if (virtual_loss <= 1) {
+            for (int i = 0; i < param.num_simulation; ++i) search_once(simulate);
+        } else {
+            for (int done = 0; done < param.num_simulation;) search_wave(simulate, done);
+        }
         auto res = policy(simulate);
         stats.max_nodes = std::max<uint64_t>(stats.max_nodes, map.size());
         // remove siblings

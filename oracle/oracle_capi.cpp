@@ -189,6 +189,7 @@ struct OracleParams {
     int32_t faithful;    // 0 lean, 1 reference cost model
     int32_t evaluator;   // 0 callback, 1 philox random evaluator
     int32_t max_moves;   // stop after this many stones (<=0: play to the end)
+    int32_t virtual_loss;  // <= 1: the reference's sequential simulations; K > 1: waves of up to K leaves (AlphaZero::search_wave)
 };
 
 struct OracleGameOut {
@@ -216,6 +217,7 @@ static void play_one(Callback cb, const OracleParams& p, uint32_t game_id, Oracl
     pol.az.faithful = p.faithful != 0;
     pol.az.ctx.seed = p.seed;
     pol.az.ctx.game_id = game_id;
+    pol.az.virtual_loss = p.virtual_loss;
     pol.trace = child_visits != nullptr;
 
     // Agent::play with an optional stone limit (bounded samples for timing)

@@ -25,7 +25,7 @@ ORACLE_TIE = {0: 0, 1: 2}               # -> OracleParams.tie_mode (1 is the ora
 class OracleParams(C.Structure):
     _fields_ = [("num_simulation", C.c_int32), ("epsilon", C.c_float), ("dirichlet_alpha", C.c_double),
                 ("c_puct", C.c_float), ("seed", C.c_uint32), ("noise_mode", C.c_int32), ("tie_mode", C.c_int32),
-                ("faithful", C.c_int32), ("evaluator", C.c_int32), ("max_moves", C.c_int32)]
+                ("faithful", C.c_int32), ("evaluator", C.c_int32), ("max_moves", C.c_int32), ("virtual_loss", C.c_int32)]
 
 
 class OracleGameOut(C.Structure):

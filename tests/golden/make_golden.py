@@ -156,16 +156,19 @@ SELFPLAY_CASES = [
     ("det_40sims_eps0_lowest_index", 0, "det_eval_callback", 40, 0.0, 0xC6, 5, 3, 16, 0),
     ("neg_40sims_noise", 0, "neg_eval_callback", 40, 0.25, 0xC6, 5, 3, 16, 1),
     ("philox_800sims_reference_default", 1, None, 800, 0.25, 0xC6, 0, 1, 4, 1),
+    # opt-in multi-leaf mode (virtual_loss = 4): not the reference's schedule; drift guard of the oracle twin + engine check
+    ("philox_64sims_noise_multi_leaf4", 1, None, 64, 0.25, 0xC6, 77, 3, 16, 1, 4),
 ]
 
 
 def selfplay_traces():
     O = c6lib.oracle()
     cases = []
-    for name, ev, cbname, sims, eps, seed, first, n, mm, tie in SELFPLAY_CASES:
+    for name, ev, cbname, sims, eps, seed, first, n, mm, tie, *rest in SELFPLAY_CASES:
+        vl = rest[0] if rest else 1
         games = []
         for g in range(n):
-            p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1 if eps != 0 else 0, c6lib.ORACLE_TIE[tie], 0, ev, mm)
+            p = c6lib.OracleParams(sims, eps, 0.03, 1.0, seed, 1 if eps != 0 else 0, c6lib.ORACLE_TIE[tie], 0, ev, mm, vl)
             out = c6lib.OracleGameOut()
             cv = np.zeros((225, 225), dtype=np.int32)
             rn = np.zeros(225, dtype=np.int32)
@@ -184,7 +187,7 @@ def selfplay_traces():
                 "sims": int(out.sims), "sum_ck": int(out.sum_ck), "sum_cleaf": int(out.sum_cleaf), "sum_depth": int(out.sum_depth),
             })
         cases.append({"name": name, "evaluator": ev, "callback": cbname, "num_simulation": sims, "epsilon": eps,
-                      "dirichlet_alpha": 0.03, "c_puct": 1.0, "seed": seed, "first_id": first, "max_moves": mm, "tie_break": tie, "games": games})
+                      "dirichlet_alpha": 0.03, "c_puct": 1.0, "seed": seed, "first_id": first, "max_moves": mm, "tie_break": tie, "virtual_loss": vl, "games": games})
     return cases
 
 

@@ -103,7 +103,7 @@ def run_oracle_case(case, g, faithful=0):
     O = c6lib.oracle()
     p = c6lib.OracleParams(case["num_simulation"], case["epsilon"], case["dirichlet_alpha"], case["c_puct"], case["seed"],
                            1 if case["epsilon"] != 0 else 0, c6lib.ORACLE_TIE[case.get("tie_break", 0)], faithful, case["evaluator"],
-                           case["max_moves"])
+                           case["max_moves"], case.get("virtual_loss", 1))
     out = c6lib.OracleGameOut()
     cv = np.zeros((225, 225), dtype=np.int32)
     rn = np.zeros(225, dtype=np.int32)

@@ -71,9 +71,11 @@ def run_engine(n_games, callback_name=None, first_id=0, prefixes=None, **cfg_kw)
         L.c6_engine_destroy(e)
 
 
-def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0, prefix=None, tie=1):
+def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, alpha=0.03, c_puct=1.0, prefix=None, tie=1,
+               virtual_loss=1):
     O = c6lib.oracle()
-    p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, c6lib.ORACLE_TIE[tie], 0, evaluator, max_moves)
+    p = c6lib.OracleParams(num_simulation, epsilon, alpha, c_puct, seed, 1 if epsilon != 0 else 0, c6lib.ORACLE_TIE[tie], 0, evaluator, max_moves,
+                           virtual_loss)
     out = c6lib.OracleGameOut()
     cv = np.zeros((225, 225), dtype=np.int32)
     rn = np.zeros(225, dtype=np.int32)
@@ -87,11 +89,11 @@ def run_oracle(game_id, callback_name, evaluator, num_simulation, epsilon, seed,
 
 
 def compare_games(n_games, rec, cv, rn, rw, first_id, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=1.0,
-                  prefixes=None, tie=1):
+                  prefixes=None, tie=1, virtual_loss=1):
     for g in range(n_games):
         pre = prefixes[g] if prefixes else []
         out, ocv, orn, orw = run_oracle(first_id + g, callback_name, evaluator, num_simulation, epsilon, seed, max_moves, c_puct=c_puct,
-                                        prefix=pre, tie=tie)
+                                        prefix=pre, tie=tie, virtual_loss=virtual_loss)
         r = rec[g]
         where = f"game {first_id + g}"
         assert r.game_id == first_id + g
@@ -320,6 +322,42 @@ def test_selfplay_late_game_with_noise(evaluator, cbname, sims, c_puct, n_stones
                   prefixes=prefixes)
 
 
+@pytest.mark.parametrize("evaluator,cbname,sims,eps,K,n_games,max_moves", [
+    # opt-in multi-leaf mode (virtual loss): waves of up to K descents per game, leaves expanded afterwards; the oracle twin
+    # (AlphaZero::search_wave) runs the same schedule on the reference's map-based tree
+    (EVAL_PHILOX, None, 64, 0.25, 2, 4, 20),
+    (EVAL_PHILOX, None, 64, 0.25, 4, 4, 20),
+    (EVAL_PHILOX, None, 50, 0.0, 8, 3, 20),      # budget not a multiple of K
+    (EVAL_PHILOX, None, 2, 0.25, 4, 6, 0),       # whole games, budget < K: the second descent of the first wave collides
+    (EVAL_DET, "det_eval_callback", 40, 0.0, 4, 3, 20),
+    (EVAL_NEG, "neg_eval_callback", 40, 0.25, 3, 3, 20),
+    (EVAL_CALLBACK, "neg_eval_callback", 40, 0.25, 4, 5, 20),   # K leaves per game in every evaluator batch
+    (EVAL_CALLBACK, "det_eval_callback", 33, 0.0, 8, 5, 16),
+    (EVAL_CALLBACK, "neg_eval_callback", 2, 0.25, 2, 4, 0),
+])
+def test_selfplay_multi_leaf_mode(evaluator, cbname, sims, eps, K, n_games, max_moves):
+    seed = 0xC6
+    rec, cv, rn, rw, st = run_engine(n_games, cbname if evaluator == EVAL_CALLBACK else None, first_id=40, num_simulation=sims, epsilon=eps,
+                                     seed=seed, evaluator=evaluator, max_moves=max_moves, virtual_loss=K)
+    compare_games(n_games, rec, cv, rn, rw, 40, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, max_moves, virtual_loss=K)
+    stones = sum(rec[g].n_moves for g in range(n_games))
+    assert st.sims == sims * stones if max_moves else st.sims >= sims * (stones - n_games)  # every stone got its full budget
+
+
+@pytest.mark.parametrize("evaluator,cbname,sims,c_puct,n_stones,K", [
+    (EVAL_NEG, "neg_eval_callback", 200, 0.2, 212, 4),     # deep late-game trees: transposed children between waiting leaves
+    (EVAL_CALLBACK, "neg_eval_callback", 120, 0.3, 208, 3),
+    (EVAL_PHILOX, None, 150, 1.0, 196, 8),
+])
+def test_multi_leaf_mode_late_game(evaluator, cbname, sims, c_puct, n_stones, K):
+    seed, n_games, eps = 0xC6, 3, 0.25
+    prefixes = [make_prefix(n_stones + g, 3000 * n_stones + g) for g in range(n_games)]
+    rec, cv, rn, rw, st = run_engine(n_games, cbname if evaluator == EVAL_CALLBACK else None, first_id=800, prefixes=prefixes,
+                                     num_simulation=sims, epsilon=eps, c_puct=c_puct, seed=seed, evaluator=evaluator, virtual_loss=K)
+    compare_games(n_games, rec, cv, rn, rw, 800, cbname, 1 if evaluator == EVAL_PHILOX else 0, sims, eps, seed, 0, c_puct=c_puct,
+                  prefixes=prefixes, virtual_loss=K)
+
+
 def test_selfplay_800_sims_reference_default():
     """Reference default budget (800 simulations, eps .25, alpha .03) for the first stones of two games."""
     seed, sims, eps, mm = 0xC6, 800, 0.25, 6
@@ -397,7 +435,7 @@ def test_engine_reproduces_golden_traces(case):
     n = len(case["games"])
     first = case["first_id"]
     kw = dict(num_simulation=case["num_simulation"], epsilon=case["epsilon"], seed=case["seed"], max_moves=case["max_moves"],
-              tie_break=case["tie_break"])
+              tie_break=case["tie_break"], virtual_loss=case.get("virtual_loss", 1))
     if case["evaluator"] == 1:
         rec, cv, rn, rw, st = run_engine(n, None, first_id=first, evaluator=EVAL_PHILOX, **kw)
     else:
