@@ -69,6 +69,32 @@ __host__ __device__ inline int win_check(const uint32_t (&B)[8], const uint32_t 
     return fb < fw ? -1 : 1;
 }
 
+// The same decision with fewer instructions (config-3a kernel; 420 ALU instructions per board made k_win_check as much issue-
+// as bandwidth-bound, profiles/r01p_micro.jsonl): the vertical direction shifts by 16 / 32 / 64 bits, and the last two are whole
+// words — register renaming, no instruction; and since a cell holds one colour, the winner is the colour owning the lowest set
+// bit of (black run ends | white run ends): one scan over eight words instead of two.
+__host__ __device__ __forceinline__ void run6_vertical(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
+    uint32_t t[8], m2[8];
+    shl256<16>(b, t);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m2[w] = b[w] & t[w];
+#pragma unroll
+    for (int w = 2; w < 8; ++w) acc[w] |= m2[w] & m2[w - 1] & m2[w - 2];  // m2 & (m2 << 32) & (m2 << 64); words 0, 1 have no room for six rows
+}
+__host__ __device__ inline int win_check_fast(const uint32_t (&B)[8], const uint32_t (&W)[8]) {
+    uint32_t eb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ew[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    run6<1>(B, eb), run6_vertical(B, eb), run6<17>(B, eb), run6<15>(B, eb);
+    run6<1>(W, ew), run6_vertical(W, ew), run6<17>(W, ew), run6<15>(W, ew);
+    uint32_t first = 0, first_b = 0;
+#pragma unroll
+    for (int w = 7; w >= 0; --w) {
+        const uint32_t e = eb[w] | ew[w];
+        if (e) first = e, first_b = eb[w];
+    }
+    if (!first) return 0;
+    return (first_b & (first & (0u - first))) ? -1 : 1;
+}
+
 // symmetry s of augment_way8 (LC/policy/alphazero_policy/augment.rs:60-73): where the content of
 // original cell (r,c) lands in plane s.
 __host__ __device__ __forceinline__ void sym_fwd(int s, int r, int c, int& rr, int& cc) {

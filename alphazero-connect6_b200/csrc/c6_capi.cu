@@ -459,6 +459,7 @@ int c6_engine_stats(c6_engine* e, c6_stats* out) {
         out->sum_depth = s.sum_depth, out->evals = s.evals, out->gc_copied = s.gc_copied, out->games_done = s.games_done,
         out->peak_rec = s.peak_rec, out->peak_lnk = s.peak_lnk, out->kernel_launches = (uint64_t)e->eng->kernel_launches(),
         out->bytes_per_game = e->eng->bytes_per_game();
+        out->degraded = s.degraded;
     });
 }
 int64_t c6_engine_games_done(c6_engine* e) {
@@ -541,6 +542,7 @@ int c6_self_play_device_sharded(const c6_config* cfg, const int* devices, int n_
         tot.gc_copied += s.gc_copied, tot.games_done += s.games_done, tot.kernel_launches += (uint64_t)eng.kernel_launches();
         tot.peak_rec = std::max(tot.peak_rec, s.peak_rec), tot.peak_lnk = std::max(tot.peak_lnk, s.peak_lnk);
         tot.bytes_per_game = eng.bytes_per_game();
+        tot.degraded += s.degraded;
         });
         if (out && n_games > 0) std::memcpy(out, rec.data(), (size_t)n_games * sizeof(GameRecord));
         if (stats) *stats = tot;

@@ -146,12 +146,34 @@ __device__ inline void init_game(const Dev& D, Warp& w, uint32_t game_id) {
         g.game_id = game_id;
         g.epoch += 1;
         g.rec_head = 1, g.rec_tail = 0, g.lnk_head = 0, g.lnk_tail = 0, g.exp_count = 0;
-        g.sim_index = 0, g.sims_this_move = 0, g.n_moves = 0, g.n_pend = 0;
+        g.sim_index = 0, g.sims_this_move = 0, g.n_moves = 0, g.n_pend = 0, g.retried = 0;
         Rec r;
         r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
         store_rec(&w.rec[0], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.orph[j] = 0;
+    }
+    __syncwarp();
+}
+
+// A game's node pool is full (a search that concentrates on one line keeps a large subtree from stone to stone; the
+// reference's HashMap has no such limit): instead of failing every game of the batch, this game drops its tree and searches
+// the current board again from an unexpanded root — what a fresh AlphaZero instance would do.  Counted in Stats::degraded.
+__device__ inline void fresh_root(const Dev& D, Warp& w) {
+    GameState& g = *w.gs;
+    if (w.lane == 0) {
+        g.epoch += 2;  // empties the key table (the collector may have inserted under epoch + 1 already)
+        g.rec_tail = g.rec_head, g.lnk_tail = g.lnk_head, g.exp_count = 0;
+        const uint32_t root = g.rec_head & (D.R - 1);
+        g.rec_head += 1;
+        Rec r;
+        r.n = 0, r.w = 0.f, r.p = 0.f, r.link = NIL;
+        store_rec(&w.rec[root], r);
+        g.root = root;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.orph[j] = 0;
+        g.degraded += 1;
+        g.n_pend = 0;
     }
     __syncwarp();
 }
@@ -279,7 +301,7 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         __syncwarp();
       }
     }
-    if (overflow) return set_error(w, D, ERR_REC_FULL);
+    if (overflow) return fresh_root(D, w);  // the kept subtree does not fit beside the old one: the next search starts afresh
     // the root itself (unexpanded roots are not on the expanded list)
     Rec rr = load_rec(&w.rec[g.root]);
     uint32_t new_root;
@@ -360,7 +382,7 @@ __device__ inline void finish_move(const Dev& D, Warp& w) {
     const int lane = w.lane;
     const uint32_t Rm = D.R - 1, Lm = D.L - 1;
     Rec r = load_rec(&w.rec[g.root]);
-    if (lane == 0) g.sims_this_move = 0;
+    if (lane == 0) g.sims_this_move = 0, g.retried = 0;
     uint32_t B[8], W[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) B[j] = g.B[j], W[j] = g.W[j];

@@ -1,6 +1,7 @@
 // Kernels + host driver of the batched self-play engine.  See c6_engine.cuh / DESIGN.md.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,7 +80,18 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
         load_cursor(*w.gs, cs, st, lane);
         if (lane == 0) st.rootrec = bits_of(load_rec(&w.rec[w.gs->root]));
         __syncwarp();
-        for (int s = 0; s < D.num_sim && !cs.err; ++s) {
+        for (int s = 0; s < D.num_sim; ++s) {
+            if (cs.err) {  // the pool is full: once per stone the search starts again from a fresh root (fresh_root)
+                if (w.gs->retried) break;
+                cs.err = 0;
+                store_cursor(D, *w.gs, cs, st, lane);
+                fresh_root(D, w);
+                if (lane == 0) w.gs->retried = 1;
+                load_cursor(*w.gs, cs, st, lane);
+                if (lane == 0) st.rootrec = bits_of(load_rec(&w.rec[w.gs->root]));
+                __syncwarp();
+                s = 0;
+            }
             Leaf L;
             descend<NOISE, true>(D, w, cs, L, st, mt);
             if (L.stones == CELLS) {
@@ -98,6 +110,7 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
                 expand_leaf<true>(D, w, cs, L, ev, ev.value(), st);
             }
             cs.sim_index += 1;
+            if (cs.err && s + 1 == D.num_sim && !w.gs->retried) s -= 1;  // the last simulation overflowed: take the restart branch
         }
         store_cursor(D, *w.gs, cs, st, lane);
 #if C6_FUSE_MOVE_END
@@ -149,7 +162,16 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device_vl(De
         Cursor cs;
         load_cursor(*w.gs, cs, st, lane);
         int done = 0;
-        while (done < D.num_sim && !cs.err) {
+        while (done < D.num_sim) {
+            if (cs.err) {  // pool full: restart the stone's search from a fresh root, once
+                if (w.gs->retried) break;
+                cs.err = 0;
+                store_cursor(D, *w.gs, cs, st, lane);
+                fresh_root(D, w);
+                if (lane == 0) w.gs->retried = 1;
+                load_cursor(*w.gs, cs, st, lane);
+                done = 0;
+            }
             wave_descents<NOISE>(D, w, cs, st, mt, done);
             if (EVAL == EVAL_PHILOX) {
                 wave_expansions<NOISE>(D, w, cs, st, [&](const PendingLeaf& p, const Leaf&) {
@@ -211,7 +233,15 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
                 ev.lane = lane;
                 return ev;
             });
-            store_cursor(D, gs, cs, st, lane);
+            if (cs.err && !gs.retried) {  // pool full: restart the stone's search from a fresh root, once
+                cs.err = 0;
+                store_cursor(D, gs, cs, st, lane);
+                fresh_root(D, w);
+                if (lane == 0) gs.retried = 1, gs.sims_this_move = 0;
+                __syncwarp();
+            } else {
+                store_cursor(D, gs, cs, st, lane);
+            }
         }
         if (gs.status == ST_ACTIVE && gs.sims_this_move >= D.num_sim) finish_move(D, w);
         __syncwarp();
@@ -441,8 +471,20 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.G = cfg_.slots;
     D.R = 1u << cfg_.log2_records;
     D.L = D.R * 2;
-    D.E = 4096;
+    // Expanded nodes alive in one game: at most num_simulation new ones per stone on top of the subtree kept from the stone
+    // before (itself at most the visits of the chosen child).  E = 4,096 holds the reference default (800); larger budgets scale.
+    D.E = std::max<uint32_t>(4096u, (uint32_t)(((long long)std::max(cfg_.num_simulation, 0) * 5 / 2 + 1023) / 1024 * 1024));
     D.I = 8192;  // key table of expanded nodes: power of two >= 2 * E
+    while (D.I < 2 * D.E) D.I *= 2;
+    // A stone's search creates at most 225 records per simulation: a FRESH tree must fit the ring, or the restart of an
+    // overflowing search (fresh_root) could not finish either.
+    if ((long long)std::max(cfg_.num_simulation, 0) * CELLS + 2 * CELLS + 2 > (long long)D.R) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "c6: %d simulations per stone need more than %u node records per game; raise log2_records (C6_LOG2_RECORDS) to at least %d",
+                      cfg_.num_simulation, D.R, (int)std::ceil(std::log2((double)cfg_.num_simulation * CELLS + 2 * CELLS + 2)));
+        g_last_error = buf;
+        throw std::runtime_error(buf);
+    }
     D.num_sim = cfg_.num_simulation, D.eps = cfg_.epsilon, D.gp = gamma_params(cfg_.dirichlet_alpha), D.cpuct = cfg_.c_puct;
     D.seed = cfg_.seed, D.trace = cfg_.trace, D.max_moves = cfg_.max_moves, D.tie_break = cfg_.tie_break;
     D.K = cfg_.virtual_loss;
@@ -888,11 +930,13 @@ static void check_errors(DeviceArrays* d, cudaStream_t s) {
                 code = gs[i].err, slot = i;
                 break;
             }
-        char buf[256];
-        std::snprintf(buf, sizeof buf,
-                      "c6: node pool exhausted in game slot %d (%s); raise C6_LOG2_RECORDS (now %u records/game)", slot,
-                      code == ERR_REC_FULL ? "record ring" : code == ERR_LNK_FULL ? "link ring" : "expanded list",
-                      d->dev.R);
+        char buf[320];
+        if (code == ERR_EXP_FULL)
+            std::snprintf(buf, sizeof buf, "c6: node pool exhausted in game slot %d (expanded list: %u entries, sized from num_simulation) even after a "
+                          "restart from a fresh root", slot, d->dev.E);
+        else
+            std::snprintf(buf, sizeof buf, "c6: node pool exhausted in game slot %d (%s) even after a restart from a fresh root; raise log2_records / "
+                          "C6_LOG2_RECORDS (now %u records per game)", slot, code == ERR_REC_FULL ? "record ring" : "link ring", d->dev.R);
         g_last_error = buf;
         throw std::runtime_error(buf);
     }
@@ -1021,6 +1065,7 @@ Stats Engine::stats() {
         s.sims += g.sims, s.sum_ck += g.sum_ck, s.sum_cleaf += g.sum_cleaf, s.sum_depth += g.sum_depth;
         s.evals += g.evals, s.gc_copied += g.gc_copied;
         s.peak_rec = std::max(s.peak_rec, g.peak_rec), s.peak_lnk = std::max(s.peak_lnk, g.peak_lnk);
+        s.degraded += g.degraded;
     }
     s.games_done = d_->h_gcount[0];
     return s;

@@ -83,6 +83,8 @@ struct GameState {
     // statistics (SURVEY §8d counters)
     unsigned long long sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied;
     uint32_t peak_rec, peak_lnk;
+    uint32_t degraded;   // searches of this slot that ran out of pool space and were restarted from a fresh root
+    uint32_t retried;    // the current stone's search has been restarted already
     uint8_t moves[232];
 };
 
@@ -120,6 +122,7 @@ struct Stats {
     unsigned long long sims, sum_ck, sum_cleaf, sum_depth, evals, gc_copied;
     unsigned long long games_done;
     uint32_t peak_rec, peak_lnk;
+    unsigned long long degraded;  // searches restarted from a fresh root because the game's node pool was full
 };
 
 using Callback = void (*)(int player, float* values, float* policies, int len);

@@ -8,20 +8,27 @@
 
 namespace c6 {
 
-// One board per thread: 64 B in (two 256-bit loads), 1 B out.  HBM-bound by design: 65 B/board.
-__global__ void __launch_bounds__(256) k_win_check(const uint32_t* __restrict__ boards, int8_t* __restrict__ winners,
-                                                   long long n) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t* p = boards + i * 16;
-    uint32_t B[8], W[8];
+// Two boards per thread (boards i and i + n/2: both request streams stay coalesced, and the two independent shift/AND chains
+// interleave): 64 B in per board (two 256-bit loads), 1 B out.  HBM-bound by design: 65 B/board.
+__device__ __forceinline__ void load_board(const uint32_t* p, uint32_t (&B)[8], uint32_t (&W)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(B[0]), "=r"(B[1]), "=r"(B[2]), "=r"(B[3]), "=r"(B[4]), "=r"(B[5]), "=r"(B[6]), "=r"(B[7])
                  : "l"(p));
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(W[0]), "=r"(W[1]), "=r"(W[2]), "=r"(W[3]), "=r"(W[4]), "=r"(W[5]), "=r"(W[6]), "=r"(W[7])
                  : "l"(p + 8));
-    winners[i] = (int8_t)win_check(B, W);
+}
+__global__ void __launch_bounds__(256) k_win_check(const uint32_t* __restrict__ boards, int8_t* __restrict__ winners,
+                                                   long long n) {
+    const long long half = (n + 1) / 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    const long long i2 = i + half;
+    uint32_t B0[8], W0[8], B1[8], W1[8];
+    load_board(boards + i * 16, B0, W0);
+    if (i2 < n) load_board(boards + i2 * 16, B1, W1);
+    winners[i] = (int8_t)win_check_fast(B0, W0);
+    if (i2 < n) winners[i2] = (int8_t)win_check_fast(B1, W1);
 }
 
 // Synthetic boards: every cell iid uniform over {Black, None, White} (the reference's own random-board
@@ -176,7 +183,7 @@ void launch_probe_tie(uint32_t seed, uint32_t game, uint32_t count, uint32_t* d_
 
 void launch_win_check(const uint32_t* d_boards, int8_t* d_winners, int64_t n, cudaStream_t s) {
     if (n <= 0) return;
-    k_win_check<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_boards, d_winners, (long long)n);
+    k_win_check<<<(unsigned)(((n + 1) / 2 + 255) / 256), 256, 0, s>>>(d_boards, d_winners, (long long)n);
 }
 void launch_random_boards(uint32_t* d_boards, int64_t n, uint32_t seed, cudaStream_t s) {
     if (n <= 0) return;

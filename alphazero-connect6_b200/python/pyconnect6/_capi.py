@@ -50,7 +50,8 @@ class Record(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("sims", "sum_ck", "sum_cleaf", "sum_depth", "evals", "gc_copied", "games_done")] + \
-               [("peak_rec", C.c_uint32), ("peak_lnk", C.c_uint32), ("kernel_launches", C.c_uint64), ("bytes_per_game", C.c_uint64)]
+               [("peak_rec", C.c_uint32), ("peak_lnk", C.c_uint32), ("kernel_launches", C.c_uint64), ("bytes_per_game", C.c_uint64),
+                ("degraded", C.c_uint64)]
 
 
 class DpStats(C.Structure):  # c6_dp_stats

@@ -10,6 +10,9 @@ collection).  `value` = simulations/s with everything resident in HBM (device Ra
 into expansion); `e2e` = the same search driven through the reference C-ABI evaluator contract
 (host Callback, host buffers, D2H + H2D inside the timed region).  Games shard by game id across
 GPUs with no collective on the data path (weak scaling).
+
+The product is reached through its own ctypes binding (alphazero-connect6_b200/python/pyconnect6/_capi.py over the C-ABI);
+the oracle (oracle/binding.py) is touched only by the cpu_baseline leg and by --impl reference.
 """
 import argparse
 import ctypes as C
@@ -21,13 +24,20 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "alphazero-connect6_b200", "python"))
 
 GAMES_PER_GPU = 4096
 SIMS = 800
 EPS, ALPHA, CPUCT, SEED = 0.25, 0.03, 1.0, 0xC6
 METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
+
+
+def oracle_binding():
+    """oracle/binding.py — only the cpu_baseline and --impl reference legs come here."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import binding
+    return binding
 
 
 def measured_peak_gbs():
@@ -103,12 +113,12 @@ def run_reference(args, rank, world):
     """--impl reference: the restated reference (oracle, reference cost model) on the host cores."""
     if rank != 0:
         return None
-    import c6lib
-    O = c6lib.oracle()
+    ob = oracle_binding()
+    O = ob.oracle()
     cores = O.oracle_hardware_concurrency()
     moves = 2  # stones per game per step: bounded sample
-    p = c6lib.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 2, 1, 1, moves)
-    outs = (c6lib.OracleGameOut * cores)()
+    p = ob.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 2, 1, 1, moves)
+    outs = (ob.OracleGameOut * cores)()
     for w in range(max(args.warmup, 0)):
         if w >= 1:
             break  # one warm-up pass is enough for a CPU job; keeps the run within minutes
@@ -123,18 +133,19 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, GAMES_PER_GPU),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
 
 
-def workload_config(n_gpus):
-    return {"workload": "4096 concurrent self-play games per GPU, AlphaZero policy + RandomEvaluator, 800 simulations/stone "
-                        "(BASELINE.json configs[1]); reference default hyper-parameters epsilon=0.25 alpha=0.03 c_puct=1",
-            "games_per_gpu": GAMES_PER_GPU, "num_simulation": SIMS, "epsilon": EPS, "dirichlet_alpha": ALPHA,
-            "step": "one stone for every resident game (4096 x 800 simulations + move choice + node collection), one kernel launch",
+def workload_config(n_gpus, games):
+    return {"workload": f"{games} concurrent self-play games per GPU, AlphaZero policy + RandomEvaluator, 800 simulations/stone "
+                        "(BASELINE.json configs[1]); reference default hyper-parameters epsilon=0.25 alpha=0.03 c_puct=1, "
+                        "exact PUCT ties broken uniformly (Philox) as the reference does",
+            "games_per_gpu": games, "num_simulation": SIMS, "epsilon": EPS, "dirichlet_alpha": ALPHA,
+            "step": f"one stone for every resident game ({games} x 800 simulations + move choice + node collection), one kernel launch",
             "sharding": f"game id -> rank, {n_gpus} rank(s), no data-path collective",
             "l2": "working set >> L2 (node pool of 4096 games is tens of GB); no flush needed"}
 
@@ -162,6 +173,132 @@ def main():
         print(line, flush=True)
 
 
+class Reducer:
+    """max / sum over ranks on the device (NCCL) — the only exchange of the benchmark: timers and counters."""
+
+    def __init__(self, dist):
+        self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max(self, x):
+        if self.dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, *xs):
+        if self.dist is None:
+            return [float(x) for x in xs]
+        import torch
+        t = torch.tensor([float(x) for x in xs], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+
+def device_leg(L, capi, red, args, rank, local, games, steps, warmup, virtual_loss=1, steady=False):
+    """`steps` stones for `games` resident games with everything in HBM; returns the metric dict."""
+    cfg = capi.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
+                           slots=games, log2_records=args.log2_records, evaluator=capi.EVAL_PHILOX, virtual_loss=virtual_loss)
+    e = L.c6_engine_create(C.byref(cfg))
+    if not e:
+        raise RuntimeError(L.c6_last_error().decode())
+    try:
+        # many more games queued than will finish: slots refill, the batch stays full
+        assert L.c6_engine_start(e, rank * 100_000_000, 50_000_000) == 0, L.c6_last_error()
+        ms = C.c_float()
+        assert L.c6_engine_timed_steps(e, warmup, C.byref(ms)) == 0, L.c6_last_error()
+        st0, st1 = capi.Stats(), capi.Stats()
+        L.c6_engine_stats(e, C.byref(st0))
+        km0, kl0, km1, kl1 = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
+        L.c6_engine_kernel_times(e, C.byref(km0), C.byref(kl0))
+        red.barrier()
+        with ClockSampler(local) as clk:
+            assert L.c6_engine_timed_steps(e, steps, C.byref(ms)) == 0, L.c6_last_error()
+        L.c6_engine_stats(e, C.byref(st1))
+        L.c6_engine_kernel_times(e, C.byref(km1), C.byref(kl1))
+        local_ms = float(ms.value)
+        elapsed_ms = red.max(local_ms)
+        total_sims, total_launches = red.sum(st1.sims - st0.sims, st1.kernel_launches - st0.kernel_launches)
+        # roofline of the dominant kernel (one launch per step) on this rank: algorithmic bytes of the launches in the timed
+        # region / their own durations (one CUDA event pair per launch on the engine stream)
+        bytes_alg, d = algorithmic_bytes(st0, st1, materialised_batch=False)
+        peak, peak_src = measured_peak_gbs()
+        k_launches = max(kl1.value - kl0.value, 1)
+        k_ms = (km1.value - km0.value) / k_launches
+        achieved = (bytes_alg / k_launches) / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(d["sims"] / k_launches) if virtual_loss == 1 else (None, None)
+        out = {"value": total_sims / (elapsed_ms * 1e-3), "ms_per_step": elapsed_ms / steps, "gpu_launches": int(total_launches),
+               "clocks": clk.summary(), "peak_records_per_game": int(st1.peak_rec), "bytes_per_game": int(st1.bytes_per_game),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "traffic_source": traffic_src,
+                            "kernel": "k_sims_device<philox,noise> (1 launch/step: 800 searches per game, then the stone and node collection)",
+                            "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * k_launches / local_ms,
+                            "algorithmic_bytes_per_launch": bytes_alg / k_launches, "peak_source": peak_src,
+                            "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
+                            "avg_depth": d["sum_depth"] / max(d["sims"], 1), "avg_sum_ck": d["sum_ck"] / max(d["sims"], 1),
+                            "avg_cleaf": d["sum_cleaf"] / max(d["evals"], 1)}}
+        # steady state: keep stepping until every slot has finished at least one game (slots refill from the queue, so
+        # the resident games are then spread over all phases of a game), then time a window: simulations/s over whole
+        # games and finished games/s (the second half of BASELINE.json's metric)
+        if steady:
+            run_in, window = 240, 60
+            assert L.c6_engine_timed_steps(e, run_in, C.byref(ms)) == 0, L.c6_last_error()
+            sa, sb = capi.Stats(), capi.Stats()
+            L.c6_engine_stats(e, C.byref(sa))
+            red.barrier()
+            assert L.c6_engine_timed_steps(e, window, C.byref(ms)) == 0, L.c6_last_error()
+            L.c6_engine_stats(e, C.byref(sb))
+            w_ms = red.max(float(ms.value))
+            w_sims, w_games = red.sum(sb.sims - sa.sims, sb.games_done - sa.games_done)
+            out["steady_state"] = {"simulations_per_sec": w_sims / (w_ms * 1e-3), "games_per_sec": w_games / (w_ms * 1e-3),
+                                   "stones_per_game": (w_sims / SIMS) / max(w_games, 1.0), "ms_per_step": w_ms / window,
+                                   "window": f"{window} steps after {warmup + steps + run_in} (every slot refilled at least once); "
+                                             f"{int(w_games)} games finished in the window"}
+        return out
+    finally:
+        L.c6_engine_destroy(e)
+
+
+def e2e_leg(L, capi, red, args, rank, local, games, callback_name, waves_w=8, waves=48):
+    """`waves` simulations for each of `games` games through the reference-facing Callback contract: host buffers, D2H of the
+    leaf boards and H2D of the evaluator's answer inside the timed region."""
+    cfg = capi.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
+                           slots=games, log2_records=args.log2_records, evaluator=capi.EVAL_CALLBACK)
+    e = L.c6_engine_create(C.byref(cfg))
+    if not e:
+        raise RuntimeError(L.c6_last_error().decode())
+    try:
+        assert L.c6_engine_start(e, rank * 100_000_000, 50_000_000) == 0
+        cb = C.cast(getattr(L, callback_name), capi.CALLBACK)
+        ms, h2d, d2h = C.c_float(), C.c_double(), C.c_double()
+        assert L.c6_engine_timed_waves(e, cb, waves_w, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
+        s0, s1 = capi.Stats(), capi.Stats()
+        L.c6_engine_stats(e, C.byref(s0))
+        red.barrier()
+        hw0, hc0, hw1, hc1 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        L.c6_engine_host_times(e, C.byref(hw0), C.byref(hc0))
+        bw0 = L.c6_engine_host_blocked_waits(e)
+        assert L.c6_engine_timed_waves(e, cb, waves, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
+        L.c6_engine_stats(e, C.byref(s1))
+        L.c6_engine_host_times(e, C.byref(hw1), C.byref(hc1))
+        bw1 = L.c6_engine_host_blocked_waits(e)
+        e2e_ms = red.max(float(ms.value))
+        (e2e_sims,) = red.sum(s1.sims - s0.sims)
+        return {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d.value / waves, "d2h_bytes_per_step": d2h.value / waves,
+                "step": f"one wave = one simulation for each of {games} games through the C-ABI Callback (host buffers, "
+                        f"{callback_name}); {waves} waves timed",
+                "ms_per_wave": e2e_ms / waves,
+                "host_ms_per_wave": {"in_callback": 1e3 * (hc1.value - hc0.value) / waves, "blocked_on_gpu": 1e3 * (hw1.value - hw0.value) / waves,
+                                     "waits_that_slept_per_wave": (bw1 - bw0) / waves, "of": "rank 0"}}
+    finally:
+        L.c6_engine_destroy(e)
+
+
 def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +309,8 @@ def run():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-steady", action="store_true", help="skip the whole-game steady-state window (games/s)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 8,192-games-per-GPU leg of multi-GPU runs (BASELINE configs[3])")
+    ap.add_argument("--virtual-loss", type=int, default=1, help="opt-in multi-leaf mode (NOT the reference's search); adds the key `multi_leaf`")
     ap.add_argument("--log2-records", type=int, default=18)
     ap.add_argument("--epsilon", type=float, default=None, help="override epsilon (0 disables Dirichlet noise)")
     args = ap.parse_args()
@@ -186,148 +325,55 @@ def run():
     if args.warmup < 3:
         args.warmup = 3
 
-    import c6lib
-    L = c6lib.product()
+    from pyconnect6 import _capi as capi
+    L = capi.product()  # fails loudly when the CUDA library is not built
     dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    red = Reducer(dist)
+    # several ranks share the host on the callback legs: keep each rank's host threads next to its GPU
+    numa_node = L.c6_bind_host_to_device_numa(local) if world > 1 and os.environ.get("C6_NUMA_BIND", "1") != "0" else -1
+    host = {"cores_per_rank": L.c6_host_cores_per_rank(), "spin_budget_us": L.c6_host_spin_budget_us(), "numa_node": numa_node,
+            "cpus": os.cpu_count()}
 
     games = args.games
-    cfg = c6lib.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
-                            slots=games, log2_records=args.log2_records, evaluator=c6lib.EVAL_PHILOX)
-    e = L.c6_engine_create(C.byref(cfg))
-    if not e:
-        raise RuntimeError(L.c6_last_error().decode())
-    # many more games queued than will finish: slots refill, the batch stays full
-    assert L.c6_engine_start(e, rank * 100_000_000, 50_000_000) == 0, L.c6_last_error()
-    ms = C.c_float()
-    assert L.c6_engine_timed_steps(e, args.warmup, C.byref(ms)) == 0, L.c6_last_error()
-    st0, st1 = c6lib.Stats(), c6lib.Stats()
-    L.c6_engine_stats(e, C.byref(st0))
-    km0, kl0, km1, kl1 = C.c_double(), C.c_longlong(), C.c_double(), C.c_longlong()
-    L.c6_engine_kernel_times(e, C.byref(km0), C.byref(kl0))
-    if dist is not None:
-        dist.barrier()
-    with ClockSampler(local) as clk:
-        assert L.c6_engine_timed_steps(e, args.steps, C.byref(ms)) == 0, L.c6_last_error()
-    L.c6_engine_stats(e, C.byref(st1))
-    L.c6_engine_kernel_times(e, C.byref(km1), C.byref(kl1))
-    elapsed_ms = float(ms.value)
-    sims = st1.sims - st0.sims
-    launches = st1.kernel_launches - st0.kernel_launches
-    if dist is not None:
-        import torch
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        s = torch.tensor([float(sims), float(launches)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        total_sims, total_launches = float(s[0].item()), int(s[1].item())
-    else:
-        total_sims, total_launches = float(sims), int(launches)
-    value = total_sims / (elapsed_ms * 1e-3)
+    dev = device_leg(L, capi, red, args, rank, local, games, args.steps, args.warmup, steady=not args.no_steady)
+    out = {"metric": METRIC, "value": dev["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": workload_config(world, games), "roofline": dev["roofline"],
+           "gpu_launches": dev["gpu_launches"], "clocks": dev["clocks"], "peak_records_per_game": dev["peak_records_per_game"],
+           "bytes_per_game": dev["bytes_per_game"], "host": host}
+    if "steady_state" in dev:
+        out["steady_state"] = dev["steady_state"]
 
-    # roofline of the dominant kernel (k_sims_device: one launch per step) on this rank: algorithmic bytes of the
-    # launches in the timed region / their own durations (one CUDA event pair per launch on the engine stream)
-    bytes_alg, d = algorithmic_bytes(st0, st1, materialised_batch=False)
-    peak, peak_src = measured_peak_gbs()
-    k_launches = max(kl1.value - kl0.value, 1)
-    k_ms = (km1.value - km0.value) / k_launches
-    achieved = (bytes_alg / k_launches) / (k_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(d["sims"] / k_launches)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src,
-                "kernel": "k_sims_device<philox,noise> (1 launch/step: 800 searches per game, then the stone and node collection)", "kernel_ms_per_launch": k_ms,
-                "kernel_share_of_step": k_ms * k_launches / float(ms.value),
-                "algorithmic_bytes_per_launch": bytes_alg / k_launches, "peak_source": peak_src,
-                "algorithmic_bytes_per_sim": bytes_alg / max(d["sims"], 1),
-                "avg_depth": d["sum_depth"] / max(d["sims"], 1), "avg_sum_ck": d["sum_ck"] / max(d["sims"], 1),
-                "avg_cleaf": d["sum_cleaf"] / max(d["evals"], 1)}
-    # steady state: keep stepping until every slot has finished at least one game (slots refill from the queue, so
-    # the resident games are then spread over all phases of a game), then time a window: simulations/s over whole
-    # games and finished games/s (the second half of BASELINE.json's metric)
-    steady = None
-    if not args.no_steady:
-        run_in, window = 240, 60
-        assert L.c6_engine_timed_steps(e, run_in, C.byref(ms)) == 0, L.c6_last_error()
-        sa, sb = c6lib.Stats(), c6lib.Stats()
-        L.c6_engine_stats(e, C.byref(sa))
-        if dist is not None:
-            dist.barrier()
-        assert L.c6_engine_timed_steps(e, window, C.byref(ms)) == 0, L.c6_last_error()
-        L.c6_engine_stats(e, C.byref(sb))
-        w_ms, w_sims, w_games = float(ms.value), float(sb.sims - sa.sims), float(sb.games_done - sa.games_done)
-        if dist is not None:
-            import torch
-            t = torch.tensor([w_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            w_ms = float(t.item())
-            s = torch.tensor([w_sims, w_games], device="cuda", dtype=torch.float64)
-            dist.all_reduce(s, op=dist.ReduceOp.SUM)
-            w_sims, w_games = float(s[0].item()), float(s[1].item())
-        steady = {"simulations_per_sec": w_sims / (w_ms * 1e-3), "games_per_sec": w_games / (w_ms * 1e-3),
-                  "stones_per_game": (w_sims / SIMS) / max(w_games, 1.0), "ms_per_step": w_ms / window,
-                  "window": f"{window} steps after {args.warmup + args.steps + run_in} (every slot refilled at least once); "
-                            f"{int(w_games)} games finished in the window"}
-    L.c6_engine_destroy(e)
+    # BASELINE configs[3]: 65,536 games over 8 GPUs = 8,192 resident games per GPU (16,384 / 32,768 at 2 / 4 GPUs)
+    if world > 1 and not args.no_config4 and games != 8192:
+        c4 = device_leg(L, capi, red, args, rank, local, 8192, max(args.steps // 2, 3), 3)
+        out["config4"] = {"workload": f"{8192 * world} concurrent games, 8192 per GPU, game-sharded over {world} GPUs, Dirichlet noise on",
+                          "value": c4["value"], "unit": UNIT, "ms_per_step": c4["ms_per_step"], "roofline_frac": c4["roofline"]["frac"],
+                          "peak_records_per_game": c4["peak_records_per_game"]}
+    if args.virtual_loss > 1:
+        vl = device_leg(L, capi, red, args, rank, local, games, max(args.steps // 2, 3), 3, virtual_loss=args.virtual_loss)
+        out["multi_leaf"] = {"virtual_loss": args.virtual_loss, "value": vl["value"], "unit": UNIT, "ms_per_step": vl["ms_per_step"],
+                             "note": "opt-in mode, not the reference's sequential search: up to K leaves per game and wave"}
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": workload_config(world), "roofline": roofline,
-           "gpu_launches": total_launches, "clocks": clk.summary(),
-           "peak_records_per_game": int(st1.peak_rec), "bytes_per_game": int(st1.bytes_per_game)}
-    if steady is not None:
-        out["steady_state"] = steady
-
-    # end to end through the reference-facing evaluator contract: host callback, host buffers
+    # end to end through the reference-facing evaluator contract: host callback, host buffers.  Headline: the write-only random
+    # evaluator, the twin of the reference's own sample callback (Connect6/sample/cpp/main.cpp:6-28 fills values and policies and
+    # never reads the boards); alongside it an evaluator that reads every board before overwriting it.
     if not args.no_e2e:
-        cfg2 = c6lib.make_config(num_simulation=SIMS, epsilon=EPS, dirichlet_alpha=ALPHA, c_puct=CPUCT, seed=SEED, device=local,
-                                 slots=games, log2_records=args.log2_records, evaluator=c6lib.EVAL_CALLBACK)
-        e2 = L.c6_engine_create(C.byref(cfg2))
-        if not e2:
-            raise RuntimeError(L.c6_last_error().decode())
-        assert L.c6_engine_start(e2, rank * 100_000_000, 50_000_000) == 0
-        cb = C.cast(L.c6_sample_random_callback, c6lib.CALLBACK)
-        h2d, d2h = C.c_double(), C.c_double()
-        waves_w, waves = 8, 48
-        assert L.c6_engine_timed_waves(e2, cb, waves_w, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
-        s0, s1 = c6lib.Stats(), c6lib.Stats()
-        L.c6_engine_stats(e2, C.byref(s0))
-        if dist is not None:
-            dist.barrier()
-        hw0, hc0 = C.c_double(), C.c_double()
-        L.c6_engine_host_times(e2, C.byref(hw0), C.byref(hc0))
-        assert L.c6_engine_timed_waves(e2, cb, waves, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
-        L.c6_engine_stats(e2, C.byref(s1))
-        hw1, hc1 = C.c_double(), C.c_double()
-        L.c6_engine_host_times(e2, C.byref(hw1), C.byref(hc1))
-        e2e_ms, e2e_sims = float(ms.value), float(s1.sims - s0.sims)
-        if dist is not None:
-            import torch
-            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-            s = torch.tensor([e2e_sims], device="cuda", dtype=torch.float64)
-            dist.all_reduce(s, op=dist.ReduceOp.SUM)
-            e2e_sims = float(s.item())
-        out["e2e"] = {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d.value / waves,
-                      "d2h_bytes_per_step": d2h.value / waves,
-                      "step": f"one wave = one simulation for each of {games} games through the C-ABI Callback "
-                              f"(host buffers, sample host RandomEvaluator); {waves} waves timed",
-                      "ms_per_wave": e2e_ms / waves,
-                      "host_ms_per_wave": {"in_callback": 1e3 * (hc1.value - hc0.value) / waves,
-                                           "blocked_on_gpu": 1e3 * (hw1.value - hw0.value) / waves}}
-        L.c6_engine_destroy(e2)
+        out["e2e"] = e2e_leg(L, capi, red, args, rank, local, games, "c6_sample_random_callback")
+        out["e2e_reading_evaluator"] = e2e_leg(L, capi, red, args, rank, local, games, "c6_sample_reading_callback", waves_w=4, waves=24)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        O = c6lib.oracle()
+        ob = oracle_binding()
+        O = ob.oracle()
         cores = O.oracle_hardware_concurrency()
         moves = 30  # ~10 s on every host core (the sample the task statement asks for: 10-30 s of CPU work)
-        p = c6lib.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 2, 1, 1, moves)
-        outs = (c6lib.OracleGameOut * cores)()
+        p = ob.OracleParams(SIMS, EPS, ALPHA, CPUCT, SEED, 1, 2, 1, 1, moves)
+        outs = (ob.OracleGameOut * cores)()
         secs = O.oracle_self_play_many(None, C.byref(p), 30_000_000, cores, cores, outs)
         csims = sum(o.sims for o in outs)
         out["cpu_baseline"] = {"value": csims / secs, "unit": UNIT, "cores": cores, "kind": "port",

@@ -139,6 +139,7 @@ typedef struct c6_stats {
     uint32_t peak_rec, peak_lnk;
     uint64_t kernel_launches;
     uint64_t bytes_per_game;
+    uint64_t degraded; /* searches restarted from a fresh root because a game's node pool was full (summed over resident slots) */
 } c6_stats;
 
 typedef struct c6_engine c6_engine;

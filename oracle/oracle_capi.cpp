@@ -52,6 +52,20 @@ void neg_eval_callback(int player, float* values, float* policies, int len) {
             b[i] = (float)(uint32_t)(splitmix64(h + (uint64_t)i + 1) >> 40) * (1.0f / 8388608.0f) - 1.0f;
     }
 }
+// a peaked evaluator (what a trained network looks like to the node pool): almost all of the prior on one empty
+// cell chosen by the board hash, so that most of a stone's simulations go down one line and a large subtree survives the stone
+void peaked_eval_callback(int player, float* values, float* policies, int len) {
+    for (int n = 0; n < len; ++n) {
+        float* b = policies + (size_t)n * BOARD_CAPACITY;
+        const uint64_t h = splitmix64(oriented_key(b) ^ (player < 0 ? 0xB1ACull : 0x3417Eull));
+        int empties[BOARD_CAPACITY], ne = 0;
+        for (int i = 0; i < BOARD_CAPACITY; ++i)
+            if (b[i] == 0.f) empties[ne++] = i;
+        const int hot = ne ? empties[h % (uint64_t)ne] : 0;
+        values[n] = (float)(uint32_t)(h >> 40) * (1.0f / 8388608.0f) * 0.1f - 0.05f;
+        for (int i = 0; i < BOARD_CAPACITY; ++i) b[i] = i == hot ? 0.9f : 0.1f / 224.f;
+    }
+}
 // SURVEY B.1 hand-derived trace evaluator
 void const_eval_callback(int, float* values, float* policies, int len) {
     for (int n = 0; n < len; ++n) values[n] = 0.5f;

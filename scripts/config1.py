@@ -26,20 +26,32 @@ for sims in (2, 800):
     print(json.dumps({"case": f"engine, device RandomEvaluator, {sims} simulations/stone", "seconds_per_game": dt, "stones": rec[0].n_moves,
                       "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
 
-    cfg2 = c6lib.make_config(num_simulation=sims, epsilon=0.25, dirichlet_alpha=0.03, c_puct=1.0, seed=0xC6, device=0, slots=1,
-                             log2_records=18, evaluator=c6lib.EVAL_CALLBACK)
-    e = L.c6_engine_create(C.byref(cfg2))
-    assert e, L.c6_last_error()
-    assert L.c6_engine_start(e, 0, 1) == 0
-    cb = C.cast(L.c6_sample_random_callback, c6lib.CALLBACK)
-    t0 = time.perf_counter()
-    assert L.c6_engine_run_callback(e, cb) == 0, L.c6_last_error()
-    dt = time.perf_counter() - t0
-    L.c6_engine_stats(e, C.byref(st))
-    L.c6_engine_records(e, rec, 1)
-    L.c6_engine_destroy(e)
-    print(json.dumps({"case": f"engine, host Callback ABI (sample evaluator), {sims} simulations/stone", "seconds_per_game": dt,
-                      "stones": rec[0].n_moves, "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
+    # through the host Callback ABI: the reference's sequential schedule (K = 1), then the opt-in multi-leaf mode — K leaves per
+    # evaluator call, so a single game needs ~K times fewer round trips per stone (not the reference's search: SURVEY 7 "virtual loss")
+    for K in ((1,) if sims == 2 else (1, 2, 4, 8)):
+        cfg2 = c6lib.make_config(num_simulation=sims, epsilon=0.25, dirichlet_alpha=0.03, c_puct=1.0, seed=0xC6, device=0, slots=1,
+                                 log2_records=18, evaluator=c6lib.EVAL_CALLBACK, virtual_loss=K)
+        e = L.c6_engine_create(C.byref(cfg2))
+        assert e, L.c6_last_error()
+        assert L.c6_engine_start(e, 0, 1) == 0
+        cb = C.cast(L.c6_sample_random_callback, c6lib.CALLBACK)
+        t0 = time.perf_counter()
+        assert L.c6_engine_run_callback(e, cb) == 0, L.c6_last_error()
+        dt = time.perf_counter() - t0
+        L.c6_engine_stats(e, C.byref(st))
+        L.c6_engine_records(e, rec, 1)
+        L.c6_engine_destroy(e)
+        print(json.dumps({"case": f"engine, host Callback ABI (sample evaluator), {sims} simulations/stone, virtual_loss {K}", "seconds_per_game": dt,
+                          "stones": rec[0].n_moves, "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
+    if sims == 800:
+        for K in (2, 4, 8):
+            cfg3 = c6lib.make_config(num_simulation=sims, epsilon=0.25, dirichlet_alpha=0.03, c_puct=1.0, seed=0xC6, device=0, slots=1,
+                                     log2_records=18, evaluator=c6lib.EVAL_PHILOX, virtual_loss=K)
+            t0 = time.perf_counter()
+            assert L.c6_self_play_device(C.byref(cfg3), 0, 1, rec, C.byref(st)) == 0, L.c6_last_error()
+            dt = time.perf_counter() - t0
+            print(json.dumps({"case": f"engine, device RandomEvaluator, {sims} simulations/stone, virtual_loss {K}", "seconds_per_game": dt,
+                              "stones": rec[0].n_moves, "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
 
     mm = 0 if sims == 2 else 12  # the 800-simulation oracle game is timed on its first 12 stones and scaled by simulations
     p = c6lib.OracleParams(sims, 0.25, 0.03, 1.0, 0xC6, 1, 2, 1, 1, mm)

@@ -287,13 +287,14 @@ def test_reference_cpp_sample_links_against_our_library():
 # the repo); outputs go to tests/_build/ (git-ignored, travels to the GPU box with the snapshot) and the GPU suite runs them.
 # ---------------------------------------------------------------------------------------------
 BUILD_DIR = os.path.join(ROOT, "tests", "_build")
-REF_PY = {"ref_test_pybind.pyc": "/root/reference/Connect6/pybind/test_pybind/test_pybind.py",
-          "ref_random_policy.pyc": "/root/reference/Connect6/sample/python/random_policy.py"}
+# (.pycode, not .pyc: the gpurun snapshot leaves *.pyc files behind)
+REF_PY = {"ref_test_pybind.pycode": "/root/reference/Connect6/pybind/test_pybind/test_pybind.py",
+          "ref_random_policy.pycode": "/root/reference/Connect6/sample/python/random_policy.py"}
 
 
 def build_reference_python():
     """The reference's Python acceptance test and sample, byte-compiled from where they lie (PB/test_pybind/test_pybind.py:16-49,
-    Connect6/sample/python/random_policy.py:28-37): the .pyc files are what the GPU box executes against our pyconnect6."""
+    Connect6/sample/python/random_policy.py:28-37): the byte-code files are what the GPU box executes against our pyconnect6."""
     import py_compile
     os.makedirs(BUILD_DIR, exist_ok=True)
     out = []

@@ -385,17 +385,69 @@ def test_zero_simulations():
     assert all(rec[g].n_moves == 0 and rec[g].winner == 0 for g in range(2))
 
 
-def test_node_pool_overflow_is_loud():
+def test_pool_too_small_for_the_budget_is_refused_loudly():
+    """A ring that cannot hold even a fresh tree of one stone's search is refused at construction, naming the right knob."""
     L = c6lib.product()
     cfg = c6lib.make_config(num_simulation=64, epsilon=0.0, evaluator=EVAL_PHILOX, slots=1, log2_records=10)
+    assert not L.c6_engine_create(C.byref(cfg))
+    assert b"raise log2_records" in L.c6_last_error() and b"at least 14" in L.c6_last_error()
+    cfg = c6lib.make_config(num_simulation=64, epsilon=0.0, evaluator=EVAL_PHILOX, slots=1, virtual_loss=9)
+    assert not L.c6_engine_create(C.byref(cfg)) and b"virtual_loss" in L.c6_last_error()
+
+
+@pytest.mark.parametrize("evaluator,cbname,log2", [(EVAL_PHILOX, None, 15), (EVAL_CALLBACK, "peaked_eval_callback", 15),
+                                                   (EVAL_NEG, "neg_eval_callback", 15)])
+def test_full_pool_restarts_the_search_instead_of_failing_the_batch(evaluator, cbname, log2):
+    """a game whose node pool fills up (here: a ring of 2^15 records for 120 simulations, which holds a fresh tree
+    but not a fresh tree next to a kept subtree) drops its tree and searches the stone again from a fresh root; the batch goes
+    on, every game ends as a legal finished game, and the restarts are counted."""
+    L = c6lib.product()
+    n, sims = 6, 120
+    cfg = c6lib.make_config(num_simulation=sims, epsilon=0.25, seed=21, evaluator=evaluator, slots=n, log2_records=log2)
     e = L.c6_engine_create(C.byref(cfg))
-    assert e
+    assert e, L.c6_last_error()
     try:
-        assert L.c6_engine_start(e, 0, 1) == 0
-        assert L.c6_engine_run_device(e) != 0
-        assert b"node pool exhausted" in L.c6_last_error()
+        assert L.c6_engine_start(e, 0, n) == 0
+        if evaluator == EVAL_CALLBACK:
+            assert L.c6_engine_run_callback(e, c6lib.CALLBACK(c6lib.oracle_callback(cbname))) == 0, L.c6_last_error()
+        else:
+            assert L.c6_engine_run_device(e) == 0, L.c6_last_error()
+        rec = (c6lib.Record * n)()
+        assert L.c6_engine_records(e, rec, n) == 0
+        st = c6lib.Stats()
+        assert L.c6_engine_stats(e, C.byref(st)) == 0
     finally:
         L.c6_engine_destroy(e)
+    assert st.games_done == n and st.degraded > 0 and st.peak_rec <= (1 << log2)
+    for g in range(n):
+        r = rec[g]
+        mv = [r.moves[i] for i in range(r.n_moves)]
+        assert r.finished == 1 and len(set(mv)) == len(mv) and (r.winner != 0 or r.n_moves == 225)
+
+
+def test_peaked_evaluator_whole_games_at_800_simulations():
+    """a concentrated evaluator (90 % of the prior on one cell) over whole games at the reference default budget in
+    the default pool (2^18 records): the games finish, and whenever no restart was needed they equal the oracle's."""
+    L = c6lib.product()
+    n, sims, seed = 2, 800, 77
+    cfg = c6lib.make_config(num_simulation=sims, epsilon=0.25, seed=seed, evaluator=EVAL_CALLBACK, slots=n, log2_records=18)
+    e = L.c6_engine_create(C.byref(cfg))
+    assert e, L.c6_last_error()
+    try:
+        assert L.c6_engine_start(e, 0, n) == 0
+        assert L.c6_engine_run_callback(e, c6lib.CALLBACK(c6lib.oracle_callback("peaked_eval_callback"))) == 0, L.c6_last_error()
+        rec = (c6lib.Record * n)()
+        assert L.c6_engine_records(e, rec, n) == 0
+        st = c6lib.Stats()
+        assert L.c6_engine_stats(e, C.byref(st)) == 0
+    finally:
+        L.c6_engine_destroy(e)
+    assert st.games_done == n
+    if st.degraded == 0:
+        for g in range(n):
+            out, *_ = run_oracle(g, "peaked_eval_callback", 0, sims, 0.25, seed, 0)
+            assert [rec[g].moves[i] for i in range(rec[g].n_moves)] == [out.moves[i] for i in range(out.n_moves)], g
+    print("peak records per game", st.peak_rec, "restarts", st.degraded)
 
 
 def test_legacy_cpp_self_play_matches_oracle(monkeypatch):
@@ -816,8 +868,8 @@ def test_reference_pybind_tests_run_unchanged():
     byte-compiled from the reference tree, imported and run against our pyconnect6."""
     import subprocess
     import sys
-    pyc = os.path.join(_BUILD, "ref_test_pybind.pyc")
-    assert os.path.exists(pyc), "tests/_build/ref_test_pybind.pyc is missing: __graft_entry__.build() makes it where /root/reference is mounted"
+    pyc = os.path.join(_BUILD, "ref_test_pybind.pycode")
+    assert os.path.exists(pyc), "tests/_build/ref_test_pybind.pycode is missing: __graft_entry__.build() makes it where /root/reference is mounted"
     code = ("import importlib.machinery, importlib.util, sys\n"
             f"loader = importlib.machinery.SourcelessFileLoader('ref_test_pybind', {pyc!r})\n"
             "spec = importlib.util.spec_from_loader('ref_test_pybind', loader)\n"
@@ -835,9 +887,13 @@ def test_reference_python_sample_runs_unchanged():
     simulations, debug transcript), byte-compiled from the reference tree and executed as a script."""
     import subprocess
     import sys
-    pyc = os.path.join(_BUILD, "ref_random_policy.pyc")
-    assert os.path.exists(pyc), "tests/_build/ref_random_policy.pyc is missing: __graft_entry__.build() makes it where /root/reference is mounted"
-    r = subprocess.run([sys.executable, pyc], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=_PYPKG), timeout=600)
+    pyc = os.path.join(_BUILD, "ref_random_policy.pycode")
+    assert os.path.exists(pyc), "tests/_build/ref_random_policy.pycode is missing: __graft_entry__.build() makes it where /root/reference is mounted"
+    code = ("import importlib.machinery, importlib.util\n"
+            f"loader = importlib.machinery.SourcelessFileLoader('__main__', {pyc!r})\n"
+            "spec = importlib.util.spec_from_loader('__main__', loader)\n"
+            "m = importlib.util.module_from_spec(spec); loader.exec_module(m)\n")  # runs the script body, as `python random_policy.py` does
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=_PYPKG), timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     last = r.stdout.strip().splitlines()[-1]
     assert last.startswith("winner ") and ", len " in last, last
