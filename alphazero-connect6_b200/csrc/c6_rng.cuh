@@ -40,6 +40,22 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
+// Rounds 2..10 of philox4x32_10 on a state that has been through round 1 already (keys as given to round 1).  The evaluator's
+// counters are (sim, cell, half, 0): round 1 of such a block is M0 * sim — the same for every cell of a leaf — and M1 * half,
+// a constant, so it is done once per leaf (EvPhilox::init) instead of once per block.  Same bits as the full function.
+__host__ __device__ __forceinline__ Philox4 philox4x32_tail9(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    k0 += W0, k1 += W1;
+#pragma unroll
+    for (int r = 1; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0, c1 = (uint32_t)p1, c2 = n2, c3 = (uint32_t)p0;
+        k0 += W0, k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

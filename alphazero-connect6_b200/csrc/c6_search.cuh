@@ -138,8 +138,14 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #ifndef C6_CHILD_CG
 #define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
 #endif
+#ifndef C6_EV_ROUND1
+#define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
+#endif
 #ifndef C6_EV_UNROLL
 #define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
+#endif
+#ifndef C6_EV_ROUND1
+#define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
 #endif
 #ifndef C6_EV_UNROLL
 #define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
@@ -501,24 +507,33 @@ __device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, WarpStage<N
 // recovered prior needs exactly the 8 draws of its own cell.
 struct EvPhilox {
     uint32_t k0, k1, sim;
+    uint32_t r2, r3;  // words 2 and 3 of a block (sim, cell, half, 0) after Philox round 1: the same for every cell of the leaf
     int lane;
-    __device__ __forceinline__ void init(const Dev& D, const Cursor& cs, int lane_) {
-        k0 = D.seed ^ DOMAIN_EVAL, k1 = cs.game_id, sim = cs.sim_index, lane = lane_;
-    }
+    __device__ __forceinline__ void init(const Dev& D, const Cursor& cs, int lane_) { init(D, cs.game_id, cs.sim_index, lane_); }
     __device__ __forceinline__ void init(const Dev& D, uint32_t game_id, uint32_t sim_index, int lane_) {
         k0 = D.seed ^ DOMAIN_EVAL, k1 = game_id, sim = sim_index, lane = lane_;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * sim;
+        r2 = (uint32_t)(p0 >> 32) ^ k1, r3 = (uint32_t)p0;
+    }
+    // block (sim, cell, half, 0): round 1 by hand (M1 * half is 0 or M1: no high word), rounds 2..10 by philox4x32_tail9
+    __device__ __forceinline__ Philox4 block(uint32_t cell, uint32_t half) const {
+#if C6_EV_ROUND1
+        return philox4x32_tail9(cell ^ k0, half ? 0xCD9E8D57u : 0u, r2, r3, k0, k1);
+#else
+        return philox4x32_10(sim, cell, half, 0, k0, k1);
+#endif
     }
     // eight U[-1,1) draws of `cell` folded pairwise in plane order: {d0+d1, d2+d3, d4+d5, d6+d7}
     __device__ __forceinline__ void pairs(uint32_t cell, float (&t)[4]) const {
 #if C6_EV_UNROLL
         // both Philox blocks in flight together: four independent multiply chains instead of two
-        const Philox4 a = philox4x32_10(sim, cell, 0u, 0, k0, k1), b = philox4x32_10(sim, cell, 1u, 0, k0, k1);
+        const Philox4 a = block(cell, 0u), b = block(cell, 1u);
         t[0] = u32_to_pm1(a.x) + u32_to_pm1(a.y), t[1] = u32_to_pm1(a.z) + u32_to_pm1(a.w);
         t[2] = u32_to_pm1(b.x) + u32_to_pm1(b.y), t[3] = u32_to_pm1(b.z) + u32_to_pm1(b.w);
 #else
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
-            Philox4 a = philox4x32_10(sim, cell, half, 0, k0, k1);
+            Philox4 a = block(cell, half);
             const float lo = u32_to_pm1(a.x) + u32_to_pm1(a.y), hi = u32_to_pm1(a.z) + u32_to_pm1(a.w);
             if (half == 0) t[0] = lo, t[1] = hi; else t[2] = lo, t[3] = hi;
         }
@@ -528,7 +543,7 @@ struct EvPhilox {
         float sum = 0.f;
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
-            Philox4 a = philox4x32_10(sim, CELLS, half, 0, k0, k1);
+            Philox4 a = block(CELLS, half);
             sum = sum + u32_to_pm1(a.x), sum = sum + u32_to_pm1(a.y), sum = sum + u32_to_pm1(a.z), sum = sum + u32_to_pm1(a.w);
         }
         return sum / 8.f;

@@ -1,6 +1,7 @@
 #!/bin/bash
-# One gpurun call: GPU parity suite, the default bench line, then an A/B of experiment builds
-# (alphazero-connect6_b200/lib/variants/lib_*.so, made with `make -C alphazero-connect6_b200 exp NAME=.. DEFS=..`) on the same box.
+# One gpurun call: GPU parity suite, the default bench line, then an A/B of experiment builds on the same box
+# (alphazero-connect6_b200/lib/variants/lib_*.so from `make -C alphazero-connect6_b200 exp NAME=.. DEFS=..` for the search kernel,
+# libm_*.so from `make expm` for the micro-benchmark kernels).
 TAG=${1:-tune3}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -20,8 +21,14 @@ PY
 }
 run base C6_DUMMY=1
 for v in alphazero-connect6_b200/lib/variants/lib_*.so; do
+  [ -e "$v" ] || continue
   n=$(basename $v .so)
   run $n C6_LIB=$PWD/$v
 done
 EXTRA="--epsilon 0" run base_eps0 C6_DUMMY=1
 run base_again C6_DUMMY=1
+echo "micro base" ; timeout 300 python scripts/micro.py --no-cpu --quick 2>&1 | head -2 | tee $OUT/micro_base.jsonl
+for v in alphazero-connect6_b200/lib/variants/libm_*.so; do
+  [ -e "$v" ] || continue
+  echo "micro $(basename $v .so)"; C6_LIB=$PWD/$v timeout 300 python scripts/micro.py --no-cpu --quick 2>&1 | head -2 | tee $OUT/micro_$(basename $v .so).jsonl
+done

@@ -27,7 +27,7 @@ print(json.dumps({"bench": "random_playouts", "playouts": n, "ms": ms.value, "pl
 
 # DefaultPolicy (pure MCTS, 50 searches per stone = DefaultPolicy::new()) self-play: whole games on the GPU, one thread per
 # game, against the oracle restatement on all host cores (one OS thread per game like AsyncAgent) on a bounded sample.
-for n_games in (65536, 262144):
+for n_games in (() if "--quick" in sys.argv else (65536, 262144)):
     rec = (c6lib.Record * n_games)()
     st = c6lib.DpStats()
     assert L.c6_default_policy_play(50, 0xC6, 0, n_games, 0, 0, rec, None, None, C.byref(st)) == 0, L.c6_last_error()

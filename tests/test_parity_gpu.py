@@ -398,11 +398,11 @@ def test_pool_too_small_for_the_budget_is_refused_loudly():
 @pytest.mark.parametrize("evaluator,cbname,log2", [(EVAL_PHILOX, None, 15), (EVAL_CALLBACK, "peaked_eval_callback", 15),
                                                    (EVAL_NEG, "neg_eval_callback", 15)])
 def test_full_pool_restarts_the_search_instead_of_failing_the_batch(evaluator, cbname, log2):
-    """a game whose node pool fills up (here: a ring of 2^15 records for 120 simulations, which holds a fresh tree
-    but not a fresh tree next to a kept subtree) drops its tree and searches the stone again from a fresh root; the batch goes
+    """a game whose node pool fills up (here: a ring of 2^15 records for 143 simulations, which holds a fresh tree —
+    143 x 225 + 452 records at most — but not a fresh tree next to the subtree kept from the stone before) drops its tree and searches the stone again from a fresh root; the batch goes
     on, every game ends as a legal finished game, and the restarts are counted."""
     L = c6lib.product()
-    n, sims = 6, 120
+    n, sims = 6, 143
     cfg = c6lib.make_config(num_simulation=sims, epsilon=0.25, seed=21, evaluator=evaluator, slots=n, log2_records=log2)
     e = L.c6_engine_create(C.byref(cfg))
     assert e, L.c6_last_error()
