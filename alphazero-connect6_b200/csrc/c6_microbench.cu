@@ -9,95 +9,14 @@
 namespace c6 {
 
 // Two boards per thread (boards i and i + n/2: both request streams stay coalesced, and the two independent shift/AND chains
-// interleave): 64 B in per board (two 256-bit loads), 1 B out.  HBM-bound by design: 65 B/board.
+// interleave): 64 B in per board (two 256-bit loads), 1 B out.  65 algorithmic bytes per board.
 //
-// The r02e capture showed what held the first versions at 0.56 of the copy bandwidth: not issue slots but the ALU pipe
-// (`math_pipe_throttle` the top stall) — every funnel shift and every AND of the 256-bit run detection is an ALU-pipe
-// instruction, and that pipe takes a warp instruction every other cycle.  Here the shifts run on the FMA pipe instead: one
-// 32 x 32 -> 64-bit multiply by 2^s yields both halves a word contributes to a 256-bit left shift, and the AND that consumes
-// the shifted value takes the two halves as separate operands (a & (lo | hi) is one LOP3), so the shifted board is never formed.
-template <int S>
-__device__ __forceinline__ void and_shl256(const uint32_t (&a)[8], const uint32_t (&x)[8], uint32_t (&out)[8]) {  // out = a & (x << S)
-    constexpr int ws = S >> 5, bs = S & 31;
-    if (bs == 0) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) out[w] = w >= ws ? a[w] & x[w - ws] : 0u;
-        return;
-    }
-    uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        unsigned long long p;
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x[j]), "r"(1u << bs));
-        lo[j] = (uint32_t)p, hi[j] = (uint32_t)(p >> 32);
-    }
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const uint32_t l = w - ws >= 0 ? lo[w - ws >= 0 ? w - ws : 0] : 0u, h = w - ws - 1 >= 0 ? hi[w - ws - 1 >= 0 ? w - ws - 1 : 0] : 0u;
-        out[w] = a[w] & (l | h);
-    }
-}
-// x << S with the halves joined on the FMA pipe too: word w = x[w] * 2^s + (the high half of the word below), one multiply-add
-// chain per shift; the shifted board exists as a value, so a run of six is m2 & (m2 << 2D) & (m2 << 4D) in ONE three-input AND.
-template <int S>
-__device__ __forceinline__ void shl256_mad(const uint32_t (&x)[8], uint32_t (&out)[8]) {
-    constexpr int ws = S >> 5, bs = S & 31;
-    if (bs == 0) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) out[w] = w >= ws ? x[w - ws] : 0u;
-        return;
-    }
-    unsigned long long carry = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w < ws) {
-            out[w] = 0u;
-            continue;
-        }
-        unsigned long long p;
-        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(x[w - ws]), "r"(1u << bs), "l"(carry));
-        out[w] = (uint32_t)p, carry = p >> 32;
-    }
-}
-#ifndef C6_WIN_CHAIN
-#define C6_WIN_CHAIN 0  // A/B on the box (scripts/gpu_tune3.sh)
-#endif
-// bits at cells that END a run of >= 6 in stride D (c6_board.cuh: run6)
-template <int D>
-__device__ __forceinline__ void run6_dev(const uint32_t (&b)[8], uint32_t (&m6)[8]) {
-#if C6_WIN_CHAIN
-    uint32_t s1[8], m2[8], s2[8], s4[8];
-    shl256_mad<D>(b, s1);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m2[w] = b[w] & s1[w];
-    shl256_mad<2 * D>(m2, s2), shl256_mad<4 * D>(m2, s4);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m6[w] = m2[w] & s2[w] & s4[w];
-#else
-    uint32_t m2[8], m4[8];
-    and_shl256<D>(b, b, m2);
-    and_shl256<2 * D>(m2, m2, m4);
-    and_shl256<4 * D>(m4, m2, m6);
-#endif
-}
-__device__ __forceinline__ void run_ends(const uint32_t (&b)[8], uint32_t (&e)[8]) {
-    uint32_t h[8], v[8], d1[8], d2[8];
-    run6_dev<1>(b, h), run6_dev<16>(b, v), run6_dev<17>(b, d1), run6_dev<15>(b, d2);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) e[w] = (h[w] | v[w] | d1[w]) | d2[w];  // two three-input logic ops per word
-}
-__device__ __forceinline__ int win_check_dev(const uint32_t (&B)[8], const uint32_t (&W)[8]) {
-    uint32_t eb[8], ew[8];
-    run_ends(B, eb), run_ends(W, ew);
-    uint32_t first = 0, first_b = 0;  // a cell holds one colour: the winner owns the lowest set bit of (black | white run ends)
-#pragma unroll
-    for (int w = 7; w >= 0; --w) {
-        const uint32_t e = eb[w] | ew[w];
-        if (e) first = e, first_b = eb[w];
-    }
-    if (!first) return 0;
-    return (first_b & (first & (0u - first))) ? -1 : 1;
-}
+// What bounds it (profiles/r02e_prof_secondary.md): not HBM and not issue slots (49.5 % busy) but the ALU pipe —
+// `math_pipe_throttle` is the top stall: every funnel shift (SHF) and every AND (LOP3) of the 256-bit run detection is an
+// ALU-pipe instruction and that pipe takes one warp instruction every other cycle; 274 of them per board are 0.25 ms of pipe
+// time for 16 M boards against 0.17 ms of HBM time.  win_check_fast (word-shift vertical pass, one winner scan) cut the
+// instructions from 420 to 328 per board without moving the bound; doing the shifts as 32 x 32 -> 64-bit multiplies on the FMA
+// pipe (r02f A/B) was slower (0.48 of the copy bandwidth against 0.56: IMAD.WIDE is not a full-rate instruction either).
 __device__ __forceinline__ void load_board(const uint32_t* p, uint32_t (&B)[8], uint32_t (&W)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(B[0]), "=r"(B[1]), "=r"(B[2]), "=r"(B[3]), "=r"(B[4]), "=r"(B[5]), "=r"(B[6]), "=r"(B[7])
@@ -115,8 +34,8 @@ __global__ void __launch_bounds__(256) k_win_check(const uint32_t* __restrict__ 
     uint32_t B0[8], W0[8], B1[8], W1[8];
     load_board(boards + i * 16, B0, W0);
     if (i2 < n) load_board(boards + i2 * 16, B1, W1);
-    winners[i] = (int8_t)win_check_dev(B0, W0);
-    if (i2 < n) winners[i2] = (int8_t)win_check_dev(B1, W1);
+    winners[i] = (int8_t)win_check_fast(B0, W0);
+    if (i2 < n) winners[i2] = (int8_t)win_check_fast(B1, W1);
 }
 
 // Synthetic boards: every cell iid uniform over {Black, None, White} (the reference's own random-board

@@ -142,13 +142,13 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
 #endif
 #ifndef C6_EV_UNROLL
-#define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
+#define C6_EV_UNROLL 1  // the evaluator's two Philox blocks per cell interleaved: +2.2 % (r02f A/B, scripts/gpu_tune3.sh)
 #endif
 #ifndef C6_EV_ROUND1
 #define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
 #endif
 #ifndef C6_EV_UNROLL
-#define C6_EV_UNROLL 0  // the evaluator's two Philox blocks per cell interleaved (A/B on the box: scripts/gpu_tune3.sh)
+#define C6_EV_UNROLL 1  // the evaluator's two Philox blocks per cell interleaved: +2.2 % (r02f A/B, scripts/gpu_tune3.sh)
 #endif
 #ifndef C6_NOISE_UNROLL
 #define C6_NOISE_UNROLL 1

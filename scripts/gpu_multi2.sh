@@ -7,6 +7,7 @@ N=${2:-8}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nproc > $OUT/nproc.txt; lscpu | head -30 >> $OUT/nproc.txt; numactl -H >> $OUT/nproc.txt 2>&1; nvidia-smi topo -m >> $OUT/nproc.txt 2>&1
+timeout 600 python -m pytest tests/test_replay.py "tests/test_parity_gpu.py::test_host_mirror_random_evaluator_and_async_agent" -m gpu -q > $OUT/pytest_tail.log 2>&1; tail -3 $OUT/pytest_tail.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 900 $TR --master-port 29511 bench.py --gpus $N > $OUT/bench_${N}gpu.json 2> $OUT/bench_${N}gpu.err; echo "rc=$?" >> $OUT/bench_${N}gpu.err
 cat $OUT/bench_${N}gpu.json

@@ -53,7 +53,7 @@ int main() {
     auto gen = [] { return std::unique_ptr<Policy>(new FirstEmpty()); };
     auto results = make_async_agent(gen).run(4);
     CHECK(results.size() == 4);
-    for (const PlayResult& r : results) CHECK(consistent(r) && r.winner == Player::White && r.path.size() == 11);
+    for (const PlayResult& r : results) CHECK(consistent(r) && r.winner == Player::Black && r.path.size() == 81);  // row-major fill: Black's column of six
 
     // AsyncAgent over AlphaZero + RandomEvaluator with the light-weight budget, one GPU engine per game
     auto az_gen = [] { return std::unique_ptr<Policy>(new AlphaZero(std::unique_ptr<Evaluator>(new RandomEvaluator()), HyperParameter::light_weight(), 0xC6, 0, 12)); };
