@@ -148,9 +148,7 @@ __global__ void k_probe_gamma(GammaParams gp, uint32_t k0, uint32_t k1, float* o
     const uint32_t k = (uint32_t)i;
     float l;
     if (gp.shape < 1.0) {
-        uint32_t u, v;
-        gamma_words(7u, 9u, k, 0u, k0, k1, u, v);
-        if (!gamma_log2_fast(mt, gp, u, v, l)) l = gamma_log2_full(mt, gp.b, gp.inv_a, gp.c1, gp.am1, 7u, 9u, k, k0, k1);
+        if (!gamma_log2_fast(mt, gp, gamma_word0(7u, 9u, k, k0, k1), l)) l = gamma_log2_full(mt, gp.b, gp.inv_a, gp.c1, gp.am1, 7u, 9u, k, k0, k1);
     } else {
         l = gamma_large_log2(gp.shape, 7u, 9u, k, k0, k1);
     }

@@ -40,22 +40,6 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
-// Rounds 2..10 of philox4x32_10 on a state that has been through round 1 already (keys as given to round 1).  The evaluator's
-// counters are (sim, cell, half, 0): round 1 of such a block is M0 * sim — the same for every cell of a leaf — and M1 * half,
-// a constant, so it is done once per leaf (EvPhilox::init) instead of once per block.  Same bits as the full function.
-__host__ __device__ __forceinline__ Philox4 philox4x32_tail9(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    k0 += W0, k1 += W1;
-#pragma unroll
-    for (int r = 1; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c0 = n0, c1 = (uint32_t)p1, c2 = n2, c3 = (uint32_t)p0;
-        k0 += W0, k1 += W1;
-    }
-    return Philox4{c0, c1, c2, c3};
-}
-
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -212,37 +196,45 @@ inline GammaParams gamma_params(double shape) {
 }
 constexpr uint32_t DOMAIN_TIE = 0x54494542u;
 #ifdef __CUDACC__
-__device__ __forceinline__ float unit_of(uint32_t w) { return det_fmaf((float)w, 0x1p-32f, 0x1p-33f); }  // (w + 1/2) 2^-32
+__device__ __forceinline__ float unit_of(uint32_t w) { return det_fmaf((float)w, 0x1p-32f, 0x1p-33f); }    // (w + 1/2) 2^-32
+__device__ __forceinline__ float unit24_of(uint32_t w) { return det_fmaf((float)w, 0x1p-24f, 0x1p-25f); }  // (w + 1/2) 2^-24, 24-bit w
 
 // shape < 1 (the reference default is 0.03): Ahrens–Dieter GS rejection sampler — exact for every 0 < shape < 1,
 // acceptance > 98% at 0.03.  With P = b U:
 //   P <= 1 : X = P^(1/shape),          accept iff V <= e^-X      (1 - V >= 1 - e^-X)
 //   P >  1 : X = -ln((b - P)/shape),   accept iff V <= X^(shape-1)
-// gamma_log2_fast tries trial 0 on the hot branch with a sufficient test (1 - V >= 2^floor(L) (1 + frac L) >= X)
-// and reports failure (~5% of the draws); gamma_log2_full is the whole loop.
-__device__ __forceinline__ bool gamma_log2_fast(const MathTab& T, const GammaParams& gp, uint32_t u, uint32_t v, float& L) {
-    const float P = gp.b * unit_of(u);
+// Uniforms (twin: oracle/c6_rng.hpp gamma_uniforms): trial 0 of draw k is ONE word of Philox block (a, b, kb, 0),
+// kb = (k >> 7) << 5 | (k & 31), word (k >> 5) & 3 — four draws per block: 24 bits of U (all the f32 conversion keeps) and the
+// top byte of V; V's other 24 bits come from block (a, b, k, 0xFFFFFFFF) and are read by the full loop only.
+// gamma_log2_fast tries trial 0 on the hot branch with a sufficient test ((255 - v8)/256 >= 2^floor(L) (1 + frac L) >= X) and
+// reports failure (~6% of the draws); gamma_log2_full is the whole loop.
+__device__ __forceinline__ bool gamma_log2_fast(const MathTab& T, const GammaParams& gp, uint32_t w, float& L) {
+    const float P = gp.b * unit24_of(w >> 8);
     L = lg2_det(T, fminf(P, 1.0f)) * gp.inv_a;
     const float Lc = fmaxf(L, -64.0f);
     const float kf = floorf(Lc);
     const float xub = __uint_as_float(__float_as_uint(1.0f + (Lc - kf)) + ((uint32_t)(int)kf << 23));
-    return P <= 1.0f && unit_of(~v) >= xub;
+    return P <= 1.0f && (float)(255u - (w & 0xFFu)) * 0x1p-8f >= xub;
 }
-// words of trial `trial` of draw k: trial 0 shares a Philox block between draws k and k ^ 32
-__device__ __forceinline__ void gamma_words(uint32_t a, uint32_t b, uint32_t k, uint32_t trial, uint32_t k0, uint32_t k1, uint32_t& u,
-                                            uint32_t& v) {
-    const bool first = trial == 0;
-    const Philox4 r = philox4x32_10(a, b, first ? (((k >> 6) << 5) | (k & 31u)) : k, trial, k0, k1);
-    const bool hi = first && ((k >> 5) & 1u);
-    u = hi ? r.z : r.x, v = hi ? r.w : r.y;
+__device__ __forceinline__ uint32_t gamma_word0(uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
+    const Philox4 r = philox4x32_10(a, b, ((k >> 7) << 5) | (k & 31u), 0u, k0, k1);
+    const uint32_t h = (k >> 5) & 3u;
+    return h == 0 ? r.x : h == 1 ? r.y : h == 2 ? r.z : r.w;
 }
 static __device__ __noinline__ float gamma_log2_full(const MathTab& T, float gb, float inv_a, float c1, float am1, uint32_t a,
                                                       uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
     float L = 0.0f;
     for (uint32_t trial = 0; trial < 64u; ++trial) {
-        uint32_t u, v;
-        gamma_words(a, b, k, trial, k0, k1, u, v);
-        const float P = gb * unit_of(u);
+        float U, Uc, V, Vc;
+        if (trial == 0) {
+            const uint32_t w = gamma_word0(a, b, k, k0, k1);
+            const uint32_t v = ((w & 0xFFu) << 24) | (philox4x32_10(a, b, k, 0xFFFFFFFFu, k0, k1).x >> 8);
+            U = unit24_of(w >> 8), Uc = unit24_of(0xFFFFFFu - (w >> 8)), V = unit_of(v), Vc = unit_of(~v);
+        } else {
+            const Philox4 r = philox4x32_10(a, b, k, trial, k0, k1);
+            U = unit_of(r.x), Uc = unit_of(~r.x), V = unit_of(r.y), Vc = unit_of(~r.y);
+        }
+        const float P = gb * U;
         if (P <= 1.0f) {
             L = lg2_det(T, P) * inv_a;
             if (L < -40.0f) break;  // 1 - e^-X < 2^-40 < the smallest 1 - V
@@ -252,11 +244,11 @@ static __device__ __noinline__ float gamma_log2_full(const MathTab& T, float gb,
                 d = X * det_fmaf(X, det_fmaf(X, det_fmaf(X, -1.0f / 24.0f, 1.0f / 6.0f), -0.5f), 1.0f);
             else
                 d = 1.0f - ex2_det(X * -1.44269504f);
-            if (unit_of(~v) >= d) break;
+            if (Vc >= d) break;
         } else {
-            const float X = lg2_det(T, c1 * unit_of(~u)) * -0.693147182f;
+            const float X = lg2_det(T, c1 * Uc) * -0.693147182f;
             L = lg2_det(T, fmaxf(X, 0x1p-100f));
-            if (lg2_det(T, unit_of(v)) <= am1 * L) break;
+            if (lg2_det(T, V) <= am1 * L) break;
         }
     }
     return L;

@@ -138,14 +138,8 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #ifndef C6_CHILD_CG
 #define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
 #endif
-#ifndef C6_EV_ROUND1
-#define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
-#endif
 #ifndef C6_EV_UNROLL
 #define C6_EV_UNROLL 1  // the evaluator's two Philox blocks per cell interleaved: +2.2 % (r02f A/B, scripts/gpu_tune3.sh)
-#endif
-#ifndef C6_EV_ROUND1
-#define C6_EV_ROUND1 1  // the evaluator's Philox round 1 once per leaf instead of once per block (same bits)
 #endif
 #ifndef C6_EV_UNROLL
 #define C6_EV_UNROLL 1  // the evaluator's two Philox blocks per cell interleaved: +2.2 % (r02f A/B, scripts/gpu_tune3.sh)
@@ -206,29 +200,30 @@ __device__ __forceinline__ Rec rec_of(const uint4& v) {
 }
 __device__ __forceinline__ uint4 bits_of(const Rec& r) { return make_uint4((uint32_t)r.n, __float_as_uint(r.w), __float_as_uint(r.p), r.link); }
 
-// One round pair of the noise draw of a select step: children k and k + 32 of this lane share a Philox block.
+// Four rounds of the noise draw of a select step: children k, k + 32, k + 64, k + 96 of this lane share a Philox block.
 template <int NOISE>
 __device__ __forceinline__ void noise_rounds(const Dev& D, const Cursor& cs, WarpStage<NOISE>& st, const MathTab& mt, int depth, int C,
                                              int lane, int& k, int kend, float& lmax, unsigned& pend) {
     const uint32_t nk0 = D.seed ^ DOMAIN_NOISE;
     if (NOISE == 1) {
 #pragma unroll 1
-        for (; k < kend; k += 64) {
-            const Philox4 r = philox4x32_10(cs.sim_index, (uint32_t)depth, (uint32_t)(((k >> 6) << 5) | lane), 0u, nk0, cs.game_id);
-            float l0, l1;
-            const bool ok0 = gamma_log2_fast(mt, D.gp, r.x, r.y, l0);
-            const bool ok1 = gamma_log2_fast(mt, D.gp, r.z, r.w, l1);
-            st.lw[0][k] = l0;
-            if (ok0) lmax = fmaxf(lmax, l0); else pend |= 1u << (k >> 5);
-            if (k + 32 < C) {
-                st.lw[0][k + 32] = l1;
-                if (ok1) lmax = fmaxf(lmax, l1); else pend |= 2u << (k >> 5);
+        for (; k < kend; k += 128) {
+            const Philox4 r = philox4x32_10(cs.sim_index, (uint32_t)depth, (uint32_t)(((k >> 7) << 5) | lane), 0u, nk0, cs.game_id);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float l;
+                const bool ok = gamma_log2_fast(mt, D.gp, w[h], l);
+                if (k + 32 * h < C) {
+                    st.lw[0][k + 32 * h] = l;
+                    if (ok) lmax = fmaxf(lmax, l); else pend |= (1u << h) << (k >> 5);
+                }
             }
         }
     } else {
 #pragma unroll 1
-        for (; k < kend; k += 64)
-            for (int kk = k; kk < C && kk <= k + 32; kk += 32) {
+        for (; k < kend; k += 128)
+            for (int kk = k; kk < C && kk <= k + 96; kk += 32) {
                 const float l = gamma_large_log2(D.gp.shape, cs.sim_index, (uint32_t)depth, (uint32_t)kk, nk0, cs.game_id);
                 st.lw[0][kk] = l;
                 lmax = fmaxf(lmax, l);
@@ -291,7 +286,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
 #pragma unroll 1
             for (int part = 0; part < 3; ++part) {
-                if (NOISE && (part < 2 ? early : (!early && s_local != 0))) noise_rounds(D, cs, st, mt, depth, C, lane, kn, part == 0 ? min(C, 64) : C, lmax, pend);
+                if (NOISE && (part < 2 ? early : (!early && s_local != 0))) noise_rounds(D, cs, st, mt, depth, C, lane, kn, part == 0 ? min(C, 128) : C, lmax, pend);
                 if (part == 2) break;
                 cp_async_wait_all();
                 if (part == 0) {
@@ -507,53 +502,50 @@ __device__ __forceinline__ void terminal_leaf(const Dev& D, Warp& w, WarpStage<N
 // recovered prior needs exactly the 8 draws of its own cell.
 struct EvPhilox {
     uint32_t k0, k1, sim;
-    uint32_t r2, r3;  // words 2 and 3 of a block (sim, cell, half, 0) after Philox round 1: the same for every cell of the leaf
     int lane;
     __device__ __forceinline__ void init(const Dev& D, const Cursor& cs, int lane_) { init(D, cs.game_id, cs.sim_index, lane_); }
     __device__ __forceinline__ void init(const Dev& D, uint32_t game_id, uint32_t sim_index, int lane_) {
         k0 = D.seed ^ DOMAIN_EVAL, k1 = game_id, sim = sim_index, lane = lane_;
-        const uint64_t p0 = (uint64_t)0xD2511F53u * sim;
-        r2 = (uint32_t)(p0 >> 32) ^ k1, r3 = (uint32_t)p0;
-    }
-    // block (sim, cell, half, 0): round 1 by hand (M1 * half is 0 or M1: no high word), rounds 2..10 by philox4x32_tail9
-    __device__ __forceinline__ Philox4 block(uint32_t cell, uint32_t half) const {
-#if C6_EV_ROUND1
-        return philox4x32_tail9(cell ^ k0, half ? 0xCD9E8D57u : 0u, r2, r3, k0, k1);
-#else
-        return philox4x32_10(sim, cell, half, 0, k0, k1);
-#endif
-    }
-    // eight U[-1,1) draws of `cell` folded pairwise in plane order: {d0+d1, d2+d3, d4+d5, d6+d7}
-    __device__ __forceinline__ void pairs(uint32_t cell, float (&t)[4]) const {
-#if C6_EV_UNROLL
-        // both Philox blocks in flight together: four independent multiply chains instead of two
-        const Philox4 a = block(cell, 0u), b = block(cell, 1u);
-        t[0] = u32_to_pm1(a.x) + u32_to_pm1(a.y), t[1] = u32_to_pm1(a.z) + u32_to_pm1(a.w);
-        t[2] = u32_to_pm1(b.x) + u32_to_pm1(b.y), t[3] = u32_to_pm1(b.z) + u32_to_pm1(b.w);
-#else
-#pragma unroll 1
-        for (uint32_t half = 0; half < 2; ++half) {
-            Philox4 a = block(cell, half);
-            const float lo = u32_to_pm1(a.x) + u32_to_pm1(a.y), hi = u32_to_pm1(a.z) + u32_to_pm1(a.w);
-            if (half == 0) t[0] = lo, t[1] = hi; else t[2] = lo, t[3] = hi;
-        }
-#endif
     }
     __device__ __forceinline__ float value() const {  // ((((((((0+v0)+v1)+..)+v7)/8 (:224)
         float sum = 0.f;
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
-            Philox4 a = block(CELLS, half);
+            Philox4 a = philox4x32_10(sim, CELLS, half, 0, k0, k1);
             sum = sum + u32_to_pm1(a.x), sum = sum + u32_to_pm1(a.y), sum = sum + u32_to_pm1(a.z), sum = sum + u32_to_pm1(a.w);
         }
         return sum / 8.f;
     }
-    __device__ __forceinline__ float prior(uint32_t bit) const {
-        float t[4];
-        pairs((uint32_t)cell_of_bit(bit), t);
+    // 24-bit draw number i (0..7) of the 192 bits in words q[0..5]: bits [24 i, 24 i + 24)
+    static __device__ __forceinline__ float draw24(const uint32_t (&q)[6], int i) {
+        const int w = (3 * i) >> 2, sh = 8 * ((3 * i) & 3);
+        const uint32_t x = sh == 0 ? q[w] : (sh == 8 ? q[w] >> 8 : __funnelshift_r(q[w], q[w + 1 < 6 ? w + 1 : 5], sh));
+        return (float)(x & 0xFFFFFFu) * (1.0f / 8388608.0f) - 1.0f;
+    }
+    static __device__ __forceinline__ float fold8(const uint32_t (&q)[6]) {  // recover_way8 order: t_i = p[2i] + flip(p[2i+1]), ((((0+t0)+t1)+t2)+t3)/8
         float total = 0.f;
-        total = total + t[0], total = total + t[1], total = total + t[2], total = total + t[3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) total = total + (draw24(q, 2 * i) + draw24(q, 2 * i + 1));
         return total / 8.f;
+    }
+    // Priors of the leaf's children by rank.  The children of ranks k and k + 32 (k = 64 j + lane) share THREE Philox blocks
+    // (sim, 32 j + lane, 0..2, 0): their 384 bits are sixteen 24-bit draws, eight per child (a cell's eight draws are what the
+    // eight symmetric planes show at its images: twin PhiloxRandomEvaluator in oracle/c6_oracle.hpp) — 1.5 blocks per child
+    // instead of 2, nothing of a block unused.
+    template <class Stage>
+    __device__ __forceinline__ void fill_priors(Stage& st, int C) const {
+#pragma unroll 1
+        for (int k = lane; k < C; k += 64) {
+            const uint32_t kb = (uint32_t)(((k >> 6) << 5) | lane);
+            const Philox4 a = philox4x32_10(sim, kb, 0u, 0, k0, k1), b = philox4x32_10(sim, kb, 1u, 0, k0, k1);
+            const uint32_t q0[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+            st.prior[0][k] = fold8(q0);
+            if (k + 32 < C) {
+                const Philox4 c = philox4x32_10(sim, kb, 2u, 0, k0, k1);
+                const uint32_t q1[6] = {b.z, b.w, c.x, c.y, c.z, c.w};
+                st.prior[0][k + 32] = fold8(q1);
+            }
+        }
     }
 };
 
@@ -587,6 +579,11 @@ struct EvHash {
         for (int s = 0; s < 8; ++s) sum = sum + ((float)(uint32_t)(h[s] >> 40) * (1.0f / 8388608.0f) - 1.0f);
         return sum / 8.f;
     }
+    template <class Stage>
+    __device__ __forceinline__ void fill_priors(Stage& st, int C) const {
+#pragma unroll 1
+        for (int k = lane; k < C; k += 32) st.prior[0][k] = prior((uint32_t)st.cell[k]);
+    }
     __device__ __forceinline__ float prior(uint32_t bit) const {
         int r = (int)(bit >> 4), c = (int)(bit & 15);
         float pv[8];
@@ -615,6 +612,11 @@ struct EvBatch {
 #pragma unroll
         for (int s = 0; s < 8; ++s) sum = sum + __shfl_sync(FULL, myv, s);  // iter().sum::<f32>() order (:224)
         return sum / 8.f;
+    }
+    template <class Stage>
+    __device__ __forceinline__ void fill_priors(Stage& st, int C) const {
+#pragma unroll 1
+        for (int k = lane; k < C; k += 32) st.prior[0][k] = prior((uint32_t)st.cell[k]);
     }
     __device__ __forceinline__ float prior(uint32_t bit) const {
         int r = (int)(bit >> 4), c = (int)(bit & 15);
@@ -762,8 +764,7 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
             }
         }
     }
-C6_UNROLL(C6_PRIOR_UNROLL)
-    for (int k = lane; k < C; k += 32) st.prior[0][k] = ev.prior((uint32_t)st.cell[k]);
+    ev.fill_priors(st, C);
     // rules S1 / S2 (warp-uniform test)
     {
         const uint32_t s1 = (uint32_t)L.stones + 1u;

@@ -78,6 +78,7 @@ def oracle():
         L.oracle_search_batch.argtypes = [C.POINTER(C.c_int8), C.c_int64, C.POINTER(C.c_int8), C.c_int]
         L.oracle_search_batch_packed.argtypes = [C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_int8), C.c_int]
         L.oracle_playout_batch.argtypes = [C.c_uint32, C.c_uint64, C.c_int64, C.POINTER(C.c_int8), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_int]
+        L.oracle_random_evaluator.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int8), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _oracle = L
     return _oracle
 

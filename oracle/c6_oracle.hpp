@@ -423,9 +423,10 @@ struct CppEval : Evaluator {
 };
 
 // The engine's device RandomEvaluator twin (replaces thread_rng RandomEvaluator, mod.rs:137-169):
-// every value / policy entry is iid U[-1,1) from Philox keyed (seed^EVAL, game) and counter
-// (sim, original-frame cell or 225 for values, half).  Plane s at oriented cell T_s(cell) holds
-// draw number s of the original-frame `cell` (a fixed permutation of iid draws is iid).
+// every value / policy entry is iid U[-1,1) on a 24-bit grid from Philox keyed (seed^EVAL, game): values from blocks
+// (sim, 225, half, 0), the eight draws of an EMPTY cell from the blocks of its rank pair (see eval below; occupied cells
+// are masked by get_from and get none).  Plane s at oriented cell T_s(cell) holds draw number s of the original-frame
+// `cell` (a fixed permutation of iid draws is iid).
 struct PhiloxRandomEvaluator : Evaluator {
     bool eval(Player, const std::vector<Board>& boards, const EvalCtx& ctx, std::vector<float>& values,
               std::vector<FBoard>& policies) override;
@@ -795,7 +796,7 @@ struct AlphaZero {
 
 inline bool PhiloxRandomEvaluator::eval(Player, const std::vector<Board>& boards, const EvalCtx& ctx,
                                         std::vector<float>& values, std::vector<FBoard>& policies) {
-    // boards.size() == 8 (one leaf); plane order = augment_way8 order.
+    // boards.size() == 8 (one leaf); plane order = augment_way8 order, so boards[6] (rotate_left four times) is the leaf itself.
     size_t len = boards.size();
     values.assign(len, 0.f);
     policies.assign(len, FBoard{});
@@ -803,15 +804,34 @@ inline bool PhiloxRandomEvaluator::eval(Player, const std::vector<Board>& boards
     Philox4 va = philox4x32_10(ctx.sim_index, BOARD_CAPACITY, 0, 0, k0, k1);
     Philox4 vb = philox4x32_10(ctx.sim_index, BOARD_CAPACITY, 1, 0, k0, k1);
     for (int s = 0; s < 8 && s < (int)len; ++s) values[s] = u32_to_pm1(s < 4 ? va.v[s] : vb.v[s - 4]);
-    // original-frame draws, then carried to each plane with the same maps augment_way8 uses
+    // Original-frame draws, then carried to each plane with the same maps augment_way8 uses.  Only empty cells get draws (the
+    // prior of an occupied cell is masked, mod.rs:227-232): the empty cell of row-major rank k takes eight 24-bit draws out of
+    // the 384 bits of Philox blocks (sim, kb, 0..2, 0), kb = (k >> 6) << 5 | (k & 31) — draws 0..7 of that string for rank
+    // kb + 64 (k >> 6) ... i.e. the lower rank of the pair (k, k + 32), draws 8..15 for the upper one.
     std::vector<FBoard> orig(8);
-    for (int r = 0; r < BOARD_SIZE; ++r)
-        for (int c = 0; c < BOARD_SIZE; ++c) {
-            uint32_t cell = r * BOARD_SIZE + c;
-            Philox4 a = philox4x32_10(ctx.sim_index, cell, 0, 0, k0, k1);
-            Philox4 b = philox4x32_10(ctx.sim_index, cell, 1, 0, k0, k1);
-            for (int s = 0; s < 8; ++s) orig[s][r][c] = u32_to_pm1(s < 4 ? a.v[s] : b.v[s - 4]);
-        }
+    for (auto& b : orig)
+        for (auto& r : b) r.fill(0.f);
+    if (len >= 7) {
+        const Board& leaf = boards[6];
+        uint32_t k = 0;
+        for (int r = 0; r < BOARD_SIZE; ++r)
+            for (int c = 0; c < BOARD_SIZE; ++c) {
+                if (leaf[r][c] != Player::None) continue;
+                const uint32_t kb = ((k >> 6) << 5) | (k & 31u), upper = (k >> 5) & 1u;
+                uint32_t w[12];
+                for (uint32_t j = 0; j < 3; ++j) {
+                    Philox4 blk = philox4x32_10(ctx.sim_index, kb, j, 0, k0, k1);
+                    for (int t = 0; t < 4; ++t) w[4 * j + t] = blk.v[t];
+                }
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t bit = 24u * (8u * upper + (uint32_t)s), q = bit >> 5, sh = bit & 31u;
+                    const uint64_t two = (uint64_t)w[q] | ((uint64_t)(q + 1 < 12 ? w[q + 1] : 0u) << 32);
+                    const uint32_t x = (uint32_t)(two >> sh) & 0xFFFFFFu;
+                    orig[s][r][c] = (float)x * (1.0f / 8388608.0f) - 1.0f;
+                }
+                k += 1;
+            }
+    }
     for (int k = 0; k < 4; ++k) {
         FBoard even = orig[2 * k], odd = orig[2 * k + 1];
         for (int t = 0; t <= k; ++t) {

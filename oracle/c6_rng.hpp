@@ -215,11 +215,10 @@ inline double gamma_sample(double shape, uint32_t a, uint32_t b, uint32_t c, uin
 // normalises like a softmax: noise_k = 2^(L_k - Lmax) / sum_j 2^(L_j - Lmax).  Same distribution
 // (Ahrens–Dieter GS is still the exact rejection sampler; only the arithmetic is f32 where the
 // reference's is f64 rounded to f32 at the end), one third of the instructions on the GPU.
-//   * uniforms: 32-bit Philox words, U = (u + 1/2) 2^-32, complement 1 - U from ~u (both exact
-//     before the conversion to f32);
-//   * draw k of a select step takes trial 0 from words (2h, 2h+1) of block (a, b, kb, 0),
-//     kb = (k >> 6) << 5 | (k & 31), h = (k >> 5) & 1 (two draws per Philox call); trial t >= 1
-//     from words (0, 1) of block (a, b, k, t);
+//   * uniforms: see gamma_uniforms — trial 0 of four draws shares one Philox block (24 bits of U and the
+//     top byte of V per draw; the rest of V from a block of its own, read only when that byte does not
+//     decide); trial t >= 1 from words (0, 1) of block (a, b, k, t) as 32-bit uniforms; complements
+//     1 - U, 1 - V from the complemented integers (exact before the conversion to f32);
 //   * trial 0 is first tried on the hot branch with a sufficient acceptance test (2^L <= 2^floor(L)
 //     (1 + frac L)); only if that fails the full rejection loop runs (from trial 0 again).
 // lg2_det / ex2_det: table + polynomial, explicit fmaf only — bit-identical on x86-64 and the GPU.
@@ -267,35 +266,47 @@ inline GammaF gamma_f(double shape) {
     const double b = (2.718281828459045 + shape) / 2.718281828459045;
     return GammaF{(float)b, (float)(1.0 / shape), (float)(b / shape), (float)(shape - 1.0)};
 }
-inline float unit_of(uint32_t w) { return fmaf1((float)w, 0x1p-32f, 0x1p-33f); }  // (w + 1/2) 2^-32, rounded once
+inline float unit_of(uint32_t w) { return fmaf1((float)w, 0x1p-32f, 0x1p-33f); }    // (w + 1/2) 2^-32, rounded once
+inline float unit24_of(uint32_t w) { return fmaf1((float)w, 0x1p-24f, 0x1p-25f); }  // (w + 1/2) 2^-24 for a 24-bit w
 
-// hot branch of trial 0; false = undecided (the full loop decides)
-inline bool gamma_log2_fast(const GammaF& g, uint32_t u, uint32_t v, float& L) {
-    const float P = g.b * unit_of(u);
+// The uniforms of trial `trial` of draw k.  Trial 0 takes ONE word of Philox block (a, b, kb, 0), kb = (k >> 7) << 5 | (k & 31),
+// word (k >> 5) & 3 — four draws per block: its top 24 bits are U (all the f32 conversion keeps of a uniform anyway), its low 8
+// bits the top byte of V, which decides almost every acceptance; the other 24 bits of V come from word 0 of block
+// (a, b, k, 0xFFFFFFFF) and are only looked at when the first byte does not decide.  Trial t >= 1 takes words 0, 1 of block
+// (a, b, k, t) as 32-bit uniforms.
+struct GammaUniforms {
+    float U, Uc, V, Vc;  // U, 1 - U, V, 1 - V
+};
+inline uint32_t gamma_word0(uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
+    return philox4x32_10(a, b, ((k >> 7) << 5) | (k & 31u), 0u, k0, k1).v[(k >> 5) & 3u];
+}
+inline GammaUniforms gamma_uniforms(uint32_t a, uint32_t b, uint32_t k, uint32_t trial, uint32_t k0, uint32_t k1) {
+    if (trial == 0) {
+        const uint32_t w = gamma_word0(a, b, k, k0, k1);
+        const uint32_t ext = philox4x32_10(a, b, k, 0xFFFFFFFFu, k0, k1).v[0];
+        const uint32_t v = ((w & 0xFFu) << 24) | (ext >> 8);
+        return GammaUniforms{unit24_of(w >> 8), unit24_of(0xFFFFFFu - (w >> 8)), unit_of(v), unit_of(~v)};
+    }
+    const Philox4 r = philox4x32_10(a, b, k, trial, k0, k1);
+    return GammaUniforms{unit_of(r.v[0]), unit_of(~r.v[0]), unit_of(r.v[1]), unit_of(~r.v[1])};
+}
+
+// hot branch of trial 0 on the draw's word alone; false = undecided (the full loop decides)
+inline bool gamma_log2_fast(const GammaF& g, uint32_t w, float& L) {
+    const float P = g.b * unit24_of(w >> 8);
     L = 0.0f;
     if (P > 1.0f) return false;
     L = lg2_det(P) * g.inv_a;
     const float Lc = L < -64.0f ? -64.0f : L;
     const float kf = __builtin_floorf(Lc);
     const float xub = u2f(f2u(1.0f + (Lc - kf)) + ((uint32_t)(int32_t)kf << 23));  // 2^k (1 + f) >= 2^(k + f)
-    return unit_of(~v) >= xub;  // 1 - V >= X >= 1 - e^-X
-}
-inline void gamma_words(uint32_t a, uint32_t b, uint32_t k, uint32_t trial, uint32_t k0, uint32_t k1, uint32_t& u, uint32_t& v) {
-    if (trial == 0) {
-        const Philox4 r = philox4x32_10(a, b, ((k >> 6) << 5) | (k & 31u), 0u, k0, k1);
-        const uint32_t h = (k >> 5) & 1u;
-        u = r.v[2 * h], v = r.v[2 * h + 1];
-    } else {
-        const Philox4 r = philox4x32_10(a, b, k, trial, k0, k1);
-        u = r.v[0], v = r.v[1];
-    }
+    return (float)(255u - (w & 0xFFu)) * 0x1p-8f >= xub;  // 1 - V > (255 - v8)/256 >= X >= 1 - e^-X whatever the other bits of V are
 }
 inline float gamma_log2_full(const GammaF& g, uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
     float L = 0.0f;
     for (uint32_t t = 0; t < 64; ++t) {
-        uint32_t u, v;
-        gamma_words(a, b, k, t, k0, k1, u, v);
-        const float P = g.b * unit_of(u);
+        const GammaUniforms q = gamma_uniforms(a, b, k, t, k0, k1);
+        const float P = g.b * q.U;
         if (P <= 1.0f) {  // X = P^(1/a); accept iff V <= e^-X, i.e. 1 - V >= 1 - e^-X
             L = lg2_det(P) * g.inv_a;
             if (L < -40.0f) return L;  // 1 - e^-X < 2^-40 < the smallest 1 - V
@@ -305,11 +316,11 @@ inline float gamma_log2_full(const GammaF& g, uint32_t a, uint32_t b, uint32_t k
                 d = X * fmaf1(X, fmaf1(X, fmaf1(X, -1.0f / 24.0f, 1.0f / 6.0f), -0.5f), 1.0f);  // X - X^2/2 + X^3/6 - X^4/24
             else
                 d = 1.0f - ex2_det(X * -1.44269504f);
-            if (unit_of(~v) >= d) return L;
+            if (q.Vc >= d) return L;
         } else {  // X = -ln((b - P)/a) = -ln((b/a)(1 - U)); accept iff V <= X^(a-1)
-            const float X = lg2_det(g.c1 * unit_of(~u)) * -0.693147182f;
+            const float X = lg2_det(g.c1 * q.Uc) * -0.693147182f;
             L = lg2_det(X > 0x1p-100f ? X : 0x1p-100f);
-            if (lg2_det(unit_of(v)) <= g.am1 * L) return L;
+            if (lg2_det(q.V) <= g.am1 * L) return L;
         }
     }
     return L;
@@ -318,10 +329,8 @@ inline float gamma_log2_full(const GammaF& g, uint32_t a, uint32_t b, uint32_t k
 inline float gamma_log2_sample(double shape, uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
     if (shape >= 1.0) return (float)(det_log(gamma_large_shape(shape, a, b, k, k0, k1)) * 1.4426950408889634);
     const GammaF g = gamma_f(shape);
-    uint32_t u, v;
-    gamma_words(a, b, k, 0, k0, k1, u, v);
     float L;
-    if (gamma_log2_fast(g, u, v, L)) return L;
+    if (gamma_log2_fast(g, gamma_word0(a, b, k, k0, k1), L)) return L;
     return gamma_log2_full(g, a, b, k, k0, k1);
 }
 

@@ -72,6 +72,21 @@ void const_eval_callback(int, float* values, float* policies, int len) {
     for (size_t i = 0; i < (size_t)len * BOARD_CAPACITY; ++i) policies[i] = 0.25f;
 }
 
+// the RandomEvaluator twin on one leaf: values[8], policies[8][225] in the API layout (planes of augment_way8)
+void oracle_random_evaluator(uint32_t seed, uint32_t game_id, uint32_t sim_index, const int8_t* board, float* values, float* policies) {
+    PhiloxRandomEvaluator ev;
+    EvalCtx ctx;
+    ctx.seed = seed, ctx.game_id = game_id, ctx.sim_index = sim_index;
+    const Board b = board_from_i8(board);
+    std::vector<float> v;
+    std::vector<FBoard> p;
+    ev.eval(Player::Black, augment_way8(b), ctx, v, p);
+    for (int s = 0; s < 8; ++s) {
+        values[s] = v[s];
+        std::memcpy(policies + (size_t)s * BOARD_CAPACITY, &p[s][0][0], sizeof(FBoard));
+    }
+}
+
 // ---- small pieces -------------------------------------------------------------------------------
 int oracle_search(const int8_t* board) { return (int)search(board_from_i8(board)); }
 

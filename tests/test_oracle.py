@@ -257,3 +257,35 @@ def test_first_level_visits_are_not_biased_to_the_top_left(oracle):
     out = c6lib.OracleGameOut()
     oracle.oracle_self_play(None, C.byref(p), 0, C.byref(out), None, None, None)
     assert out.moves[0] == 0  # lowest-index mode: 2 simulations always end on cell (0, 0)
+
+
+def test_random_evaluator_twin_is_iid_uniform(oracle):
+    """The RandomEvaluator twin (alphazero_policy/mod.rs:137-169: every value and policy entry ~ U(-1, 1)): the eight draws of
+    every empty cell — sixteen 24-bit draws out of three Philox blocks per pair of cells — are uniform on [-1, 1), uncorrelated
+    within a cell, between the two cells of a pair and between planes; occupied cells get none."""
+    from scipy import stats
+    FP = C.POINTER(C.c_float)
+    rng = np.random.default_rng(5)
+    board = np.zeros(225, dtype=np.int8)
+    board[rng.choice(225, size=40, replace=False)] = rng.choice([-1, 1], size=40)
+    sims = 600
+    pol = np.zeros((sims, 8, 225), dtype=np.float32)
+    val = np.zeros((sims, 8), dtype=np.float32)
+    for s in range(sims):
+        oracle.oracle_random_evaluator(0xC6, 3, s, board.ctypes.data_as(C.POINTER(C.c_int8)), val[s].ctypes.data_as(FP), pol[s].ctypes.data_as(FP))
+    # plane 6 is the leaf itself (rotate_left four times): original-frame draw number 6 of every cell
+    ident = pol[:, 6, :]
+    empty = board == 0
+    assert not ident[:, ~empty].any()
+    x = ident[:, empty].astype(np.float64)
+    assert x.min() >= -1.0 and x.max() < 1.0
+    assert stats.kstest((x.ravel() + 1) / 2, "uniform").statistic < 0.006
+    assert abs(x.mean()) < 0.01 and abs(x.var() - 1 / 3) < 0.01
+    # the two cells of a rank pair (k, k + 32) share Philox blocks: still uncorrelated; so are different planes of one cell
+    ranks = np.flatnonzero(empty)
+    a, b = ident[:, ranks[:32]].ravel(), ident[:, ranks[32:64]].ravel()
+    assert abs(np.corrcoef(a, b)[0, 1]) < 0.02
+    # every plane is a permutation of its own draw: compare plane 7 (flip of the identity) mapped back against plane 6
+    p7 = pol[:, 7, :].reshape(sims, 15, 15)[:, :, ::-1].reshape(sims, 225)
+    assert abs(np.corrcoef(p7[:, empty].ravel(), ident[:, empty].ravel())[0, 1]) < 0.02
+    assert stats.kstest((val.ravel().astype(np.float64) + 1) / 2, "uniform").statistic < 0.03
