@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
             }
             n_search += 1;
             if (won) continue;  // search_winner() != None: return without expanding (:241-243)
+            if (stones == CELLS) continue;  // full board, no six: the reference's expand() would panic (:165); the search changes nothing
             // expand (:164-184)
             const int turn = turn_of(stones);
             const uint32_t ue = philox4x32_10((uint32_t)rstones, it, 0xFFFFFFFFu, 0, k0, k1).x;
@@ -283,7 +284,11 @@ float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, l
     if (n_games == 0) return 0.f;
     const int moves = (max_moves > 0 && max_moves < CELLS) ? max_moves : CELLS;
     // every search creates at most one node and one entry; init() creates at most one node per move
-    const uint32_t ecap = (uint32_t)std::max(1, num_iter * moves);
+    const long long ecap64 = std::max<long long>(1, (long long)num_iter * moves);
+    // child entries pack `child | move << 24`: node ids must stay below 2^24 (num_iter up to ~74,000 for whole games)
+    if (ecap64 + moves + 2 >= (1ll << 24))
+        throw std::runtime_error("default_policy_play: num_iter * moves must stay below 2^24 nodes per game (child ids are packed in 24 bits)");
+    const uint32_t ecap = (uint32_t)ecap64;
     const uint32_t ncap = ecap + (uint32_t)moves + 2;
     uint32_t tsize = 64;
     while (tsize < 2 * ncap) tsize <<= 1;

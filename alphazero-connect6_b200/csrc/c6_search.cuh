@@ -138,6 +138,12 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #ifndef C6_CHILD_CG
 #define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
 #endif
+#ifndef C6_W_UNROLL
+#define C6_W_UNROLL 1
+#endif
+#ifndef C6_PUCT_UNROLL
+#define C6_PUCT_UNROLL 1
+#endif
 #ifndef C6_EV_UNROLL
 #define C6_EV_UNROLL 1  // the evaluator's two Philox blocks per cell interleaved: +2.2 % (r02f A/B, scripts/gpu_tune3.sh)
 #endif
@@ -349,7 +355,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                     for (int off = 16; off >= 1; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(FULL, lmax, off));
                     __syncwarp();  // pass B wrote other lanes' slots
                     float part = 0.f;
-#pragma unroll 1
+C6_UNROLL(C6_W_UNROLL)
                     for (int k = lane; k < C; k += 32) {
                         const float wk = ex2_det(st.lw[0][k] - lmax);
                         st.lw[0][k] = wk;
@@ -364,7 +370,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                 float bs = 0.f;
                 uint32_t cnt = 0;
                 const float sqrt_s = sqrtf(visit_sum);  // visit_sum >= 1 here
-#pragma unroll 1
+C6_UNROLL(C6_PUCT_UNROLL)
                 for (int k = lane; k - lane < C; k += 32) {  // every lane runs every round (warp vote inside)
                     const bool in = k < C;
                     const uint4 ch = st.child[0][in ? k : 0];

@@ -126,6 +126,9 @@ struct DefaultPolicy : Policy {
         }
         stats.searches += 1;
         if (search(sim.board) != Player::None) return;
+        // a descent that ends on a FULL board without a winner: the reference's expand() panics (`choose().unwrap()` on an empty
+        // list, :165); restated as "this search changes nothing" — the engine does the same
+        if (sim.possible.empty()) return;
         Pos p = expand(sim);
         path.push_back(p);
         sim.simulate_in(p.first, p.second);

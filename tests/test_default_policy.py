@@ -103,3 +103,13 @@ def test_pyconnect6_default_policy_play():
         for turn, b, (r, c) in path:  # Path.board is the board BEFORE the stone (agent_impl/mod.rs:139-143)
             assert b == board and b[r * 15 + c] == 0
             board[r * 15 + c] = turn
+
+
+@pytest.mark.gpu
+def test_default_policy_rejects_budgets_whose_node_ids_do_not_fit():
+    """child ids are packed in 24 bits; a budget that could exceed them is refused instead of corrupting moves."""
+    L = c6lib.product()
+    rec = (c6lib.Record * 1)()
+    assert L.c6_default_policy_play(80000, 1, 0, 1, 0, 0, rec, None, None, None) != 0
+    assert b"2^24" in L.c6_last_error()
+    assert L.c6_default_policy_play(0, 1, 0, 1, 0, 0, rec, None, None, None) != 0  # num_iter 0 panics in the reference
