@@ -159,6 +159,33 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #define C6_PRAGMA_(x) _Pragma(#x)
 #define C6_UNROLL(n) C6_PRAGMA_(unroll n)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// The same copies with an L2 eviction policy.  A game's ROOT is descended through by every simulation: its link run and its
+// children's records (~4 KB per game, 17 MB for 4,096 games) are the one part of the node pool that is re-read 800 times per
+// stone, while everything deeper streams through; the root step asks L2 to keep them (evict_last), so they are served from
+// L2 instead of DRAM (r02c capture: 36.9 GB of DRAM reads per launch at an L2 hit rate of 33 %).
+#ifndef C6_ROOT_L2
+#define C6_ROOT_L2 2  // 0: no hints; 1: root step evict_last; 2: also evict_first below the root.  r02j A/B (gpurun_out/r02j,
+                      // profiles/r02j_l2_hints.md): DRAM traffic per launch 54.9 GB -> 51.1 GB -> 48.9 GB (1.34 x -> 1.20 x the
+                      // algorithmic bytes), time unchanged (+0.2 % / +0.8 %: the kernel is issue-bound)
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async4_hint(void* smem_dst, const void* gmem_src, uint64_t pol) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg_hint(void* smem_dst, const void* gmem_src, uint64_t pol) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
+}
 
 // Memory phase of a select step: for the node with C children whose link run starts at `link`, record indices
 // into st.ci, then records into st.child; ceil(C/32) requests of each kind in flight per lane.
@@ -288,21 +315,38 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             unsigned pend = 0;
             int s_local = 0;
             int kn = lane;  // next rank this lane draws
+#if C6_ROOT_L2
+            const bool hinted = C6_ROOT_L2 == 2 || depth == 0;
+            const uint64_t pol = depth == 0 ? l2_policy_evict_last() : l2_policy_evict_first();
+#else
+            const bool hinted = false;
+            const uint64_t pol = 0;
+#endif
+            if (hinted) {
 #pragma unroll 1
-            for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
+                for (int k = lane; k < C; k += 32) cp_async4_hint(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm], pol);
+            } else {
+#pragma unroll 1
+                for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
+            }
 #pragma unroll 1
             for (int part = 0; part < 3; ++part) {
                 if (NOISE && (part < 2 ? early : (!early && s_local != 0))) noise_rounds(D, cs, st, mt, depth, C, lane, kn, part == 0 ? min(C, 128) : C, lmax, pend);
                 if (part == 2) break;
                 cp_async_wait_all();
                 if (part == 0) {
+                    if (hinted) {
 #pragma unroll 1
-                    for (int k = lane; k < C; k += 32) {
+                        for (int k = lane; k < C; k += 32) cp_async16_cg_hint(&st.child[0][k], &w.rec[st.ci[0][k] & Rm], pol);
+                    } else {
+#pragma unroll 1
+                        for (int k = lane; k < C; k += 32) {
 #if C6_CHILD_CG
-                        cp_async16_cg(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+                            cp_async16_cg(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
 #else
-                        cp_async16(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
+                            cp_async16(&st.child[0][k], &w.rec[st.ci[0][k] & Rm]);
 #endif
+                        }
                     }
                 } else {
                     // visit sum (:265)

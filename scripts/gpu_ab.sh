@@ -20,3 +20,14 @@ done
 run l2_32 C6_L2_FETCH=32
 run l2_128 C6_L2_FETCH=128
 run base_again C6_DUMMY=1
+# DRAM traffic of one launch of the search kernel per build (two-metric ncu pass: cheap)
+traffic() { name=$1; shift
+  env "$@" timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:k_sims_device -s 3 -c 1 --csv --log-file $OUT/traffic_$name.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-steady > /dev/null 2>&1
+  echo "traffic $name: $(grep -E 'dram__bytes|hit_rate' $OUT/traffic_$name.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | tr -d '"' | tr '\n' ';')"
+}
+traffic base C6_DUMMY=1
+for v in alphazero-connect6_b200/lib/variants/lib_*.so; do
+  [ -e "$v" ] || continue
+  traffic $(basename $v .so) C6_LIB=$PWD/$v
+done

@@ -23,7 +23,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sims_device -s 3 -c 1 -o $OUT/prof_sims \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-steady > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" >> $OUT/ncu_full.log
 tail -3 $OUT/ncu_full.log
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_win_check|k_playouts|k_default_policy|k_expand_records" -c 6 -o $OUT/prof_secondary \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_win_check|k_playouts|k_expand_records" -c 5 -o $OUT/prof_secondary \
     python scripts/secondary_kernels.py > $OUT/ncu_secondary.log 2>&1; echo "ncu secondary rc=$?" >> $OUT/ncu_secondary.log
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_step|k_gather" -s 40 -c 4 -o $OUT/prof_callback \
     python scripts/secondary_kernels.py > $OUT/ncu_callback.log 2>&1; echo "ncu callback rc=$?" >> $OUT/ncu_callback.log
