@@ -224,7 +224,7 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         const uint32_t erec = w.exp_rec(D)[ei];
         const uint64_t ekey = w.exp_key(D)[ei];
         const int C = CELLS - est;
-        if (rec_head - old_rec_tail + (uint32_t)C + 1 > D.R || lnk_head - old_lnk_tail + (uint32_t)C > D.L) {
+        if (rec_head - old_rec_tail + (uint32_t)C + 1 > D.R || lnk_head - old_lnk_tail + (uint32_t)C + 3 > D.L) {
             overflow = true;
             break;
         }
@@ -248,8 +248,8 @@ __device__ inline void collect(const Dev& D, Warp& w) {
         }
         if (lane == 0) xh_insert(w.idx, Im, epoch, ekey, new_e);  // expanded nodes stay findable by key
         __syncwarp();
-        const uint32_t new_link = lnk_head;
-        lnk_head += (uint32_t)C;
+        const uint32_t new_link = (lnk_head + 3u) & ~3u;  // link runs start on 16-byte boundaries (four links per cp.async)
+        lnk_head = new_link + (uint32_t)C;
         if (lane == 0) w.rec[new_e].link = new_link & Lm;
         // children
         uint32_t e[8];

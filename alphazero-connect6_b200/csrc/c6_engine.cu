@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device(Dev D
     const uint64_t* Zs = D.Z;
     __shared__ WarpStage<NOISE> stage[4];
     __shared__ MathTab mt;
-    if (NOISE) load_math_tab(mt);
+    if (NOISE || C6_SQRT_TAB) load_math_tab(mt);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128, C6_SIM_BLOCKS_PER_SM) k_sims_device_vl(De
     const uint64_t* Zs = D.Z;
     __shared__ WarpStage<NOISE> stage[4];
     __shared__ MathTab mt;
-    if (NOISE) load_math_tab(mt);
+    if (NOISE || C6_SQRT_TAB) load_math_tab(mt);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage<NOISE>& st = stage[threadIdx.x >> 5];
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) k_step(Dev D, int g0, int g1, int do_back
     const uint64_t* Zs = D.Z;  // global (__ldg in descend / expand_leaf)
     __shared__ WarpStage<NOISE> stage[4];
     __shared__ MathTab mt;
-    if (NOISE) load_math_tab(mt);
+    if (NOISE || C6_SQRT_TAB) load_math_tab(mt);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     WarpStage<NOISE>& st = stage[threadIdx.x >> 5];

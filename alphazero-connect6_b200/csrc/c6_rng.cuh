@@ -87,11 +87,20 @@ __device__ __forceinline__ float det_fmaf(float a, float b, float c) { return __
 // Table of the f32 log2 below, staged in shared memory by every kernel that samples noise (per-lane indices
 // would serialise in the constant cache).  The f64 log / exp of the alpha >= 1 sampler (not the default, out of
 // line) read their tables from the constant bank.
+#ifndef C6_SQRT_TAB
+#define C6_SQRT_TAB 0
+#endif
 struct MathTab {
     float2 lg2t[33];  // {r_i, -log2 r_i}, r_i = f32(1/c_i), c_i = bits 0x3F340000 + i 2^18
+#if C6_SQRT_TAB
+    float sqrt_tab[1024];  // sqrtf(i) (IEEE, correctly rounded: the value the PUCT pass would compute)
+#endif
 };
 __device__ __forceinline__ void load_math_tab(MathTab& T) {
     if (threadIdx.x < 33) T.lg2t[threadIdx.x] = LG2F_TAB_C[threadIdx.x];  // blocks have at least 64 threads
+#if C6_SQRT_TAB
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) T.sqrt_tab[i] = sqrtf((float)i);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -138,6 +138,12 @@ __device__ __forceinline__ uint64_t ldz(const uint64_t* p) {
 #ifndef C6_CHILD_CG
 #define C6_CHILD_CG 1  // child records bypass L1 (each is read once per step; tune_h: +1%)
 #endif
+#ifndef C6_LINK16
+#define C6_LINK16 1  // link runs fetched four links per 16-byte request (runs are 16-byte aligned in the ring)
+#endif
+#ifndef C6_SQRT_TAB
+#define C6_SQRT_TAB 0  // sqrt(S - n) of the PUCT pass from a 1,024-entry shared-memory table (same bits; A/B: scripts/gpu_ab.sh)
+#endif
 #ifndef C6_W_UNROLL
 #define C6_W_UNROLL 1
 #endif
@@ -182,6 +188,10 @@ __device__ __forceinline__ void cp_async4_hint(void* smem_dst, const void* gmem_
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void cp_async16_ca_hint(void* smem_dst, const void* gmem_src, uint64_t pol) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async16_cg_hint(void* smem_dst, const void* gmem_src, uint64_t pol) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
@@ -193,8 +203,9 @@ template <int NOISE>
 __device__ __forceinline__ void stage_children(const Warp& w, WarpStage<NOISE>& st, uint32_t link, int C, int lane, uint32_t Rm,
                                                uint32_t Lm) {
 #pragma unroll 1
-    for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(link + (uint32_t)k) & Lm]);
+    for (int k = 4 * lane; k < C; k += 128) cp_async16(&st.ci[0][k], &w.lnk[(link + (uint32_t)k) & Lm]);  // 16-byte aligned runs
     cp_async_wait_all();
+    __syncwarp();  // a lane's links were fetched by another lane
 #pragma unroll 1
     for (int k = lane; k < C; k += 32) {
 #if C6_CHILD_CG
@@ -322,6 +333,17 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
             const bool hinted = false;
             const uint64_t pol = 0;
 #endif
+            // the link run: 16-byte aligned in the ring, four links per request (a run's last request may read up to three
+            // entries past it: unused)
+#if C6_LINK16
+            if (hinted) {
+#pragma unroll 1
+                for (int k = 4 * lane; k < C; k += 128) cp_async16_ca_hint(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm], pol);
+            } else {
+#pragma unroll 1
+                for (int k = 4 * lane; k < C; k += 128) cp_async16(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
+            }
+#else
             if (hinted) {
 #pragma unroll 1
                 for (int k = lane; k < C; k += 32) cp_async4_hint(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm], pol);
@@ -329,12 +351,14 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
 #pragma unroll 1
                 for (int k = lane; k < C; k += 32) cp_async4(&st.ci[0][k], &w.lnk[(r.link + (uint32_t)k) & Lm]);
             }
+#endif
 #pragma unroll 1
             for (int part = 0; part < 3; ++part) {
                 if (NOISE && (part < 2 ? early : (!early && s_local != 0))) noise_rounds(D, cs, st, mt, depth, C, lane, kn, part == 0 ? min(C, 128) : C, lmax, pend);
                 if (part == 2) break;
                 cp_async_wait_all();
                 if (part == 0) {
+                    __syncwarp();  // a lane's links were fetched by another lane (four per request)
                     if (hinted) {
 #pragma unroll 1
                         for (int k = lane; k < C; k += 32) cp_async16_cg_hint(&st.child[0][k], &w.rec[st.ci[0][k] & Rm], pol);
@@ -414,6 +438,9 @@ C6_UNROLL(C6_W_UNROLL)
                 float bs = 0.f;
                 uint32_t cnt = 0;
                 const float sqrt_s = sqrtf(visit_sum);  // visit_sum >= 1 here
+#if C6_SQRT_TAB
+                const float* const sqt = mt.sqrt_tab;  // sqrtf(i), i < 1024: S - n is a small integer
+#endif
 C6_UNROLL(C6_PUCT_UNROLL)
                 for (int k = lane; k - lane < C; k += 32) {  // every lane runs every round (warp vote inside)
                     const bool in = k < C;
@@ -438,8 +465,13 @@ C6_UNROLL(C6_PUCT_UNROLL)
                         const bool seen = cn > 0 && cw != 0.f;
                         const float qd = (seen ? cw : 1.f) / (seen ? visit : 1.f);
                         const float q = cn > 0 ? (cw != 0.f ? qd : cw) : 0.f;  // +-0 / visit = +-0
+#if C6_SQRT_TAB
+                        const int sai = s_local - cn;  // >= 0
+                        const float un = prob * (sai < 1024 ? sqt[sai] : sqrtf((float)sai));  // sqt[0] = +0 = S - n itself
+#else
                         const float sa = visit_sum - visit;  // >= 0; sqrtf(0) would also leave the fast path
                         const float un = prob * (sa != 0.f ? sqrtf(sa != 0.f ? sa : 1.f) : sa);
+#endif
                         const float ud = (un != 0.f ? un : 1.f) / (1.f + visit);
                         const float u = un != 0.f ? ud : un;  // :270; +-0 / (1 + visit) = +-0
                         sc = (turn < 0 ? -q : q) + cpuct * u;  // :272-280
@@ -759,10 +791,10 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     const int C = CELLS - L.stones;
     const int turn = turn_of(L.stones);
     const uint32_t zoff = turn > 0 ? 256u : 0u;
-    const uint32_t link_base = cs.lnk_head;
+    const uint32_t link_base = (cs.lnk_head + 3u) & ~3u;  // link runs start on 16-byte boundaries (four links per cp.async)
     const uint32_t ec = cs.exp_count;
     const uint32_t rec_tail = st.meta.rec_tail, lnk_tail = st.meta.lnk_tail, epoch = st.meta.epoch;
-    if (cs.lnk_head - lnk_tail + (uint32_t)C > D.L) cs.err = ERR_LNK_FULL;
+    if (link_base - lnk_tail + (uint32_t)C > D.L) cs.err = ERR_LNK_FULL;
     if (cs.rec_head - rec_tail + (uint32_t)C > D.R) cs.err = ERR_REC_FULL;
     if (ec + 1 > D.E) cs.err = ERR_EXP_FULL;
     if (cs.err) return;
