@@ -244,6 +244,14 @@ __device__ __forceinline__ Rec rec_of(const uint4& v) {
 }
 __device__ __forceinline__ uint4 bits_of(const Rec& r) { return make_uint4((uint32_t)r.n, __float_as_uint(r.w), __float_as_uint(r.p), r.link); }
 
+// Warp-wide maximum of floats through the integer reduction unit (redux.sync): floats map to unsigned keys that order the
+// same way (-0 is canonicalised to +0 first: the two compare equal as floats and must get one key).  No NaNs here.
+__device__ __forceinline__ uint32_t float_key(float f) {
+    const uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
 // Four rounds of the noise draw of a select step: children k, k + 32, k + 64, k + 96 of this lane share a Philox block.
 template <int NOISE>
 __device__ __forceinline__ void noise_rounds(const Dev& D, const Cursor& cs, WarpStage<NOISE>& st, const MathTab& mt, int depth, int C,
@@ -376,8 +384,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                     // visit sum (:265)
 #pragma unroll 1
                     for (int k = lane; k < C; k += 32) s_local += (int)st.child[0][k].x;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) s_local += __shfl_xor_sync(FULL, s_local, off);
+                    s_local = __reduce_add_sync(FULL, s_local);  // one redux.sync instead of a five-step butterfly
                 }
             }
             const float visit_sum = (float)s_local;
@@ -419,8 +426,7 @@ __device__ __forceinline__ void descend(const Dev& D, Warp& w, Cursor& cs, Leaf&
                             lmax = fmaxf(lmax, l);
                         }
                     }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(FULL, lmax, off));
+                    lmax = key_float(__reduce_max_sync(FULL, float_key(lmax)));
                     __syncwarp();  // pass B wrote other lanes' slots
                     float part = 0.f;
 C6_UNROLL(C6_W_UNROLL)
@@ -482,16 +488,15 @@ C6_UNROLL(C6_PUCT_UNROLL)
                         else if (sc == bs) cnt += 1;
                     }
                 }
-                // maximum over the warp: score, lowest rank holding it, number of children holding it
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const float os = __shfl_xor_sync(FULL, bs, off);
-                    const uint32_t ob = __shfl_xor_sync(FULL, bb, off);
-                    const uint32_t oc = __shfl_xor_sync(FULL, cnt, off);
-                    if (ob != NIL) {
-                        if (bb == NIL || os > bs) bs = os, bb = ob, cnt = oc;
-                        else if (os == bs) cnt += oc, bb = min(bb, ob);
-                    }
+                // maximum over the warp: score, lowest rank holding it, number of children holding it — three integer warp
+                // reductions (scores through order-preserving keys; a lane without children has key 0, below every score)
+                {
+                    const uint32_t my_key = bb == NIL ? 0u : float_key(bs);
+                    const uint32_t top = __reduce_max_sync(FULL, my_key);
+                    const bool mine = bb != NIL && my_key == top;
+                    cnt = __reduce_add_sync(FULL, mine ? cnt : 0u);
+                    bb = __reduce_min_sync(FULL, mine ? bb : NIL);
+                    bs = key_float(top);
                 }
                 // exact ties: uniformly among the tied children (:291-295) or, for hand-checkable traces, the lowest rank
                 if (tie_philox && cnt > 1) {
