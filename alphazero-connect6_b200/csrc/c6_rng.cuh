@@ -90,14 +90,23 @@ __device__ __forceinline__ float det_fmaf(float a, float b, float c) { return __
 #ifndef C6_SQRT_TAB
 #define C6_SQRT_TAB 0
 #endif
+#ifndef C6_GAMMA_THR
+#define C6_GAMMA_THR 1  // 1: acceptance threshold of the hot branch from a 256-entry table; 0: computed (2^floor(L) (1 + frac L))
+#endif
 struct MathTab {
     float2 lg2t[33];  // {r_i, -log2 r_i}, r_i = f32(1/c_i), c_i = bits 0x3F340000 + i 2^18
+#if C6_GAMMA_THR
+    float thr[256];  // log2((255 - v)/256) - 2^-20 rounded down, v = top byte of V (v = 255: never)
+#endif
 #if C6_SQRT_TAB
     float sqrt_tab[1024];  // sqrtf(i) (IEEE, correctly rounded: the value the PUCT pass would compute)
 #endif
 };
 __device__ __forceinline__ void load_math_tab(MathTab& T) {
     if (threadIdx.x < 33) T.lg2t[threadIdx.x] = LG2F_TAB_C[threadIdx.x];  // blocks have at least 64 threads
+#if C6_GAMMA_THR
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) T.thr[i] = GAMMA_THR_C[i];
+#endif
 #if C6_SQRT_TAB
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) T.sqrt_tab[i] = sqrtf((float)i);
 #endif
@@ -215,11 +224,17 @@ __device__ __forceinline__ float unit24_of(uint32_t w) { return det_fmaf((float)
 // Uniforms (twin: oracle/c6_rng.hpp gamma_uniforms): trial 0 of draw k is ONE word of Philox block (a, b, kb, 0),
 // kb = (k >> 7) << 5 | (k & 31), word (k >> 5) & 3 — four draws per block: 24 bits of U (all the f32 conversion keeps) and the
 // top byte of V; V's other 24 bits come from block (a, b, k, 0xFFFFFFFF) and are read by the full loop only.
-// gamma_log2_fast tries trial 0 on the hot branch with a sufficient test ((255 - v8)/256 >= 2^floor(L) (1 + frac L) >= X) and
-// reports failure (~6% of the draws); gamma_log2_full is the whole loop.
+// gamma_log2_fast tries trial 0 on the hot branch with a sufficient test and reports failure (~6% of the draws);
+// gamma_log2_full is the whole loop.  Any sufficient test gives the same draws (a draw the test passes is the draw the loop
+// accepts at trial 0): with v8 the top byte of V, 1 - V >= (255 - v8)/256, and the loop accepts when 1 - V >= d,
+// d = 1 - e^-X <= X = 2^L.  Tabulated: L <= log2((255 - v8)/256) - 2^-20 (the margin covers ex2_det's and d's rounding);
+// computed (C6_GAMMA_THR=0): (255 - v8)/256 >= 2^floor(L) (1 + frac L) >= X.
 __device__ __forceinline__ bool gamma_log2_fast(const MathTab& T, const GammaParams& gp, uint32_t w, float& L) {
     const float P = gp.b * unit24_of(w >> 8);
     L = lg2_det(T, fminf(P, 1.0f)) * gp.inv_a;
+#if C6_GAMMA_THR
+    return P <= 1.0f && L <= T.thr[w & 0xFFu];
+#endif
     const float Lc = fmaxf(L, -64.0f);
     const float kf = floorf(Lc);
     const float xub = __uint_as_float(__float_as_uint(1.0f + (Lc - kf)) + ((uint32_t)(int)kf << 23));

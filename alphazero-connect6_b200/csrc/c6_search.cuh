@@ -603,16 +603,20 @@ struct EvPhilox {
         }
         return sum / 8.f;
     }
-    // 24-bit draw number i (0..7) of the 192 bits in words q[0..5]: bits [24 i, 24 i + 24)
-    static __device__ __forceinline__ float draw24(const uint32_t (&q)[6], int i) {
+    // 24-bit draw number i (0..7) of the 192 bits in words q[0..5]: bits [24 i, 24 i + 24); the draw is x 2^-23 - 1 in [-1, 1)
+    static __device__ __forceinline__ uint32_t bits24(const uint32_t (&q)[6], int i) {
         const int w = (3 * i) >> 2, sh = 8 * ((3 * i) & 3);
         const uint32_t x = sh == 0 ? q[w] : (sh == 8 ? q[w] >> 8 : __funnelshift_r(q[w], q[w + 1 < 6 ? w + 1 : 5], sh));
-        return (float)(x & 0xFFFFFFu) * (1.0f / 8388608.0f) - 1.0f;
+        return x & 0xFFFFFFu;
     }
-    static __device__ __forceinline__ float fold8(const uint32_t (&q)[6]) {  // recover_way8 order: t_i = p[2i] + flip(p[2i+1]), ((((0+t0)+t1)+t2)+t3)/8
+    // recover_way8 order: t_i = p[2i] + flip(p[2i+1]), ((((0+t0)+t1)+t2)+t3)/8.  A pair sum t_i = (x 2^-23 - 1) + (y 2^-23 - 1) is a
+    // multiple of 2^-23 below 2 in magnitude — exact in f32 — so it is formed in integers, (x + y - 2^24) 2^-23: the same bits
+    // (the oracle adds the two f32 draws) with one conversion per pair instead of two.
+    static __device__ __forceinline__ float fold8(const uint32_t (&q)[6]) {
         float total = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) total = total + (draw24(q, 2 * i) + draw24(q, 2 * i + 1));
+        for (int i = 0; i < 4; ++i)
+            total = total + (float)((int)(bits24(q, 2 * i) + bits24(q, 2 * i + 1)) - (1 << 24)) * (1.0f / 8388608.0f);
         return total / 8.f;
     }
     // Priors of the leaf's children by rank.  The children of ranks k and k + 32 (k = 64 j + lane) share THREE Philox blocks
@@ -820,23 +824,33 @@ __device__ __forceinline__ void expand_leaf(const Dev& D, Warp& w, Cursor& cs, c
     if (lane < 8) st.empty[lane] = ~(st.B[lane] | st.W[lane]) & (lane < 7 ? 0x7FFF7FFFu : 0x00007FFFu);
     __syncwarp();
     const uint64_t key = L.key;
-    // bit position of every child by rank, and r0 = rank of the last path stone among the empties of a sibling that
-    // lacks it (before the c < a_d correction)
-    uint32_t r0 = 0;
+    // Bit position of every child by rank (st.cell), byte-wise: lane l owns bits 8 l .. 8 l + 7 of the 256-bit empty mask
+    // (byte l & 3 of word l >> 2); an exclusive prefix sum of the per-byte counts over the warp gives the rank of a lane's first
+    // empty cell, and the lane writes its (at most eight) cells.  r0 = rank of the last path stone among the empties of a
+    // sibling that lacks it (before the c < a_d correction): the empties below that bit, counted per word by lanes 0..7.
+    uint32_t r0;
     {
-        int pre = 0;
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t e = st.empty[j];
-            if ((e >> lane) & 1u) st.cell[pre + __popc(e & lt)] = (uint8_t)(32 * j + lane);
-            r0 += j < (int)lj ? __popc(e) : (j == (int)lj ? __popc(e & (lm - 1u)) : 0);
-            pre += __popc(e);
+        const uint32_t ew = st.empty[lane >> 2];
+        uint32_t eb = (ew >> (8 * (lane & 3))) & 0xFFu;
+        const int c = __popc(eb);
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += o;
         }
+        int at = incl - c;
+        while (eb) {
+            st.cell[at++] = (uint8_t)(8 * lane + (__ffs((int)eb) - 1));
+            eb &= eb - 1;
+        }
+        const uint32_t e = lane < 8 ? st.empty[lane & 7] : 0u;
+        const uint32_t below = lane < (int)lj ? e : (lane == (int)lj ? e & (lm - 1u) : 0u);
+        r0 = __reduce_add_sync(FULL, (uint32_t)__popc(below));
     }
     __syncwarp();
-    unsigned mine = 0;  // bit i: this lane has child k = 32 i + lane
-#pragma unroll 1
-    for (int k = lane; k < C; k += 32) mine |= 1u << (k >> 5);
+    // bit i: this lane has child k = 32 i + lane
+    const unsigned mine = ((1u << (C >> 5)) - 1u) | (lane < (C & 31) ? 1u << (C >> 5) : 0u);
     // A: rule F — the link of every shared child in flight; priors computed under the latency.  The sibling P + c
     // of the leaf under its parent P has rank k + [c > a_d] there.
     unsigned res = 0;  // bit i: child k already has a record, index in st.pos

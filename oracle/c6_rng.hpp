@@ -291,16 +291,16 @@ inline GammaUniforms gamma_uniforms(uint32_t a, uint32_t b, uint32_t k, uint32_t
     return GammaUniforms{unit_of(r.v[0]), unit_of(~r.v[0]), unit_of(r.v[1]), unit_of(~r.v[1])};
 }
 
-// hot branch of trial 0 on the draw's word alone; false = undecided (the full loop decides)
+// hot branch of trial 0 on the draw's word alone; false = undecided (the full loop decides).  The test only has to be
+// SUFFICIENT for the loop's trial-0 acceptance (then both return the same L): 1 - V >= (255 - v8)/256 whatever the other
+// bits of V are, and the loop accepts when 1 - V >= d with d = 1 - e^-X <= X = 2^L; GAMMA_THR[v8] = log2((255 - v8)/256)
+// - 2^-20 (rounded down; the margin covers the rounding of ex2_det and of d), GAMMA_THR[255] = -3e38 (never).
 inline bool gamma_log2_fast(const GammaF& g, uint32_t w, float& L) {
     const float P = g.b * unit24_of(w >> 8);
     L = 0.0f;
     if (P > 1.0f) return false;
     L = lg2_det(P) * g.inv_a;
-    const float Lc = L < -64.0f ? -64.0f : L;
-    const float kf = __builtin_floorf(Lc);
-    const float xub = u2f(f2u(1.0f + (Lc - kf)) + ((uint32_t)(int32_t)kf << 23));  // 2^k (1 + f) >= 2^(k + f)
-    return (float)(255u - (w & 0xFFu)) * 0x1p-8f >= xub;  // 1 - V > (255 - v8)/256 >= X >= 1 - e^-X whatever the other bits of V are
+    return L <= GAMMA_THR[w & 0xFFu];
 }
 inline float gamma_log2_full(const GammaF& g, uint32_t a, uint32_t b, uint32_t k, uint32_t k0, uint32_t k1) {
     float L = 0.0f;

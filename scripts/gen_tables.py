@@ -101,10 +101,27 @@ _coef, *_ = np.linalg.lstsq(np.vander(_x, 6, increasing=True) * _w[:, None], ((_
 ex2f_poly = [1.0] + [float(np.float32(v)) for v in _coef]
 
 
+# fast acceptance thresholds of the log2-space Gamma sampler: with the top byte v of V known, 1 - V > (255 - v)/256 whatever the
+# other 24 bits are, so a draw X = 2^L with 2^L <= (255 - v)/256 is accepted for sure.  T[v] = log2((255 - v)/256) - 2^-20 rounded
+# DOWN to f32 (the margin covers the 1.2e-7 relative error of ex2_det in the exact test the full loop applies); T[255] = -inf.
+gthr = []
+for v in range(256):
+    if v == 255:
+        gthr.append(-3.0e38)
+        continue
+    t = math.log2((255 - v) / 256) - 2.0 ** -20  # double precision is ample next to the margin
+    f = float(np.float32(t))
+    if f > t:
+        f = float(np.nextafter(np.float32(f), np.float32(-np.inf)))
+    gthr.append(f)
+assert all(2.0 ** gthr[v] < (255 - v) / 256 for v in range(255)) and gthr[0] < 0
+
+
 def fhex(v):
     return float(v).hex() + "f"
 
 
+gthr_init = ",\n".join("    " + ", ".join(fhex(v) for v in gthr[i:i + 4]) for i in range(0, 256, 4))
 lg2f_init = ",\n".join(f"    {{{fhex(a)}, {fhex(b)}}}" for a, b in lg2f_rows)
 lg2f_poly_init = ", ".join(fhex(v) for v in lg2f_poly)
 ex2f_poly_init = ", ".join(fhex(v) for v in ex2f_poly)
@@ -125,6 +142,8 @@ with open(os.path.join(ROOT, "alphazero-connect6_b200", "csrc", "c6_tables.cuh")
             f"static __device__ __constant__ float2 LG2F_TAB_C[33] = {{\n{lg2f_init}}};\n"
             f"static __device__ __constant__ float LG2F_POLY_C[4] = {{{lg2f_poly_init}}};\n"
             f"static __device__ __constant__ float EX2F_POLY_C[7] = {{{ex2f_poly_init}}};\n"
+            "// fast acceptance thresholds of the Gamma sampler by the top byte of V: log2((255 - v)/256) - 2^-20, rounded down\n"
+            f"static __device__ __constant__ float GAMMA_THR_C[256] = {{\n{gthr_init}}};\n"
             "}  // namespace c6\n")
 with open(os.path.join(ROOT, "oracle", "c6_tables.hpp"), "w") as f:
     f.write("// ORACLE — TEST INFRASTRUCTURE ONLY.\n" + BODY + "#pragma once\nnamespace c6o {\n"
@@ -136,5 +155,7 @@ with open(os.path.join(ROOT, "oracle", "c6_tables.hpp"), "w") as f:
             f"static const float LG2F_TABLE[33][2] = {{\n{lg2f_init}}};\n"
             f"static const float LG2F_POLY[4] = {{{lg2f_poly_init}}};\n"
             f"static const float EX2F_POLY[7] = {{{ex2f_poly_init}}};\n"
+            "// fast acceptance thresholds of the Gamma sampler by the top byte of V: log2((255 - v)/256) - 2^-20, rounded down\n"
+            f"static const float GAMMA_THR[256] = {{\n{gthr_init}}};\n"
             "}  // namespace c6o\n")
 print("tables written")
