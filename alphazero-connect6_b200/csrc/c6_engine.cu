@@ -422,6 +422,8 @@ struct Group {
 
 struct DeviceArrays {
     Dev dev{};
+    char* arena = nullptr;     // the one device allocation every array of `dev` is carved from (records / traces apart)
+    char* h_pinned = nullptr;  // the one small pinned allocation: h_sync, h_gcount
     float* h_batch = nullptr;  // mapped pinned host memory, same layout as Dev::batch
     int* h_sync = nullptr;     // mapped pinned host memory, per group {Black leaves, White leaves, seq, -}
     std::vector<Group> groups;
@@ -504,38 +506,47 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         g_last_error = buf;
         throw std::runtime_error(buf);
     }
-    C6_CUDA(cudaMalloc(&D.rec, d_->rec_bytes));
-    C6_CUDA(cudaMalloc(&D.lnk, d_->lnk_bytes));
-    C6_CUDA(cudaMalloc(&D.idx, d_->idx_bytes));
-    C6_CUDA(cudaMemsetAsync(D.idx, 0, d_->idx_bytes, stream_));  // epoch 0 = never valid
-    C6_CUDA(cudaMalloc(&D.expB, G * D.E * 64));
-    C6_CUDA(cudaMalloc(&D.exp_rec, G * D.E * 4));
-    C6_CUDA(cudaMalloc(&D.exp_key, G * D.E * 8));
-    C6_CUDA(cudaMalloc(&D.path, G * D.K * 232 * 4));
-    C6_CUDA(cudaMalloc(&D.gs, G * sizeof(GameState)));
-    C6_CUDA(cudaMemsetAsync(D.gs, 0, G * sizeof(GameState), stream_));
-    uint64_t hz[512];
-    make_zobrist(hz);
-    uint64_t* dz = nullptr;
-    C6_CUDA(cudaMalloc(&dz, sizeof hz));
-    C6_CUDA(cudaMemcpyAsync(dz, hz, sizeof hz, cudaMemcpyHostToDevice, stream_));
-    D.Z = dz;
-    C6_CUDA(cudaMalloc(&D.cursor, sizeof(int)));
-    C6_CUDA(cudaMalloc(&D.gcount, 4 * sizeof(unsigned long long)));
     int n_groups = 1;
-    if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
+    const bool callback = cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK;
+    if (callback) {
         // pipeline depth of the callback path: while the host evaluates one group, the others run their
         // kernels and copies.  Small batches are not worth splitting.
         const char* pe = std::getenv("C6_PIPELINE");
         n_groups = pe && *pe ? std::atoi(pe) : std::max(1, std::min(16, D.G / 1024));  // 4 groups of 1024 games at G = 4096: profiles/e2e/e2e7.md
         n_groups = std::max(1, std::min(n_groups, std::min(D.G, 16)));
     }
-    C6_CUDA(cudaMalloc(&D.gdone, n_groups * sizeof(int)));
-    C6_CUDA(cudaMemsetAsync(D.gdone, 0, n_groups * sizeof(int), stream_));
-    C6_CUDA(cudaMalloc(&D.leaf_flag, G * D.K));
-    C6_CUDA(cudaMemsetAsync(D.leaf_flag, 0, G * D.K, stream_));
-    C6_CUDA(cudaHostAlloc(&d_->h_sync, 4 * n_groups * sizeof(int), cudaHostAllocMapped));
-    std::memset(d_->h_sync, 0, 4 * n_groups * sizeof(int));
+    // ONE device allocation, carved into the arrays (256-byte aligned), and one small pinned block: a short job (the
+    // reference's 2-simulation sample game) is otherwise dominated by ~20 cudaMalloc / cudaFree round trips to the driver.
+    size_t top = 0;
+    auto carve = [&top](size_t bytes) { const size_t o = top; top = (top + bytes + 255) & ~(size_t)255; return o; };
+    const size_t batch_bytes = callback ? G * D.K * 8 * (CELLS + 1) * sizeof(float) : 0;
+    const size_t o_rec = carve(d_->rec_bytes), o_lnk = carve(d_->lnk_bytes), o_idx = carve(d_->idx_bytes);
+    const size_t o_expB = carve(G * D.E * 64), o_exp_rec = carve(G * D.E * 4), o_exp_key = carve(G * D.E * 8);
+    const size_t o_path = carve(G * D.K * 232 * 4);
+    // zero-initialised tail: game states, group counters, leaf flags, the cursors
+    const size_t o_zero = top;
+    const size_t o_gs = carve(G * sizeof(GameState)), o_gdone = carve(n_groups * sizeof(int)), o_flag = carve(G * D.K);
+    const size_t o_cursor = carve(sizeof(int)), o_gcount = carve(4 * sizeof(unsigned long long));
+    const size_t zero_bytes = top - o_zero;
+    const size_t o_Z = carve(512 * sizeof(uint64_t)), o_batch = carve(batch_bytes);
+    C6_CUDA(cudaMalloc(&d_->arena, top));
+    char* base = d_->arena;
+    D.rec = (Rec*)(base + o_rec), D.lnk = (uint32_t*)(base + o_lnk), D.idx = (Slot*)(base + o_idx);
+    D.expB = (uint32_t*)(base + o_expB), D.exp_rec = (uint32_t*)(base + o_exp_rec), D.exp_key = (uint64_t*)(base + o_exp_key);
+    D.path = (uint32_t*)(base + o_path), D.gs = (GameState*)(base + o_gs), D.gdone = (int*)(base + o_gdone);
+    D.leaf_flag = (uint8_t*)(base + o_flag), D.cursor = (int*)(base + o_cursor), D.gcount = (unsigned long long*)(base + o_gcount);
+    if (callback) D.batch = (float*)(base + o_batch);
+    C6_CUDA(cudaMemsetAsync(D.idx, 0, d_->idx_bytes, stream_));  // epoch 0 = never valid
+    C6_CUDA(cudaMemsetAsync(base + o_zero, 0, zero_bytes, stream_));
+    uint64_t hz[512];
+    make_zobrist(hz);
+    C6_CUDA(cudaMemcpyAsync(base + o_Z, hz, sizeof hz, cudaMemcpyHostToDevice, stream_));
+    D.Z = (const uint64_t*)(base + o_Z);
+    // pinned: per group {Black leaves, White leaves, seq, -} (mapped: k_gather publishes into it), then the 4 game counters
+    const size_t sync_bytes = ((size_t)4 * n_groups * sizeof(int) + 63) & ~(size_t)63;
+    C6_CUDA(cudaHostAlloc(&d_->h_pinned, sync_bytes + 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    std::memset(d_->h_pinned, 0, sync_bytes + 4 * sizeof(unsigned long long));
+    d_->h_sync = (int*)d_->h_pinned, d_->h_gcount = (unsigned long long*)(d_->h_pinned + sync_bytes);
     C6_CUDA(cudaHostGetDevicePointer((void**)&D.hsync, d_->h_sync, 0));
     if (const char* ul = std::getenv("C6_LAUNCHER")) use_launcher_ = std::atoi(ul) != 0;
     if (const char* uz = std::getenv("C6_ZEROCOPY")) zero_copy_ = std::atoi(uz) != 0;
@@ -553,18 +564,11 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
         C6_CUDA(cudaEventCreateWithFlags(&gr.ev, cudaEventDisableTiming | cudaEventBlockingSync));
     }
     spin_us_ = host_spin_budget_us();
-    C6_CUDA(cudaMallocHost(&d_->h_gcount, 4 * sizeof(unsigned long long)));
-    if (cfg_.evaluator == EVAL_CALLBACK || cfg_.evaluator == EVAL_DEVICE_CALLBACK) {
-        const size_t nb = G * D.K * 8 * (CELLS + 1) * sizeof(float);
-        C6_CUDA(cudaMalloc(&D.batch, nb));
-        if (cfg_.evaluator == EVAL_CALLBACK) {
-            C6_CUDA(cudaHostAlloc(&d_->h_batch, nb, cudaHostAllocMapped));
-            C6_CUDA(cudaHostGetDevicePointer((void**)&D.hbatch, d_->h_batch, 0));
-        }
+    if (cfg_.evaluator == EVAL_CALLBACK) {
+        C6_CUDA(cudaHostAlloc(&d_->h_batch, batch_bytes, cudaHostAllocMapped));
+        C6_CUDA(cudaHostGetDevicePointer((void**)&D.hbatch, d_->h_batch, 0));
     }
-    cudaDeviceProp prop;
-    C6_CUDA(cudaGetDeviceProperties(&prop, cfg_.device));
-    d_->sm_count = prop.multiProcessorCount;
+    C6_CUDA(cudaDeviceGetAttribute(&d_->sm_count, cudaDevAttrMultiProcessorCount, cfg_.device));
     C6_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -572,10 +576,9 @@ Engine::~Engine() {
     if (!d_) return;
     Dev& D = d_->dev;
     cudaStreamSynchronize(stream_);
-    cudaFree(D.rec), cudaFree(D.lnk), cudaFree(D.idx), cudaFree(D.expB), cudaFree(D.exp_rec), cudaFree(D.exp_key);
-    cudaFree(D.path), cudaFree(D.gs), cudaFree((void*)D.Z), cudaFree(D.cursor), cudaFree(D.gcount), cudaFree(D.gdone), cudaFree(D.leaf_flag);
-    cudaFree(D.records), cudaFree(D.batch), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
-    cudaFreeHost(d_->h_batch), cudaFreeHost(d_->h_sync), cudaFreeHost(d_->h_gcount);
+    cudaFree(d_->arena);
+    cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
+    cudaFreeHost(d_->h_batch), cudaFreeHost(d_->h_pinned);
     for (Group& gr : d_->groups) {
         if (gr.s && gr.s != stream_) cudaStreamSynchronize(gr.s), cudaStreamDestroy(gr.s);
         if (gr.ev) cudaEventDestroy(gr.ev);

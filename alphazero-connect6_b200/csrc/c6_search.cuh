@@ -594,13 +594,16 @@ struct EvPhilox {
     __device__ __forceinline__ void init(const Dev& D, uint32_t game_id, uint32_t sim_index, int lane_) {
         k0 = D.seed ^ DOMAIN_EVAL, k1 = game_id, sim = sim_index, lane = lane_;
     }
-    __device__ __forceinline__ float value() const {  // ((((((((0+v0)+v1)+..)+v7)/8 (:224)
-        float sum = 0.f;
-#pragma unroll 1
-        for (uint32_t half = 0; half < 2; ++half) {
-            Philox4 a = philox4x32_10(sim, CELLS, half, 0, k0, k1);
-            sum = sum + u32_to_pm1(a.x), sum = sum + u32_to_pm1(a.y), sum = sum + u32_to_pm1(a.z), sum = sum + u32_to_pm1(a.w);
-        }
+    // ((((((((0+v0)+v1)+..)+v7)/8 (:224): v0..3 are Philox block (sim, 225, 0, 0), v4..7 block (sim, 225, 1, 0).  Even lanes compute
+    // the first block, odd lanes the second (one block's worth of instructions for the warp instead of two); lane 1's four draws
+    // are then added in order.  Call with the whole warp.
+    __device__ __forceinline__ float value() const {
+        const Philox4 a = philox4x32_10(sim, CELLS, (uint32_t)(lane & 1), 0, k0, k1);
+        const float x = u32_to_pm1(a.x), y = u32_to_pm1(a.y), z = u32_to_pm1(a.z), t = u32_to_pm1(a.w);
+        float sum = (((0.f + x) + y) + z) + t;  // lane 0: the first half
+        sum = __shfl_sync(FULL, sum, 0);
+        sum = sum + __shfl_sync(FULL, x, 1), sum = sum + __shfl_sync(FULL, y, 1);
+        sum = sum + __shfl_sync(FULL, z, 1), sum = sum + __shfl_sync(FULL, t, 1);
         return sum / 8.f;
     }
     // 24-bit draw number i (0..7) of the 192 bits in words q[0..5]: bits [24 i, 24 i + 24); the draw is x 2^-23 - 1 in [-1, 1)

@@ -26,6 +26,17 @@ for sims in (2, 800):
     print(json.dumps({"case": f"engine, device RandomEvaluator, {sims} simulations/stone", "seconds_per_game": dt, "stones": rec[0].n_moves,
                       "simulations": st.sims, "simulations_per_s": st.sims / dt}), flush=True)
 
+    if sims == 2:  # where the wall time of so short a job goes: driver round trips, not the search
+        tt = [time.perf_counter()]
+        e = L.c6_engine_create(C.byref(cfg)); tt.append(time.perf_counter())
+        assert e, L.c6_last_error()
+        assert L.c6_engine_start(e, 0, 1) == 0; tt.append(time.perf_counter())
+        assert L.c6_engine_run_device(e) == 0, L.c6_last_error(); tt.append(time.perf_counter())
+        L.c6_engine_records(e, rec, 1); L.c6_engine_stats(e, C.byref(st)); tt.append(time.perf_counter())
+        L.c6_engine_destroy(e); tt.append(time.perf_counter())
+        print(json.dumps({"case": "engine, device RandomEvaluator, 2 simulations/stone: breakdown", "ms": dict(zip(
+            ["create", "start", "run", "records+stats", "destroy"], [round(1e3 * (b - a), 3) for a, b in zip(tt, tt[1:])]))}), flush=True)
+
     # through the host Callback ABI: the reference's sequential schedule (K = 1), then the opt-in multi-leaf mode — K leaves per
     # evaluator call, so a single game needs ~K times fewer round trips per stone (not the reference's search: SURVEY 7 "virtual loss")
     for K in ((1,) if sims == 2 else (1, 2, 4, 8)):
