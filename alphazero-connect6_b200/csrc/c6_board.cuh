@@ -32,19 +32,40 @@ __host__ __device__ __forceinline__ void shl256(const uint32_t (&b)[8], uint32_t
     }
 }
 // bits at cells that END a run of >= 6 in stride D (the cells where search() returns,
-// LC/game/search_winner/mod.rs:213-217)
+// LC/game/search_winner/mod.rs:213-217): x3 = b & b<<D & b<<2D (three in a row ending here), six = x3 & x3<<3D.
+// Three shifts and two 3-input logic operations (LOP3) per word — the shift/AND ladder over pairs (b & b<<D, then <<2D, <<4D)
+// costs three of each; on the GPU both kinds issue on the ALU pipe, which is what bounds k_win_check.
+// Column 15 of every row is never occupied, so a run cannot continue across a row end in any of the four strides.
 template <int D>
 __host__ __device__ __forceinline__ void run6(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
-    uint32_t t[8], m2[8], m4[8];
-    shl256<D>(b, t);
+    uint32_t t1[8], t2[8], x3[8];
+    shl256<D>(b, t1);
+    shl256<2 * D>(b, t2);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x3[w] = b[w] & t1[w] & t2[w];
+    shl256<3 * D>(x3, t1);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc[w] |= x3[w] & t1[w];
+}
+// stride 1 (along a row): bits 15 and 31 of every word are the unoccupied column, so nothing a run could use crosses a word
+// boundary and the shifts are plain 32-bit ones — which the compiler may issue as multiplies on the FMA pipe (IMAD.SHL).
+template <>
+__host__ __device__ __forceinline__ void run6<1>(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t x3 = b[w] & (b[w] << 1) & (b[w] << 2);
+        acc[w] |= x3 & (x3 << 3);
+    }
+}
+// stride 16 (down a column): 32 and 64 bits are whole words — register renaming, no instruction
+template <>
+__host__ __device__ __forceinline__ void run6<16>(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
+    uint32_t t[8], m2[8];
+    shl256<16>(b, t);
 #pragma unroll
     for (int w = 0; w < 8; ++w) m2[w] = b[w] & t[w];
-    shl256<2 * D>(m2, t);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) m4[w] = m2[w] & t[w];
-    shl256<4 * D>(m2, t);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) acc[w] |= m4[w] & t[w];
+    for (int w = 2; w < 8; ++w) acc[w] |= m2[w] & m2[w - 1] & m2[w - 2];  // m2 & (m2 << 32) & (m2 << 64); words 0, 1 have no room for six rows
 }
 __host__ __device__ __forceinline__ int first_bit256(const uint32_t (&a)[8]) {
     int r = 256;
@@ -59,6 +80,52 @@ __host__ __device__ __forceinline__ int first_bit256(const uint32_t (&a)[8]) {
         }
     return r;
 }
+// All four strides of one colour, sharing the board moved one row down (s = b << 16).  A move by k rows and c columns is a
+// 16-bit move (k odd: the view s) and / or a move by whole words (k / 2: register renaming) followed by a plain 32-bit shift
+// by |c| inside each word: what such a shift drops at a word boundary, and what it carries across the row boundary in the
+// middle of a word, only ever lands on cells whose run would have to pass the unoccupied column 15 — the AND with the board
+// clears them (checked exhaustively against a cell-by-cell scan, tests/cpp/host_mirror.cpp).  Against run6<17> / run6<15>
+// this trades two funnel shifts per word (ALU pipe, like the LOP3s) for plain shifts, which the FMA pipe can take
+// (IMAD.SHL for left shifts; right shifts as IMAD.HI when C6_SHR_MULHI).
+#ifndef C6_SHR_MULHI
+#define C6_SHR_MULHI 1
+#endif
+template <int K>
+__host__ __device__ __forceinline__ uint32_t shr_plain(uint32_t x) {
+#if defined(__CUDA_ARCH__) && C6_SHR_MULHI
+    return __umulhi(x, 1u << (32 - K));
+#else
+    return x >> K;
+#endif
+}
+__host__ __device__ __forceinline__ void run6_all(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
+    uint32_t s[8], x[8], sx[8];
+    shl256<16>(b, s);
+    // stride 16 (down a column): pairs, then three pairs two rows apart
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x[w] = b[w] & s[w];
+#pragma unroll
+    for (int w = 2; w < 8; ++w) acc[w] |= x[w] & x[w - 1] & x[w - 2];
+    // stride 1 (along a row)
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t x3 = b[w] & (b[w] << 1) & (b[w] << 2);
+        acc[w] |= x3 & (x3 << 3);
+    }
+    // stride 17 (one row down, one column right): b << 17 = s << 1, b << 34 = one word up << 2, x << 51 = (x << 16) one word up << 3
+    x[0] = 0;
+#pragma unroll
+    for (int w = 1; w < 8; ++w) x[w] = b[w] & (s[w] << 1) & (b[w - 1] << 2);
+    shl256<16>(x, sx);
+#pragma unroll
+    for (int w = 2; w < 8; ++w) acc[w] |= x[w] & (sx[w - 1] << 3);
+    // stride 15 (one row down, one column left): the same with right shifts
+#pragma unroll
+    for (int w = 1; w < 8; ++w) x[w] = b[w] & shr_plain<1>(s[w]) & shr_plain<2>(b[w - 1]);
+    shl256<16>(x, sx);
+#pragma unroll
+    for (int w = 2; w < 8; ++w) acc[w] |= x[w] & shr_plain<3>(sx[w - 1]);
+}
 // search(): winner = colour whose first run-end cell comes first in row-major order
 __host__ __device__ inline int win_check(const uint32_t (&B)[8], const uint32_t (&W)[8]) {
     uint32_t eb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ew[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -69,22 +136,11 @@ __host__ __device__ inline int win_check(const uint32_t (&B)[8], const uint32_t 
     return fb < fw ? -1 : 1;
 }
 
-// The same decision with fewer instructions (config-3a kernel; 420 ALU instructions per board made k_win_check as much issue-
-// as bandwidth-bound, profiles/r01p_micro.jsonl): the vertical direction shifts by 16 / 32 / 64 bits, and the last two are whole
-// words — register renaming, no instruction; and since a cell holds one colour, the winner is the colour owning the lowest set
-// bit of (black run ends | white run ends): one scan over eight words instead of two.
-__host__ __device__ __forceinline__ void run6_vertical(const uint32_t (&b)[8], uint32_t (&acc)[8]) {
-    uint32_t t[8], m2[8];
-    shl256<16>(b, t);
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m2[w] = b[w] & t[w];
-#pragma unroll
-    for (int w = 2; w < 8; ++w) acc[w] |= m2[w] & m2[w - 1] & m2[w - 2];  // m2 & (m2 << 32) & (m2 << 64); words 0, 1 have no room for six rows
-}
+// The same decision with one scan (config-3a kernel): since a cell holds one colour, the winner is the colour owning the
+// lowest set bit of (black run ends | white run ends) — one pass over eight words instead of two.
 __host__ __device__ inline int win_check_fast(const uint32_t (&B)[8], const uint32_t (&W)[8]) {
     uint32_t eb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ew[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    run6<1>(B, eb), run6_vertical(B, eb), run6<17>(B, eb), run6<15>(B, eb);
-    run6<1>(W, ew), run6_vertical(W, ew), run6<17>(W, ew), run6<15>(W, ew);
+    run6_all(B, eb), run6_all(W, ew);
     uint32_t first = 0, first_b = 0;
 #pragma unroll
     for (int w = 7; w >= 0; --w) {

@@ -125,9 +125,9 @@ __device__ __forceinline__ uint32_t dp_pick(const uint32_t (&B)[8], const uint32
 __device__ __forceinline__ bool dp_won(const uint32_t (&B)[8], const uint32_t (&W)[8], int turn) {
     uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (turn < 0) {
-        run6<1>(B, acc), run6<16>(B, acc), run6<17>(B, acc), run6<15>(B, acc);
+        run6_all(B, acc);
     } else {
-        run6<1>(W, acc), run6<16>(W, acc), run6<17>(W, acc), run6<15>(W, acc);
+        run6_all(W, acc);
     }
     uint32_t any = 0;
 #pragma unroll

@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(128) k_playouts(long long first, long long n, 
         s += 1;
         uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (turn < 0) {
-            run6<1>(B, acc), run6<16>(B, acc), run6<17>(B, acc), run6<15>(B, acc);
+            run6_all(B, acc);
         } else {
-            run6<1>(W, acc), run6<16>(W, acc), run6<17>(W, acc), run6<15>(W, acc);
+            run6_all(W, acc);
         }
         uint32_t any = 0;
 #pragma unroll

@@ -336,6 +336,20 @@ def build_host_mirror():
     return HOST_MIRROR_EXE
 
 
+def test_win_check_against_cell_scan():
+    """tests/cpp/win_check_scan.cpp: the kernels' bit-packed win detection (c6_board.cuh, compiled for the host) against a
+    cell-by-cell scan of search()'s rule on 200,000 random boards and on runs laid across row ends and board edges."""
+    src = os.path.join(ROOT, "tests", "cpp", "win_check_scan.cpp")
+    exe = os.path.join(BUILD_DIR, "win_check_scan")
+    csrc = os.path.join(c6lib.PKG, "csrc")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(f) for f in (src, os.path.join(csrc, "c6_board.cuh"))):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-I", csrc, "-I", "/usr/local/cuda/include", src, "-o", exe], check=True,
+                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6/pybind"), reason="reference tree not mounted")
 def test_reference_pybind_echo_test_runs_in_place():
     """PB/test_pybind/test_pybind.py::test_echo_pyeval, the reference's own file run where it lies against our pyconnect6
