@@ -84,7 +84,7 @@ __host__ __device__ __forceinline__ int first_bit256(const uint32_t (&a)[8]) {
 // 16-bit move (k odd: the view s) and / or a move by whole words (k / 2: register renaming) followed by a plain 32-bit shift
 // by |c| inside each word: what such a shift drops at a word boundary, and what it carries across the row boundary in the
 // middle of a word, only ever lands on cells whose run would have to pass the unoccupied column 15 — the AND with the board
-// clears them (checked exhaustively against a cell-by-cell scan, tests/cpp/host_mirror.cpp).  Against run6<17> / run6<15>
+// clears them (checked against a cell-by-cell scan, tests/cpp/win_check_scan.cpp).  Against run6<17> / run6<15>
 // this trades two funnel shifts per word (ALU pipe, like the LOP3s) for plain shifts, which the FMA pipe can take
 // (IMAD.SHL for left shifts; right shifts as IMAD.HI when C6_SHR_MULHI).
 #ifndef C6_SHR_MULHI

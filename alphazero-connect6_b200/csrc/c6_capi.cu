@@ -452,6 +452,8 @@ int c6_engine_kernel_times(c6_engine* e, double* sims_kernel_ms, long long* sims
         *sims_kernel_launches = e->eng->sims_kernel_launches();
     });
 }
+
+void c6_release_cached_memory(void) { release_cached_memory(); }
 int c6_engine_stats(c6_engine* e, c6_stats* out) {
     return guarded([&] {
         Stats s = e->eng->stats();

@@ -6,8 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
+#include <vector>
 
 #include "c6_search.cuh"
 
@@ -420,8 +422,76 @@ struct Group {
     int seq = 0;  // sequence number of the last leaf batch asked for (k_gather publishes it to hsync when the batch is ready)
 };
 
+// Blocks an engine frees are kept for the next engine of the process (same device, same kind, same size): a run of short
+// jobs — the reference's 2-simulation sample game, a test suite — otherwise spends its time in cudaMalloc / cudaHostAlloc /
+// cudaFree (6 ms each way for a one-game engine against 5 ms of search, profiles/r02o_config1.jsonl).  Bounded: at most
+// C6_ALLOC_CACHE_MB (default 256) in total and 16 blocks, so a 30 GB node pool is never held back.  Contents are whatever the
+// last owner left: the constructor clears what it reads before writing, as it must for fresh memory too.
+namespace {
+struct CachedBlock {
+    int device;
+    bool pinned;
+    size_t bytes;
+    void* p;
+};
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+size_t g_cache_bytes = 0;
+size_t cache_limit_bytes() {
+    static const size_t lim = [] {
+        const char* v = std::getenv("C6_ALLOC_CACHE_MB");
+        return (size_t)(v && *v ? std::max(0, std::atoi(v)) : 256) << 20;
+    }();
+    return lim;
+}
+void* cached_alloc(int device, size_t bytes, bool pinned) {
+    {
+        std::lock_guard<std::mutex> l(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size(); ++i)
+            if (g_cache[i].device == device && g_cache[i].pinned == pinned && g_cache[i].bytes == bytes) {
+                void* p = g_cache[i].p;
+                g_cache_bytes -= bytes;
+                g_cache.erase(g_cache.begin() + (long)i);
+                return p;
+            }
+    }
+    void* p = nullptr;
+    if (pinned)
+        C6_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocMapped));
+    else
+        C6_CUDA(cudaMalloc(&p, bytes));
+    return p;
+}
+// the caller has synchronised every stream that touched the block
+void cached_free(int device, void* p, size_t bytes, bool pinned) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> l(g_cache_mu);
+        if (bytes <= cache_limit_bytes() / 2 && g_cache_bytes + bytes <= cache_limit_bytes() && g_cache.size() < 16) {
+            g_cache.push_back(CachedBlock{device, pinned, bytes, p});
+            g_cache_bytes += bytes;
+            return;
+        }
+    }
+    if (pinned) cudaFreeHost(p); else cudaFree(p);
+}
+}  // namespace
+void release_cached_memory() {
+    std::vector<CachedBlock> blocks;
+    {
+        std::lock_guard<std::mutex> l(g_cache_mu);
+        blocks.swap(g_cache);
+        g_cache_bytes = 0;
+    }
+    for (const CachedBlock& b : blocks) {
+        cudaSetDevice(b.device);
+        if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p);
+    }
+}
+
 struct DeviceArrays {
     Dev dev{};
+    size_t arena_bytes = 0, pinned_bytes = 0, batch_bytes = 0, records_bytes = 0, trace_rows = 0;
     char* arena = nullptr;     // the one device allocation every array of `dev` is carved from (records / traces apart)
     char* h_pinned = nullptr;  // the one small pinned allocation: h_sync, h_gcount
     float* h_batch = nullptr;  // mapped pinned host memory, same layout as Dev::batch
@@ -529,7 +599,8 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     const size_t o_cursor = carve(sizeof(int)), o_gcount = carve(4 * sizeof(unsigned long long));
     const size_t zero_bytes = top - o_zero;
     const size_t o_Z = carve(512 * sizeof(uint64_t)), o_batch = carve(batch_bytes);
-    C6_CUDA(cudaMalloc(&d_->arena, top));
+    d_->arena_bytes = top;
+    d_->arena = (char*)cached_alloc(cfg_.device, top, false);
     char* base = d_->arena;
     D.rec = (Rec*)(base + o_rec), D.lnk = (uint32_t*)(base + o_lnk), D.idx = (Slot*)(base + o_idx);
     D.expB = (uint32_t*)(base + o_expB), D.exp_rec = (uint32_t*)(base + o_exp_rec), D.exp_key = (uint64_t*)(base + o_exp_key);
@@ -544,8 +615,9 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     D.Z = (const uint64_t*)(base + o_Z);
     // pinned: per group {Black leaves, White leaves, seq, -} (mapped: k_gather publishes into it), then the 4 game counters
     const size_t sync_bytes = ((size_t)4 * n_groups * sizeof(int) + 63) & ~(size_t)63;
-    C6_CUDA(cudaHostAlloc(&d_->h_pinned, sync_bytes + 4 * sizeof(unsigned long long), cudaHostAllocMapped));
-    std::memset(d_->h_pinned, 0, sync_bytes + 4 * sizeof(unsigned long long));
+    d_->pinned_bytes = sync_bytes + 4 * sizeof(unsigned long long);
+    d_->h_pinned = (char*)cached_alloc(cfg_.device, d_->pinned_bytes, true);
+    std::memset(d_->h_pinned, 0, d_->pinned_bytes);
     d_->h_sync = (int*)d_->h_pinned, d_->h_gcount = (unsigned long long*)(d_->h_pinned + sync_bytes);
     C6_CUDA(cudaHostGetDevicePointer((void**)&D.hsync, d_->h_sync, 0));
     if (const char* ul = std::getenv("C6_LAUNCHER")) use_launcher_ = std::atoi(ul) != 0;
@@ -565,24 +637,37 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
     }
     spin_us_ = host_spin_budget_us();
     if (cfg_.evaluator == EVAL_CALLBACK) {
-        C6_CUDA(cudaHostAlloc(&d_->h_batch, batch_bytes, cudaHostAllocMapped));
+        d_->batch_bytes = batch_bytes;
+        d_->h_batch = (float*)cached_alloc(cfg_.device, batch_bytes, true);
         C6_CUDA(cudaHostGetDevicePointer((void**)&D.hbatch, d_->h_batch, 0));
     }
     C6_CUDA(cudaDeviceGetAttribute(&d_->sm_count, cudaDevAttrMultiProcessorCount, cfg_.device));
     C6_CUDA(cudaStreamSynchronize(stream_));
 }
 
+void Engine::free_records() {
+    Dev& D = d_->dev;
+    cached_free(cfg_.device, D.records, d_->records_bytes, false);
+    cached_free(cfg_.device, D.tr_visits, d_->trace_rows * CELLS * 4, false);
+    cached_free(cfg_.device, D.tr_n, d_->trace_rows * 4, false);
+    cached_free(cfg_.device, D.tr_w, d_->trace_rows * 4, false);
+    D.records = nullptr, D.tr_visits = nullptr, D.tr_n = nullptr, D.tr_w = nullptr;
+    d_->records_bytes = 0, d_->trace_rows = 0;
+}
+
 Engine::~Engine() {
     if (!d_) return;
-    Dev& D = d_->dev;
+    cudaSetDevice(cfg_.device);
     cudaStreamSynchronize(stream_);
-    cudaFree(d_->arena);
-    cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
-    cudaFreeHost(d_->h_batch), cudaFreeHost(d_->h_pinned);
     for (Group& gr : d_->groups) {
         if (gr.s && gr.s != stream_) cudaStreamSynchronize(gr.s), cudaStreamDestroy(gr.s);
         if (gr.ev) cudaEventDestroy(gr.ev);
     }
+    // nothing of this engine is in flight any more: the blocks may go to the next one
+    free_records();
+    cached_free(cfg_.device, d_->arena, d_->arena_bytes, false);
+    cached_free(cfg_.device, d_->h_batch, d_->batch_bytes, true);
+    cached_free(cfg_.device, d_->h_pinned, d_->pinned_bytes, true);
     cudaStreamDestroy(stream_);
     delete d_;
 }
@@ -595,15 +680,16 @@ void Engine::start(uint32_t first_id, int64_t total_games) {
     sync();
     total_games_ = total_games, first_id_ = first_id;
     D.total_games = total_games, D.first_id = first_id;
-    cudaFree(D.records), cudaFree(D.tr_visits), cudaFree(D.tr_n), cudaFree(D.tr_w);
-    D.records = nullptr, D.tr_visits = nullptr, D.tr_n = nullptr, D.tr_w = nullptr;
-    C6_CUDA(cudaMalloc(&D.records, std::max<int64_t>(total_games, 1) * sizeof(GameRecord)));
-    C6_CUDA(cudaMemsetAsync(D.records, 0, std::max<int64_t>(total_games, 1) * sizeof(GameRecord), stream_));
+    free_records();
+    d_->records_bytes = (size_t)std::max<int64_t>(total_games, 1) * sizeof(GameRecord);
+    D.records = (GameRecord*)cached_alloc(cfg_.device, d_->records_bytes, false);
+    C6_CUDA(cudaMemsetAsync(D.records, 0, d_->records_bytes, stream_));
     if (cfg_.trace) {
         size_t n = (size_t)total_games * CELLS;
-        C6_CUDA(cudaMalloc(&D.tr_visits, n * CELLS * 4));
-        C6_CUDA(cudaMalloc(&D.tr_n, n * 4));
-        C6_CUDA(cudaMalloc(&D.tr_w, n * 4));
+        d_->trace_rows = n;
+        D.tr_visits = (int32_t*)cached_alloc(cfg_.device, n * CELLS * 4, false);
+        D.tr_n = (int32_t*)cached_alloc(cfg_.device, n * 4, false);
+        D.tr_w = (float*)cached_alloc(cfg_.device, n * 4, false);
         C6_CUDA(cudaMemsetAsync(D.tr_visits, 0xFF, n * CELLS * 4, stream_));
         C6_CUDA(cudaMemsetAsync(D.tr_n, 0, n * 4, stream_));
         C6_CUDA(cudaMemsetAsync(D.tr_w, 0, n * 4, stream_));

@@ -192,6 +192,7 @@ class Engine {
     void cancel() { cancel_.store(true); }
 
    private:
+    void free_records();
     void group_issue(int p, size_t len, bool do_back, bool do_front);  // launching thread: every CUDA enqueue of a wave
     size_t group_eval(int p, Callback cb);                             // calling thread: wait for the leaves, run the user Callback(s)
     void waves_callback_threaded(Callback cb, int waves);
@@ -244,5 +245,7 @@ const char* last_error();
 // host cores this process may keep busy (hardware threads / ranks sharing the box) and the polling budget derived from it
 int host_cores_per_rank();
 int host_spin_budget_us();
+// frees the device / pinned blocks kept from destroyed engines for reuse (C6_ALLOC_CACHE_MB, default 256 MB in total)
+void release_cached_memory();
 
 }  // namespace c6

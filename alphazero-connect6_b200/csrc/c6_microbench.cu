@@ -11,12 +11,12 @@ namespace c6 {
 // Two boards per thread (boards i and i + n/2: both request streams stay coalesced, and the two independent shift/AND chains
 // interleave): 64 B in per board (two 256-bit loads), 1 B out.  65 algorithmic bytes per board.
 //
-// What bounds it (profiles/r02e_prof_secondary.md): not HBM and not issue slots (49.5 % busy) but the ALU pipe —
-// `math_pipe_throttle` is the top stall: every funnel shift (SHF) and every AND (LOP3) of the 256-bit run detection is an
-// ALU-pipe instruction and that pipe takes one warp instruction every other cycle; 274 of them per board are 0.25 ms of pipe
-// time for 16 M boards against 0.17 ms of HBM time.  win_check_fast (word-shift vertical pass, one winner scan) cut the
-// instructions from 420 to 328 per board without moving the bound; doing the shifts as 32 x 32 -> 64-bit multiplies on the FMA
-// pipe (r02f A/B) was slower (0.48 of the copy bandwidth against 0.56: IMAD.WIDE is not a full-rate instruction either).
+// What bounds it (profiles/r02o_prof_secondary.md): not HBM and not issue slots (63 % busy) but the ALU pipe (76 % busy,
+// `math_pipe_throttle` the top stall): every LOP3 and every funnel shift (SHF) of the 256-bit run detection is an ALU-pipe
+// instruction and that pipe takes one warp instruction every other cycle.  c6_board.cuh's run6_all keeps it to 168 of them per
+// board (2 LOP3 per word, stride and colour; the plain in-word shifts of its row-view formulation issue on the FMA pipe as
+// IMAD.SHL / IMAD.HI): 0.73 of the copy bandwidth, from 0.56 with 272 (pair ladder, funnel shifts everywhere).  Doing ALL
+// shifts as 32 x 32 -> 64-bit multiplies (r02f A/B) was slower: IMAD.WIDE is half rate.
 __device__ __forceinline__ void load_board(const uint32_t* p, uint32_t (&B)[8], uint32_t (&W)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(B[0]), "=r"(B[1]), "=r"(B[2]), "=r"(B[3]), "=r"(B[4]), "=r"(B[5]), "=r"(B[6]), "=r"(B[7])

@@ -109,6 +109,8 @@ def product():
         L.c6_engine_waves_device_callback.argtypes = [C.c_void_p, DEVICE_CALLBACK, C.c_void_p, C.c_int]
         L.c6_engine_run_device_callback.argtypes = [C.c_void_p, DEVICE_CALLBACK, C.c_void_p]
         L.c6_engine_run_device.argtypes = [C.c_void_p]
+        L.c6_release_cached_memory.argtypes = []
+        L.c6_release_cached_memory.restype = None
         L.c6_engine_run_callback.argtypes = [C.c_void_p, CALLBACK]
         L.c6_engine_sync.argtypes = [C.c_void_p]
         L.c6_engine_cancel.argtypes = [C.c_void_p]

@@ -289,12 +289,23 @@ def e2e_leg(L, capi, red, args, rank, local, games, callback_name, waves_w=8, wa
         bw1 = L.c6_engine_host_blocked_waits(e)
         e2e_ms = red.max(float(ms.value))
         (e2e_sims,) = red.sum(s1.sims - s0.sims)
+        # what the host link of THIS box carries (rank 0's GPU, nothing else running): the floor under ms_per_wave
+        up, down, both = C.c_double(), C.c_double(), C.c_double()
+        per_wave = int(h2d.value / waves)
+        red.barrier()
+        link = None
+        if rank == 0 and L.c6_probe_pcie(per_wave, 8, local, C.byref(up), C.byref(down), C.byref(both)) == 0:
+            link = {"h2d_GBps": up.value, "d2h_GBps": down.value, "each_way_GBps_when_both_run": both.value,
+                    "floor_ms_per_wave": per_wave / both.value / 1e6,
+                    "note": "pinned-memory copies of one wave's bytes alone on rank 0's link, measured after the timed waves"}
+        red.barrier()
         return {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d.value / waves, "d2h_bytes_per_step": d2h.value / waves,
                 "step": f"one wave = one simulation for each of {games} games through the C-ABI Callback (host buffers, "
                         f"{callback_name}); {waves} waves timed",
                 "ms_per_wave": e2e_ms / waves,
                 "host_ms_per_wave": {"in_callback": 1e3 * (hc1.value - hc0.value) / waves, "blocked_on_gpu": 1e3 * (hw1.value - hw0.value) / waves,
-                                     "waits_that_slept_per_wave": (bw1 - bw0) / waves, "of": "rank 0"}}
+                                     "waits_that_slept_per_wave": (bw1 - bw0) / waves, "of": "rank 0"},
+                "host_link": link}
     finally:
         L.c6_engine_destroy(e)
 

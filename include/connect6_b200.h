@@ -250,6 +250,10 @@ int c6_host_cores_per_rank(void);
 int c6_host_spin_budget_us(void);
 /* callback path, cumulative: waits of the calling thread that outlasted the polling budget and slept in the driver */
 long long c6_engine_host_blocked_waits(c6_engine* e);
+/* Destroyed engines leave their device and pinned blocks (up to C6_ALLOC_CACHE_MB, default 256 MB in total, never a block
+ * above half of that) to the next engine of the process, so that a run of short jobs does not pay the driver's
+ * allocation round trips each time; this frees them now. */
+void c6_release_cached_memory(void);
 
 #ifdef __cplusplus
 }

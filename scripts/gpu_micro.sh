@@ -14,6 +14,9 @@ for v in alphazero-connect6_b200/lib/variants/libm_*.so; do
 done
 echo "micro base again"; timeout 600 python scripts/micro.py --no-cpu --quick 2>&1 | tee $OUT/micro_again.jsonl
 timeout 600 python scripts/config1.py > $OUT/config1.jsonl 2> $OUT/config1.err; cat $OUT/config1.jsonl
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_win_check|k_playouts|k_default_policy" -c 8 -o $OUT/prof_secondary \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_win_check|k_playouts" -c 5 -o $OUT/prof_secondary \
     python scripts/secondary_kernels.py > $OUT/ncu_secondary.log 2>&1; echo "ncu secondary rc=$?" >> $OUT/ncu_secondary.log
 tail -2 $OUT/ncu_secondary.log
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_default_policy" -c 1 -o $OUT/prof_default_policy \
+    python scripts/secondary_kernels.py > $OUT/ncu_default_policy.log 2>&1; echo "ncu default policy rc=$?" >> $OUT/ncu_default_policy.log
+tail -2 $OUT/ncu_default_policy.log

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One small launch of every secondary kernel of the path, for `ncu --set full -k regex:...` (scripts/gpu_round2.sh):
 k_win_check / k_random_boards / k_playouts (configs[2]), k_step + k_gather (callback path, 1,024 games, a few waves),
-k_default_policy (16,384 games), k_expand_records (replay feed)."""
+k_default_policy (4,096 games), k_expand_records (replay feed)."""
 import ctypes as C
 import os
 import sys
@@ -22,7 +22,7 @@ assert L.c6_engine_start(e, 0, 1 << 20) == 0
 h2d, d2h = C.c_double(), C.c_double()
 assert L.c6_engine_timed_waves(e, C.cast(L.c6_sample_random_callback, capi.CALLBACK), 40, C.byref(ms), C.byref(h2d), C.byref(d2h)) == 0, L.c6_last_error()
 L.c6_engine_destroy(e)
-n = 16384
+n = 4096
 rec = (capi.Record * n)()
 st = capi.DpStats()
 assert L.c6_default_policy_play(50, 0xC6, 0, n, 0, 0, rec, None, None, C.byref(st)) == 0, L.c6_last_error()

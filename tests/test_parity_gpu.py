@@ -380,6 +380,27 @@ def test_slot_refill_and_game_order():
             assert r.winner == turn
 
 
+def test_engine_on_recycled_blocks_equals_engine_on_fresh_memory():
+    """A destroyed engine leaves its device and pinned blocks to the next one of the same shape (c6_engine.cu: cached_alloc): the
+    second engine starts on whatever the first left there — another seed's tree, another budget's counters — and must play
+    exactly what an engine on fresh memory plays, on the device path and on the callback path."""
+    L = c6lib.product()
+    L.c6_release_cached_memory()
+    kw = dict(slots=3, num_simulation=24, epsilon=0.25, evaluator=EVAL_PHILOX, max_moves=9)
+    fresh = [bytes(run_engine(5, None, seed=s, **kw)[0]) for s in (11, 12)]
+    L.c6_release_cached_memory()
+    first = bytes(run_engine(5, None, seed=11, **kw)[0])  # fresh memory again
+    second = bytes(run_engine(5, None, seed=12, **kw)[0])  # the blocks seed 11 has just left
+    third = bytes(run_engine(5, None, seed=11, **kw)[0])
+    assert [first, second, third] == [fresh[0], fresh[1], fresh[0]]
+    kw = dict(slots=3, num_simulation=24, epsilon=0.25, evaluator=EVAL_CALLBACK, max_moves=9)
+    a = bytes(run_engine(5, "det_eval_callback", seed=11, **kw)[0])
+    b = bytes(run_engine(5, "neg_eval_callback", seed=12, **kw)[0])
+    L.c6_release_cached_memory()
+    assert bytes(run_engine(5, "neg_eval_callback", seed=12, **kw)[0]) == b and bytes(run_engine(5, "det_eval_callback", seed=11, **kw)[0]) == a
+    L.c6_release_cached_memory()
+
+
 def test_zero_simulations():
     rec, *_ = run_engine(2, None, num_simulation=0, epsilon=0.0, evaluator=EVAL_PHILOX)
     assert all(rec[g].n_moves == 0 and rec[g].winner == 0 for g in range(2))
