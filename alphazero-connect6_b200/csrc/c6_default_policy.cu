@@ -5,8 +5,12 @@
 //   DefaultPolicy::{init,select,expand,update,search,policy,next}   LC/policy/default_policy/mod.rs:121-271
 //   Agent::play                                                     LC/agent/agent_impl/mod.rs:121-178
 // (LC = /root/reference/Connect6/libconnect6/src).  What the reference keeps in `HashMap<u64, Node>`:
-//   node  {visit, black_win, head, tail}  16 B  — `next_node: Vec<u64>` is a linked list of entries in push order
-//   entry {child | move << 24, next}       8 B  — one per expand(); the same child may be listed twice (:181)
+//   node  {visit, black_win, head, tail}  16 B  — `next_node: Vec<u64>` is a list of CHUNKS in push order
+//   chunk {7 x (child | move << 24), next} 32 B  — one entry per expand(); the same child may be listed twice (:181).
+//         One sector holds seven children: select() reads a chunk, then has the seven child nodes and the next chunk in
+//         flight together — one memory round trip per seven children where a list of single entries took one per child
+//         (a search scans ~150 entries in 3.9 select steps, and that dependent chain was what a game's time went into).
+//         tail = chunk | fill << 24 (fill 1..7); free slots hold NIL
 //   key   64-bit Zobrist board key -> node, open addressing; `map.insert` on an existing board RESETS that node
 //         (visit = black_win = 0, no children, :174), `entry().or_insert` in init() does not (:123)
 // Random choices are the Philox streams the oracle documents (oracle/c6_default_policy.hpp): key (seed ^ "DPOL", game),
@@ -27,7 +31,7 @@ struct DpDev {
     int4* nodes;       // [n][ncap] {visit, black_win, head, tail}
     uint64_t* keys;    // [n][ncap]
     uint32_t* table;   // [n][tmask + 1] node index + 1, 0 = empty
-    uint2* ents;       // [n][ecap]
+    uint4* chunks;     // [n][ecap][2]
     uint32_t* path;    // [232][n] node indices of the current search (game-minor: coalesced across a warp)
     GameRecord* rec;   // [n]
     int32_t* root_visit;  // [n][225] or null: root node after the searches of each move
@@ -44,8 +48,8 @@ struct DpTree {
     int4* nodes;
     uint64_t* keys;
     uint32_t* table;
-    uint2* ents;
-    uint32_t tmask, n_nodes, n_ents;
+    uint4* chunks;
+    uint32_t tmask, n_nodes, n_ents;  // n_ents: chunks in use
     __device__ __forceinline__ uint32_t find(uint64_t key) const {
         uint32_t pos = (uint32_t)(key ^ (key >> 32)) & tmask;
         for (;;) {
@@ -69,27 +73,36 @@ struct DpTree {
 // select (:129-161): the LAST child with the maximal signed win ratio, if that ratio is non-zero
 __device__ __forceinline__ bool dp_select(const DpTree& t, uint32_t node, int turn, uint32_t& child, uint32_t& bit,
                                           unsigned long long& scanned) {
-    uint32_t e = (uint32_t)t.nodes[node].z;
+    uint32_t ch = (uint32_t)t.nodes[node].z;
+    if (ch == NIL) return false;
     bool any = false;
     float bp = 0.f;
-    uint2 en = make_uint2(0u, NIL);
-    if (e != NIL) en = t.ents[e];
-    while (e != NIL) {
-        // the next entry is requested before this entry's child node arrives: one memory round trip per hop, not two
-        // (a search scans ~160 entries, r01k)
-        const uint32_t next = en.y;
-        uint2 en_next = make_uint2(0u, NIL);
-        if (next != NIL) en_next = t.ents[next];
-        const uint32_t c = en.x & 0xFFFFFFu;
-        const int4 cn = t.nodes[c];
-        // black_win / (1 + visit); a zero numerator would send the IEEE division into its subroutine, and most
-        // children have no black win yet: stand-in operand, exact result (+0) selected afterwards
-        float p = (cn.y != 0 ? (float)cn.y : 1.f) / (1.f + (float)cn.x);
-        if (cn.y == 0) p = 0.f;
-        if (turn > 0) p = -p;
-        if (!any || !(p < bp)) any = true, bp = p, child = c, bit = en.x >> 24;
-        e = next, en = en_next;
-        scanned += 1;
+    uint4 a = t.chunks[2 * (size_t)ch], b = t.chunks[2 * (size_t)ch + 1];
+    for (;;) {
+        // the next chunk and this chunk's seven child nodes are all requested before the first of them is looked at
+        const uint32_t next = b.w;
+        uint4 na = make_uint4(NIL, NIL, NIL, NIL), nb = na;
+        if (next != NIL) na = t.chunks[2 * (size_t)next], nb = t.chunks[2 * (size_t)next + 1];
+        const uint32_t e[7] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+        int2 cn[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            cn[i] = make_int2(0, 0);
+            if (e[i] != NIL) cn[i] = *reinterpret_cast<const int2*>(&t.nodes[e[i] & 0xFFFFFFu]);  // {visit, black_win}
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            if (e[i] == NIL) continue;  // slots fill in order: everything behind a free slot is free
+            // black_win / (1 + visit); a zero numerator would send the IEEE division into its subroutine, and most
+            // children have no black win yet: stand-in operand, exact result (+0) selected afterwards
+            float p = (cn[i].y != 0 ? (float)cn[i].y : 1.f) / (1.f + (float)cn[i].x);
+            if (cn[i].y == 0) p = 0.f;
+            if (turn > 0) p = -p;
+            if (!any || !(p < bp)) any = true, bp = p, child = e[i] & 0xFFFFFFu, bit = e[i] >> 24;
+            scanned += 1;
+        }
+        if (next == NIL) break;
+        a = na, b = nb;
     }
     return any && bp != 0.f;
 }
@@ -141,14 +154,19 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
     if (g >= D.n) return;
     DpTree t;
     t.nodes = D.nodes + (size_t)g * D.ncap, t.keys = D.keys + (size_t)g * D.ncap;
-    t.table = D.table + (size_t)g * (D.tmask + 1), t.ents = D.ents + (size_t)g * D.ecap;
+    t.table = D.table + (size_t)g * (D.tmask + 1), t.chunks = D.chunks + (size_t)g * D.ecap * 2;
     t.tmask = D.tmask, t.n_nodes = 0, t.n_ents = 0;
     uint32_t* path = D.path + g;
     const size_t pstride = (size_t)D.n;
     const uint32_t k0 = D.seed ^ DOMAIN_DEFPOL, k1 = D.first_id + (uint32_t)g;
     unsigned long long n_search = 0, n_roll = 0, n_stones = 0, n_sel = 0, n_scan = 0, n_repl = 0;
 
-    uint32_t RB[8] = {0, 0, 0, 0, 0, 0, 0, 0}, RW[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the game (Game::board)
+    // the game (Game::board): read once per search and written once per stone — kept in shared memory (word-major: no bank
+    // conflicts) so that its sixteen registers are free for the loads a select step keeps in flight
+    __shared__ uint32_t sroot[16][32];
+    const int ln = (int)threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sroot[j][ln] = 0;
     uint64_t rkey = 0;
     int rstones = 0, winner = 0, finished = 1, n_moves = 0, err = 0;
     GameRecord* out = D.rec + g;
@@ -163,7 +181,7 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
             if (t.n_nodes + 1 > D.ncap || t.n_ents + 1 > D.ecap) { err = 1; break; }
             uint32_t B[8], W[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) B[j] = RB[j], W[j] = RW[j];
+            for (int j = 0; j < 8; ++j) B[j] = sroot[j][ln], W[j] = sroot[8 + j][ln];
             uint64_t key = rkey;
             int stones = rstones, depth = 0;
             uint32_t node = root;
@@ -201,11 +219,20 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
                 child = t.create(key);
             }
             {
-                const uint32_t e = t.n_ents++;
-                t.ents[e] = make_uint2(child | (ebit << 24), NIL);
+                const uint32_t entry = child | (ebit << 24);
                 int4 pn = t.nodes[node];
-                if ((uint32_t)pn.w != NIL) t.ents[(uint32_t)pn.w].y = e; else pn.z = (int)e;
-                pn.w = (int)e;
+                const uint32_t tw = (uint32_t)pn.w;
+                if (tw == NIL || (tw >> 24) == 7u) {  // first child, or the tail chunk is full: a new chunk
+                    const uint32_t c = t.n_ents++;
+                    t.chunks[2 * (size_t)c] = make_uint4(entry, NIL, NIL, NIL);
+                    t.chunks[2 * (size_t)c + 1] = make_uint4(NIL, NIL, NIL, NIL);
+                    if (tw != NIL) reinterpret_cast<uint32_t*>(&t.chunks[2 * (size_t)(tw & 0xFFFFFFu)])[7] = c; else pn.z = (int)c;
+                    pn.w = (int)(c | (1u << 24));
+                } else {
+                    const uint32_t c = tw & 0xFFFFFFu, f = tw >> 24;
+                    reinterpret_cast<uint32_t*>(&t.chunks[2 * (size_t)c])[f] = entry;
+                    pn.w = (int)(c | ((f + 1u) << 24));
+                }
                 t.nodes[node] = pn;
             }
             path[(size_t)depth * pstride] = child;
@@ -239,7 +266,10 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
         n_sel += 1;
         if (!dp_select(t, root, turn_of(rstones), child, bit, n_scan)) {
             const uint32_t u = philox4x32_10((uint32_t)rstones, 0xFFFFFFFFu, 0, 0, k0, k1).x;
-            bit = dp_pick(RB, RW, (uint32_t)(((unsigned long long)u * (unsigned long long)(CELLS - rstones)) >> 32));
+            uint32_t B[8], W[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) B[j] = sroot[j][ln], W[j] = sroot[8 + j][ln];
+            bit = dp_pick(B, W, (uint32_t)(((unsigned long long)u * (unsigned long long)(CELLS - rstones)) >> 32));
         }
         if (D.root_visit) {
             const int4 rn = t.nodes[root];
@@ -248,11 +278,16 @@ __global__ void __launch_bounds__(32) k_default_policy(DpDev D) {
         }
         // Agent::play: Game::set, record, is_game_end
         const int turn = turn_of(rstones);
-        dp_place(RB, RW, bit, turn);
+        sroot[(turn > 0 ? 8 : 0) + (bit >> 5)][ln] |= 1u << (bit & 31);
         rkey ^= D.Z[(turn > 0 ? 256 : 0) + bit];
         rstones += 1;
         out->moves[n_moves++] = (uint8_t)cell_of_bit(bit);
-        if (dp_won(RB, RW, turn)) { winner = turn; break; }
+        {
+            uint32_t B[8], W[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) B[j] = sroot[j][ln], W[j] = sroot[8 + j][ln];
+            if (dp_won(B, W, turn)) { winner = turn; break; }
+        }
     }
     out->winner = (int8_t)winner;
     out->n_moves = (uint8_t)n_moves;
@@ -283,7 +318,7 @@ float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, l
     for (int i = 0; i < 8; ++i) stats[i] = 0;
     if (n_games == 0) return 0.f;
     const int moves = (max_moves > 0 && max_moves < CELLS) ? max_moves : CELLS;
-    // every search creates at most one node and one entry; init() creates at most one node per move
+    // every search creates at most one node and one chunk of entries; init() creates at most one node per move
     const long long ecap64 = std::max<long long>(1, (long long)num_iter * moves);
     // child entries pack `child | move << 24`: node ids must stay below 2^24 (num_iter up to ~74,000 for whole games)
     if (ecap64 + moves + 2 >= (1ll << 24))
@@ -292,7 +327,7 @@ float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, l
     const uint32_t ncap = ecap + (uint32_t)moves + 2;
     uint32_t tsize = 64;
     while (tsize < 2 * ncap) tsize <<= 1;
-    const size_t per_game = (size_t)ncap * (16 + 8) + (size_t)tsize * 4 + (size_t)ecap * 8 + 232 * 4 + sizeof(GameRecord) + 2 * CELLS * 4;
+    const size_t per_game = (size_t)ncap * (16 + 8) + (size_t)tsize * 4 + (size_t)ecap * 32 + 232 * 4 + sizeof(GameRecord) + 2 * CELLS * 4;
     size_t free_b = 0, total_b = 0;
     DP_CK(cudaMemGetInfo(&free_b, &total_b));
     long long batch = (long long)((free_b * 8 / 10) / per_game);
@@ -314,7 +349,7 @@ float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, l
     DP_CK(cudaMalloc(&D.nodes, (size_t)batch * ncap * 16));
     DP_CK(cudaMalloc(&D.keys, (size_t)batch * ncap * 8));
     DP_CK(cudaMalloc(&D.table, (size_t)batch * tsize * 4));
-    DP_CK(cudaMalloc(&D.ents, (size_t)batch * ecap * 8));
+    DP_CK(cudaMalloc(&D.chunks, (size_t)batch * ecap * 32));
     DP_CK(cudaMalloc(&D.path, (size_t)batch * 232 * 4));
     DP_CK(cudaMalloc(&D.rec, (size_t)batch * sizeof(GameRecord)));
     DP_CK(cudaMalloc(&D.stats, 8 * sizeof(unsigned long long)));
@@ -348,7 +383,7 @@ float default_policy_play(int num_iter, uint32_t seed, uint32_t first_game_id, l
         }
     }
     DP_CK(cudaMemcpy(stats, D.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    cudaFree(D.nodes), cudaFree(D.keys), cudaFree(D.table), cudaFree(D.ents), cudaFree(D.path), cudaFree(D.rec), cudaFree(D.stats);
+    cudaFree(D.nodes), cudaFree(D.keys), cudaFree(D.table), cudaFree(D.chunks), cudaFree(D.path), cudaFree(D.rec), cudaFree(D.stats);
     cudaFree(D.root_visit), cudaFree(D.root_bw), cudaFree(dZ);
     cudaEventDestroy(a), cudaEventDestroy(b), cudaStreamDestroy(s);
     if (stats[7]) throw std::runtime_error("default_policy_play: node pool of a game overflowed");
