@@ -126,6 +126,44 @@ __host__ __device__ __forceinline__ void run6_all(const uint32_t (&b)[8], uint32
 #pragma unroll
     for (int w = 2; w < 8; ++w) acc[w] |= x[w] & shr_plain<3>(sx[w - 1]);
 }
+// position of the n-th (0-based) set bit of x, n < popc(x): binary search on the popcounts of the lower halves, five branch-free
+// steps.  (`__fns` does the same in a data-dependent software loop, and eight predicated copies of it — one per board word —
+// left 4 to 8 of a warp's 32 lanes active in every loop that picks a random empty cell.)
+__host__ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t x, uint32_t n) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const uint32_t lo = x & ((1u << w) - 1u);
+#ifdef __CUDA_ARCH__
+        const uint32_t c = (uint32_t)__popc(lo);
+#else
+        const uint32_t c = (uint32_t)__builtin_popcount(lo);
+#endif
+        const bool up = n >= c;
+        n -= up ? c : 0u, pos += up ? (uint32_t)w : 0u, x = up ? (x >> w) : lo;
+    }
+    return pos;
+}
+// bit position of the pick-th (0-based) empty cell in row-major order, pick < number of empty cells
+__host__ __device__ __forceinline__ uint32_t pick_empty_cell(const uint32_t (&B)[8], const uint32_t (&W)[8], uint32_t pick) {
+    uint32_t word = 0, mask = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = ~(B[j] | W[j]) & valid_mask(j);
+#ifdef __CUDA_ARCH__
+        const uint32_t c = (uint32_t)__popc(e);
+#else
+        const uint32_t c = (uint32_t)__builtin_popcount(e);
+#endif
+        const bool here = !found && pick < c;
+        if (here) word = (uint32_t)j, mask = e;
+        found = found || here;
+        if (!found) pick -= c;
+    }
+    return 32u * word + nth_set_bit(mask, pick);
+}
+
 // search(): winner = colour whose first run-end cell comes first in row-major order
 __host__ __device__ inline int win_check(const uint32_t (&B)[8], const uint32_t (&W)[8]) {
     uint32_t eb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ew[8] = {0, 0, 0, 0, 0, 0, 0, 0};

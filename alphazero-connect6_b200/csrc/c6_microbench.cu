@@ -88,22 +88,7 @@ __global__ void __launch_bounds__(128) k_playouts(long long first, long long n, 
         if ((s & 3) == 0) r = philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(s >> 2), 0, seed ^ DOMAIN_PLAYOUT, 0);
         uint32_t u = (s & 3) == 0 ? r.x : (s & 3) == 1 ? r.y : (s & 3) == 2 ? r.z : r.w;
         uint32_t pick = (uint32_t)(((unsigned long long)u * (unsigned long long)(CELLS - s)) >> 32);
-        // pick-th empty cell
-        uint32_t bit = 0;
-        bool found = false;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t e = ~(B[j] | W[j]) & valid_mask(j);
-            uint32_t c = __popc(e);
-            if (!found) {
-                if (pick < c) {
-                    bit = 32u * j + __fns(e, 0, (int)pick + 1);
-                    found = true;
-                } else {
-                    pick -= c;
-                }
-            }
-        }
+        const uint32_t bit = pick_empty_cell(B, W, pick);
         const int turn = turn_of(s);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

@@ -508,7 +508,7 @@ C6_UNROLL(C6_PUCT_UNROLL)
                         const unsigned bal = __ballot_sync(FULL, k < C && st.lw[0][k] == bs);
                         const uint32_t c = (uint32_t)__popc(bal);
                         if (j < c) {
-                            bb = 32u * i + __fns(bal, 0, (int)j + 1);
+                            bb = 32u * i + nth_set_bit(bal, j);
                             break;
                         }
                         j -= c;

@@ -107,7 +107,7 @@ ex2f_poly = [1.0] + [float(np.float32(v)) for v in _coef]
 gthr = []
 for v in range(256):
     if v == 255:
-        gthr.append(-3.0e38)
+        gthr.append(-float(2.0 ** 127))  # "never": below every log2 the sampler can produce
         continue
     t = math.log2((255 - v) / 256) - 2.0 ** -20  # double precision is ample next to the margin
     f = float(np.float32(t))

@@ -3,7 +3,7 @@
 TAG=${1:-dp}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout 900 python -m pytest tests/test_default_policy.py -m gpu -x -q > $OUT/pytest_dp.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_dp.log
+timeout 900 python -m pytest tests/test_default_policy.py tests/test_parity_gpu.py -m gpu -k "default_policy or playout or win_check" -x -q > $OUT/pytest_dp.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_dp.log
 tail -4 $OUT/pytest_dp.log
 timeout 600 python scripts/micro.py --no-cpu 2>&1 | tee $OUT/micro.jsonl | cut -c1-330
 for v in alphazero-connect6_b200/lib/variants/libm_*.so; do

@@ -38,8 +38,13 @@ def test_oracle_default_policy_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("num_iter,n_games,max_moves,seed", [(50, 48, 0, 0xC6), (2, 40, 0, 7), (200, 8, 30, 11), (1, 16, 0, 1)])
-def test_default_policy_gpu_matches_oracle(num_iter, n_games, max_moves, seed):
+@pytest.mark.parametrize("num_iter,n_games,max_moves,seed,slots", [(50, 48, 0, 0xC6, 0), (2, 40, 0, 7, 0), (200, 8, 30, 11, 0), (1, 16, 0, 1, 0),
+                                                                 (50, 48, 0, 0xC6, 5), (3, 150, 0, 9, 37)])
+def test_default_policy_gpu_matches_oracle(num_iter, n_games, max_moves, seed, slots, monkeypatch):
+    """slots > 0: fewer tree slots than games (C6_DP_SLOTS) — a lane whose game is over takes the next game into the same slot,
+    on a tree it has to empty first; 5 and 37 slots also leave a warp partly filled."""
+    if slots:
+        monkeypatch.setenv("C6_DP_SLOTS", str(slots))
     L = c6lib.product()
     first = 1000
     rec = (c6lib.Record * n_games)()
