@@ -29,5 +29,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_s
     python scripts/secondary_kernels.py > $OUT/ncu_callback.log 2>&1; echo "ncu callback rc=$?" >> $OUT/ncu_callback.log
 timeout 600 python scripts/micro.py > $OUT/micro.jsonl 2> $OUT/micro.err; cat $OUT/micro.jsonl
 timeout 600 python scripts/config1.py > $OUT/config1.jsonl 2> $OUT/config1.err; cat $OUT/config1.jsonl
+timeout 400 ncu --section SpeedOfLight --section WarpStateStats --section SchedulerStats --section Occupancy --section LaunchStats --section MemoryWorkloadAnalysis \
+    --clock-control none -k regex:k_default_policy -c 1 -o $OUT/prof_default_policy python scripts/dp_profile.py > $OUT/ncu_dp.log 2>&1; echo "ncu dp rc=$?" >> $OUT/ncu_dp.log
 kill $SMI
 ls -la $OUT
