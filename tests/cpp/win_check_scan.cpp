@@ -1,7 +1,8 @@
 // The bit-packed win detection of the kernels (c6_board.cuh: win_check, win_check_fast / run6_all), compiled for the host,
 // against a cell-by-cell scan of search()'s rule (LC/game/search_winner/mod.rs:201-246: the colour whose run of six ENDS
 // first in row-major order).  Random boards of several densities plus boards built around a run that touches the board
-// edge or sits next to the row boundary, where a shift that carried across a row would show.
+// edge or sits next to the row boundary, where a shift that carried across a row would show.  Also the n-th-empty-cell pick
+// (nth_set_bit, pick_empty_cell) against a bit-by-bit walk.
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -67,6 +68,41 @@ int main(int argc, char** argv) {
                         }
                         bad += check(cell, wins);
                     }
-    std::printf("boards=%ld wins=%ld bad=%ld\n", boards, wins, bad);
+    // nth_set_bit / pick_empty_cell (the random-empty-cell pick of the playout and DefaultPolicy kernels) against a bit-by-bit walk
+    long picks = 0;
+    for (int it = 0; it < 400000; ++it) {
+        uint32_t x = rng();
+        if (it % 5 == 0) x &= rng();
+        if (it % 7 == 0) x |= rng();
+        if (it % 11 == 0) x = 1u << (rng() & 31);
+        if (!x) continue;
+        const uint32_t n = rng() % (uint32_t)__builtin_popcount(x);
+        uint32_t want = 0, k = n;
+        for (int b = 0; b < 32; ++b)
+            if ((x >> b) & 1u) {
+                if (k == 0) { want = (uint32_t)b; break; }
+                --k;
+            }
+        bad += c6::nth_set_bit(x, n) != want;
+        ++picks;
+    }
+    for (int it = 0; it < 100000; ++it) {
+        uint32_t B[8], W[8];
+        int order[256], empties = 0;
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rng() & (it % 3 ? rng() : 0xFFFFFFFFu), b = rng() & rng() & ~a;
+            B[j] = a & c6::valid_mask(j), W[j] = b & c6::valid_mask(j);
+        }
+        for (int bit = 0; bit < 256; ++bit) {
+            const int j = bit >> 5;
+            if (((c6::valid_mask(j) >> (bit & 31)) & 1u) && !(((B[j] | W[j]) >> (bit & 31)) & 1u)) order[empties++] = bit;
+        }
+        if (!empties) continue;
+        for (int rep = 0; rep < 4; ++rep, ++picks) {
+            const uint32_t p = rep == 0 ? 0u : (rep == 1 ? (uint32_t)empties - 1u : rng() % (uint32_t)empties);
+            bad += c6::pick_empty_cell(B, W, p) != (uint32_t)order[p];
+        }
+    }
+    std::printf("boards=%ld wins=%ld picks=%ld bad=%ld\n", boards, wins, picks, bad);
     return bad != 0;
 }
