@@ -1,7 +1,8 @@
 // DefaultPolicy — the reference's pure Monte-Carlo tree search with random rollouts — played by the GPU for many
 // games at once.  One THREAD per game: the tree of a game is touched by one search at a time
 // (search i+1 reads what search i wrote), so the parallelism is across games, and a thread carries its game's
-// board in registers through the rollout exactly like the config-3b playout kernel (c6_microbench.cu).
+// board in registers through the rollout exactly like the config-3b playout kernel (c6_microbench.cu).  The GPU keeps
+// 75,776 such threads resident (128 registers each); each owns one tree slot and plays game after game in it.
 //   DefaultPolicy::{init,select,expand,update,search,policy,next}   LC/policy/default_policy/mod.rs:121-271
 //   Agent::play                                                     LC/agent/agent_impl/mod.rs:121-178
 // (LC = /root/reference/Connect6/libconnect6/src).  What the reference keeps in `HashMap<u64, Node>`:
@@ -34,8 +35,8 @@ struct DpDev {
     uint32_t* table;   // [n][tmask + 1] node index + 1, 0 = empty
     uint4* chunks;     // [n][ecap][2]
     uint32_t* path;    // [232][n] node indices of the current search (game-minor: coalesced across a warp)
-    GameRecord* rec;   // [n]
-    int32_t* root_visit;  // [n][225] or null: root node after the searches of each move
+    GameRecord* rec;   // [total]
+    int32_t* root_visit;  // [total][225] or null: root node after the searches of each move
     int32_t* root_bw;
     const uint64_t* Z;
     unsigned long long* stats;  // searches, rollouts, rollout stones, select steps, children scanned, replaced, nodes, errors
@@ -99,7 +100,7 @@ __device__ __forceinline__ bool dp_won(const uint32_t (&B)[8], const uint32_t (&
     return any != 0;
 }
 
-// One THREAD per game, one warp per block (a block retires when its 32 games are over), and every lane a small state machine.
+// One THREAD per game, one warp per block, and every lane a small state machine.
 // Written as nested loops (game > stone > search > {select steps > children, rollout stones}) the 32 games of a warp spent
 // most of their time waiting for each other: 7.7 of 32 lanes active per instruction (profiles/r02q), because SIMT runs every
 // inner loop for the longest of its 32 trip counts.  Here one pass of the single loop gives every lane ONE unit of whatever
