@@ -209,7 +209,10 @@ int c6_bench_playouts(int64_t first, int64_t n, uint32_t seed, int iters, int de
  * Agent::play (agent/agent_impl/mod.rs:121-178) for n_games games on the GPU, `num_iter` searches per stone
  * (DefaultPolicy::new() uses 50, mod.rs:104).  One policy instance per game plays both colours, as
  * `Agent::new(&mut policy).play()` does.  Random choices: Philox streams keyed (seed, game id).
- * root_visit / root_black_win (may be NULL): n_games x 225 i32, the root node's counters when stone m was chosen. */
+ * root_visit / root_black_win (may be NULL): n_games x 225 i32, the root node's counters when stone m was chosen.
+ * Tree memory is per RESIDENT game (one thread each, as many as the GPU keeps resident or the free memory allows; C6_DP_SLOTS
+ * caps it): a thread whose game is over takes the next game id, so n_games may be far larger; results depend on
+ * (seed, game id) only. */
 typedef struct c6_dp_stats {
     uint64_t searches, rollouts, rollout_stones, select_steps, children_scanned, replaced, nodes, errors;
     float kernel_ms;
