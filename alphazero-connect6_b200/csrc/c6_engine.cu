@@ -427,6 +427,7 @@ struct Group {
 // cudaFree (6 ms each way for a one-game engine against 5 ms of search, profiles/r02o_config1.jsonl).  Bounded: at most
 // C6_ALLOC_CACHE_MB (default 256) in total and 16 blocks, so a 30 GB node pool is never held back.  Contents are whatever the
 // last owner left: the constructor clears what it reads before writing, as it must for fresh memory too.
+void release_cached_memory();
 namespace {
 struct CachedBlock {
     int device;
@@ -456,10 +457,12 @@ void* cached_alloc(int device, size_t bytes, bool pinned) {
             }
     }
     void* p = nullptr;
-    if (pinned)
-        C6_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocMapped));
-    else
-        C6_CUDA(cudaMalloc(&p, bytes));
+    auto try_alloc = [&] { return pinned ? cudaHostAlloc(&p, bytes, cudaHostAllocMapped) : cudaMalloc(&p, bytes); };
+    if (try_alloc() != cudaSuccess) {  // out of memory with blocks held back: give them up and try once more
+        cudaGetLastError();
+        release_cached_memory();
+        C6_CUDA(try_alloc());
+    }
     return p;
 }
 // the caller has synchronised every stream that touched the block
