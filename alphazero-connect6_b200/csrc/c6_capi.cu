@@ -853,6 +853,7 @@ static void sample_fill_scalar(uint32_t base, float* out, size_t lo, size_t hi) 
 }
 #if defined(__GNUC__) && defined(__x86_64__)
 #include <immintrin.h>
+template <bool NT>
 __attribute__((target("avx2")))
 static void sample_fill_avx2(uint32_t base, float* out, size_t lo, size_t hi) {
     size_t e = lo;
@@ -867,10 +868,31 @@ static void sample_fill_avx2(uint32_t base, float* out, size_t lo, size_t hi) {
         x = _mm256_mullo_epi32(x, m2);
         x = _mm256_xor_si256(x, _mm256_srli_epi32(x, 13));
         const __m256 f = _mm256_sub_ps(_mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_srli_epi32(x, 8)), scale), one);
-        _mm256_stream_ps(out + e, f);
+        if (NT) _mm256_stream_ps(out + e, f); else _mm256_store_ps(out + e, f);
     }
     for (; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
-    _mm_sfence();
+    if (NT) _mm_sfence();
+}
+// the same with 512-bit registers: one non-temporal store writes a whole cache line
+template <bool NT>
+__attribute__((target("avx512f")))
+static void sample_fill_avx512(uint32_t base, float* out, size_t lo, size_t hi) {
+    size_t e = lo;
+    for (; e < hi && ((uintptr_t)(out + e) & 63u); ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+    const __m512i step = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    const __m512i m1 = _mm512_set1_epi32((int)0xC2B2AE3Du), m2 = _mm512_set1_epi32((int)0x85EBCA77u);
+    const __m512 scale = _mm512_set1_ps(1.0f / 8388608.0f), one = _mm512_set1_ps(1.0f);
+    for (; e + 16 <= hi; e += 16) {
+        __m512i x = _mm512_add_epi32(_mm512_set1_epi32((int)(base + (uint32_t)e)), step);
+        x = _mm512_mullo_epi32(x, m1);
+        x = _mm512_xor_si512(x, _mm512_srli_epi32(x, 15));
+        x = _mm512_mullo_epi32(x, m2);
+        x = _mm512_xor_si512(x, _mm512_srli_epi32(x, 13));
+        const __m512 f = _mm512_sub_ps(_mm512_mul_ps(_mm512_cvtepi32_ps(_mm512_srli_epi32(x, 8)), scale), one);
+        if (NT) _mm512_stream_ps(out + e, f); else _mm512_store_ps(out + e, f);
+    }
+    for (; e < hi; ++e) out[e] = sample_unit(sample_mix(base + (uint32_t)e));
+    if (NT) _mm_sfence();
 }
 // policy = f(board): reads every board cell and overwrites it in place (cached read-modify-write: the evaluator of a
 // real network reads its input).  p = 1/2 - board/4 + cell pattern/1024 — cheap on purpose: the leg measures the path.
@@ -895,9 +917,11 @@ static void reading_fill_avx2(float* pol, size_t lo, size_t hi, float* acc_out) 
     *acc_out = acc;
 }
 static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+static const bool g_have_avx512 = __builtin_cpu_supports("avx512f");
 #else
-static const bool g_have_avx2 = false;
-static void sample_fill_avx2(uint32_t, float*, size_t, size_t) {}
+static const bool g_have_avx2 = false, g_have_avx512 = false;
+template <bool NT> static void sample_fill_avx2(uint32_t, float*, size_t, size_t) {}
+template <bool NT> static void sample_fill_avx512(uint32_t, float*, size_t, size_t) {}
 static void reading_fill_avx2(float*, size_t, size_t, float*) {}
 #endif
 static void reading_fill_scalar(float* pol, size_t lo, size_t hi, float* acc_out) {
@@ -907,8 +931,18 @@ static void reading_fill_scalar(float* pol, size_t lo, size_t hi, float* acc_out
 }
 static void sample_fill(uint32_t base, float* values, float* policies, int lo, int hi) {
     for (int n = lo; n < hi; ++n) values[n] = sample_unit(sample_mix((base ^ 0x5bd1e995u) + (uint32_t)n));
-    // runtime dispatch: the AVX2 body must not run on an x86-64 host without AVX2
-    (g_have_avx2 ? sample_fill_avx2 : sample_fill_scalar)(base * 0x9E3779B1u, policies, (size_t)lo * 225, (size_t)hi * 225);
+    // runtime dispatch: a vector body must not run on an x86-64 host without its instruction set.  C6_SAMPLE_ISA = avx512 |
+    // avx2 | scalar narrows the choice, C6_SAMPLE_NT=0 uses cached stores (tuning knobs of the sample evaluator only).
+    using Fill = void (*)(uint32_t, float*, size_t, size_t);
+    static const Fill fill = [] {
+        const char* isa = std::getenv("C6_SAMPLE_ISA");
+        const std::string want = isa ? isa : "";
+        const bool nt = env_int("C6_SAMPLE_NT", 1) != 0;
+        if (g_have_avx512 && (want.empty() || want == "avx512")) return nt ? (Fill)sample_fill_avx512<true> : (Fill)sample_fill_avx512<false>;
+        if (g_have_avx2 && want != "scalar") return nt ? (Fill)sample_fill_avx2<true> : (Fill)sample_fill_avx2<false>;
+        return (Fill)sample_fill_scalar;
+    }();
+    fill(base * 0x9E3779B1u, policies, (size_t)lo * 225, (size_t)hi * 225);
 }
 
 extern "C" void c6_sample_random_callback(int player, float* values, float* policies, int len) {
