@@ -11,6 +11,7 @@
 #include <array>
 #include <cstdio>
 #include <optional>
+#include <random>
 #include <string>
 #include <utility>
 #include <vector>
@@ -157,6 +158,26 @@ class IoPolicy : public Policy {
 
    private:
     FILE *in_, *out_;
+};
+
+// LC/policy/random_policy/mod.rs:31-49 — a uniformly chosen empty cell (`possible.choose(thread_rng())`), None on a full
+// board.  Host-only, no search in it; seeded from the OS like thread_rng() unless a seed is given.
+class RandomPolicy : public Policy {
+   public:
+    RandomPolicy() : rng_(std::random_device{}()) {}
+    explicit RandomPolicy(uint64_t seed) : rng_(seed) {}
+    std::optional<Pos> next(const Game& game) override {
+        std::vector<Pos> possible;  // row-major, as Simulate::from_game builds it
+        const Board& b = game.get_board();
+        for (size_t r = 0; r < BOARD_SIZE; ++r)
+            for (size_t c = 0; c < BOARD_SIZE; ++c)
+                if (b[r][c] == Player::None) possible.emplace_back(r, c);
+        if (possible.empty()) return std::nullopt;
+        return possible[std::uniform_int_distribution<size_t>(0, possible.size() - 1)(rng_)];
+    }
+
+   private:
+    std::mt19937_64 rng_;
 };
 
 struct Path {

@@ -350,6 +350,20 @@ def test_win_check_against_cell_scan():
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
 
 
+def test_host_policies_random_and_multi():
+    """tests/cpp/host_policies.cpp: RandomPolicy under Agent::play (port of random_policy/tests.rs:7-25 over 300 seeds), MultiPolicy
+    dispatch, Game::set error strings — the host-only part of the mirror, no GPU and no library needed."""
+    src = os.path.join(ROOT, "tests", "cpp", "host_policies.cpp")
+    exe = os.path.join(BUILD_DIR, "host_policies")
+    csrc = os.path.join(c6lib.PKG, "csrc")
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(f) for f in (src, os.path.join(csrc, "connect6_host.hpp"))):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-I", csrc, "-I", "/usr/local/cuda/include", src, "-o", exe], check=True,
+                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/Connect6/pybind"), reason="reference tree not mounted")
 def test_reference_pybind_echo_test_runs_in_place():
     """PB/test_pybind/test_pybind.py::test_echo_pyeval, the reference's own file run where it lies against our pyconnect6
